@@ -1,0 +1,30 @@
+import os
+import sys
+import types
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def repo_namespace():
+    """Data-model + potential classes of this repo, in the shape ``specs`` builders expect."""
+    import lhvi_b200
+    ns = types.SimpleNamespace()
+    for mod in (lhvi_b200.Graph, lhvi_b200.Potential, lhvi_b200.MLNPotential):
+        for name in dir(mod):
+            if not name.startswith("_"):
+                setattr(ns, name, getattr(mod, name))
+    return ns
+
+
+@pytest.fixture(scope="session")
+def ns():
+    return repo_namespace()

@@ -1,0 +1,217 @@
+"""Small graphs used to pin the oracle (and through it the CUDA path) to the reference.
+
+Every builder takes a namespace ``ns`` exposing the data-model and potential classes
+(``Domain, RV, F, Graph, TablePotential, GaussianPotential, LinearGaussianPotential,
+X2Potential, XYPotential, MLNPotential`` and the soft-logic operators).  ``make_golden.py``
+passes the *reference's* modules (imported from ``/root/reference``), the tests pass this
+repo's -- the same code therefore builds the same graph on both sides.  Builders return
+``(graph, rvs)`` with ``rvs`` in creation order; that order indexes every golden array.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _graph(ns, rvs, factors):
+    g = ns.Graph()
+    g.rvs = set(rvs)
+    g.factors = set(factors)
+    g.init_nb()
+    return g, rvs
+
+
+def chain_table(ns):
+    """A-B-C-D-E boolean chain, B observed (reference Demo/old/VarInferenceTestDemo.py)."""
+    dom = ns.Domain((0, 1))
+    pot = ns.TablePotential({(0, 0): 1, (0, 1): 0.1, (1, 0): 0.1, (1, 1): 1})
+    A, B, C, D, E = ns.RV(dom), ns.RV(dom, 1), ns.RV(dom), ns.RV(dom), ns.RV(dom)
+    fs = [ns.F(pot, [A, B]), ns.F(pot, [E, D]), ns.F(pot, [B, C]), ns.F(pot, [D, C])]
+    return _graph(ns, [A, B, C, D, E], fs)
+
+
+def tri_table3(ns):
+    """Three-state variables with a ternary table factor plus pairwise ones."""
+    dom = ns.Domain((0, 1, 2))
+    rng = np.random.default_rng(5)
+    t3 = rng.uniform(0.2, 2.0, size=(3, 3, 3))
+    t2 = rng.uniform(0.2, 2.0, size=(3, 3))
+    p3 = ns.TablePotential(t3)
+    p2 = ns.TablePotential(t2)
+    X = [ns.RV(dom) for _ in range(4)] + [ns.RV(dom, 2)]
+    fs = [ns.F(p3, [X[0], X[1], X[2]]), ns.F(p2, [X[2], X[3]]), ns.F(p2, [X[3], X[4]]),
+          ns.F(p2, [X[0], X[3]])]
+    return _graph(ns, X, fs)
+
+
+def gauss_net(ns):
+    """All-continuous net with every exp-quadratic potential class and point evidence."""
+    dom = ns.Domain((-10, 10), continuous=True)
+    X = [ns.RV(dom) for _ in range(5)] + [ns.RV(dom, 1.3), ns.RV(dom, -0.4)]
+    pg = ns.GaussianPotential([0.0, 0.0], [[10.0, -7.0], [-7.0, 10.0]])
+    pg2 = ns.GaussianPotential([1.0, -1.0], [[2.0, 0.5], [0.5, 1.0]])
+    lg = ns.LinearGaussianPotential(0.8, 0.5)
+    x2 = ns.X2Potential(1.0, 2.0)
+    xy = ns.XYPotential(-0.6, 2.0)
+    fs = [ns.F(pg, [X[0], X[1]]), ns.F(pg2, [X[1], X[2]]), ns.F(lg, [X[2], X[5]]),
+          ns.F(lg, [X[3], X[6]]), ns.F(xy, [X[2], X[3]]), ns.F(xy, [X[3], X[4]]),
+          ns.F(pg, [X[4], X[0]])]
+    fs += [ns.F(x2, [X[i]]) for i in range(5)]
+    return _graph(ns, X, fs)
+
+
+def _paper_pop(ns, n_paper, n_topic, hidden_in, seed):
+    """Paper-popularity HMLN (reference Demo/Data/HMLN/GeneratorPaperPopularity.py) built
+    by hand: PaperIn(p,t) boolean, PaperPopularity(p) / TopicPopularity(t) real."""
+    rng = np.random.default_rng(seed)
+    d_bool = ns.Domain((0, 1))
+    d_real = ns.Domain((-15, 15), continuous=True)
+    prior = ns.MLNPotential(lambda x: ns.eq_op(x[0], 1), w=0.3)
+    link = ns.MLNPotential(lambda x: x[0] * ns.eq_op(x[1], x[2]), w=1)
+    sess = ns.MLNPotential(lambda x: x[0] * ns.eq_op(x[1], x[2]), w=0.5)
+    topics = [ns.RV(d_real, None if t % 3 else float(rng.uniform(0, 10))) for t in range(n_topic)]
+    papers = [ns.RV(d_real, None if rng.random() < 0.5 else float(rng.uniform(0, 10)))
+              for _ in range(n_paper)]
+    rvs = topics + papers
+    fs = [ns.F(prior, [p]) for p in papers]
+    for i, p in enumerate(papers):
+        for j, t in enumerate(topics):
+            is_hidden = hidden_in and (i + j) % 3 == 0
+            pin = ns.RV(d_bool, None if is_hidden else int(rng.integers(0, 2)))
+            rvs.append(pin)
+            fs.append(ns.F(link, [pin, p, t]))
+    for a in range(n_topic):
+        for b in range(n_topic):
+            if a != b and (a + b) % 2 == 1:
+                same = ns.RV(d_bool, int(rng.integers(0, 2)))
+                rvs.append(same)
+                fs.append(ns.F(sess, [same, topics[a], topics[b]]))
+    return _graph(ns, rvs, fs)
+
+
+def hmln_evidence(ns):
+    """Relation atoms all observed: the reference's category-gradient bug cannot fire."""
+    return _paper_pop(ns, n_paper=4, n_topic=3, hidden_in=False, seed=11)
+
+
+def hmln_hidden(ns):
+    """Some PaperIn atoms hidden next to hidden popularities: H2 fires in the reference."""
+    return _paper_pop(ns, n_paper=3, n_topic=2, hidden_in=True, seed=12)
+
+
+def robot_like(ns):
+    """Arity-5 boolean clause, boolean pair clauses and hybrid bool x real factors
+    (shapes of reference Demo/Data/HMLN/GeneratorRobotMapping.py)."""
+    d_bool = ns.Domain((0, 1))
+    d_len = ns.Domain((0, 1), continuous=True)
+    clause5 = ns.MLNPotential(
+        lambda x: 1 - (x[0] == 1) * (x[1] == 1) * (x[2] == 0) * (x[3] == 1) * (1 - x[4]), w=1.591)
+    excl = ns.MLNPotential(lambda x: ns.or_op(ns.neg_op(x[0]), ns.neg_op(x[1])), w=3)
+    unit = ns.MLNPotential(lambda x: x[0], w=-0.737)
+    door = ns.MLNPotential(lambda x: x[0] * ns.eq_op(x[1], 0.1), w=3.228)
+    wall = ns.MLNPotential(lambda x: x[0] * ns.eq_op(x[1], 0.341), w=3.754)
+    sw = [ns.RV(d_bool) for _ in range(2)]          # SegType(s, W)
+    sd = [ns.RV(d_bool) for _ in range(2)]          # SegType(s, D)
+    po = [ns.RV(d_bool), ns.RV(d_bool, 1)]          # PartOf(s, l), one observed
+    al = ns.RV(d_bool, 0)                           # Aligned(s2, s1) observed
+    ln = [ns.RV(d_len), ns.RV(d_len, 0.27)]         # Length(s), one observed
+    rvs = sw + sd + po + [al] + ln
+    fs = [ns.F(clause5, [sw[0], sw[1], po[0], po[1], al]),
+          ns.F(excl, [sw[0], sd[0]]), ns.F(excl, [sw[1], sd[1]]),
+          ns.F(unit, [sd[0]]), ns.F(unit, [sd[1]]),
+          ns.F(door, [sd[0], ln[0]]), ns.F(door, [sd[1], ln[1]]),
+          ns.F(wall, [sw[0], ln[0]]), ns.F(wall, [sw[1], ln[1]])]
+    return _graph(ns, rvs, fs)
+
+
+def rgm_small(ns, evidence="split"):
+    """Relational Gaussian model recession -> market(c) -> loss(c,b) -> revenue(b)
+    (reference Demo/Data/RGM/Generator.py) with 3 categories x 2 banks.
+
+    ``evidence='split'``: observed losses take two well-separated groups of values so the
+    C2F k-means split (k=2) is unambiguous; ``'exact'``: repeated exact values so plain
+    colour passing lifts them."""
+    d = ns.Domain((-50, 50), continuous=True)
+    p1 = ns.GaussianPotential([0.0, 0.0], [[10.0, -7.0], [-7.0, 10.0]])
+    p2 = ns.GaussianPotential([0.0, 0.0], [[10.0, 5.0], [5.0, 10.0]])
+    p3 = ns.GaussianPotential([0.0, 0.0], [[10.0, 7.0], [7.0, 10.0]])
+    n_cat, n_bank = 3, 2
+    if evidence == "split":
+        obs = {(0, 0): 4.0, (1, 0): 4.5, (2, 1): -6.0, (0, 1): -6.25}
+    else:
+        obs = {(0, 0): 4.0, (1, 0): 4.0, (2, 0): 4.0, (0, 1): -6.0}
+    recession = ns.RV(d)
+    market = [ns.RV(d) for _ in range(n_cat)]
+    revenue = [ns.RV(d) for _ in range(n_bank)]
+    loss = {(c, b): ns.RV(d, obs.get((c, b))) for c in range(n_cat) for b in range(n_bank)}
+    rvs = [recession] + market + revenue + list(loss.values())
+    fs = [ns.F(p1, [recession, m]) for m in market]
+    for (c, b), l in loss.items():
+        fs.append(ns.F(p2, [market[c], l]))
+        fs.append(ns.F(p3, [l, revenue[b]]))
+    return _graph(ns, rvs, fs)
+
+
+def rgm_exact(ns):
+    return rgm_small(ns, evidence="exact")
+
+
+def smokers(ns):
+    """Boolean friends-and-smokers MLN (reference Demo/old/DiscreteVarInferenceDemo.py),
+    3 people; symmetric enough that colour passing merges variables."""
+    d_bool = ns.Domain((0, 1))
+    f_fs = ns.MLNPotential(lambda a: ns.imp_op(a[0], ns.bic_op(a[1], a[2])), 0.1)
+    f_sc = ns.MLNPotential(lambda a: ns.imp_op(a[0], a[1]), 1)
+    n = 3
+    smoke = [ns.RV(d_bool, 1 if i == 2 else None) for i in range(n)]
+    cancer = [ns.RV(d_bool) for _ in range(n)]
+    rvs = smoke + cancer
+    fs = [ns.F(f_sc, [smoke[i], cancer[i]]) for i in range(n)]
+    for i in range(n):
+        for j in range(n):
+            if i > j:
+                fr = ns.RV(d_bool, 1 if (i + j) % 2 else None)
+                rvs.append(fr)
+                fs.append(ns.F(f_fs, [fr, smoke[i], smoke[j]]))
+    return _graph(ns, rvs, fs)
+
+
+def ring_xy(ns):
+    """Symmetric ring of identical continuous variables: colour passing collapses it to one
+    class whose factor touches that class twice (exercises SURVEY H6, first-occurrence
+    index + count)."""
+    d = ns.Domain((-5, 5), continuous=True)
+    n = 4
+    X = [ns.RV(d) for _ in range(n)]
+    xy = ns.XYPotential(-0.8, 1.0)
+    x2 = ns.X2Potential(2.0, 1.0)
+    fs = [ns.F(xy, [X[i], X[(i + 1) % n]]) for i in range(n)] + [ns.F(x2, [x]) for x in X]
+    return _graph(ns, X, fs)
+
+
+CASES = {
+    # name: (builder, K, T, engines)
+    "chain_table": (chain_table, 3, 3, ("ground", "lifted", "c2f")),
+    "tri_table3": (tri_table3, 2, 3, ("ground",)),
+    "gauss_net": (gauss_net, 2, 3, ("ground", "lifted")),
+    "gauss_net_t5": (gauss_net, 1, 5, ("ground",)),
+    "hmln_evidence": (hmln_evidence, 2, 3, ("ground", "lifted", "c2f")),
+    "hmln_hidden": (hmln_hidden, 2, 3, ("ground",)),
+    "robot_like": (robot_like, 2, 3, ("ground",)),
+    "rgm_split": (rgm_small, 2, 3, ("ground", "lifted", "c2f")),
+    "rgm_exact": (rgm_exact, 1, 3, ("lifted", "c2f")),
+    "smokers": (smokers, 2, 4, ("ground", "lifted")),
+    "ring_xy": (ring_xy, 2, 3, ("ground", "lifted")),
+}
+
+
+def inject_values(rv_index, is_continuous, n_states, K, seed):
+    """Deterministic initial parameters for the variable (or class) whose smallest member
+    has creation index ``rv_index``; same distribution as ``init_param``
+    (reference VarInference.py:197-208)."""
+    rng = np.random.default_rng([seed, rv_index])
+    if is_continuous:
+        out = np.ones((K, 2))
+        out[:, 0] = rng.random(K) * 3 - 1.5
+        out[:, 1] = 0.5 + rng.random(K)      # vary the variances too (init_param uses 1)
+        return out
+    return rng.random((K, n_states)) * 10

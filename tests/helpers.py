@@ -1,0 +1,105 @@
+"""Shared test plumbing: build spec graphs with this repo's classes, set up the three engine
+modes on the host, inject the golden parameters."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+
+import lhvi_b200
+import specs
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*__*.npz")))
+
+
+def golden_id(path):
+    return os.path.basename(path)[:-4]
+
+
+def load_golden(path):
+    name, engine = golden_id(path).split("__")
+    return name, engine, dict(np.load(path))
+
+
+def setup_mode(g, engine):
+    """Host-side graph for an engine mode: returns (variable handles, factor handles,
+    compressed graph or None).  For c2f this is the state at the golden snapshot: coarse
+    evidence clustering followed by colour passing (C2FVarInference.py:306,332)."""
+    cgmod = lhvi_b200.CompressedGraphWithObs
+    if engine == "ground":
+        return sorted(g.rvs), sorted(g.factors), None
+    cg = cgmod.CompressedGraph(g)
+    if engine == "lifted":
+        cg.run()
+    else:
+        cg.init_cluster(is_split_cont_evidence=False)
+        for rv in g.rvs:
+            rv.initial_cluster = rv.cluster
+        mark_initial_members(g)
+        n = -1
+        while n != len(cg.rvs):
+            n = len(cg.rvs)
+            cg.split_factors()
+            cg.split_rvs()
+    return sorted(cg.rvs), sorted(cg.factors), cg
+
+
+def injected_params(handles, rvs, engine, K, seed):
+    """{handle: array} for continuous (mu,var) and discrete (logits) hidden handles, keyed
+    exactly as make_golden.py keys them (smallest creation index of the class; for c2f of
+    the *initial* class, whose parameters the children inherit)."""
+    order = {rv: i for i, rv in enumerate(rvs)}
+    cont, disc = {}, {}
+    for h in handles:
+        if h.value is not None:
+            continue
+        if engine == "ground":
+            idx = order[h]
+        elif engine == "lifted":
+            idx = min(order[rv] for rv in h.rvs)
+        else:
+            idx = min(order[rv] for rv in h.rvs[0].initial_cluster_members)
+        if h.domain.continuous:
+            cont[h] = specs.inject_values(idx, True, 0, K, seed)
+        else:
+            disc[h] = specs.inject_values(idx, False, len(h.domain.values), K, seed)
+    return cont, disc
+
+
+def mark_initial_members(g):
+    """For c2f: remember the members of each variable's initial class."""
+    groups = {}
+    for rv in g.rvs:
+        groups.setdefault(id(rv.initial_cluster), []).append(rv)
+    for rv in g.rvs:
+        rv.initial_cluster_members = groups[id(rv.initial_cluster)]
+
+
+def injected_w_tau(K):
+    return np.linspace(-0.3, 0.4, K) if K > 1 else np.zeros(1)
+
+
+def handle_of(rv, engine):
+    return rv if engine == "ground" else rv.cluster
+
+
+def partition_of(rvs, engine):
+    """Canonical description of the variable partition: tuple of sorted index tuples."""
+    if engine == "ground":
+        return None
+    groups = {}
+    for i, rv in enumerate(rvs):
+        groups.setdefault(id(rv.cluster), []).append(i)
+    return sorted(tuple(v) for v in groups.values())
+
+
+def partition_from_ids(ids):
+    groups = {}
+    for i, c in enumerate(ids):
+        groups.setdefault(int(c), []).append(i)
+    return sorted(tuple(v) for v in groups.values())
