@@ -1,0 +1,146 @@
+/*
+ * lhvi.h -- C ABI of the B200 variational-inference hot path.
+ *
+ * This is the boundary a host binds with ctypes / cffi / cgo / JNI.  Every entry point
+ *   - takes raw DEVICE pointers and plain sizes (no framework types),
+ *   - is asynchronous on the CUDA stream passed as `stream` (a cudaStream_t cast to void*,
+ *     NULL = legacy default stream),
+ *   - never allocates, frees or synchronises: the caller owns every buffer,
+ *   - returns 0 on success or a negative LHVI_E* code; lhvi_last_error() then holds a
+ *     human-readable message (thread-local).
+ *
+ * What each call replaces in the reference (leodd/Lifted-Hybrid-Variational-Inference):
+ *
+ *   lhvi_factor_expect_grad   the per-factor loops of gradient_w_tau / gradient_mu_var /
+ *                             gradient_category_tau / free_energy with their calls into
+ *                             expectation() and rvs_belief()
+ *                             (VarInference.py:40-55,57-195,336-353; lifted weights
+ *                             LiftedVarInference.py:74,90,131-132,162; Gaussian evidence
+ *                             C2FVarInference.py:110-113,266-267).  The variables' own
+ *                             (N-1) E[log b] terms (VarInference.py:60-72,96-106,138-139)
+ *                             are the same kernel run over "node" record groups.
+ *   lhvi_elbo_reduce          the running sums `energy -= ...` / `g_w[k] -= ...`
+ *                             (VarInference.py:72,88,177,193).
+ *   lhvi_step_tick            `self.t += 1` and the bias corrections 1-b1^t, 1-b2^t
+ *                             (VarInference.py:253,272-273).
+ *   lhvi_param_step           softmax Jacobians (VarInference.py:90,160), the Adam moment and
+ *                             parameter update with the variance clip and re-normalisation
+ *                             (VarInference.py:256-287), or the plain SGD step (:302-329).
+ *   lhvi_mixture_belief       belief(x, rv) for a batch of (variable, x) queries
+ *                             (VarInference.py:333-353).
+ *
+ * Data layout: a flat parameter vector with one slot per hidden variable
+ * (continuous: K x (mu, var) interleaved; discrete: K x D row-major probabilities), a
+ * coefficient table `ptab`, and per-signature record groups stored column-major.
+ */
+#ifndef LHVI_H
+#define LHVI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LHVI_ABI_VERSION 1
+
+/* element type of every `void*` buffer of reals */
+#define LHVI_F32 0
+#define LHVI_F64 1
+
+/* error codes */
+#define LHVI_OK 0
+#define LHVI_EINVAL (-1)   /* bad argument (message says which) */
+#define LHVI_ELIMIT (-2)   /* model exceeds a compiled-in limit */
+#define LHVI_ECUDA (-3)    /* CUDA runtime error at launch */
+
+/* compiled-in limits of the generic kernel (the specialised kernels are stricter) */
+#define LHVI_MAX_AXES 6      /* hidden + Gaussian-evidence arguments of one factor */
+#define LHVI_MAX_K 8
+#define LHVI_MAX_T 32
+#define LHVI_MAX_DSTATES 16
+#define LHVI_MAX_NODES 64    /* sum over axes of quadrature nodes / states */
+#define LHVI_MAX_GACC 256    /* sum over hidden arguments of K * (2 | D) */
+#define LHVI_PARTIAL_ROWS 1184   /* rows of `partials` one launch may write (8 per SM) */
+
+/*
+ * One record group: `n` factor records sharing a canonical signature.  Arguments are
+ * ordered [hidden discrete | hidden continuous | Gaussian evidence | point evidence].
+ * All arrays are device pointers, column-major over records (column a starts at a*n).
+ */
+typedef struct lhvi_group {
+    int32_t nd, nc, ng, ne;        /* argument counts per role */
+    int32_t dims[LHVI_MAX_AXES];   /* states of each hidden discrete argument */
+    int32_t node;                  /* 1: node-entropy records, F = nscale * log b, no ptab */
+    int32_t weighted;              /* 1: wf / gam present; 0: all weights are 1 */
+    int64_t n;                     /* records in this group */
+    const int32_t* pot;            /* [n]          offset of the coefficient block in ptab */
+    const int32_t* poff;           /* [(nd+nc)*n]  parameter slot offsets */
+    const void* egval;             /* [ng*n]       Gaussian-evidence means */
+    const void* egvar;             /* [ng*n]       Gaussian-evidence variances */
+    const void* ecval;             /* [ne*n]       point-evidence values */
+    const void* wf;                /* [n]          W_f, weight on energy and g_w */
+    const void* gam;               /* [(nd+nc)*n]  gamma, weight on each parameter gradient */
+    const void* nscale;            /* [n]          node groups: N_v - 1 */
+} lhvi_group;
+
+/* Model-wide device buffers shared by every group launch. */
+typedef struct lhvi_model {
+    int32_t dtype;                 /* LHVI_F32 | LHVI_F64 */
+    int32_t K, T;                  /* mixture components, quadrature points */
+    int64_t n_param;               /* elements of eta / grad parameter part */
+    const void* quad;              /* [2T]  Gauss-Hermite nodes, then weights / sqrt(pi) */
+    const void* ptab;              /* coefficient table */
+    const void* eta;               /* [n_param]  (mu,var) | probabilities */
+    const void* w;                 /* [K]  mixture weights */
+    void* grad;                    /* [n_param + K + 1]  parameter grads | G_w | energy */
+    double* partials;              /* [rows][K+1] per-block partial sums of G_w | energy */
+} lhvi_model;
+
+const char* lhvi_last_error(void);
+int lhvi_abi_version(void);
+
+/* 1 if a template-specialised kernel exists for this (model, group), else 0 (generic). */
+int lhvi_has_specialisation(const lhvi_model* m, const lhvi_group* g);
+
+/*
+ * Accumulate one group's contribution: atomically adds parameter gradients into m->grad
+ * and writes per-block partial sums of (G_w[0..K-1], energy) to rows
+ * [row0, row0 + LHVI_PARTIAL_ROWS) of m->partials (rows the launch does not use are zeroed).
+ * force_generic != 0 bypasses the specialised kernels (used by the parity tests).
+ */
+int lhvi_factor_expect_grad(const lhvi_model* m, const lhvi_group* g, int64_t row0,
+                            int force_generic, void* stream);
+
+/* Sum `rows` rows of partials into grad[n_param .. n_param+K] (G_w, energy). */
+int lhvi_elbo_reduce(const lhvi_model* m, int64_t rows, void* stream);
+
+/* step[0] = t, step[1] = 1-b1^t, step[2] = 1-b2^t (doubles, device).  Increments t. */
+int lhvi_step_tick(double* step, double b1, double b2, void* stream);
+
+/*
+ * Parameter update for every hidden variable and for w_tau.
+ *   var_kind[v] 0 continuous / 1 discrete, var_dim[v] 2 / D, var_off[v] slot offset.
+ *   eta: read by the factor kernels; tau: logits of discrete slots; mom1 / mom2: Adam moments.
+ *   wstate: [5K] reals: w_tau | w | mom1_w | mom2_w | scratch.
+ *   sgd != 0 -> theta -= lr * g (moments untouched); else Adam with eps outside the sqrt.
+ *   The softmax Jacobian is applied here to raw G_c and G_w.
+ */
+int lhvi_param_step(int dtype, int K, int64_t n_vars, const uint8_t* var_kind,
+                    const int32_t* var_dim, const int32_t* var_off, void* eta, void* tau,
+                    const void* grad, int64_t n_param, void* mom1, void* mom2, void* wstate,
+                    const double* step, double lr, double b1, double b2, double eps,
+                    double var_threshold, int sgd, void* stream);
+
+/*
+ * out[i] = sum_k w_k q_{v_i,k}(x_i) for n queries; continuous variables use the
+ * reference's density (normaliser 1/(sqrt(2 pi) var)); for discrete ones x_i is the state index.
+ */
+int lhvi_mixture_belief(int dtype, int K, int64_t n, const int32_t* q_off, const int32_t* q_dim,
+                        const uint8_t* q_kind, const void* x, const void* eta, const void* w,
+                        void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LHVI_H */

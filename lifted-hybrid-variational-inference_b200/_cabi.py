@@ -1,0 +1,105 @@
+"""ctypes binding of ``liblhvi.so`` (declarations mirror ``include/lhvi.h`` one to one).
+
+There is no fallback: if the library is missing or a symbol is absent, importing the engines
+fails with an explicit error instead of computing anything on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+LHVI_F32, LHVI_F64 = 0, 1
+LHVI_MAX_AXES = 6
+LHVI_MAX_K = 8
+LHVI_MAX_T = 32
+LHVI_PARTIAL_ROWS = 1184
+ABI_VERSION = 1
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblhvi.so")
+
+SYMBOLS = ("lhvi_last_error", "lhvi_abi_version", "lhvi_has_specialisation",
+           "lhvi_factor_expect_grad", "lhvi_elbo_reduce", "lhvi_step_tick",
+           "lhvi_param_step", "lhvi_mixture_belief")
+
+
+class LhviGroup(C.Structure):
+    _fields_ = [
+        ("nd", C.c_int32), ("nc", C.c_int32), ("ng", C.c_int32), ("ne", C.c_int32),
+        ("dims", C.c_int32 * LHVI_MAX_AXES),
+        ("node", C.c_int32), ("weighted", C.c_int32),
+        ("n", C.c_int64),
+        ("pot", C.c_void_p), ("poff", C.c_void_p),
+        ("egval", C.c_void_p), ("egvar", C.c_void_p), ("ecval", C.c_void_p),
+        ("wf", C.c_void_p), ("gam", C.c_void_p), ("nscale", C.c_void_p),
+    ]
+
+
+class LhviModel(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("K", C.c_int32), ("T", C.c_int32),
+        ("n_param", C.c_int64),
+        ("quad", C.c_void_p), ("ptab", C.c_void_p), ("eta", C.c_void_p), ("w", C.c_void_p),
+        ("grad", C.c_void_p), ("partials", C.c_void_p),
+    ]
+
+
+class LhviError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load(build_if_missing: bool = False):
+    """Load (once) and type the library.  Raises ``LhviError`` when it cannot be loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH) and build_if_missing:
+        from . import build as _build
+        _build.build()
+    if not os.path.exists(LIB_PATH):
+        raise LhviError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+            "(there is no CPU fallback for the variational-inference hot path)")
+    lib = C.CDLL(LIB_PATH)
+    missing = [s for s in SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise LhviError(f"{LIB_PATH} does not export {missing}")
+    lib.lhvi_last_error.restype = C.c_char_p
+    lib.lhvi_last_error.argtypes = []
+    lib.lhvi_abi_version.restype = C.c_int
+    lib.lhvi_abi_version.argtypes = []
+    if lib.lhvi_abi_version() != ABI_VERSION:
+        raise LhviError(f"ABI version mismatch: library {lib.lhvi_abi_version()}, binding {ABI_VERSION}")
+    lib.lhvi_has_specialisation.restype = C.c_int
+    lib.lhvi_has_specialisation.argtypes = [C.POINTER(LhviModel), C.POINTER(LhviGroup)]
+    lib.lhvi_factor_expect_grad.restype = C.c_int
+    lib.lhvi_factor_expect_grad.argtypes = [C.POINTER(LhviModel), C.POINTER(LhviGroup), C.c_int64,
+                                            C.c_int, C.c_void_p]
+    lib.lhvi_elbo_reduce.restype = C.c_int
+    lib.lhvi_elbo_reduce.argtypes = [C.POINTER(LhviModel), C.c_int64, C.c_void_p]
+    lib.lhvi_step_tick.restype = C.c_int
+    lib.lhvi_step_tick.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+    lib.lhvi_param_step.restype = C.c_int
+    lib.lhvi_param_step.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                    C.c_double, C.c_int, C.c_void_p]
+    lib.lhvi_mixture_belief.restype = C.c_int
+    lib.lhvi_mixture_belief.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, lib=None):
+    """Turn a negative return code into an exception (reference callers see RuntimeError /
+    ValueError, SURVEY section 8 b "Errors")."""
+    if rc == 0:
+        return
+    lib = lib or load()
+    msg = lib.lhvi_last_error().decode("utf-8", "replace")
+    if rc in (-1, -2):
+        raise ValueError(f"lhvi: {msg}")
+    raise LhviError(f"lhvi: {msg} (code {rc})")

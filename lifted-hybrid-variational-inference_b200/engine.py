@@ -1,0 +1,242 @@
+"""Device-side state and launch sequence of one VI model (the hot path behind the drop-in
+classes).
+
+``DeviceEngine`` owns PyTorch tensors for the flat parameter vector, Adam moments, the record
+groups and the gradient buffer, and drives the CUDA kernels of ``liblhvi.so`` through the
+C ABI (``include/lhvi.h``).  One iteration (reference ``ADAM_update`` body,
+``VarInference.py:249-287``) is:
+
+    grad = 0
+    for every record group:  lhvi_factor_expect_grad   (node-entropy groups included)
+    lhvi_elbo_reduce                                    -> G_w[K], free energy
+    [all-reduce of grad | G_w | energy over NCCL when the records are sharded across GPUs]
+    lhvi_step_tick; lhvi_param_step                     -> new eta, tau, w, moments
+
+PyTorch is plumbing only (allocation, streams, torch.distributed).  There is no CPU path:
+constructing the engine without CUDA or without the built library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .lowering import LoweredModel
+
+
+def hermgauss_scaled(T):
+    """Gauss-Hermite nodes and weights / sqrt(pi) (VarInference.py:18-19)."""
+    x, w = np.polynomial.hermite.hermgauss(T)
+    return x, w / np.sqrt(np.pi)
+
+
+class DeviceEngine:
+    def __init__(self, model: LoweredModel, dtype="float64", device=None, var_threshold=0.1,
+                 process_group=None, shard=True, force_generic=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "lhvi: no CUDA device visible. The variational-inference update loop runs only "
+                "on the GPU (hand-written sm_100a kernels); there is no CPU fallback.")
+        self.lib = _cabi.load()
+        self.full_model = model
+        self.K, self.T = model.K, model.T
+        self.dtype_name = "float64" if str(dtype) in ("float64", "torch.float64", "f64", "double") else "float32"
+        self.tdtype = torch.float64 if self.dtype_name == "float64" else torch.float32
+        self.dcode = _cabi.LHVI_F64 if self.dtype_name == "float64" else _cabi.LHVI_F32
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.var_threshold = float(var_threshold)
+        self.force_generic = bool(force_generic)
+        self.b1, self.b2, self.eps = 0.9, 0.999, 1e-8      # VarInference.py:223-225
+
+        self.pg = process_group
+        self.world, self.rank = 1, 0
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized() and shard):
+            self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
+        self.model = model.shard(self.rank, self.world) if (shard and self.world > 1) else model
+        self.reduce_grads = shard and self.world > 1
+
+        self._upload()
+
+    # ---- buffers --------------------------------------------------------------------------
+    def _dev(self, arr, dtype=None):
+        t = torch.as_tensor(np.ascontiguousarray(arr))
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=False).contiguous()
+
+    def _upload(self):
+        m, K = self.model, self.K
+        n_param = int(m.n_param)
+        self.n_param = n_param
+        qx, qw = hermgauss_scaled(self.T)
+        self.quad = self._dev(np.concatenate([qx, qw]), self.tdtype)
+        self.ptab = self._dev(m.ptab, self.tdtype)
+        self.var_kind = self._dev(m.var_kind.astype(np.uint8))
+        self.var_dim = self._dev(m.var_dim.astype(np.int32))
+        self.var_off = self._dev(m.var_off.astype(np.int32))
+        self.n_vars = int(m.n_vars)
+
+        def z(n, dt=None):
+            return torch.zeros(int(n), dtype=dt or self.tdtype, device=self.device)
+        self.eta = z(n_param)
+        self.tau = z(n_param)
+        self.mom1 = z(n_param)
+        self.mom2 = z(n_param)
+        self.grad = z(n_param + K + 1)
+        self.wstate = z(5 * K)
+        self.wstate[K:2 * K] = 1.0 / K
+        self.step = z(4, torch.float64)
+
+        self.groups = []      # (descriptor struct, tensors kept alive, RecordGroup)
+        for g in self.model.groups:
+            keep = {}
+            d = _cabi.LhviGroup()
+            d.nd, d.nc, d.ng, d.ne = g.nd, g.nc, g.ng, g.ne
+            for i in range(_cabi.LHVI_MAX_AXES):
+                d.dims[i] = int(g.dims[i]) if i < len(g.dims) else 0
+            d.node, d.weighted, d.n = int(g.node), int(g.weighted), int(g.n)
+
+            def put(name, arr, dt):
+                if arr.size == 0:
+                    return None
+                keep[name] = self._dev(arr, dt)
+                return keep[name].data_ptr()
+            d.pot = None if g.node else put("pot", g.pot, torch.int32)
+            d.poff = put("poff", g.poff, torch.int32)
+            d.egval = put("egval", g.egval, self.tdtype)
+            d.egvar = put("egvar", g.egvar, self.tdtype)
+            d.ecval = put("ecval", g.ecval, self.tdtype)
+            d.wf = put("wf", g.wf, self.tdtype) if g.weighted else None
+            d.gam = put("gam", g.gam, self.tdtype) if g.weighted else None
+            d.nscale = put("nscale", g.nscale, self.tdtype) if g.node else None
+            self.groups.append((d, keep, g))
+
+        rows = max(1, len(self.groups)) * _cabi.LHVI_PARTIAL_ROWS
+        self.partial_rows = rows
+        self.partials = z(rows * (K + 1), torch.float64)
+
+        md = _cabi.LhviModel()
+        md.dtype, md.K, md.T, md.n_param = self.dcode, K, self.T, n_param
+        md.quad, md.ptab = self.quad.data_ptr(), self.ptab.data_ptr()
+        md.eta, md.w = self.eta.data_ptr(), self.wstate[K:2 * K].data_ptr()
+        md.grad, md.partials = self.grad.data_ptr(), self.partials.data_ptr()
+        self.desc = md
+        self.launches_per_pass = 0
+
+    # ---- state exchange with the host -----------------------------------------------------
+    @property
+    def w_tau(self):
+        return self.wstate[:self.K]
+
+    @property
+    def w(self):
+        return self.wstate[self.K:2 * self.K]
+
+    def set_state(self, eta, tau, w_tau):
+        """``eta``: (mu,var) on continuous slots, probabilities on discrete ones; ``tau``:
+        logits on discrete slots; ``w_tau``: mixture logits.  w = softmax(w_tau) is derived."""
+        K = self.K
+        self.eta.copy_(torch.as_tensor(np.asarray(eta, dtype=np.float64)).to(self.tdtype))
+        self.tau.copy_(torch.as_tensor(np.asarray(tau, dtype=np.float64)).to(self.tdtype))
+        wt = np.asarray(w_tau, dtype=np.float64)
+        e = np.e ** wt
+        self.wstate[:K].copy_(torch.as_tensor(wt).to(self.tdtype))
+        self.wstate[K:2 * K].copy_(torch.as_tensor(e / e.sum()).to(self.tdtype))
+
+    def get_state(self):
+        K = self.K
+        ws = self.wstate.double().cpu().numpy()
+        return (self.eta.double().cpu().numpy(), self.tau.double().cpu().numpy(),
+                ws[:K].copy(), ws[K:2 * K].copy())
+
+    def reset_moments(self):
+        K = self.K
+        self.mom1.zero_()
+        self.mom2.zero_()
+        self.wstate[2 * K:].zero_()
+        self.step.zero_()
+
+    def get_moments(self):
+        K = self.K
+        ws = self.wstate.double().cpu().numpy()
+        return (self.mom1.double().cpu().numpy(), self.mom2.double().cpu().numpy(),
+                ws[2 * K:3 * K].copy(), ws[3 * K:4 * K].copy(), float(self.step[0].item()))
+
+    def set_moments(self, mom1, mom2, m_w, u_w, t):
+        K = self.K
+        self.mom1.copy_(torch.as_tensor(np.asarray(mom1, dtype=np.float64)).to(self.tdtype))
+        self.mom2.copy_(torch.as_tensor(np.asarray(mom2, dtype=np.float64)).to(self.tdtype))
+        self.wstate[2 * K:3 * K].copy_(torch.as_tensor(np.asarray(m_w, dtype=np.float64)).to(self.tdtype))
+        self.wstate[3 * K:4 * K].copy_(torch.as_tensor(np.asarray(u_w, dtype=np.float64)).to(self.tdtype))
+        t = float(t)
+        self.step.copy_(torch.tensor([t, 1 - self.b1 ** t, 1 - self.b2 ** t, 0.0], dtype=torch.float64))
+
+    # ---- the hot path ---------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def grad_pass(self):
+        """Fill ``self.grad`` = [parameter gradients | raw G_w | free energy] at the current
+        parameters (all-reduced over the process group when records are sharded)."""
+        lib, st = self.lib, self._stream()
+        self.grad.zero_()
+        launches = 1
+        for i, (d, _, _) in enumerate(self.groups):
+            _cabi.check(lib.lhvi_factor_expect_grad(C.byref(self.desc), C.byref(d),
+                                                    i * _cabi.LHVI_PARTIAL_ROWS,
+                                                    int(self.force_generic), st), lib)
+            launches += 2
+        _cabi.check(lib.lhvi_elbo_reduce(C.byref(self.desc), self.partial_rows, st), lib)
+        launches += 1
+        if self.reduce_grads:
+            torch.distributed.all_reduce(self.grad, group=self.pg)
+        self.launches_per_pass = launches
+        return self.grad
+
+    def param_step(self, lr, sgd=False):
+        lib, st = self.lib, self._stream()
+        if not sgd:
+            _cabi.check(lib.lhvi_step_tick(self.step.data_ptr(), self.b1, self.b2, st), lib)
+        _cabi.check(lib.lhvi_param_step(
+            self.dcode, self.K, self.n_vars, self.var_kind.data_ptr(), self.var_dim.data_ptr(),
+            self.var_off.data_ptr(), self.eta.data_ptr(), self.tau.data_ptr(), self.grad.data_ptr(),
+            self.n_param, self.mom1.data_ptr(), self.mom2.data_ptr(), self.wstate.data_ptr(),
+            self.step.data_ptr(), float(lr), self.b1, self.b2, self.eps, self.var_threshold,
+            int(bool(sgd)), st), lib)
+
+    def iterate(self, n, lr, sgd=False):
+        """``n`` Jacobi iterations: all gradients at the old parameters, then the step."""
+        for _ in range(int(n)):
+            self.grad_pass()
+            self.param_step(lr, sgd=sgd)
+
+    @property
+    def launches_per_iteration(self):
+        return self.launches_per_pass + 2
+
+    def free_energy(self):
+        self.grad_pass()
+        return float(self.grad[self.n_param + self.K].item())
+
+    def gradients(self):
+        """Host copies of (raw parameter gradients [n_param], raw G_w [K], free energy)."""
+        g = self.grad_pass().double().cpu().numpy()
+        return g[:self.n_param].copy(), g[self.n_param:self.n_param + self.K].copy(), float(g[-1])
+
+    def mixture_belief(self, q_off, q_dim, q_kind, x):
+        """Batched ``belief(x, rv)`` (VarInference.py:333-353); discrete x are state indices."""
+        n = len(q_off)
+        out = torch.empty(n, dtype=self.tdtype, device=self.device)
+        if n == 0:
+            return out
+        off = self._dev(np.asarray(q_off, dtype=np.int32))
+        dim = self._dev(np.asarray(q_dim, dtype=np.int32))
+        kind = self._dev(np.asarray(q_kind, dtype=np.uint8))
+        xs = self._dev(np.asarray(x, dtype=np.float64), self.tdtype)
+        _cabi.check(self.lib.lhvi_mixture_belief(
+            self.dcode, self.K, n, off.data_ptr(), dim.data_ptr(), kind.data_ptr(), xs.data_ptr(),
+            self.eta.data_ptr(), self.w.data_ptr(), out.data_ptr(), self._stream()), self.lib)
+        return out

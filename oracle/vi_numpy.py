@@ -30,6 +30,9 @@ def _pdf(x, mu, var):
     return np.exp(-u * u * 0.5 / var) / (SQRT_2PI * var)
 
 
+norm_pdf_ref = _pdf
+
+
 def _on_axis(arr, lead, axis, n_axes):
     """View ``arr`` (shape lead-dims + (n,)) with its last dim placed on grid axis ``axis``."""
     shape = list(arr.shape[:lead]) + [1] * n_axes

@@ -103,3 +103,37 @@ def partition_from_ids(ids):
     for i, c in enumerate(ids):
         groups.setdefault(int(c), []).append(i)
     return sorted(tuple(v) for v in groups.values())
+
+
+# ---- lowered-model plumbing ---------------------------------------------------------------
+
+def lower_for(engine, g, cg, K, T):
+    low = lhvi_b200.lowering
+    if engine == "ground":
+        return low.lower_ground(g, K, T)
+    return low.lower_compressed(cg, K, T, gaussian_obs=(engine == "c2f"), min_obs_var=0.0)
+
+
+def flat_params(model, cont, disc):
+    """Flat (eta-or-logit) vector from {handle: array} dictionaries."""
+    K = model.K
+    flat = np.zeros(model.n_param)
+    for h, i in model.index.items():
+        off, d = int(model.var_off[i]), int(model.var_dim[i])
+        src = cont[h] if model.var_kind[i] == 0 else disc[h]
+        flat[off:off + K * d] = np.asarray(src, dtype=float).reshape(-1)
+    return flat
+
+
+def rows_from_flat(model, flat, rvs, engine, width):
+    """Per-ground-variable rows (NaN padded) out of a flat vector, golden layout."""
+    K = model.K
+    out = np.full((len(rvs), width), np.nan)
+    for r, rv in enumerate(rvs):
+        h = handle_of(rv, engine)
+        if h.value is not None:
+            continue
+        i = model.index[h]
+        off, d = int(model.var_off[i]), int(model.var_dim[i])
+        out[r, :K * d] = flat[off:off + K * d]
+    return out

@@ -1,0 +1,115 @@
+"""Host logic of the drop-in classes on the CPU (numpy-oracle engine injected as a test
+double): the classes must drive lowering / push / pull / C2F refinement so that whole
+trajectories land on the reference's numbers (goldens of the patched reference)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+import helpers
+import lhvi_b200
+import specs
+from oracle_engine import use_oracle_engine
+
+ENGINE_CLASS = {
+    "ground": lambda: lhvi_b200.VarInference.VarInference,
+    "lifted": lambda: lhvi_b200.LiftedVarInference.VarInference,
+    "c2f": lambda: lhvi_b200.C2FVarInference.VarInference,
+}
+
+
+def make_injector(vi, rvs, engine, K, seed):
+    order = {rv: i for i, rv in enumerate(rvs)}
+
+    def inject():
+        vi.w_tau = helpers.injected_w_tau(K)
+        vi.eta, vi.eta_tau = {}, {}
+        for h in vi._handles():
+            if h.value is not None:
+                continue
+            idx = order[h] if engine == "ground" else min(order[rv] for rv in h.rvs)
+            if h.domain.continuous:
+                vi.eta[h] = specs.inject_values(idx, True, 0, K, seed)
+            else:
+                vi.eta_tau[h] = specs.inject_values(idx, False, len(h.domain.values), K, seed)
+        e = np.e ** vi.w_tau
+        vi.w = e / e.sum()
+        for h, t in vi.eta_tau.items():
+            r = np.e ** t
+            vi.eta[h] = r / r.sum(axis=1, keepdims=True)
+    return inject
+
+
+def run_trajectory(name, engine, ns, gold, patch):
+    builder, K, T, _ = specs.CASES[name]
+    g, rvs = builder(ns)
+    vi = ENGINE_CLASS[engine]()(g, K, T)
+    patch(vi)
+    vi.init_param = make_injector(vi, rvs, engine, K, int(gold["seed"]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        vi.run(int(gold["steps"]), lr=float(gold["lr"]), is_log=False)
+    return vi, rvs
+
+
+def check_trajectory(vi, rvs, engine, gold, rtol, atol):
+    np.testing.assert_allclose(vi.w_tau, gold["w_tau1_fixed"], rtol=rtol, atol=atol)
+    want = gold["eta1_fixed"]
+    got = np.full_like(want, np.nan)
+    for i, rv in enumerate(rvs):
+        h = helpers.handle_of(rv, engine)
+        if h.value is None:
+            v = vi.eta[h].reshape(-1)
+            got[i, :v.size] = v
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
+    if engine != "ground":
+        assert helpers.partition_of(rvs, engine) == helpers.partition_from_ids(gold["cluster1_fixed"])
+        ev = np.array([np.nan if helpers.handle_of(rv, engine).value is None
+                       else float(helpers.handle_of(rv, engine).value) for rv in rvs])
+        np.testing.assert_allclose(ev, gold["evidence1_fixed"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(vi.free_energy(), gold["fe1_fixed"], rtol=rtol)
+
+
+@pytest.mark.parametrize("path", helpers.golden_files(), ids=helpers.golden_id)
+def test_trajectory_matches_reference(path, ns):
+    name, engine, gold = helpers.load_golden(path)
+    vi, rvs = run_trajectory(name, engine, ns, gold, use_oracle_engine)
+    check_trajectory(vi, rvs, engine, gold, rtol=1e-8, atol=1e-10)
+
+
+def test_queries_and_logging(ns):
+    g, rvs = specs.hmln_evidence(ns)
+    vi = use_oracle_engine(lhvi_b200.VarInference.VarInference(g, 2, 3))
+    np.random.seed(0)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        vi.run(3, lr=0.2, is_log=True, log_fe=True)
+    assert len(vi.time_log) == 3 and vi.t == 3
+    assert len(buf.getvalue().strip().splitlines()) == 3
+    hidden_c = [rv for rv in rvs if rv.value is None and rv.domain.continuous]
+    rv = hidden_c[0]
+    # belief == rvs_belief, map is a local maximum of the belief and beats the component means
+    x = 0.3
+    assert np.isclose(vi.belief(x, rv), vi.rvs_belief((x,), (rv,)))
+    xm = vi.map(rv)
+    assert vi.belief(xm, rv) >= max(vi.belief(mu, rv) for mu in vi.eta[rv][:, 0]) - 1e-12
+    assert vi.belief(xm, rv) >= vi.belief(xm + 1e-4, rv) and vi.belief(xm, rv) >= vi.belief(xm - 1e-4, rv)
+    ev = [r for r in rvs if r.value is not None][0]
+    assert vi.map(ev) == ev.value and vi.belief(ev.value, ev) == pytest.approx(1.0)
+    res = vi.rvs_map(rvs[:6])
+    assert set(res) == set(rvs[:6])
+    with contextlib.redirect_stdout(io.StringIO()):
+        vi.run(2, lr=0.2, is_log=True, log_fe=False)      # MAP + log-likelihood logging
+    assert len(vi.time_log) == 2 and np.isfinite(vi.time_log[-1][1])
+
+
+def test_gd_update(ns):
+    g, rvs = specs.gauss_net(ns)
+    vi = use_oracle_engine(lhvi_b200.VarInference.VarInference(g, 2, 3))
+    np.random.seed(1)
+    vi._rebuild()
+    vi.init_param()
+    f0 = vi.free_energy()
+    with contextlib.redirect_stdout(io.StringIO()):
+        vi.GD_update(5, 0.01)
+    assert vi.free_energy() < f0

@@ -1,0 +1,219 @@
+"""Parity of the CUDA path (through the C ABI) with the goldens of the reference and with
+the numpy oracle.  Tolerances: fp64 mode 1e-6 relative per north_star (we assert tighter,
+1e-9, since only the summation order differs); fp32 mode is checked against the fp64 oracle
+with the tolerance stated at each assert."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+import helpers
+import lhvi_b200
+import specs
+from oracle.vi_numpy import NumpyVI, grad_pass
+from test_dropin_host import ENGINE_CLASS, check_trajectory, run_trajectory
+
+pytestmark = pytest.mark.gpu
+
+FP64_RTOL = 1e-9
+
+
+def _engine_for(model, dtype="float64", **kw):
+    from lhvi_b200.engine import DeviceEngine
+    return DeviceEngine(model, dtype=dtype, **kw)
+
+
+def _golden_setup(path, ns):
+    name, engine, gold = helpers.load_golden(path)
+    builder, K, T, _ = specs.CASES[name]
+    g, rvs = builder(ns)
+    handles, _, cg = helpers.setup_mode(g, engine)
+    model = helpers.lower_for(engine, g, cg, K, T)
+    cont, disc = helpers.injected_params(handles, rvs, engine, K, int(gold["seed"]))
+    tau = helpers.flat_params(model, cont, disc)
+    ref = NumpyVI(model)
+    ref.eta[:] = tau
+    ref.tau[:] = tau
+    ref.w_tau = helpers.injected_w_tau(K)
+    ref.refresh()
+    return name, engine, gold, model, rvs, ref
+
+
+@pytest.mark.parametrize("path", helpers.golden_files(), ids=helpers.golden_id)
+@pytest.mark.parametrize("force_generic", [True, False], ids=["generic", "dispatch"])
+def test_snapshot_fp64(path, force_generic, ns):
+    name, engine, gold, model, rvs, ref = _golden_setup(path, ns)
+    eng = _engine_for(model, "float64", force_generic=force_generic)
+    eng.set_state(ref.eta, ref.tau, ref.w_tau)
+    grad, g_w, energy = eng.gradients()
+    # against the reference (patched for H2) through the golden file
+    np.testing.assert_allclose(energy, gold["fe0_fixed"], rtol=FP64_RTOL)
+    from oracle.vi_numpy import tau_gradients
+    g_flat, g_wtau = tau_gradients(model, grad, g_w, ref.eta, ref.w)
+    np.testing.assert_allclose(g_wtau, gold["gw0_fixed"], rtol=FP64_RTOL, atol=1e-11)
+    want = gold["grad0_fixed"]
+    got = helpers.rows_from_flat(model, g_flat, rvs, engine, want.shape[1])
+    np.testing.assert_allclose(got, want, rtol=FP64_RTOL, atol=1e-10)
+    # and against the oracle on the raw accumulators
+    og, ogw, oe = grad_pass(model, ref.eta, ref.w)
+    np.testing.assert_allclose(grad, og, rtol=FP64_RTOL, atol=1e-10)
+    np.testing.assert_allclose(g_w, ogw, rtol=FP64_RTOL, atol=1e-10)
+
+
+@pytest.mark.parametrize("path", helpers.golden_files(), ids=helpers.golden_id)
+def test_snapshot_fp32(path, ns):
+    name, engine, gold, model, rvs, ref = _golden_setup(path, ns)
+    eng = _engine_for(model, "float32")
+    eng.set_state(ref.eta, ref.tau, ref.w_tau)
+    grad, g_w, energy = eng.gradients()
+    og, ogw, oe = grad_pass(model, ref.eta, ref.w)
+    scale = max(1.0, np.abs(og).max())
+    # fp32 arithmetic: 2e-5 of the largest gradient entry
+    np.testing.assert_allclose(energy, oe, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(g_w, ogw, rtol=2e-5, atol=2e-5 * max(1.0, np.abs(ogw).max()))
+    np.testing.assert_allclose(grad, og, rtol=2e-5, atol=2e-5 * scale)
+
+
+@pytest.mark.parametrize("path", helpers.golden_files(), ids=helpers.golden_id)
+def test_trajectory_fp64(path, ns):
+    """Drop-in classes on the real engine: same Adam trajectory as the reference, including
+    the C2F split rounds."""
+    name, engine, gold = helpers.load_golden(path)
+    vi, rvs = run_trajectory(name, engine, ns, gold, lambda v: v)
+    check_trajectory(vi, rvs, engine, gold, rtol=1e-7, atol=1e-9)
+
+
+def test_param_step_matches_oracle_sgd_and_adam(ns):
+    g, rvs = specs.robot_like(ns)
+    model = lhvi_b200.lowering.lower_ground(g, 3, 3)
+    eta, tau, w_tau = lhvi_b200.synthetic.random_state(model, 4)
+    for sgd in (False, True):
+        ref = NumpyVI(model)
+        ref.eta[:], ref.tau[:], ref.w_tau = eta, tau, w_tau + np.array([0.1, -0.2, 0.05])
+        ref.refresh()
+        eng = _engine_for(model)
+        eng.set_state(ref.eta, ref.tau, ref.w_tau)
+        eng.reset_moments()
+        for _ in range(4):
+            ref.sgd_step(0.05) if sgd else ref.adam_step(0.1)
+        eng.iterate(4, 0.05 if sgd else 0.1, sgd=sgd)
+        e2, t2, wt2, w2 = eng.get_state()
+        np.testing.assert_allclose(e2, ref.eta, rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(wt2, ref.w_tau, rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(w2, ref.w, rtol=1e-9)
+
+
+def test_belief_queries(ns):
+    g, rvs = specs.hmln_hidden(ns)
+    vi = lhvi_b200.VarInference.VarInference(g, 2, 3)
+    np.random.seed(3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        vi.run(3, lr=0.2, is_log=False)
+    for rv in rvs:
+        if rv.value is None:
+            xs = (0.37, -1.2) if rv.domain.continuous else rv.domain.values
+            for x in xs:
+                assert np.isclose(vi.belief(x, rv), vi.rvs_belief((x,), (rv,)), rtol=1e-12)
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-9), ("float32", 5e-5)])
+def test_generated_models_against_oracle(dtype, tol):
+    syn = lhvi_b200.synthetic
+    for model in (syn.relational_hybrid(300, 5, 3, 3, seed=2, weighted=True),
+                  syn.relational_hybrid(300, 5, 2, 3, seed=2, order="entity"),
+                  syn.gaussian_grid(12, 1, 3), syn.gaussian_grid(7, 2, 5)):
+        eta, tau, w_tau = syn.random_state(model, 1)
+        K = model.K
+        w = np.full(K, 1.0 / K)
+        og, ogw, oe = grad_pass(model, eta, w)
+        eng = _engine_for(model, dtype)
+        eng.set_state(eta, tau, w_tau)
+        grad, g_w, energy = eng.gradients()
+        np.testing.assert_allclose(energy, oe, rtol=tol)
+        np.testing.assert_allclose(g_w, ogw, rtol=tol, atol=tol * np.abs(ogw).max())
+        np.testing.assert_allclose(grad, og, rtol=tol, atol=tol * np.abs(og).max())
+
+
+def test_fp32_underflow_fallback():
+    """Far-apart mixture components: float pdfs underflow to zero, the kernel must redo those
+    points in double like the reference's log(b + 1e-100)."""
+    syn = lhvi_b200.synthetic
+    model = syn.gaussian_grid(4, 2, 3)
+    eta, tau, w_tau = syn.random_state(model, 0)
+    K = 2
+    cont = model.var_off.astype(np.int64)
+    eta[cont] = -40.0          # component 0 mean
+    eta[cont + 2] = 45.0       # component 1 mean
+    eta[cont + 1] = 0.1
+    eta[cont + 3] = 0.1
+    w_tau = np.array([-60.0, 0.0])      # w_0 ~ 1e-26
+    e = np.e ** w_tau
+    og, ogw, oe = grad_pass(model, eta, e / e.sum())
+    eng = _engine_for(model, "float32")
+    eng.set_state(eta, tau, w_tau)
+    grad, g_w, energy = eng.gradients()
+    assert np.isfinite(grad).all() and np.isfinite(g_w).all()
+    np.testing.assert_allclose(energy, oe, rtol=1e-4)
+    np.testing.assert_allclose(g_w, ogw, rtol=1e-4, atol=1e-4 * np.abs(ogw).max())
+
+
+def test_large_scale_properties():
+    """1 M-record model (fp32): the pass is a sum over records, so (a) it is invariant to the
+    record order and (b) shards add up; (c) a bounded random sample of records agrees with
+    the oracle evaluated on the same sample."""
+    syn = lhvi_b200.synthetic
+    P, G, K, T = 100_000, 10, 3, 3
+    hub = syn.relational_hybrid(P, G, K, T, seed=0, order="hub")
+    ent = syn.relational_hybrid(P, G, K, T, seed=0, order="entity")
+    eta, tau, w_tau = syn.random_state(hub, 0)
+    outs = []
+    for m in (hub, ent):
+        eng = _engine_for(m, "float32")
+        eng.set_state(eta, tau, w_tau)
+        outs.append(eng.gradients())
+    np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-5)
+    np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=1e-5)
+    scale = np.abs(outs[0][0]).max()
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-4, atol=1e-5 * scale)
+    # shards add up (what the NCCL all-reduce computes)
+    tot = None
+    for r in range(4):
+        eng = _engine_for(hub.shard(r, 4), "float32")
+        eng.set_state(eta, tau, w_tau)
+        part = eng.gradients()
+        tot = part if tot is None else tuple(a + b for a, b in zip(tot, part))
+    np.testing.assert_allclose(tot[2], outs[0][2], rtol=1e-5)
+    np.testing.assert_allclose(tot[0], outs[0][0], rtol=1e-4, atol=1e-5 * scale)
+    # bounded sample against the oracle
+    rng = np.random.default_rng(0)
+    sample_groups = []
+    for g in hub.groups:
+        sel = np.sort(rng.choice(g.n, size=min(g.n, 2000), replace=False))
+        sample_groups.append(g.take(sel))
+    import dataclasses
+    sample = dataclasses.replace(hub, groups=sample_groups)
+    w = np.full(K, 1.0 / K)
+    og, ogw, oe = grad_pass(sample, eta, w)
+    eng = _engine_for(sample, "float32")
+    eng.set_state(eta, tau, w_tau)
+    grad, g_w, energy = eng.gradients()
+    np.testing.assert_allclose(energy, oe, rtol=2e-5)
+    np.testing.assert_allclose(grad, og, rtol=1e-4, atol=2e-5 * np.abs(og).max())
+
+
+def test_cabi_rejects_bad_arguments():
+    import ctypes as C
+    from lhvi_b200 import _cabi
+    syn = lhvi_b200.synthetic
+    eng = _engine_for(syn.gaussian_grid(3, 1, 3))
+    d, _, _ = eng.groups[-1]
+    saved = d.pot
+    d.pot = None
+    rc = eng.lib.lhvi_factor_expect_grad(C.byref(eng.desc), C.byref(d), 0, 0, None)
+    d.pot = saved
+    assert rc == -1
+    with pytest.raises(ValueError):
+        _cabi.check(rc, eng.lib)
+    with pytest.raises(ValueError):
+        lhvi_b200.lowering.lower_ground(syn.gaussian_grid_graph(2)[0], 9, 3)
