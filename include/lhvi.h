@@ -73,6 +73,11 @@ typedef struct lhvi_group {
     int32_t dims[LHVI_MAX_AXES];   /* states of each hidden discrete argument */
     int32_t node;                  /* 1: node-entropy records, F = nscale * log b, no ptab */
     int32_t weighted;              /* 1: wf / gam present; 0: all weights are 1 */
+    int32_t hub_mask;              /* bit a set: hidden argument a mostly comes in long runs of the
+                                      same variable (a hub); its gradient is accumulated in shared
+                                      memory per block before touching global memory.  A hint:
+                                      results do not depend on it. */
+    int32_t reserved;
     int64_t n;                     /* records in this group */
     const int32_t* pot;            /* [n]          offset of the coefficient block in ptab */
     const int32_t* poff;           /* [(nd+nc)*n]  parameter slot offsets */

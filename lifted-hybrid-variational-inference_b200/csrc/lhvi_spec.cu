@@ -1,10 +1,40 @@
-// Template-specialised factor kernels (register-resident tables, compile-time K / T / arity).
+// Dispatcher of the template-specialised factor kernels (see lhvi_spec_impl.cuh).  Each
+// (dtype, K) pair is instantiated in its own translation unit (lhvi_spec_<dtype>_k<K>.cu) so the
+// build parallelises.
 #include "lhvi_common.cuh"
 
 namespace lhvi {
 
-bool spec_available(const lhvi_model*, const lhvi_group*) { return false; }
+#define LHVI_SPEC_SIGS(X) X(1, 0, 0) X(2, 0, 0) X(1, 0, 1) X(1, 1, 0) X(2, 0, 1) X(2, 1, 0) X(3, 0, 0) X(1, 0, 2)
 
-int launch_spec(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t) { return 1; }
+int spec_f32_k1(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+int spec_f32_k2(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+int spec_f32_k3(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+int spec_f64_k1(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+int spec_f64_k2(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+int spec_f64_k3(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+
+bool spec_available(const lhvi_model* m, const lhvi_group* g) {
+    if (g->nd != 0 || m->T != 3 || m->K < 1 || m->K > 3) return false;
+    if (g->node) return (g->nc == 1 && g->ng == 0 && g->ne == 0) || (g->nc == 0 && g->ng == 1 && g->ne == 0);
+    const int code = g->nc * 100 + g->ng * 10 + g->ne;
+    switch (code) {
+#define X(NC_, NG_, NE_) case NC_ * 100 + NG_ * 10 + NE_: return true;
+        LHVI_SPEC_SIGS(X)
+#undef X
+        default: return false;
+    }
+}
+
+int launch_spec(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStream_t s) {
+    if (!spec_available(m, g)) return 1;
+    const bool f64 = m->dtype == LHVI_F64;
+    switch (m->K) {
+        case 1: return f64 ? spec_f64_k1(m, g, row0, s) : spec_f32_k1(m, g, row0, s);
+        case 2: return f64 ? spec_f64_k2(m, g, row0, s) : spec_f32_k2(m, g, row0, s);
+        case 3: return f64 ? spec_f64_k3(m, g, row0, s) : spec_f32_k3(m, g, row0, s);
+        default: return 1;
+    }
+}
 
 }  // namespace lhvi

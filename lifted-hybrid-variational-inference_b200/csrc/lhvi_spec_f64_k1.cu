@@ -1,0 +1,8 @@
+// Instantiation unit: double, K=1, T=3 (see lhvi_spec_impl.cuh).
+#include "lhvi_spec_impl.cuh"
+
+namespace lhvi {
+int spec_f64_k1(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStream_t s) {
+    return launch_kt<double, 1, 3>(m, g, row0, s);
+}
+}  // namespace lhvi

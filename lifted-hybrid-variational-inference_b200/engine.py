@@ -32,6 +32,19 @@ def hermgauss_scaled(T):
     return x, w / np.sqrt(np.pi)
 
 
+def hub_mask(g):
+    """Bit a set when hidden argument a mostly repeats the previous record's variable (runs of
+    a hub variable): the kernels then accumulate its gradient per block in shared memory."""
+    mask = 0
+    if g.n < 64:
+        return mask
+    for a in range(g.nh):
+        col = g.poff[a]
+        if np.count_nonzero(col[1:] == col[:-1]) > 0.5 * (g.n - 1):
+            mask |= 1 << a
+    return mask
+
+
 class DeviceEngine:
     def __init__(self, model: LoweredModel, dtype="float64", device=None, var_threshold=0.1,
                  process_group=None, shard=True, force_generic=False):
@@ -100,6 +113,7 @@ class DeviceEngine:
             for i in range(_cabi.LHVI_MAX_AXES):
                 d.dims[i] = int(g.dims[i]) if i < len(g.dims) else 0
             d.node, d.weighted, d.n = int(g.node), int(g.weighted), int(g.n)
+            d.hub_mask = hub_mask(g)
 
             def put(name, arr, dt):
                 if arr.size == 0:
