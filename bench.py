@@ -78,10 +78,10 @@ def group_bytes(g, K, s):
         per += 4                                    # pot
     per += 4 * g.nh                                 # parameter offsets
     per += s * (2 * g.ng + g.ne)                    # evidence columns
-    if g.weighted:
-        per += s * (1 + g.nh)                       # W_f, gamma
     if g.node:
-        per += s                                    # N_v - 1
+        per += 2 * s                                # energy scale, gradient scale
+    elif g.weighted:
+        per += s * (1 + g.nh)                       # W_f, gamma
     elems = sum(K * d for d in g.dims) + 2 * K * g.nc
     per += 2 * s * elems                            # gather + gradient write
     return per * g.n
@@ -287,7 +287,7 @@ def run_ours(a):
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak if achieved else None, "traffic": None,
             "kernel": f"factor kernel over group nd={dom_group.nd} nc={dom_group.nc} ng={dom_group.ng} "
-                      f"ne={dom_group.ne} ({dom_group.n} records on rank 0)",
+                      f"ne={dom_group.ne} pure={int(dom_group.pure)} ({dom_group.n} records on rank 0)",
             "kernel_ms": dom_ms, "kernel_bytes": dom_bytes, "peak_source": peak_src,
             "step_bytes": step_bytes, "step_achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
             "step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,

@@ -71,22 +71,24 @@ extern "C" {
 typedef struct lhvi_group {
     int32_t nd, nc, ng, ne;        /* argument counts per role */
     int32_t dims[LHVI_MAX_AXES];   /* states of each hidden discrete argument */
-    int32_t node;                  /* 1: node-entropy records, F = nscale * log b, no ptab */
+    int32_t node;                  /* 1: node-entropy records: F = log b (no ptab); energy and G_w are
+                                      scaled by wf, parameter gradients by nscale */
     int32_t weighted;              /* 1: wf / gam present; 0: all weights are 1 */
     int32_t hub_mask;              /* bit a set: hidden argument a mostly comes in long runs of the
                                       same variable (a hub); its gradient is accumulated in shared
                                       memory per block before touching global memory.  A hint:
                                       results do not depend on it. */
-    int32_t reserved;
+    int32_t pure;                  /* 1: F = log psi only (unary split: the -log b part of these
+                                      records is carried by the node records); no belief evaluated */
     int64_t n;                     /* records in this group */
     const int32_t* pot;            /* [n]          offset of the coefficient block in ptab */
     const int32_t* poff;           /* [(nd+nc)*n]  parameter slot offsets */
     const void* egval;             /* [ng*n]       Gaussian-evidence means */
     const void* egvar;             /* [ng*n]       Gaussian-evidence variances */
     const void* ecval;             /* [ne*n]       point-evidence values */
-    const void* wf;                /* [n]          W_f, weight on energy and g_w */
+    const void* wf;                /* [n]          W_f, weight on energy and g_w (node: energy scale) */
     const void* gam;               /* [(nd+nc)*n]  gamma, weight on each parameter gradient */
-    const void* nscale;            /* [n]          node groups: N_v - 1 */
+    const void* nscale;            /* [n]          node groups: parameter-gradient scale */
 } lhvi_group;
 
 /* Model-wide device buffers shared by every group launch. */

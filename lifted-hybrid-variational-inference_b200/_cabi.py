@@ -26,7 +26,7 @@ class LhviGroup(C.Structure):
     _fields_ = [
         ("nd", C.c_int32), ("nc", C.c_int32), ("ng", C.c_int32), ("ne", C.c_int32),
         ("dims", C.c_int32 * LHVI_MAX_AXES),
-        ("node", C.c_int32), ("weighted", C.c_int32), ("hub_mask", C.c_int32), ("reserved", C.c_int32),
+        ("node", C.c_int32), ("weighted", C.c_int32), ("hub_mask", C.c_int32), ("pure", C.c_int32),
         ("n", C.c_int64),
         ("pot", C.c_void_p), ("poff", C.c_void_p),
         ("egval", C.c_void_p), ("egvar", C.c_void_p), ("ecval", C.c_void_p),

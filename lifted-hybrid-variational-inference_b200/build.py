@@ -41,8 +41,12 @@ def sources():
 
 
 def dependencies():
-    return sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h")) \
-        + [os.path.abspath(__file__)]
+    return sources() + headers() + [os.path.abspath(__file__)]
+
+
+def headers():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) \
+        + glob.glob(os.path.join(INCLUDE, "*.h"))
 
 
 def up_to_date() -> bool:
@@ -55,8 +59,7 @@ def up_to_date() -> bool:
 def _compile(src: str, verbose: bool) -> str:
     obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
     if os.path.exists(obj):
-        newest = max(os.path.getmtime(p) for p in [src] + glob.glob(os.path.join(CSRC, "*.cuh"))
-                     + glob.glob(os.path.join(INCLUDE, "*.h")) + [os.path.abspath(__file__)])
+        newest = max(os.path.getmtime(p) for p in [src] + headers() + [os.path.abspath(__file__)])
         if os.path.getmtime(obj) >= newest:
             return obj
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]

@@ -38,7 +38,8 @@ static int validate(const lhvi_model* m, const lhvi_group* g, int64_t row0) {
     if (g->ne > 0 && !g->ecval) { set_error("group has point evidence but ecval is null"); return LHVI_EINVAL; }
     if (g->weighted && (!g->wf || (nh > 0 && !g->gam))) { set_error("weighted group without wf/gam"); return LHVI_EINVAL; }
     if (g->node) {
-        if (!g->nscale) { set_error("node group without nscale"); return LHVI_EINVAL; }
+        if (!g->nscale || !g->wf) { set_error("node group without nscale/wf"); return LHVI_EINVAL; }
+        if (g->pure) { set_error("a node group cannot be pure"); return LHVI_EINVAL; }
         if (nh + g->ng != 1 || g->ne != 0) { set_error("node group must have exactly one integrated argument"); return LHVI_EINVAL; }
     } else if (!g->pot || !m->ptab) {
         set_error("factor group without pot/ptab");

@@ -36,6 +36,12 @@ template <> struct Math<double> {
     static __device__ __forceinline__ bool belief_underflow(double) { return false; }
 };
 
+// float cannot hold 1e-100: the floor only matters once exp(q) is below ~1e-35, so the rare
+// deep-tail points take an out-of-line double evaluation (keeps the hot loop small)
+static __device__ __noinline__ float log_psi_deep_tail(float q) {
+    return (float)::log(::exp((double)q) + kEps);
+}
+
 template <> struct Math<float> {
 #ifdef LHVI_FAST_MATH
     static __device__ __forceinline__ float exp(float x) { return __expf(x); }
@@ -48,7 +54,7 @@ template <> struct Math<float> {
     static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
     static __device__ __forceinline__ float log_psi(float q) {
         if (q > -80.0f) return q;
-        return (float)::log(::exp((double)q) + kEps);
+        return log_psi_deep_tail(q);
     }
     // valid only when !belief_underflow(b); callers recompute in double otherwise
     static __device__ __forceinline__ float log_belief(float b) { return log(b); }
@@ -98,7 +104,7 @@ __device__ __forceinline__ void block_sum_to(const double* vals, int nvals, doub
 
 template <typename real>
 struct GroupView {
-    int nd, nc, ng, ne, node, weighted;
+    int nd, nc, ng, ne, node, weighted, pure;
     int dims[LHVI_MAX_AXES];
     long long n;
     const int* pot;
@@ -123,7 +129,7 @@ template <typename real>
 inline GroupView<real> make_view(const lhvi_model* m, const lhvi_group* g, int64_t row0) {
     GroupView<real> v;
     v.nd = g->nd; v.nc = g->nc; v.ng = g->ng; v.ne = g->ne;
-    v.node = g->node; v.weighted = g->weighted;
+    v.node = g->node; v.weighted = g->weighted; v.pure = g->pure;
     for (int i = 0; i < LHVI_MAX_AXES; ++i) v.dims[i] = g->dims[i];
     v.n = g->n;
     v.pot = g->pot; v.poff = g->poff;

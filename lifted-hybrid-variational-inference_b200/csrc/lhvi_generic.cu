@@ -59,8 +59,8 @@ factor_generic_kernel(const GroupView<real> g) {
 
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < g.n;
          r += (long long)gridDim.x * blockDim.x) {
-        const real wf = g.weighted ? g.wf[r] : real(1);
-        const real nscale = g.node ? g.nscale[r] : real(0);
+        const real wf = (g.weighted || g.node) ? g.wf[r] : real(1);
+        const real nscale = g.node ? g.nscale[r] : real(1);
         const real* coef0 = g.node ? nullptr : g.ptab + g.pot[r];
         for (int i = 0; i < goff[nh]; ++i) gacc[i] = real(0);
 
@@ -118,7 +118,9 @@ factor_generic_kernel(const GroupView<real> g) {
                     b += p;
                 }
                 real lb;
-                if (M::belief_underflow(b)) {
+                if (g.pure) {
+                    lb = real(0);          // unary split: -log b is carried by the node record
+                } else if (M::belief_underflow(b)) {
                     // float only: redo this point's belief in double from the parameters
                     double bd = 0.0;
                     for (int k2 = 0; k2 < K; ++k2) {
@@ -142,7 +144,7 @@ factor_generic_kernel(const GroupView<real> g) {
 
                 real F;
                 if (g.node) {
-                    F = nscale * lb;
+                    F = lb;
                 } else {
                     int cfg = 0;
                     for (int a = 0; a < g.nd; ++a) cfg += idx[a] * cstride[a];
@@ -197,7 +199,7 @@ factor_generic_kernel(const GroupView<real> g) {
 
         // ---- scatter the parameter gradients
         for (int a = 0; a < nh; ++a) {
-            const real gam = g.weighted ? g.gam[a * g.n + r] : real(1);
+            const real gam = (g.weighted && !g.node ? g.gam[a * g.n + r] : real(1)) * nscale;
             if (gam == real(0)) continue;
             real* dst = g.grad + g.poff[a * g.n + r];
             const int cnt = goff[a + 1] - goff[a];

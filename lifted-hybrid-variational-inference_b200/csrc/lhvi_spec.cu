@@ -2,10 +2,9 @@
 // (dtype, K) pair is instantiated in its own translation unit (lhvi_spec_<dtype>_k<K>.cu) so the
 // build parallelises.
 #include "lhvi_common.cuh"
+#include "lhvi_spec_sigs.h"
 
 namespace lhvi {
-
-#define LHVI_SPEC_SIGS(X) X(1, 0, 0) X(2, 0, 0) X(1, 0, 1) X(1, 1, 0) X(2, 0, 1) X(2, 1, 0) X(3, 0, 0) X(1, 0, 2)
 
 int spec_f32_k1(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
 int spec_f32_k2(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
@@ -17,10 +16,18 @@ int spec_f64_k3(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
 bool spec_available(const lhvi_model* m, const lhvi_group* g) {
     if (g->nd != 0 || m->T != 3 || m->K < 1 || m->K > 3) return false;
     if (g->node) return (g->nc == 1 && g->ng == 0 && g->ne == 0) || (g->nc == 0 && g->ng == 1 && g->ne == 0);
-    const int code = g->nc * 100 + g->ng * 10 + g->ne;
-    switch (code) {
+    if (g->pure) {
+        if (g->ng != 0) return false;
+        switch (g->nc * 10 + g->ne) {
+#define X(NC_, NE_) case NC_ * 10 + NE_: return true;
+            LHVI_SPEC_PURE(X)
+#undef X
+            default: return false;
+        }
+    }
+    switch (g->nc * 100 + g->ng * 10 + g->ne) {
 #define X(NC_, NG_, NE_) case NC_ * 100 + NG_ * 10 + NE_: return true;
-        LHVI_SPEC_SIGS(X)
+        LHVI_SPEC_FULL(X)
 #undef X
         default: return false;
     }

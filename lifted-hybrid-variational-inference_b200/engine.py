@@ -114,6 +114,7 @@ class DeviceEngine:
                 d.dims[i] = int(g.dims[i]) if i < len(g.dims) else 0
             d.node, d.weighted, d.n = int(g.node), int(g.weighted), int(g.n)
             d.hub_mask = hub_mask(g)
+            d.pure = int(g.pure)
 
             def put(name, arr, dt):
                 if arr.size == 0:

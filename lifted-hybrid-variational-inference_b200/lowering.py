@@ -17,7 +17,15 @@ per C2F refinement round) into
   evidence travels as a per-record value column.
 
 The variables' own ``(N-1) E[log b]`` terms (``VarInference.py:60-72,96-106,138-139``) are
-emitted as *node groups*: unary records with ``log psi = 0`` and a per-record scale.
+emitted as *node groups*: unary records with ``F = log b`` and two per-record scales (one for
+the energy / G_w, one for the parameter gradients).
+
+*Unary split.*  A factor with a single integrated argument v has
+``F = log psi(x) - log b_v(x)``; its ``-log b_v`` part depends on the variable only, so by
+linearity of the expectation it is moved into v's node record (its scales become
+``C_v (N_v-1) - sum W_f`` and ``(N_v-1) - sum gamma_f``) and the factor is stored as a *pure*
+record that evaluates ``log psi`` alone -- no density, exp or log per record.  The sums the
+reference computes are unchanged; only their grouping differs.
 
 Nothing here touches the GPU; ``engine.py`` uploads the result.
 """
@@ -57,16 +65,17 @@ class RecordGroup:
     ng: int
     ne: int
     dims: tuple            # states of each hidden discrete argument
-    node: bool             # node-entropy pseudo factors (log psi = 0, F = nscale * log b)
+    node: bool             # node-entropy pseudo factors: F = log b, energy x wf, gradients x nscale
     pot: np.ndarray        # int32 [n]            offset of the coefficient block in ptab
     poff: np.ndarray       # int32 [nd+nc, n]     parameter-slot offsets
     egval: np.ndarray      # f64   [ng, n]        Gaussian-evidence mean
     egvar: np.ndarray      # f64   [ng, n]        Gaussian-evidence variance
     ecval: np.ndarray      # f64   [ne, n]        point-evidence values (continuous args)
-    wf: np.ndarray         # f64   [n]            W_f: energy / g_w weight
+    wf: np.ndarray         # f64   [n]            W_f: energy / g_w weight (node: energy scale)
     gam: np.ndarray        # f64   [nd+nc, n]     gamma: parameter-gradient weight per arg
-    nscale: np.ndarray     # f64   [n]            node groups: (N_v - 1)
+    nscale: np.ndarray     # f64   [n]            node groups: parameter-gradient scale
     weighted: bool         # False -> wf == gam == 1 everywhere (columns not shipped)
+    pure: bool = False     # True -> F = log psi only (the -log b part lives in the node records)
 
     @property
     def n(self) -> int:
@@ -86,14 +95,14 @@ class RecordGroup:
 
     @property
     def signature(self):
-        return (self.node, self.nd, self.nc, self.ng, self.ne, tuple(self.dims), self.weighted)
+        return (self.node, self.pure, self.nd, self.nc, self.ng, self.ne, tuple(self.dims), self.weighted)
 
     def take(self, sel) -> "RecordGroup":
         """Sub-group (used to shard records across ranks)."""
         return RecordGroup(self.nd, self.nc, self.ng, self.ne, self.dims, self.node,
                            self.pot[sel], self.poff[:, sel], self.egval[:, sel],
                            self.egvar[:, sel], self.ecval[:, sel], self.wf[sel],
-                           self.gam[:, sel], self.nscale[sel], self.weighted)
+                           self.gam[:, sel], self.nscale[sel], self.weighted, self.pure)
 
 
 @dataclass
@@ -302,8 +311,9 @@ class PotentialTable:
 # ----------------------------------------------------------------------------------------
 
 class _GroupBuilder:
-    def __init__(self, nd, nc, ng, ne, dims, node):
+    def __init__(self, nd, nc, ng, ne, dims, node, pure=False):
         self.sig = (nd, nc, ng, ne, tuple(dims), node)
+        self.pure = pure
         self.pot, self.poff, self.egval, self.egvar, self.ecval = [], [], [], [], []
         self.wf, self.gam, self.nscale = [], [], []
 
@@ -327,12 +337,12 @@ class _GroupBuilder:
 
         wf = np.asarray(self.wf, dtype=float)
         gam = cols(self.gam, nd + nc, float)
-        weighted = bool(np.any(wf != 1.0) or np.any(gam != 1.0))
+        weighted = bool(node or np.any(wf != 1.0) or np.any(gam != 1.0))
         return RecordGroup(nd, nc, ng, ne, dims, node,
                            np.asarray(self.pot, dtype=np.int32), cols(self.poff, nd + nc, np.int32),
                            cols(self.egval, ng, float), cols(self.egvar, ng, float),
                            cols(self.ecval, ne, float), wf, gam,
-                           np.asarray(self.nscale, dtype=float), weighted)
+                           np.asarray(self.nscale, dtype=float), weighted, self.pure)
 
 
 def lower_graph(rvs, factors, K, T, *, factor_weight=None, arg_weight=None, var_weight=None,
@@ -384,29 +394,15 @@ def lower_graph(rvs, factors, K, T, *, factor_weight=None, arg_weight=None, var_
     table = PotentialTable()
     builders = {}
 
-    def builder(nd, nc, ng, ne, dims, node):
-        key = (nd, nc, ng, ne, tuple(dims), node)
+    def builder(nd, nc, ng, ne, dims, node, pure=False):
+        key = (nd, nc, ng, ne, tuple(dims), node, pure)
         if key not in builders:
-            builders[key] = _GroupBuilder(nd, nc, ng, ne, dims, node)
+            builders[key] = _GroupBuilder(nd, nc, ng, ne, dims, node, pure)
         return builders[key]
 
-    # ---- node-entropy pseudo factors
-    for rv in rvs:
-        scale = float(rv.N - 1)
-        if rv.value is None:
-            h = index[rv]
-            if kind[h] == 0:
-                b = builder(0, 1, 0, 0, (), True)
-            else:
-                b = builder(1, 0, 0, 0, (dim[h],), True)
-            b.add(0, [off[h]], [], [], float(var_weight(rv)), [1.0], scale)
-        else:
-            ge = gaussian_evidence(rv)
-            if ge is not None:
-                builder(0, 0, 1, 0, (), True).add(0, [], [ge], [], float(var_weight(rv)), [], scale)
-            # point evidence: b = sum_k w_k = 1, log term vanishes (VarInference.py:65-66)
-
     # ---- factor records
+    unary_w = {}     # hidden variable -> sum of W_f over its unary (single integrated arg) factors
+    unary_g = {}     # hidden variable -> sum of gamma over the same factors
     for f in factors:
         nb = list(f.nb)
         roles, args = [], []
@@ -435,16 +431,42 @@ def lower_graph(rvs, factors, K, T, *, factor_weight=None, arg_weight=None, var_
             raise ValueError(f"factor with {nd + nc + ng} integrated arguments (max {MAX_ARITY})")
         dims = tuple(len(args[i]) for i in pos[HD])
         hidden = pos[HD] + pos[HC]
-        builder(nd, nc, ng, ne, dims, False).add(
+        w_f = float(factor_weight(f))
+        gam = [float(arg_weight(f, i, nb[i])) for i in hidden]
+        # unary split: a single integrated argument (or none) -> pure log-psi record
+        pure = (nd + nc + ng == 0) or (nd + nc == 1 and ng == 0)
+        if pure and hidden:
+            v = nb[hidden[0]]
+            unary_w[v] = unary_w.get(v, 0.0) + w_f
+            unary_g[v] = unary_g.get(v, 0.0) + gam[0]
+        builder(nd, nc, ng, ne, dims, False, pure).add(
             table.block(f.potential, roles, args),
             [off[index[nb[i]]] for i in hidden],
             [args[i] for i in pos[EG]],
             [args[i] for i in pos[EC]],
-            float(factor_weight(f)),
-            [float(arg_weight(f, i, nb[i])) for i in hidden])
+            w_f, gam)
+
+    # ---- node-entropy pseudo factors: F = log b_v, energy scale wf, gradient scale nscale
+    for rv in rvs:
+        scale = float(rv.N - 1)
+        c_v = float(var_weight(rv))
+        if rv.value is None:
+            h = index[rv]
+            s_e = c_v * scale - unary_w.get(rv, 0.0)
+            s_g = scale - unary_g.get(rv, 0.0)
+            if kind[h] == 0:
+                b = builder(0, 1, 0, 0, (), True)
+            else:
+                b = builder(1, 0, 0, 0, (dim[h],), True)
+            b.add(0, [off[h]], [], [], s_e, [1.0], s_g)
+        else:
+            ge = gaussian_evidence(rv)
+            if ge is not None:
+                builder(0, 0, 1, 0, (), True).add(0, [], [ge], [], c_v * scale, [], scale)
+            # point evidence: b = sum_k w_k = 1, log term vanishes (VarInference.py:65-66)
 
     groups = [b.finish() for b in builders.values()]
-    groups.sort(key=lambda g: (not g.node, g.nd + g.nc + g.ng, g.nd, g.nc, g.ng, g.ne, g.dims))
+    groups.sort(key=lambda g: (not g.node, not g.pure, g.nd + g.nc + g.ng, g.nd, g.nc, g.ng, g.ne, g.dims))
     return LoweredModel(K, T, max(cursor, 2), np.asarray(kind, dtype=np.uint8),
                         np.asarray(dim, dtype=np.int32), np.asarray(off, dtype=np.int32),
                         table.array(), groups, handles, index)

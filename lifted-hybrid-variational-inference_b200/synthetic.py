@@ -44,7 +44,8 @@ def _relational_draws(P, G, observed_frac, seed):
     return observed, value, member, sess
 
 
-def _group(nd, nc, ng, ne, node, pot, poff, ecval, nscale=None, weighted=False, wf=None, gam=None):
+def _group(nd, nc, ng, ne, node, pot, poff, ecval, nscale=None, weighted=False, wf=None, gam=None,
+           pure=False):
     n = len(pot)
     nh = nd + nc
     f64 = np.float64
@@ -57,7 +58,7 @@ def _group(nd, nc, ng, ne, node, pot, poff, ecval, nscale=None, weighted=False, 
         np.ones(n, f64) if wf is None else wf,
         np.ones((nh, n), f64) if gam is None else gam,
         np.zeros(n, f64) if nscale is None else np.asarray(nscale, dtype=f64),
-        weighted)
+        weighted or node, pure)
 
 
 def relational_hybrid(P, G, K, T, *, observed_frac=0.7, seed=0, order="hub", weighted=False):
@@ -87,19 +88,22 @@ def relational_hybrid(P, G, K, T, *, observed_frac=0.7, seed=0, order="hub", wei
     deg_paper = G + 1
 
     groups = []
-    # node-entropy records: (N_v - 1) E[log b_v]
+    # node-entropy records: F = log b_v scaled by (N_v - 1) minus the variable's unary factors
+    # (lowering.py "unary split"): every observed-entity link is unary in its group variable,
+    # every hidden entity has one unary prior
+    n_obs = int(observed.sum())
+    scale = np.concatenate([deg_topic - 1 - n_obs, np.full(hidden_p.size, deg_paper - 1 - 1)]).astype(np.float64)
     groups.append(_group(0, 1, 0, 0, True, np.zeros(n_hidden, np.int32), var_off[None, :], np.zeros((0, n_hidden)),
-                         nscale=np.concatenate([deg_topic - 1, np.full(hidden_p.size, deg_paper - 1)]),
-                         weighted=weighted))
+                         nscale=scale, wf=scale.copy()))
 
     # priors: hidden entity -> one continuous argument; observed entity -> constant record
     blk_prior_h = table.block(prior, (HC,), (None,))
     blk_prior_e = table.block(prior, (EC,), (0.0,))
     groups.append(_group(0, 1, 0, 0, False, np.full(hidden_p.size, blk_prior_h), off_paper[hidden_p][None, :],
-                         np.zeros((0, hidden_p.size)), weighted=weighted))
+                         np.zeros((0, hidden_p.size)), weighted=weighted, pure=True))
     obs_p = np.flatnonzero(observed)
     groups.append(_group(0, 0, 0, 1, False, np.full(obs_p.size, blk_prior_e), np.zeros((0, obs_p.size)),
-                         value[obs_p][None, :], weighted=weighted))
+                         value[obs_p][None, :], weighted=weighted, pure=True))
 
     # link factors In(p,t) * -(Pop(p) - Pop(t))^2
     if order == "hub":
@@ -114,7 +118,7 @@ def relational_hybrid(P, G, K, T, *, observed_frac=0.7, seed=0, order="hub", wei
     blk_e = np.array([table.block(link, (ED, EC, HC), (v, 0.0, None)) for v in (0, 1)])
     sel = np.flatnonzero(is_obs)
     groups.append(_group(0, 1, 0, 1, False, blk_e[mem[sel]], off_topic[tt[sel]][None, :],
-                         value[pp[sel]][None, :], weighted=weighted))
+                         value[pp[sel]][None, :], weighted=weighted, pure=True))
     # hidden entity: canonical args [Pop(p), Pop(t)]
     blk_h = np.array([table.block(link, (ED, HC, HC), (v, None, None)) for v in (0, 1)])
     sel = np.flatnonzero(~is_obs)
@@ -186,9 +190,11 @@ def gaussian_grid(n, K, T, *, unary_coeff=1.0, unary_sig=2.0):
     blk_u = table.block(X2Potential(unary_coeff, unary_sig), (HC,), (None,))
     blk_e = table.block(GaussianPotential([0.0, 0.0], _GRID_SIG), (HC, HC), (None, None))
     E = edges.shape[1]
+    scale = (deg - 1 - 1).astype(np.float64)       # minus the unary X2 factor (unary split)
     groups = [
-        _group(0, 1, 0, 0, True, np.zeros(V, np.int32), var_off[None, :], np.zeros((0, V)), nscale=deg - 1),
-        _group(0, 1, 0, 0, False, np.full(V, blk_u), var_off[None, :], np.zeros((0, V))),
+        _group(0, 1, 0, 0, True, np.zeros(V, np.int32), var_off[None, :], np.zeros((0, V)), nscale=scale,
+               wf=scale.copy()),
+        _group(0, 1, 0, 0, False, np.full(V, blk_u), var_off[None, :], np.zeros((0, V)), pure=True),
         _group(0, 2, 0, 0, False, np.full(E, blk_e), var_off[edges], np.zeros((0, E))),
     ]
     return LoweredModel(K, T, int(V * slot), np.zeros(V, np.uint8), np.full(V, 2, np.int32),

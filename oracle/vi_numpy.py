@@ -91,13 +91,18 @@ def grad_pass(model, eta, w, chunk_elems=1 << 24):
                 Q.append(np.broadcast_to(q[:, :, None, :], (m, K, K, T)))
 
             # belief on the grid: [m, K, grid...]
-            prod = np.broadcast_to(w.reshape([1, 1, K] + [1] * n_ax), [m, K, K] + sizes).copy()
-            for a in range(n_ax):
-                prod *= _on_axis(Q[a], 3, a, n_ax)
-            lb = np.log(prod.sum(axis=2) + EPS)
+            if g.pure:
+                lb = 0.0         # the -log b part of unary factors lives in the node records
+            else:
+                prod = np.broadcast_to(w.reshape([1, 1, K] + [1] * n_ax), [m, K, K] + sizes).copy()
+                for a in range(n_ax):
+                    prod *= _on_axis(Q[a], 3, a, n_ax)
+                lb = np.log(prod.sum(axis=2) + EPS)
 
+            gscale = 1.0
             if g.node:
-                F = g.nscale[sl].reshape([m, 1] + [1] * n_ax) * lb
+                F = lb            # energy / G_w weighted by wf, gradients by nscale
+                gscale = g.nscale[sl]
             else:
                 cfg = np.zeros([m] + [1] * n_ax, dtype=np.int64)
                 stride = 1
@@ -137,7 +142,7 @@ def grad_pass(model, eta, w, chunk_elems=1 << 24):
                 a = g.nd + c
                 dx = _on_axis(X[a] - mus[c][:, :, None], 2, a, n_ax)
                 var = vars_[c]
-                gam = g.gam[a, sl][:, None]
+                gam = (g.gam[a, sl] * gscale)[:, None]
                 gmu = -gam * (S * dx).sum(axis=grid_axes) / var
                 gvar = -gam * (S * (dx * dx - var.reshape([m, K] + [1] * n_ax))).sum(axis=grid_axes) \
                     / (2 * var * var)
@@ -151,7 +156,7 @@ def grad_pass(model, eta, w, chunk_elems=1 << 24):
                     if a2 != a:
                         Wo = Wo * _on_axis(Wt[a2], 2, a2, n_ax)
                 other = tuple(ax for ax in grid_axes if ax != 2 + a)
-                gc = -(g.gam[a, sl][:, None, None]) * (Wo * F).sum(axis=other)     # [m, K, D]
+                gc = -((g.gam[a, sl] * gscale)[:, None, None]) * (Wo * F).sum(axis=other)     # [m, K, D]
                 idx = g.poff[a, sl][:, None, None] + karange[None, :, None] * D + np.arange(D)[None, None, :]
                 np.add.at(grad, idx, gc)
     return grad, g_w, energy
