@@ -36,8 +36,8 @@ template <> struct Math<double> {
     static __device__ __forceinline__ bool belief_underflow(double) { return false; }
 };
 
-// float cannot hold 1e-100: the floor only matters once exp(q) is below ~1e-35, so the rare
-// deep-tail points take an out-of-line double evaluation (keeps the hot loop small)
+// float cannot hold 1e-100: log(exp(q) + 1e-100) - q = log1p(exp(-230.26 - q)) is below half a
+// float ulp of q for q > -218, so only deep-tail points take this out-of-line double evaluation
 static __device__ __noinline__ float log_psi_deep_tail(float q) {
     return (float)::log(::exp((double)q) + kEps);
 }
@@ -53,7 +53,7 @@ template <> struct Math<float> {
     static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
     static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
     static __device__ __forceinline__ float log_psi(float q) {
-        if (q > -80.0f) return q;
+        if (q > -210.0f) return q;       // the 1e-100 floor is below float resolution up here
         return log_psi_deep_tail(q);
     }
     // valid only when !belief_underflow(b); callers recompute in double otherwise

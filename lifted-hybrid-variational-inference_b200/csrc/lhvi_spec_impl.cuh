@@ -45,12 +45,16 @@ template <> struct Fast<float> {
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
         return y;
     }
+    // the walk works in log2 units: F2 = log2(psi) - log2(b); kUnit converts back at the end
+    static constexpr float kUnit = 0.6931471805599453f;
     static __device__ __forceinline__ float log_belief(float b) {
         float y;
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(b));
-        return y * 0.6931471805599453f;
+        return y;
     }
-    static constexpr float kQFloor = -80.0f;      // below: exp(q) is within 1e-35 of the 1e-100 floor scale
+    // log(exp(q) + 1e-100) - q = log1p(exp(-230.26 - q)) exceeds half a float ulp of q only for
+    // q < -218; above the threshold (in log2 units here) the floor is invisible in float
+    static constexpr float kQFloor = -210.0f * 1.4426950408889634f;
     static constexpr float kBFloor = 1e-30f;      // below: float products may have flushed to zero
     static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
     static __device__ __forceinline__ float sqrt(float x) { return __fsqrt_rn(x); }
@@ -58,6 +62,7 @@ template <> struct Fast<float> {
 
 template <> struct Fast<double> {
     static constexpr double kExpScale = 1.0;
+    static constexpr double kUnit = 1.0;
     static __device__ __forceinline__ double exp_scaled(double x) { return ::exp(x); }
     static __device__ __forceinline__ double log_belief(double b) { return ::log(b + kEps); }
     static constexpr double kQFloor = -180.0;     // below: log(exp(q)+1e-100) differs from q in double
@@ -126,7 +131,7 @@ struct PointCtx {
     real egval[NG > 0 ? NG : 1], egvar[NG > 0 ? NG : 1];
 };
 
-// log(b + 1e-100) with the belief recomputed in double from the parameters
+// log(b + 1e-100) (in the walk's units) with the belief recomputed in double from the parameters
 template <typename real, int K, int NC, int NG>
 __device__ __noinline__ real checked_log_belief(const real* __restrict__ eta, const real* s_w,
                                                  const PointCtx<real, NC, NG> c) {
@@ -138,13 +143,14 @@ __device__ __noinline__ real checked_log_belief(const real* __restrict__ eta, co
         for (int j = 0; j < NG; ++j) p *= norm_pdf_d((double)c.x[NC + j], (double)c.egval[j], (double)c.egvar[j]);
         b += p;
     }
-    return (real)::log(b + kEps);
+    return (real)(::log(b + kEps) / (double)Fast<real>::kUnit);
 }
 
-// log(exp(q) + 1e-100)
+// log(exp(q) + 1e-100), argument and result in the walk's units
 template <typename real>
 __device__ __noinline__ real checked_log_psi(real q) {
-    return (real)::log(::exp((double)q) + kEps);
+    const double unit = (double)Fast<real>::kUnit;
+    return (real)(::log(::exp((double)q * unit) + kEps) / unit);
 }
 
 // ---- compile-time grid walk ------------------------------------------------------------------
@@ -158,10 +164,10 @@ struct Ctx {
     static constexpr int NQ = NCT > 0 ? NCT : 1;
     real x[NA > 0 ? NA : 1][T];            // node positions under the current component
     real q[NA > 0 ? NA : 1][K][T];         // cross densities q_{k'}(x_t)
-    real qw[T], xi[T];
+    real w0[T], w1[T], w2[T];              // omega_t, omega_t xi_t, omega_t xi_t^2
     real A[NQ][NQ];                        // upper-triangular quadratic coefficients
     real m1[NC > 0 ? NC : 1], m2[NC > 0 ? NC : 1];   // sum W F xi_t, sum W F xi_t^2 per hidden axis
-    real qmin, bmin;                       // bounds tracked by the unchecked walk
+    real qmin;                             // smallest log psi seen by the unchecked walk
     const real* eta;
     const real* s_w;
     PointCtx<real, NC, NG> pt;
@@ -171,6 +177,7 @@ template <typename real, int K, int T, int NC, int NG, int NE, int FL, bool CHEC
 struct Walk {
     using C = Ctx<real, K, T, NC, NG, NE>;
     using F = Fast<real>;
+    // returns sum over the inner axes of (prod inner omega) * F ; Wout = prod of outer omegas
     static __device__ __forceinline__ real run(C& c, const real (&pk)[K], real Wout, real cst,
                                                const real (&lin)[C::NQ]) {
         if constexpr (AX == C::NA) {
@@ -180,13 +187,12 @@ struct Walk {
                 else c.qmin = cst < c.qmin ? cst : c.qmin;
             }
             if constexpr (FL != kPure) {
-                real b = pk[0];
-#pragma unroll
-                for (int k2 = 1; k2 < K; ++k2) b += pk[k2];
                 if constexpr (CHECKED) {
                     lb = checked_log_belief<real, K, NC, NG>(c.eta, c.s_w, c.pt);
                 } else {
-                    c.bmin = b < c.bmin ? b : c.bmin;
+                    real b = pk[0];
+#pragma unroll
+                    for (int k2 = 1; k2 < K; ++k2) b += pk[k2];
                     lb = F::log_belief(b);
                 }
             }
@@ -194,7 +200,7 @@ struct Walk {
             else if constexpr (FL == kPure) return lpsi;
             else return lpsi - lb;
         } else {
-            real ret = real(0);
+            real s0 = real(0), s1 = real(0), s2 = real(0);
 #pragma unroll
             for (int t = 0; t < T; ++t) {
                 real pk2[K];
@@ -216,16 +222,18 @@ struct Walk {
                     for (int j = AX + 1; j < C::NA; ++j) lin2[j] = lin[j] + c.A[AX][j] * xv;
                 }
                 if constexpr (CHECKED) c.pt.x[AX] = xv;
-                const real R = Walk<real, K, T, NC, NG, NE, FL, CHECKED, AX + 1>::run(c, pk2, Wout * c.qw[t], cst2, lin2);
-                const real wr = c.qw[t] * R;
-                ret += wr;
+                const real R = Walk<real, K, T, NC, NG, NE, FL, CHECKED, AX + 1>::run(c, pk2, Wout * c.w0[t], cst2, lin2);
+                s0 += c.w0[t] * R;
                 if constexpr (AX < NC) {
-                    const real m = Wout * wr * c.xi[t];
-                    c.m1[AX] += m;
-                    c.m2[AX] += m * c.xi[t];
+                    s1 += c.w1[t] * R;
+                    s2 += c.w2[t] * R;
                 }
             }
-            return ret;
+            if constexpr (AX < NC) {
+                c.m1[AX] += Wout * s1;
+                c.m2[AX] += Wout * s2;
+            }
+            return s0;
         }
     }
 };
@@ -236,7 +244,7 @@ struct SpecLaunch {
 
 // HUB: index of the hidden argument accumulated per thread across records (-1: none)
 template <typename real, int K, int T, int NC, int NG, int NE, int FL, bool WEIGHTED, int HUB>
-__global__ void __launch_bounds__(kSpecThreads, (FL == kFull && NC + NG >= 2) ? 2 : 3)
+__global__ void __launch_bounds__(kSpecThreads, 2)
 factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
     using F = Fast<real>;
     using C = Ctx<real, K, T, NC, NG, NE>;
@@ -259,9 +267,17 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
     __syncthreads();
 
     C c;
-    real eq[T], wk[K];
+    real eq[T], xi[T], wk[K];
+    real eq_min = real(1);
 #pragma unroll
-    for (int t = 0; t < T; ++t) { c.xi[t] = s_quad[t]; c.qw[t] = s_quad[T + t]; eq[t] = s_eq[t]; }
+    for (int t = 0; t < T; ++t) {
+        xi[t] = s_quad[t];
+        c.w0[t] = s_quad[T + t];
+        c.w1[t] = c.w0[t] * xi[t];
+        c.w2[t] = c.w1[t] * xi[t];
+        eq[t] = s_eq[t];
+        eq_min = eq[t] < eq_min ? eq[t] : eq_min;
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) wk[k] = s_w[k];
     c.eta = g.eta;
@@ -289,13 +305,49 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
         }
     };
 
+    // pure unary records: the quadrature nodes depend on the variable only, so they are kept
+    // across records and rebuilt when the variable changes (never, inside a hub's run)
+    constexpr bool kUnaryPure = FL == kPure && NC == 1 && NG == 0;
+    int node_key = -1;
+    real node_x[K][T], node_s[K], node_inv[K];
+
     const int lane = threadIdx.x & 31;
     const long long lo = (long long)blockIdx.x * L.chunk;
     const long long hi = lo + L.chunk < g.n ? lo + L.chunk : g.n;
 
+    // software pipeline: record columns are fetched one tile ahead (plain register arrays --
+    // nothing here may have its address taken, or the prefetch lands in local memory and the
+    // store stalls on the load).  The general path prefetches what a record needs first
+    // (offsets, potential id, evidence); the light unary-pure path also prefetches the weights.
+    constexpr bool kPrefetchWeights = kUnaryPure && WEIGHTED;
+    int c_pot = 0, n_pot = 0;
+    int c_poff[NCS], n_poff[NCS];
+    real c_egv[NG > 0 ? NG : 1], c_egs[NG > 0 ? NG : 1], n_egv[NG > 0 ? NG : 1], n_egs[NG > 0 ? NG : 1];
+    real c_ec[NE > 0 ? NE : 1], n_ec[NE > 0 ? NE : 1];
+    real c_wf = real(1), n_wf = real(1), c_gam = real(1), n_gam = real(1);
+#define LHVI_FETCH(RR, POT, POFF, EGV, EGS, EC, WF, GAM)                                  \
+    do {                                                                                   \
+        if constexpr (FL != kNode) POT = __ldcs(g.pot + (RR));                             \
+        _Pragma("unroll") for (int a = 0; a < NC; ++a) POFF[a] = __ldcs(g.poff + a * g.n + (RR)); \
+        _Pragma("unroll") for (int j = 0; j < NG; ++j) {                                   \
+            EGV[j] = __ldcs(g.egval + j * g.n + (RR));                                     \
+            EGS[j] = __ldcs(g.egvar + j * g.n + (RR));                                     \
+        }                                                                                  \
+        _Pragma("unroll") for (int e = 0; e < NE; ++e) EC[e] = __ldcs(g.ecval + e * g.n + (RR)); \
+        if constexpr (kPrefetchWeights) { WF = __ldcs(g.wf + (RR)); GAM = __ldcs(g.gam + (RR)); } \
+    } while (0)
+    if (lo + threadIdx.x < hi) {
+        const long long r0 = lo + threadIdx.x;
+        LHVI_FETCH(r0, c_pot, c_poff, c_egv, c_egs, c_ec, c_wf, c_gam);
+    }
+
     for (long long base = lo; base < hi; base += blockDim.x) {
         const long long r = base + threadIdx.x;
         const bool active = r < hi;
+        if (r + blockDim.x < hi) {
+            const long long r1 = r + blockDim.x;
+            LHVI_FETCH(r1, n_pot, n_poff, n_egv, n_egs, n_ec, n_wf, n_gam);
+        }
         int key[NCS];
         real gv[NCS][NV];
 #pragma unroll
@@ -305,12 +357,97 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
             for (int i = 0; i < NV; ++i) gv[a][i] = real(0);
         }
 
-        if (active) {
+        if constexpr (kUnaryPure) {
+          if (active) {
+            const real wf = c_wf;
+            key[0] = c_poff[0];
+            if (key[0] != node_key) {
+                node_key = key[0];
+                real slot[NV];
+                load_vec<NV>(g.eta + key[0], slot);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    node_s[k] = F::sqrt(real(2) * slot[2 * k + 1]);
+                    node_inv[k] = F::rcp(slot[2 * k + 1]);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) node_x[k][t] = node_s[k] * xi[t] + slot[2 * k];
+                }
+            }
+            // log psi(x) = c0 + l0 x + a0 x^2 after folding the point evidence (walk units)
+            const real* cf = g.ptab + c_pot;
+            constexpr real to_unit = real(1) / F::kUnit;
+            constexpr int NCOEF = (NCT + 1) * (NCT + 2) / 2;
+            real cq[NCOEF];
+#pragma unroll
+            for (int i = 0; i < NCOEF; ++i) cq[i] = __ldg(cf + i);
+            real c0 = cq[0], l0 = cq[1], a0 = cq[1 + NCT];
+            {
+                // coefficient layout: c, b[NCT], then upper-triangular A row-major
+                real ev[NE > 0 ? NE : 1];
+#pragma unroll
+                for (int e = 0; e < NE; ++e) ev[e] = c_ec[e];
+                int p = 1 + NCT;
+#pragma unroll
+                for (int i = 0; i < NCT; ++i) {
+#pragma unroll
+                    for (int j = i; j < NCT; ++j) {
+                        const real coef = cq[p++];
+                        if (i == 0 && j > 0) l0 += coef * ev[j - 1];
+                        else if (i > 0) c0 += coef * ev[i - 1] * ev[j - 1];
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NE; ++e) c0 += cq[2 + e] * ev[e];
+            }
+            c0 *= to_unit; l0 *= to_unit; a0 *= to_unit;
+
+            real Eks[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                real e0 = real(0), e1 = real(0), e2 = real(0), qmin = real(0);
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const real x = node_x[k][t];
+                    const real q = c0 + x * (l0 + a0 * x);
+                    qmin = q < qmin ? q : qmin;
+                    e0 += c.w0[t] * q;
+                    e1 += c.w1[t] * q;
+                    e2 += c.w2[t] * q;
+                }
+                if (qmin < F::kQFloor) {
+                    e0 = e1 = e2 = real(0);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        const real x = node_x[k][t];
+                        const real q = checked_log_psi<real>(c0 + x * (l0 + a0 * x));
+                        e0 += c.w0[t] * q;
+                        e1 += c.w1[t] * q;
+                        e2 += c.w2[t] * q;
+                    }
+                }
+                const real Ek = e0 * F::kUnit;
+                Eks[k] = Ek;
+                gv[0][2 * k] = -(node_s[k] * F::kUnit * e1) * node_inv[k];
+                gv[0][2 * k + 1] = -(e2 * F::kUnit - real(0.5) * Ek) * node_inv[k];
+            }
+            real e_sum = real(0);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                acc[k] -= (double)(wf * Eks[k]);
+                e_sum += wk[k] * Eks[k];
+            }
+            acc[K] -= (double)(wf * e_sum);
+            if constexpr (WEIGHTED) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) gv[0][i] *= c_gam;
+            }
+          }
+        } else if (active) {
             const real wf = (WEIGHTED || FL == kNode) ? __ldcs(g.wf + r) : real(1);
             real mu[NCS][K], var[NCS][K], hvar[NCS][K], nrm[NCS][K];
 #pragma unroll
             for (int a = 0; a < NC; ++a) {
-                key[a] = __ldcs(g.poff + a * g.n + r);
+                key[a] = c_poff[a];
                 c.pt.poff[a] = key[a];
                 real slot[NV];
                 load_vec<NV>(g.eta + key[a], slot);
@@ -328,8 +465,8 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
             real egval[NG > 0 ? NG : 1], egs[NG > 0 ? NG : 1], egn[NG > 0 ? NG : 1];
 #pragma unroll
             for (int j = 0; j < NG; ++j) {
-                egval[j] = __ldcs(g.egval + j * g.n + r);
-                const real v = __ldcs(g.egvar + j * g.n + r);
+                egval[j] = c_egv[j];
+                const real v = c_egs[j];
                 c.pt.egval[j] = egval[j];
                 c.pt.egvar[j] = v;
                 egs[j] = F::sqrt(real(2) * v);
@@ -341,20 +478,21 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
 #pragma unroll
             for (int j = 0; j < NQ; ++j) lin0[j] = real(0);
             if constexpr (FL != kNode) {
-                const real* cf = g.ptab + __ldcs(g.pot + r);
-                cst0 = __ldg(cf);
+                const real* cf = g.ptab + c_pot;
+                constexpr real to_unit = real(1) / F::kUnit;         // natural log -> walk units
+                cst0 = __ldg(cf) * to_unit;
                 if constexpr (NCT > 0) {
 #pragma unroll
-                    for (int i = 0; i < NCT; ++i) lin0[i] = __ldg(cf + 1 + i);
+                    for (int i = 0; i < NCT; ++i) lin0[i] = __ldg(cf + 1 + i) * to_unit;
                     int p = 1 + NCT;
 #pragma unroll
                     for (int i = 0; i < NCT; ++i)
 #pragma unroll
-                        for (int j = i; j < NCT; ++j) c.A[i][j] = __ldg(cf + p++);
+                        for (int j = i; j < NCT; ++j) c.A[i][j] = __ldg(cf + p++) * to_unit;
 #pragma unroll
                     for (int e = 0; e < NE; ++e) {
                         const int j = NA + e;
-                        const real xv = __ldcs(g.ecval + e * g.n + r);
+                        const real xv = c_ec[e];
                         cst0 += xv * (lin0[j] + c.A[j][j] * xv);
 #pragma unroll
                         for (int i = 0; i < j; ++i) lin0[i] += c.A[i][j] * xv;
@@ -374,7 +512,7 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
                     sdev[a] = F::sqrt(real(2) * var[a][k]);
 #pragma unroll
                     for (int t = 0; t < T; ++t) {
-                        const real dx = sdev[a] * c.xi[t];
+                        const real dx = sdev[a] * xi[t];
                         c.x[a][t] = dx + mu[a][k];
                         if constexpr (FL != kPure) {
 #pragma unroll
@@ -393,7 +531,7 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
                 for (int j = 0; j < NG; ++j) {
 #pragma unroll
                     for (int t = 0; t < T; ++t) {
-                        c.x[NC + j][t] = egs[j] * c.xi[t] + egval[j];
+                        c.x[NC + j][t] = egs[j] * xi[t] + egval[j];
                         const real qe = eq[t] * egn[j];
 #pragma unroll
                         for (int k2 = 0; k2 < K; ++k2) c.q[NC + j][k2][t] = qe;
@@ -406,22 +544,31 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
 #pragma unroll
                 for (int a = 0; a < NC; ++a) { c.m1[a] = real(0); c.m2[a] = real(0); }
                 c.qmin = real(0);
-                c.bmin = real(1);
+                // every belief on this grid is at least the own-component term, so float products
+                // cannot have underflowed if that term is comfortably representable
+                real own = wk[k];
+                if constexpr (FL != kPure) {
+#pragma unroll
+                    for (int a = 0; a < NC; ++a) own *= eq_min * nrm[a][k];
+#pragma unroll
+                    for (int j = 0; j < NG; ++j) own *= eq_min * egn[j];
+                }
                 real Ek = Walk<real, K, T, NC, NG, NE, FL, false, 0>::run(c, pk, real(1), cst0, lin0);
-                if (c.qmin < F::kQFloor || c.bmin < F::kBFloor) {
-                    // a floor is active somewhere on this grid: redo it with the literal formulas
+                if (c.qmin < F::kQFloor || own < F::kBFloor) {
+                    // a floor may be active on this grid: redo it with the literal formulas
 #pragma unroll
                     for (int a = 0; a < NC; ++a) { c.m1[a] = real(0); c.m2[a] = real(0); }
                     Ek = Walk<real, K, T, NC, NG, NE, FL, true, 0>::run(c, pk, real(1), cst0, lin0);
                 }
+                Ek *= F::kUnit;
                 Eks[k] = Ek;
 
 #pragma unroll
                 for (int a = 0; a < NC; ++a) {
                     // g_mu = -sum W F (x-mu) / var ; g_var = -sum W F ((x-mu)^2 - var) / (2 var^2)
                     const real inv = F::rcp(var[a][k]);
-                    gv[a][2 * k] = -(sdev[a] * c.m1[a]) * inv;
-                    gv[a][2 * k + 1] = -(c.m2[a] - real(0.5) * Ek) * inv;
+                    gv[a][2 * k] = -(sdev[a] * F::kUnit * c.m1[a]) * inv;
+                    gv[a][2 * k + 1] = -(c.m2[a] * F::kUnit - real(0.5) * Ek) * inv;
                 }
             }
             real e_sum = real(0);
@@ -496,7 +643,17 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
             }
             if (writer && key[a] >= 0) red_vec<NV>(g.grad + key[a], gv[a]);
         }
+        c_pot = n_pot;
+        c_wf = n_wf;
+        c_gam = n_gam;
+#pragma unroll
+        for (int a = 0; a < NCS; ++a) c_poff[a] = n_poff[a];
+#pragma unroll
+        for (int j = 0; j < (NG > 0 ? NG : 1); ++j) { c_egv[j] = n_egv[j]; c_egs[j] = n_egs[j]; }
+#pragma unroll
+        for (int e = 0; e < (NE > 0 ? NE : 1); ++e) c_ec[e] = n_ec[e];
     }
+#undef LHVI_FETCH
 
     // ---- end of the block's chunk: flush running sums (warp-combined when the warp agrees)
     if constexpr (HUB >= 0) {
@@ -531,8 +688,6 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
     }
 }
 
-// ---- dispatch ----------------------------------------------------------------------------------
-
 template <typename KernelT>
 static int resident_blocks(KernelT kernel) {
     int per_sm = 0, sms = 0, dev = 0;
@@ -541,6 +696,276 @@ static int resident_blocks(KernelT kernel) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSpecThreads, 0);
     return (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
 }
+
+// ---- pure unary records: a streaming kernel ------------------------------------------------------
+//
+// F = log psi only, one hidden continuous argument: per record a handful of FMAs, so the kernel
+// is bound by how many bytes it keeps in flight.  Each thread owns QUAD consecutive records per
+// iteration and fetches every column with one 16-byte load, one iteration ahead (double-buffered
+// in registers): 5 columns x 512 B per warp in flight.  Quadrature nodes depend on the variable
+// only and are cached across records; gradients of a run of records on the same variable are
+// summed in registers and flushed when the variable changes -- through the block's shared cache
+// for a hub (USE_CACHE), straight to global REDs otherwise.
+
+constexpr int kQuad = 4;
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<int> { using type = int4; };
+
+template <typename T>
+__device__ __forceinline__ void load_quad(const T* __restrict__ p, T (&v)[kQuad]) {
+    if constexpr (sizeof(T) == 4) {
+        const int4 t = __ldcs(reinterpret_cast<const int4*>(p));
+        v[0] = *reinterpret_cast<const T*>(&t.x);
+        v[1] = *reinterpret_cast<const T*>(&t.y);
+        v[2] = *reinterpret_cast<const T*>(&t.z);
+        v[3] = *reinterpret_cast<const T*>(&t.w);
+    } else {
+        const double2 a = __ldcs(reinterpret_cast<const double2*>(p));
+        const double2 b = __ldcs(reinterpret_cast<const double2*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+}
+
+template <typename real, int K, int T, int NE, bool WEIGHTED, bool USE_CACHE>
+__global__ void __launch_bounds__(kSpecThreads, 2)
+pure_unary_kernel(const GroupView<real> g, const SpecLaunch L) {
+    using F = Fast<real>;
+    constexpr int NV = 2 * K, NCT = 1 + NE, NCOEF = (NCT + 1) * (NCT + 2) / 2;
+    constexpr int kSlotElems = NV <= 2 ? 2 : ((NV + 3) / 4) * 4;
+    constexpr int NES = NE > 0 ? NE : 1;
+
+    __shared__ real s_quad[2 * T];
+    __shared__ real s_w[K];
+    __shared__ int s_tag[kCacheSlots];
+    __shared__ real s_val[kCacheSlots][NV];
+    __shared__ double s_scratch[(kSpecThreads / 32) * (K + 1)];
+    for (int i = threadIdx.x; i < 2 * T; i += blockDim.x) s_quad[i] = g.quad[i];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) s_w[i] = g.w[i];
+    for (int i = threadIdx.x; i < kCacheSlots; i += blockDim.x) s_tag[i] = -1;
+    for (int i = threadIdx.x; i < kCacheSlots * NV; i += blockDim.x) (&s_val[0][0])[i] = real(0);
+    __syncthreads();
+
+    real xi[T], w0[T], w1[T], w2[T], wk[K];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        xi[t] = s_quad[t];
+        w0[t] = s_quad[T + t];
+        w1[t] = w0[t] * xi[t];
+        w2[t] = w1[t] * xi[t];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) wk[k] = s_w[k];
+
+    double acc[K + 1];
+#pragma unroll
+    for (int i = 0; i <= K; ++i) acc[i] = 0.0;
+
+    int run_key = -1;                    // variable of the current run of records
+    real run_acc[NV];                    // its gradient so far
+    real node_x[K][T], node_s[K], node_inv[K];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) run_acc[i] = real(0);
+
+    auto flush = [&](int key, const real (&v)[NV]) {
+        if constexpr (USE_CACHE) {
+            const int slot = (key / kSlotElems) & (kCacheSlots - 1);
+            const int old = atomicCAS(&s_tag[slot], -1, key);
+            if (old == -1 || old == key) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) atomicAdd(&s_val[slot][i], v[i]);
+                return;
+            }
+        }
+        red_vec<NV>(g.grad + key, v);
+    };
+
+    const long long lo = (long long)blockIdx.x * L.chunk;
+    const long long hi = lo + L.chunk < g.n ? lo + L.chunk : g.n;
+    const long long stride = (long long)blockDim.x * kQuad;
+
+    // double-buffered column quads (all in registers)
+    int c_pot[kQuad], n_pot[kQuad], c_off[kQuad], n_off[kQuad];
+    real c_ec[NES][kQuad], n_ec[NES][kQuad], c_wf[kQuad], n_wf[kQuad], c_gam[kQuad], n_gam[kQuad];
+#define LHVI_FETCH_QUAD(RR, POT, OFF, EC, WF, GAM)                                         \
+    do {                                                                                    \
+        if ((RR) + kQuad <= hi) {                                                           \
+            load_quad<int>(g.pot + (RR), POT);                                              \
+            load_quad<int>(g.poff + (RR), OFF);                                             \
+            _Pragma("unroll") for (int e = 0; e < NE; ++e) load_quad<real>(g.ecval + e * g.n + (RR), EC[e]); \
+            if constexpr (WEIGHTED) { load_quad<real>(g.wf + (RR), WF); load_quad<real>(g.gam + (RR), GAM); } \
+        } else {                                                                            \
+            _Pragma("unroll") for (int j = 0; j < kQuad; ++j) {                             \
+                const long long q_ = (RR) + j;                                              \
+                const bool ok_ = q_ < hi;                                                   \
+                POT[j] = ok_ ? g.pot[q_] : 0;                                               \
+                OFF[j] = ok_ ? g.poff[q_] : -1;                                             \
+                _Pragma("unroll") for (int e = 0; e < NE; ++e) EC[e][j] = ok_ ? g.ecval[e * g.n + q_] : real(0); \
+                if constexpr (WEIGHTED) { WF[j] = ok_ ? g.wf[q_] : real(0); GAM[j] = ok_ ? g.gam[q_] : real(0); } \
+            }                                                                               \
+        }                                                                                   \
+    } while (0)
+
+    long long r = lo + (long long)threadIdx.x * kQuad;
+    if (r < hi) LHVI_FETCH_QUAD(r, c_pot, c_off, c_ec, c_wf, c_gam);
+
+    for (; r < hi; r += stride) {
+        const long long rn = r + stride;
+        if (rn < hi) LHVI_FETCH_QUAD(rn, n_pot, n_off, n_ec, n_wf, n_gam);
+
+#pragma unroll
+        for (int j = 0; j < kQuad; ++j) {
+            const int key = c_off[j];
+            if (key < 0) continue;                       // past the end of the chunk
+            if (key != run_key) {
+                if (run_key >= 0) flush(run_key, run_acc);
+                run_key = key;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) run_acc[i] = real(0);
+                real slot[NV];
+                load_vec<NV>(g.eta + key, slot);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    node_s[k] = F::sqrt(real(2) * slot[2 * k + 1]);
+                    node_inv[k] = F::rcp(slot[2 * k + 1]);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) node_x[k][t] = node_s[k] * xi[t] + slot[2 * k];
+                }
+            }
+            // log psi(x) = c0 + l0 x + a0 x^2 after folding the point evidence (walk units);
+            // coefficient layout: c, b[NCT], then upper-triangular A row-major
+            const real* cf = g.ptab + c_pot[j];
+            real cq[NCOEF];
+#pragma unroll
+            for (int i = 0; i < NCOEF; ++i) cq[i] = __ldg(cf + i);
+            real c0 = cq[0], l0 = cq[1], a0 = cq[1 + NCT];
+            {
+                int p = 1 + NCT;
+#pragma unroll
+                for (int i = 0; i < NCT; ++i) {
+#pragma unroll
+                    for (int jj = i; jj < NCT; ++jj) {
+                        const real coef = cq[p++];
+                        if (i == 0 && jj > 0) l0 += coef * c_ec[jj - 1 < NES ? jj - 1 : 0][j];
+                        else if (i > 0) c0 += coef * c_ec[i - 1 < NES ? i - 1 : 0][j] * c_ec[jj - 1 < NES ? jj - 1 : 0][j];
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NE; ++e) c0 += cq[2 + e] * c_ec[e][j];
+            }
+            constexpr real to_unit = real(1) / F::kUnit;
+            c0 *= to_unit; l0 *= to_unit; a0 *= to_unit;
+
+            const real wf = WEIGHTED ? c_wf[j] : real(1);
+            const real gam = WEIGHTED ? c_gam[j] : real(1);
+            real e_sum = real(0);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                real e0 = real(0), e1 = real(0), e2 = real(0), qmin = real(0);
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const real x = node_x[k][t];
+                    const real q = c0 + x * (l0 + a0 * x);
+                    qmin = q < qmin ? q : qmin;
+                    e0 += w0[t] * q;
+                    e1 += w1[t] * q;
+                    e2 += w2[t] * q;
+                }
+                if (qmin < F::kQFloor) {                 // the 1e-100 floor is active: literal formula
+                    e0 = e1 = e2 = real(0);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        const real x = node_x[k][t];
+                        const real q = checked_log_psi<real>(c0 + x * (l0 + a0 * x));
+                        e0 += w0[t] * q;
+                        e1 += w1[t] * q;
+                        e2 += w2[t] * q;
+                    }
+                }
+                const real Ek = e0 * F::kUnit;
+                // g_mu = -sum W F (x-mu) / var ; g_var = -sum W F ((x-mu)^2 - var) / (2 var^2)
+                run_acc[2 * k] -= gam * (node_s[k] * F::kUnit * e1) * node_inv[k];
+                run_acc[2 * k + 1] -= gam * (e2 * F::kUnit - real(0.5) * Ek) * node_inv[k];
+                acc[k] -= (double)(wf * Ek);
+                e_sum += wk[k] * Ek;
+            }
+            acc[K] -= (double)(wf * e_sum);
+        }
+
+#pragma unroll
+        for (int j = 0; j < kQuad; ++j) {
+            c_pot[j] = n_pot[j];
+            c_off[j] = n_off[j];
+            c_wf[j] = n_wf[j];
+            c_gam[j] = n_gam[j];
+#pragma unroll
+            for (int e = 0; e < NES; ++e) c_ec[e][j] = n_ec[e][j];
+        }
+    }
+#undef LHVI_FETCH_QUAD
+
+    // end of the block's chunk: flush the open runs (warp-combined when the whole warp agrees)
+    {
+        const int lane = threadIdx.x & 31;
+        const int k0 = __shfl_sync(0xffffffffu, run_key, 0);
+        if (__all_sync(0xffffffffu, run_key == k0)) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                real v = run_acc[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                run_acc[i] = v;
+            }
+            if (lane == 0 && run_key >= 0) flush(run_key, run_acc);
+        } else if (run_key >= 0) {
+            flush(run_key, run_acc);
+        }
+    }
+
+    block_sum_to(acc, K + 1, s_scratch, g.partials + (long long)blockIdx.x * (K + 1));
+
+    if constexpr (USE_CACHE) {
+        for (int slot = threadIdx.x; slot < kCacheSlots; slot += blockDim.x) {
+            const int tag = s_tag[slot];
+            if (tag >= 0) {
+                real v[NV];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) v[j] = s_val[slot][j];
+                red_vec<NV>(g.grad + tag, v);
+            }
+        }
+    }
+}
+
+template <typename real, int K, int T, int NE>
+static int launch_pure_unary(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStream_t s) {
+    const GroupView<real> v = make_view<real>(m, g, row0);
+    const bool weighted = g->weighted != 0;
+    const bool hub = ((g->hub_mask >> g->nd) & 1) != 0;
+    // 16-byte column loads need every column start aligned: single-column arrays always are
+    // (allocation granularity), a second evidence column only if n is a multiple of 4
+    if (NE > 1 && (g->n % kQuad) != 0) return 1;
+    auto go = [&](auto kernel) {
+        static int resident = 0;
+        if (resident == 0) resident = resident_blocks(kernel);
+        const long long tile = (long long)kSpecThreads * kQuad;
+        long long blocks = (v.n + tile - 1) / tile;
+        if (blocks > resident) blocks = resident;
+        if (blocks > LHVI_PARTIAL_ROWS) blocks = LHVI_PARTIAL_ROWS;
+        SpecLaunch L;
+        L.chunk = ((v.n + blocks - 1) / blocks + tile - 1) / tile * tile;
+        blocks = (v.n + L.chunk - 1) / L.chunk;
+        kernel<<<(unsigned)blocks, kSpecThreads, 0, s>>>(v, L);
+        return check_launch("pure_unary_kernel");
+    };
+    if (weighted) return hub ? go(pure_unary_kernel<real, K, T, NE, true, true>)
+                             : go(pure_unary_kernel<real, K, T, NE, true, false>);
+    return hub ? go(pure_unary_kernel<real, K, T, NE, false, true>)
+               : go(pure_unary_kernel<real, K, T, NE, false, false>);
+}
+
+// ---- dispatch ----------------------------------------------------------------------------------
 
 template <typename real, int K, int T, int NC, int NG, int NE, int FL, bool WEIGHTED, int HUB>
 static int launch_final(const GroupView<real>& v, cudaStream_t s) {
@@ -600,6 +1025,12 @@ int launch_kt(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStream
     if (g->pure) {
         const int code = g->nc * 10 + g->ne;
         if (g->ng != 0) return 1;
+        switch (code) {
+            case 10: { const int rc = launch_pure_unary<real, K, T, 0>(m, g, row0, s); if (rc <= 0) return rc; break; }
+            case 11: { const int rc = launch_pure_unary<real, K, T, 1>(m, g, row0, s); if (rc <= 0) return rc; break; }
+            case 12: { const int rc = launch_pure_unary<real, K, T, 2>(m, g, row0, s); if (rc <= 0) return rc; break; }
+            default: break;
+        }
         switch (code) {
 #define X(NC_, NE_) case NC_ * 10 + NE_: return launch_one<real, K, T, NC_, 0, NE_, kPure>(m, g, row0, s);
             LHVI_SPEC_PURE(X)
