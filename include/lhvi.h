@@ -61,7 +61,7 @@ extern "C" {
 #define LHVI_MAX_DSTATES 16
 #define LHVI_MAX_NODES 64    /* sum over axes of quadrature nodes / states */
 #define LHVI_MAX_GACC 256    /* sum over hidden arguments of K * (2 | D) */
-#define LHVI_PARTIAL_ROWS 1184   /* rows of `partials` one launch may write (8 per SM) */
+#define LHVI_PARTIAL_ROWS 1184   /* rows of `partials` reserved per launch: 1 header + 1183 data */
 
 /*
  * One record group: `n` factor records sharing a canonical signature.  Arguments are
@@ -112,14 +112,17 @@ int lhvi_has_specialisation(const lhvi_model* m, const lhvi_group* g);
 
 /*
  * Accumulate one group's contribution: atomically adds parameter gradients into m->grad
- * and writes per-block partial sums of (G_w[0..K-1], energy) to rows
- * [row0, row0 + LHVI_PARTIAL_ROWS) of m->partials (rows the launch does not use are zeroed).
+ * and writes per-block partial sums of (G_w[0..K-1], energy) to the region of
+ * LHVI_PARTIAL_ROWS rows of m->partials starting at row0 (a multiple of LHVI_PARTIAL_ROWS):
+ * row0 is a header whose first element is the number of valid data rows that follow.
  * force_generic != 0 bypasses the specialised kernels (used by the parity tests).
  */
 int lhvi_factor_expect_grad(const lhvi_model* m, const lhvi_group* g, int64_t row0,
                             int force_generic, void* stream);
 
-/* Sum `rows` rows of partials into grad[n_param .. n_param+K] (G_w, energy). */
+/* Sum the valid rows of the first rows / LHVI_PARTIAL_ROWS regions of partials into
+ * grad[n_param .. n_param+K] (G_w, energy).  Every region must have been written by a
+ * lhvi_factor_expect_grad call since the buffer was allocated. */
 int lhvi_elbo_reduce(const lhvi_model* m, int64_t rows, void* stream);
 
 /* step[0] = t, step[1] = 1-b1^t, step[2] = 1-b2^t (doubles, device).  Increments t. */

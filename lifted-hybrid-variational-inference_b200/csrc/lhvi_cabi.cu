@@ -66,11 +66,12 @@ extern "C" int lhvi_factor_expect_grad(const lhvi_model* m, const lhvi_group* g,
     int rc = validate(m, g, row0);
     if (rc != LHVI_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    // rows a launch does not reach must read as zero in lhvi_elbo_reduce
-    cudaError_t e = cudaMemsetAsync(m->partials + row0 * (m->K + 1), 0,
-                                    sizeof(double) * LHVI_PARTIAL_ROWS * (m->K + 1), s);
-    if (e != cudaSuccess) { set_error("cudaMemsetAsync(partials): %s", cudaGetErrorString(e)); return LHVI_ECUDA; }
-    if (g->n == 0) return LHVI_OK;
+    if (g->n == 0) {
+        // empty group: publish "0 valid rows" in the region's header row
+        cudaError_t e = cudaMemsetAsync(m->partials + row0 * (m->K + 1), 0, sizeof(double), s);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync(partials): %s", cudaGetErrorString(e)); return LHVI_ECUDA; }
+        return LHVI_OK;
+    }
     if (!force_generic) {
         rc = launch_spec(m, g, row0, s);
         if (rc <= 0) return rc;      // launched (0) or failed (<0); 1 means "no specialisation"

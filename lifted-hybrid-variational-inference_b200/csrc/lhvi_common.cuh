@@ -84,6 +84,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Block-wide sums of `nvals` doubles per thread; thread 0 of the block writes them to out[].
 // `scratch` must hold (blockDim.x / 32) * nvals doubles of shared memory.
+// Every factor kernel ends with this: block b writes its partial sums to data row b of the
+// launch's region and block 0 records how many rows are valid in the header row, so the
+// reduction needs no zero-filled buffer.
+__device__ __forceinline__ void publish_partials(const double* vals, int nvals, double* scratch, double* region);
+
 __device__ __forceinline__ void block_sum_to(const double* vals, int nvals, double* scratch,
                                              double* out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -98,6 +103,11 @@ __device__ __forceinline__ void block_sum_to(const double* vals, int nvals, doub
         out[threadIdx.x] = s;
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ void publish_partials(const double* vals, int nvals, double* scratch, double* region) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) region[-nvals] = (double)gridDim.x;
+    block_sum_to(vals, nvals, scratch, region + (long long)blockIdx.x * nvals);
 }
 
 // ---- typed view of a record group ---------------------------------------------------------
@@ -122,7 +132,7 @@ struct GroupView {
     const real* eta;
     const real* w;
     real* grad;
-    double* partials;   // already offset to this launch's first row
+    double* partials;   // this launch's first data row (the region's header row sits just before)
 };
 
 template <typename real>
@@ -140,7 +150,8 @@ inline GroupView<real> make_view(const lhvi_model* m, const lhvi_group* g, int64
     v.quad = (const real*)m->quad; v.ptab = (const real*)m->ptab;
     v.eta = (const real*)m->eta; v.w = (const real*)m->w;
     v.grad = (real*)m->grad;
-    v.partials = m->partials + row0 * (m->K + 1);
+    // row `row0` of the launch's region is a header (valid row count), data rows follow
+    v.partials = m->partials + (row0 + 1) * (m->K + 1);
     return v;
 }
 

@@ -207,14 +207,14 @@ factor_generic_kernel(const GroupView<real> g) {
         }
     }
 
-    block_sum_to(acc, K + 1, s_scratch, g.partials + (long long)blockIdx.x * (K + 1));
+    publish_partials(acc, K + 1, s_scratch, g.partials);
 }
 
 template <typename real>
 static int launch_generic_t(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStream_t s) {
     GroupView<real> v = make_view<real>(m, g, row0);
     long long blocks = (g->n + kGenericThreads - 1) / kGenericThreads;
-    if (blocks > LHVI_PARTIAL_ROWS) blocks = LHVI_PARTIAL_ROWS;
+    if (blocks > LHVI_PARTIAL_ROWS - 1) blocks = LHVI_PARTIAL_ROWS - 1;
     if (blocks < 1) blocks = 1;
     factor_generic_kernel<real><<<(unsigned)blocks, kGenericThreads, 0, s>>>(v);
     return check_launch("factor_generic_kernel");

@@ -7,16 +7,23 @@ namespace lhvi {
 
 // ---- G_w / energy: deterministic two-stage sum of the per-block partial rows ---------------
 
+// partials is a sequence of regions of LHVI_PARTIAL_ROWS rows; row 0 of a region holds the number
+// of valid data rows that follow (written by the factor kernel that owns the region).
 template <typename real>
-__global__ void __launch_bounds__(256)
-elbo_reduce_kernel(const double* __restrict__ partials, long long rows, int K, real* __restrict__ out) {
-    __shared__ double s[8 * (LHVI_MAX_K + 1)];
+__global__ void __launch_bounds__(1024)
+elbo_reduce_kernel(const double* __restrict__ partials, long long regions, int K, real* __restrict__ out) {
+    __shared__ double s[32 * (LHVI_MAX_K + 1)];
+    __shared__ double res[LHVI_MAX_K + 1];
     double acc[LHVI_MAX_K + 1];
     for (int i = 0; i <= K; ++i) acc[i] = 0.0;
-    for (long long r = threadIdx.x; r < rows; r += blockDim.x)
-        for (int i = 0; i <= K; ++i) acc[i] += partials[r * (K + 1) + i];
-    __shared__ double res[LHVI_MAX_K + 1];
-    block_sum_to(acc, K + 1, s, res);
+    const int W = K + 1;
+    for (long long reg = 0; reg < regions; ++reg) {
+        const double* base = partials + reg * LHVI_PARTIAL_ROWS * W;
+        const int valid = (int)base[0];
+        for (int r = threadIdx.x; r < valid; r += blockDim.x)
+            for (int i = 0; i < W; ++i) acc[i] += base[(long long)(1 + r) * W + i];
+    }
+    block_sum_to(acc, W, s, res);
     if (threadIdx.x <= K) out[threadIdx.x] = (real)res[threadIdx.x];
 }
 
@@ -49,6 +56,10 @@ struct StepArgs {
     real lr, b1, b2, eps, var_floor;
     int sgd;
 };
+
+template <typename real> struct PairVec;
+template <> struct PairVec<float> { using type = float4; static constexpr int pairs = 2; };
+template <> struct PairVec<double> { using type = double2; static constexpr int pairs = 1; };
 
 template <typename real>
 __device__ __forceinline__ real moved(real theta, real g, real& m1, real& m2, const StepArgs<real>& a,
@@ -91,11 +102,37 @@ param_step_kernel(const StepArgs<real> a) {
          v += (long long)gridDim.x * blockDim.x) {
         const int off = a.off[v];
         if (a.kind[v] == 0) {
-            for (int k = 0; k < K; ++k) {
-                const int i = off + 2 * k;
-                a.eta[i] = moved<real>(a.eta[i], a.grad[i], a.m1[i], a.m2[i], a, c1, c2);
-                real var = moved<real>(a.eta[i + 1], a.grad[i + 1], a.m1[i + 1], a.m2[i + 1], a, c1, c2);
-                a.eta[i + 1] = var < a.var_floor ? a.var_floor : var;   // VarInference.py:281
+            // slots are 16-byte aligned (8 for K == 1): move them with vector loads / stores
+            using V = typename PairVec<real>::type;
+            constexpr int PER = PairVec<real>::pairs;                 // (mu, var) pairs per vector
+            const int nvec = (K + PER - 1) / PER;
+            for (int c = 0; c < nvec; ++c) {
+                const int i = off + 2 * PER * c;
+                if (PER == 2 && K == 1) {                              // lone pair: scalar fallback
+                    a.eta[i] = moved<real>(a.eta[i], a.grad[i], a.m1[i], a.m2[i], a, c1, c2);
+                    real var = moved<real>(a.eta[i + 1], a.grad[i + 1], a.m1[i + 1], a.m2[i + 1], a, c1, c2);
+                    a.eta[i + 1] = var < a.var_floor ? a.var_floor : var;
+                    continue;
+                }
+                V ve = *reinterpret_cast<V*>(a.eta + i);
+                const V vg = *reinterpret_cast<const V*>(a.grad + i);
+                V vm = *reinterpret_cast<V*>(a.m1 + i);
+                V vu = *reinterpret_cast<V*>(a.m2 + i);
+                real* e = reinterpret_cast<real*>(&ve);
+                const real* gq = reinterpret_cast<const real*>(&vg);
+                real* m = reinterpret_cast<real*>(&vm);
+                real* u = reinterpret_cast<real*>(&vu);
+#pragma unroll
+                for (int p = 0; p < PER; ++p) {
+                    if (PER * c + p < K) {
+                        e[2 * p] = moved<real>(e[2 * p], gq[2 * p], m[2 * p], u[2 * p], a, c1, c2);
+                        const real var = moved<real>(e[2 * p + 1], gq[2 * p + 1], m[2 * p + 1], u[2 * p + 1], a, c1, c2);
+                        e[2 * p + 1] = var < a.var_floor ? a.var_floor : var;   // VarInference.py:281
+                    }
+                }
+                *reinterpret_cast<V*>(a.eta + i) = ve;
+                *reinterpret_cast<V*>(a.m1 + i) = vm;
+                *reinterpret_cast<V*>(a.m2 + i) = vu;
             }
         } else {
             const int D = a.dim[v];
@@ -158,10 +195,12 @@ extern "C" int lhvi_elbo_reduce(const lhvi_model* m, int64_t rows, void* stream)
     if (!m || !m->partials || !m->grad || rows < 0) { set_error("lhvi_elbo_reduce: null buffer or negative rows"); return LHVI_EINVAL; }
     if (m->K < 1 || m->K > LHVI_MAX_K) { set_error("K=%d out of range 1..%d", m->K, LHVI_MAX_K); return LHVI_ELIMIT; }
     cudaStream_t s = (cudaStream_t)stream;
+    if (rows % LHVI_PARTIAL_ROWS != 0) { set_error("lhvi_elbo_reduce: rows must be a multiple of LHVI_PARTIAL_ROWS"); return LHVI_EINVAL; }
+    const long long regions = rows / LHVI_PARTIAL_ROWS;
     if (m->dtype == LHVI_F64)
-        elbo_reduce_kernel<double><<<1, 256, 0, s>>>(m->partials, rows, m->K, (double*)m->grad + m->n_param);
+        elbo_reduce_kernel<double><<<1, 1024, 0, s>>>(m->partials, regions, m->K, (double*)m->grad + m->n_param);
     else
-        elbo_reduce_kernel<float><<<1, 256, 0, s>>>(m->partials, rows, m->K, (float*)m->grad + m->n_param);
+        elbo_reduce_kernel<float><<<1, 1024, 0, s>>>(m->partials, regions, m->K, (float*)m->grad + m->n_param);
     return check_launch("elbo_reduce_kernel");
 }
 

@@ -672,7 +672,7 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
         }
     }
 
-    block_sum_to(acc, K + 1, s_scratch, g.partials + (long long)blockIdx.x * (K + 1));
+    publish_partials(acc, K + 1, s_scratch, g.partials);
 
     // flush the hub cache (block_sum_to ends with a barrier, so every shared atomic has landed)
     if constexpr (HUB >= 0) {
@@ -923,7 +923,7 @@ pure_unary_kernel(const GroupView<real> g, const SpecLaunch L) {
         }
     }
 
-    block_sum_to(acc, K + 1, s_scratch, g.partials + (long long)blockIdx.x * (K + 1));
+    publish_partials(acc, K + 1, s_scratch, g.partials);
 
     if constexpr (USE_CACHE) {
         for (int slot = threadIdx.x; slot < kCacheSlots; slot += blockDim.x) {
@@ -952,7 +952,7 @@ static int launch_pure_unary(const lhvi_model* m, const lhvi_group* g, int64_t r
         const long long tile = (long long)kSpecThreads * kQuad;
         long long blocks = (v.n + tile - 1) / tile;
         if (blocks > resident) blocks = resident;
-        if (blocks > LHVI_PARTIAL_ROWS) blocks = LHVI_PARTIAL_ROWS;
+        if (blocks > LHVI_PARTIAL_ROWS - 1) blocks = LHVI_PARTIAL_ROWS - 1;
         SpecLaunch L;
         L.chunk = ((v.n + blocks - 1) / blocks + tile - 1) / tile * tile;
         blocks = (v.n + L.chunk - 1) / L.chunk;
@@ -974,7 +974,7 @@ static int launch_final(const GroupView<real>& v, cudaStream_t s) {
     if (resident == 0) resident = resident_blocks(kernel);
     long long blocks = (v.n + kSpecThreads - 1) / kSpecThreads;
     if (blocks > resident) blocks = resident;
-    if (blocks > LHVI_PARTIAL_ROWS) blocks = LHVI_PARTIAL_ROWS;
+    if (blocks > LHVI_PARTIAL_ROWS - 1) blocks = LHVI_PARTIAL_ROWS - 1;
     SpecLaunch L;
     L.chunk = ((v.n + blocks - 1) / blocks + kSpecThreads - 1) / kSpecThreads * kSpecThreads;
     blocks = (v.n + L.chunk - 1) / L.chunk;

@@ -64,6 +64,8 @@ class DeviceEngine:
         self.b1, self.b2, self.eps = 0.9, 0.999, 1e-8      # VarInference.py:223-225
         self.profile_group = None
         self.dom_events = []
+        self.use_graph = True          # replay one captured iteration instead of ~10 launches
+        self._graphs = {}
 
         self.pg = process_group
         self.world, self.rank = 1, 0
@@ -231,11 +233,41 @@ class DeviceEngine:
             self.step.data_ptr(), float(lr), self.b1, self.b2, self.eps, self.var_threshold,
             int(bool(sgd)), st), lib)
 
+    def _iteration(self, lr, sgd):
+        self.grad_pass()
+        self.param_step(lr, sgd=sgd)
+
+    def _graph_for(self, lr, sgd):
+        """CUDA graph of one iteration for these hyper-parameters (captured once).  The step
+        counter and bias corrections live on the device, so the same graph serves every t."""
+        key = (float(lr), bool(sgd), self.b1, self.b2, self.eps, self.var_threshold)
+        graph = self._graphs.get(key)
+        if graph is None:
+            self.grad_pass()                       # warm-up outside capture (lazy kernel setup)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._iteration(lr, sgd)
+            self._graphs[key] = graph
+        return graph
+
     def iterate(self, n, lr, sgd=False):
         """``n`` Jacobi iterations: all gradients at the old parameters, then the step."""
-        for _ in range(int(n)):
-            self.grad_pass()
-            self.param_step(lr, sgd=sgd)
+        n = int(n)
+        if n <= 0:
+            return
+        if self.use_graph and self.profile_group is None:
+            try:
+                graph = self._graph_for(lr, sgd)
+            except Exception:                      # capture unsupported here (e.g. a collective)
+                self.use_graph = False
+                graph = None
+            if graph is not None:
+                for _ in range(n):
+                    graph.replay()
+                return
+        for _ in range(n):
+            self._iteration(lr, sgd)
 
     @property
     def launches_per_iteration(self):
