@@ -56,8 +56,18 @@ template <> struct Fast<float> {
     // q < -218; above the threshold (in log2 units here) the floor is invisible in float
     static constexpr float kQFloor = -210.0f * 1.4426950408889634f;
     static constexpr float kBFloor = 1e-30f;      // below: float products may have flushed to zero
-    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
-    static __device__ __forceinline__ float sqrt(float x) { return __fsqrt_rn(x); }
+    // MUFU approximations (about 1 ulp); the IEEE versions cost ~8 instructions and a branch each
+    static __device__ __forceinline__ float rcp(float x) {
+        float y;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
+    }
+    static __device__ __forceinline__ float sqrt(float x) {
+        float y;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
+    }
+    static __device__ __forceinline__ float min(float a, float b) { return fminf(a, b); }
 };
 
 template <> struct Fast<double> {
@@ -69,6 +79,7 @@ template <> struct Fast<double> {
     static constexpr double kBFloor = -1.0;       // never trips: log(b + 1e-100) is always literal
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double min(double a, double b) { return ::fmin(a, b); }
 };
 
 // ---- vector helpers ------------------------------------------------------------------------
@@ -184,7 +195,7 @@ struct Walk {
             real lpsi = cst, lb = real(0);
             if constexpr (FL != kNode) {
                 if constexpr (CHECKED) lpsi = checked_log_psi<real>(cst);
-                else c.qmin = cst < c.qmin ? cst : c.qmin;
+                else c.qmin = F::min(c.qmin, cst);
             }
             if constexpr (FL != kPure) {
                 if constexpr (CHECKED) {
@@ -321,7 +332,7 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
     // (offsets, potential id, evidence); the light unary-pure path also prefetches the weights.
     constexpr bool kPrefetchWeights = kUnaryPure && WEIGHTED;
     int c_pot = 0, n_pot = 0;
-    int c_poff[NCS], n_poff[NCS];
+    int c_poff[NCS], n_poff[NCS], f_poff[NCS];      // current, next, and far (two tiles ahead)
     real c_egv[NG > 0 ? NG : 1], c_egs[NG > 0 ? NG : 1], n_egv[NG > 0 ? NG : 1], n_egs[NG > 0 ? NG : 1];
     real c_ec[NE > 0 ? NE : 1], n_ec[NE > 0 ? NE : 1];
     real c_wf = real(1), n_wf = real(1), c_gam = real(1), n_gam = real(1);
@@ -336,9 +347,20 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
         _Pragma("unroll") for (int e = 0; e < NE; ++e) EC[e] = __ldcs(g.ecval + e * g.n + (RR)); \
         if constexpr (kPrefetchWeights) { WF = __ldcs(g.wf + (RR)); GAM = __ldcs(g.gam + (RR)); } \
     } while (0)
+    // non-hub parameter slots are prefetched into L1 one tile ahead, which needs their offsets
+    // two tiles ahead (f_poff)
+    constexpr bool kSlotPrefetch = FL == kFull;
+#pragma unroll
+    for (int a = 0; a < NCS; ++a) { c_poff[a] = -1; n_poff[a] = -1; f_poff[a] = -1; }
     if (lo + threadIdx.x < hi) {
         const long long r0 = lo + threadIdx.x;
         LHVI_FETCH(r0, c_pot, c_poff, c_egv, c_egs, c_ec, c_wf, c_gam);
+    }
+    if constexpr (kSlotPrefetch) {
+        if (lo + blockDim.x + threadIdx.x < hi) {
+#pragma unroll
+            for (int a = 0; a < NC; ++a) f_poff[a] = __ldcs(g.poff + a * g.n + lo + blockDim.x + threadIdx.x);
+        }
     }
 
     for (long long base = lo; base < hi; base += blockDim.x) {
@@ -347,6 +369,17 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
         if (r + blockDim.x < hi) {
             const long long r1 = r + blockDim.x;
             LHVI_FETCH(r1, n_pot, n_poff, n_egv, n_egs, n_ec, n_wf, n_gam);
+        }
+        if constexpr (kSlotPrefetch) {
+            // f_poff holds the offsets of tile +1 (loaded one tile ago): warm L1 with those slots
+#pragma unroll
+            for (int a = 0; a < NC; ++a) {
+                if (a != HUB && f_poff[a] >= 0)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.eta + f_poff[a]));
+            }
+            const long long r2 = r + 2 * (long long)blockDim.x;
+#pragma unroll
+            for (int a = 0; a < NC; ++a) f_poff[a] = r2 < hi ? __ldcs(g.poff + a * g.n + r2) : -1;
         }
         int key[NCS];
         real gv[NCS][NV];
@@ -409,7 +442,7 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
                 for (int t = 0; t < T; ++t) {
                     const real x = node_x[k][t];
                     const real q = c0 + x * (l0 + a0 * x);
-                    qmin = q < qmin ? q : qmin;
+                    qmin = F::min(qmin, q);
                     e0 += c.w0[t] * q;
                     e1 += c.w1[t] * q;
                     e2 += c.w2[t] * q;
@@ -443,7 +476,17 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
             }
           }
         } else if (active) {
+            // weights are consumed at the end of the record: issue their loads now
             const real wf = (WEIGHTED || FL == kNode) ? __ldcs(g.wf + r) : real(1);
+            real gam_r[NCS];
+#pragma unroll
+            for (int a = 0; a < NCS; ++a) gam_r[a] = real(1);
+            if constexpr (FL == kNode) {
+                gam_r[0] = __ldcs(g.nscale + r);
+            } else if constexpr (WEIGHTED) {
+#pragma unroll
+                for (int a = 0; a < NC; ++a) gam_r[a] = __ldcs(g.gam + a * g.n + r);
+            }
             real mu[NCS][K], var[NCS][K], hvar[NCS][K], nrm[NCS][K];
 #pragma unroll
             for (int a = 0; a < NC; ++a) {
@@ -566,7 +609,7 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
 #pragma unroll
                 for (int a = 0; a < NC; ++a) {
                     // g_mu = -sum W F (x-mu) / var ; g_var = -sum W F ((x-mu)^2 - var) / (2 var^2)
-                    const real inv = F::rcp(var[a][k]);
+                    const real inv = FL != kPure ? hvar[a][k] * (real(-2) / F::kExpScale) : F::rcp(var[a][k]);
                     gv[a][2 * k] = -(sdev[a] * F::kUnit * c.m1[a]) * inv;
                     gv[a][2 * k + 1] = -(c.m2[a] * F::kUnit - real(0.5) * Ek) * inv;
                 }
@@ -580,17 +623,15 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
             acc[K] -= (double)(wf * e_sum);
 
             if constexpr (FL == kNode) {
-                const real gs = __ldcs(g.nscale + r);
 #pragma unroll
                 for (int a = 0; a < NC; ++a)
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) gv[a][i] *= gs;
+                    for (int i = 0; i < NV; ++i) gv[a][i] *= gam_r[0];
             } else if constexpr (WEIGHTED) {
 #pragma unroll
                 for (int a = 0; a < NC; ++a) {
-                    const real gam = __ldcs(g.gam + a * g.n + r);
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) gv[a][i] *= gam;
+                    for (int i = 0; i < NV; ++i) gv[a][i] *= gam_r[a];
                 }
             }
         }
@@ -867,7 +908,7 @@ pure_unary_kernel(const GroupView<real> g, const SpecLaunch L) {
                 for (int t = 0; t < T; ++t) {
                     const real x = node_x[k][t];
                     const real q = c0 + x * (l0 + a0 * x);
-                    qmin = q < qmin ? q : qmin;
+                    qmin = F::min(qmin, q);
                     e0 += w0[t] * q;
                     e1 += w1[t] * q;
                     e2 += w2[t] * q;
