@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _cabi
+from .dist import ShardPlan
 from .lowering import LoweredModel
 
 
@@ -67,13 +68,10 @@ class DeviceEngine:
         self.use_graph = True          # replay one captured iteration instead of ~10 launches
         self._graphs = {}
 
-        self.pg = process_group
-        self.world, self.rank = 1, 0
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized() and shard):
-            self.world = torch.distributed.get_world_size(process_group)
-            self.rank = torch.distributed.get_rank(process_group)
-        self.model = model.shard(self.rank, self.world) if (shard and self.world > 1) else model
-        self.reduce_grads = shard and self.world > 1
+        self.plan = ShardPlan(process_group, enabled=shard)
+        self.world, self.rank = self.plan.world, self.plan.rank
+        self.model = self.plan.shard(model)
+        self.reduce_grads = self.plan.active
 
         self._upload()
 
@@ -218,7 +216,7 @@ class DeviceEngine:
         _cabi.check(lib.lhvi_elbo_reduce(C.byref(self.desc), self.partial_rows, st), lib)
         launches += 1
         if self.reduce_grads:
-            torch.distributed.all_reduce(self.grad, group=self.pg)
+            self.plan.all_reduce(self.grad)
         self.launches_per_pass = launches
         return self.grad
 
