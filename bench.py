@@ -311,9 +311,15 @@ def run_ours(a):
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(a, model.n_records).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing NCCL down: destroy_process_group() after CUDA-graph capture of a
+        # collective was seen to hang at exit; every rank has passed its last collective here
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
