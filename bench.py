@@ -5,14 +5,16 @@
     torchrun --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A *step* is one Jacobi VI iteration over the whole record table: node-entropy + factor
-expectation/gradient kernels for every record group, the ELBO reduction, (N>1) one NCCL
-all-reduce of the gradient vector, and the Adam parameter step.
+expectation/gradient kernels for every record group, lhvi_finish (ELBO reduction, step counter
+and -- N>1 -- the cross-GPU sum of G_w, the free energy and the shared variables' gradients over
+NVLink peer memory) and the Adam parameter step.
 
 Workload (``config.workload``): the relational hybrid model of SURVEY section 8 d config 5 in its
 fully refined C2F state -- 1 M entities x 10 groups = 10 M hybrid link factors + 1 M priors +
 90 session factors, lifted record format (W_f, gamma columns shipped), K=3 mixtures, Gauss-
-Hermite degree 3, fp32 arithmetic.  With N GPUs the records are sharded N ways (strong scaling:
-the total stays 10 M) and parameters are replicated.
+Hermite degree 3, fp32 arithmetic.  With N GPUs the records are partitioned owner-computes
+(dist.py; strong scaling: the total stays 10 M): entity variables live on one rank together with
+their records, only the group variables are shared.
 
 Printed JSON (one line, rank 0): see the task contract; ``roofline`` is for the dominant
 kernel (the largest record group's launch), ``cpu_baseline`` times the CPU port of the same
@@ -56,7 +58,7 @@ def parse():
     return ap.parse_args()
 
 
-def workload_config(a, n_records):
+def workload_config(a, n_records, parallelism=None):
     return {
         "workload": f"config5 relational hybrid MLN, C2F fully-refined state: {a.entities} entities x "
                     f"{a.groups} groups = {a.entities * a.groups} link factors (+priors, sessions), "
@@ -64,7 +66,7 @@ def workload_config(a, n_records):
         "factor_records": int(n_records),
         "K": a.K, "T": a.T, "record_order": a.order,
         "l2_policy": "inputs larger than L2 (record table ~1 GB >> 126 MB), no explicit flush",
-        "parallelism": f"records sharded {a.gpus}-way, parameters replicated, 1 all-reduce/iteration",
+        "parallelism": parallelism or f"{a.gpus} rank(s), owner-computes record partition",
     }
 
 
@@ -244,33 +246,40 @@ def run_ours(a):
     eng.profile_group = None
     launches = eng.launches_per_iteration * a.steps
 
-    # ---- end to end through the public engine API with host-resident parameters
+    # ---- end to end through the public engine API with host-resident parameters: the state a
+    # caller of ADAM_update holds (eta, and the logits when the model has discrete variables)
+    # goes up from pinned memory, one iteration runs, the new state and [G_w | free energy] come back
     n = model.n_param
-    host_eta = torch.from_numpy(eta.astype(np.float32 if s == 4 else np.float64)).pin_memory()
-    host_tau = torch.from_numpy(tau.astype(np.float32 if s == 4 else np.float64)).pin_memory()
-    host_out = torch.empty(n + a.K + 1, dtype=host_eta.dtype).pin_memory()
+    np_t = np.float32 if s == 4 else np.float64
+    has_disc = bool((model.var_kind == 1).any())
+    host_eta = torch.from_numpy(eta.astype(np_t)).pin_memory()
+    host_tau = torch.from_numpy(tau.astype(np_t)).pin_memory() if has_disc else None
+    host_tail = torch.empty(a.K + 1, dtype=host_eta.dtype).pin_memory()
     e2e_steps = max(3, a.steps // 2)
 
     def e2e_step():
         eng.eta.copy_(host_eta, non_blocking=True)
-        eng.tau.copy_(host_tau, non_blocking=True)
+        if has_disc:
+            eng.tau.copy_(host_tau, non_blocking=True)
         eng.iterate(1, lr)
         host_eta.copy_(eng.eta, non_blocking=True)
-        host_tau.copy_(eng.tau, non_blocking=True)
-        host_out.copy_(eng.grad, non_blocking=True)          # gradients, G_w and free energy
+        if has_disc:
+            host_tau.copy_(eng.tau, non_blocking=True)
+        host_tail.copy_(eng.grad[n:], non_blocking=True)          # G_w and the free energy
         torch.cuda.synchronize()
-        return float(host_out[-1])
+        return float(host_tail[-1])
 
     for _ in range(2):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_step()
+        fe_last = e2e_step()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    h2d = 2 * n * s
-    d2h = (3 * n + a.K + 1) * s
+    h2d = (2 if has_disc else 1) * n * s
+    d2h = h2d + (a.K + 1) * s
+    eng.check_exchange()
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
@@ -300,11 +309,13 @@ def run_ours(a):
             "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if s == 4 else "f64", "data": "synthetic",
-            "config": workload_config(a, model.n_records),
+            "config": workload_config(a, model.n_records, eng.plan.describe() + (
+                f"; exchange={eng.exchange}" if eng.exchange else "")),
             "clocks": clocks.summary(),
             "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "per step: parameters host->device from pinned memory, one iteration, parameters + "
-                            "gradient vector + free energy device->host; record table resident"},
+                    "note": "per step: variational parameters host->device from pinned memory, one iteration, "
+                            "new parameters + G_w + free energy device->host; record table resident",
+                    "free_energy_last": fe_last},
             "gpu_launches": launches,
             "roofline": roofline,
         }

@@ -28,6 +28,14 @@
  *                             (VarInference.py:256-287), or the plain SGD step (:302-329).
  *   lhvi_mixture_belief       belief(x, rv) for a batch of (variable, x) queries
  *                             (VarInference.py:333-353).
+ *   lhvi_finish               lhvi_elbo_reduce + lhvi_step_tick in one launch, and -- when the
+ *                             records are sharded over several GPUs -- the sum over ranks of
+ *                             G_w, the free energy and the gradients of the variables that
+ *                             more than one rank touches, exchanged through NVLink peer
+ *                             memory inside the same kernel.  The reference is single-process:
+ *                             these are still its `energy -= ...` / `g_w[k] -= ...` /
+ *                             `g_mu -= ...` sums (VarInference.py:72,88,120-129), split by rank.
+ *   lhvi_peer_*               life cycle of the peer-visible exchange buffers (CUDA IPC).
  *
  * Data layout: a flat parameter vector with one slot per hidden variable
  * (continuous: K x (mu, var) interleaved; discrete: K x D row-major probabilities), a
@@ -42,7 +50,7 @@
 extern "C" {
 #endif
 
-#define LHVI_ABI_VERSION 1
+#define LHVI_ABI_VERSION 2
 
 /* element type of every `void*` buffer of reals */
 #define LHVI_F32 0
@@ -62,6 +70,8 @@ extern "C" {
 #define LHVI_MAX_NODES 64    /* sum over axes of quadrature nodes / states */
 #define LHVI_MAX_GACC 256    /* sum over hidden arguments of K * (2 | D) */
 #define LHVI_PARTIAL_ROWS 1184   /* rows of `partials` reserved per launch: 1 header + 1183 data */
+#define LHVI_MAX_PEERS 16    /* GPUs of one NVLink domain taking part in lhvi_finish's exchange */
+#define LHVI_IPC_HANDLE_BYTES 64
 
 /*
  * One record group: `n` factor records sharing a canonical signature.  Arguments are
@@ -129,18 +139,66 @@ int lhvi_elbo_reduce(const lhvi_model* m, int64_t rows, void* stream);
 int lhvi_step_tick(double* step, double b1, double b2, void* stream);
 
 /*
+ * Exchange descriptor of lhvi_finish (one per rank).  The exchanged vector is
+ * x = [G_w[K] | energy | grad[idx[0]] .. grad[idx[n_idx-1]]].  recv[p] / flags[p] are rank p's
+ * buffers as mapped into THIS process (entry `rank` is the local buffer itself):
+ *   recv  : [2][world][K+1+n_idx] reals   (double-buffered by the parity of the sequence number)
+ *   flags : [world][blocks] uint64        (sequence number of the last completed send)
+ * Every rank writes its x into slot `rank` of every peer's recv, publishes the sequence number
+ * with a system-scope release, waits for all `world` flags of its own buffer, and adds the
+ * slots in rank order -- so all ranks obtain bit-identical sums.  A wait that exceeds ~2 s sets
+ * *status = 1 and gives up instead of hanging the device.
+ */
+typedef struct lhvi_exchange {
+    int32_t world, rank;
+    int32_t blocks;                       /* thread blocks of the launch (1..32); fixed per buffer */
+    int32_t reserved;
+    int64_t n_idx;                        /* gathered gradient elements */
+    const int32_t* idx;                   /* [n_idx] offsets into grad (device) */
+    void* recv[LHVI_MAX_PEERS];
+    uint64_t* flags[LHVI_MAX_PEERS];
+    uint64_t* seq;                        /* [blocks] local sequence counters (device, zero-initialised) */
+    int32_t* status;                      /* [1] local, device */
+} lhvi_exchange;
+
+/*
+ * One launch after the factor kernels of an iteration: sums the partial rows like
+ * lhvi_elbo_reduce; if step != NULL also advances the step counter like lhvi_step_tick; if
+ * x != NULL and x->world > 1 exchanges and sums x over the ranks (every rank must make the
+ * matching call).  grad[n_param..] and grad[idx[*]] hold the all-rank sums afterwards.
+ */
+int lhvi_finish(const lhvi_model* m, int64_t rows, double* step, double b1, double b2,
+                const lhvi_exchange* x, void* stream);
+
+/*
+ * Peer-visible device memory for lhvi_exchange (the only memory this library allocates).
+ *   lhvi_peer_alloc  cudaMalloc + zero-fill + cudaIpcGetMemHandle -> *ptr, handle[64]
+ *   lhvi_peer_open   map another process's handle (enables peer access lazily) -> *ptr
+ *   lhvi_peer_close  unmap a pointer returned by lhvi_peer_open
+ *   lhvi_peer_free   free a pointer returned by lhvi_peer_alloc
+ * These synchronise the device; call them at set-up / tear-down only.
+ */
+int lhvi_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle);
+int lhvi_peer_open(const unsigned char* handle, void** ptr);
+int lhvi_peer_close(void* ptr);
+int lhvi_peer_free(void* ptr);
+
+/*
  * Parameter update for every hidden variable and for w_tau.
  *   var_kind[v] 0 continuous / 1 discrete, var_dim[v] 2 / D, var_off[v] slot offset.
  *   eta: read by the factor kernels; tau: logits of discrete slots; mom1 / mom2: Adam moments.
  *   wstate: [5K] reals: w_tau | w | mom1_w | mom2_w | scratch.
  *   sgd != 0 -> theta -= lr * g (moments untouched); else Adam with eps outside the sqrt.
  *   The softmax Jacobian is applied here to raw G_c and G_w.
+ *   zero_grad != 0 -> every gradient slot of the listed variables is reset to 0 after it has been
+ *   consumed, so the next iteration's factor kernels accumulate into a clean buffer without a
+ *   separate memset (the variables listed must cover every slot the factor kernels touch).
  */
 int lhvi_param_step(int dtype, int K, int64_t n_vars, const uint8_t* var_kind,
                     const int32_t* var_dim, const int32_t* var_off, void* eta, void* tau,
-                    const void* grad, int64_t n_param, void* mom1, void* mom2, void* wstate,
+                    void* grad, int64_t n_param, void* mom1, void* mom2, void* wstate,
                     const double* step, double lr, double b1, double b2, double eps,
-                    double var_threshold, int sgd, void* stream);
+                    double var_threshold, int sgd, int zero_grad, void* stream);
 
 /*
  * out[i] = sum_k w_k q_{v_i,k}(x_i) for n queries; continuous variables use the

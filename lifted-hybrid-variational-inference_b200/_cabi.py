@@ -13,13 +13,16 @@ LHVI_MAX_AXES = 6
 LHVI_MAX_K = 8
 LHVI_MAX_T = 32
 LHVI_PARTIAL_ROWS = 1184
-ABI_VERSION = 1
+LHVI_MAX_PEERS = 16
+LHVI_IPC_HANDLE_BYTES = 64
+ABI_VERSION = 2
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblhvi.so")
 
 SYMBOLS = ("lhvi_last_error", "lhvi_abi_version", "lhvi_has_specialisation",
            "lhvi_factor_expect_grad", "lhvi_elbo_reduce", "lhvi_step_tick",
-           "lhvi_param_step", "lhvi_mixture_belief")
+           "lhvi_param_step", "lhvi_mixture_belief", "lhvi_finish",
+           "lhvi_peer_alloc", "lhvi_peer_open", "lhvi_peer_close", "lhvi_peer_free")
 
 
 class LhviGroup(C.Structure):
@@ -40,6 +43,17 @@ class LhviModel(C.Structure):
         ("n_param", C.c_int64),
         ("quad", C.c_void_p), ("ptab", C.c_void_p), ("eta", C.c_void_p), ("w", C.c_void_p),
         ("grad", C.c_void_p), ("partials", C.c_void_p),
+    ]
+
+
+class LhviExchange(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32), ("blocks", C.c_int32), ("reserved", C.c_int32),
+        ("n_idx", C.c_int64),
+        ("idx", C.c_void_p),
+        ("recv", C.c_void_p * LHVI_MAX_PEERS),
+        ("flags", C.c_void_p * LHVI_MAX_PEERS),
+        ("seq", C.c_void_p), ("status", C.c_void_p),
     ]
 
 
@@ -85,7 +99,18 @@ def load(build_if_missing: bool = False):
     lib.lhvi_param_step.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
-                                    C.c_double, C.c_int, C.c_void_p]
+                                    C.c_double, C.c_int, C.c_int, C.c_void_p]
+    lib.lhvi_finish.restype = C.c_int
+    lib.lhvi_finish.argtypes = [C.POINTER(LhviModel), C.c_int64, C.c_void_p, C.c_double, C.c_double,
+                                C.POINTER(LhviExchange), C.c_void_p]
+    lib.lhvi_peer_alloc.restype = C.c_int
+    lib.lhvi_peer_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.lhvi_peer_open.restype = C.c_int
+    lib.lhvi_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.lhvi_peer_close.restype = C.c_int
+    lib.lhvi_peer_close.argtypes = [C.c_void_p]
+    lib.lhvi_peer_free.restype = C.c_int
+    lib.lhvi_peer_free.argtypes = [C.c_void_p]
     lib.lhvi_mixture_belief.restype = C.c_int
     lib.lhvi_mixture_belief.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -1,6 +1,8 @@
 // Elementwise kernels around the factor pass: ELBO / G_w reduction, the optimiser step
 // (softmax Jacobians + Adam or SGD + variance clip + re-normalisation) and batched belief
 // queries.  All are HBM-streaming kernels over the flat parameter vector.
+#include <cstring>
+
 #include "lhvi_common.cuh"
 
 namespace lhvi {
@@ -37,6 +39,112 @@ __global__ void step_tick_kernel(double* step, double b1, double b2) {
     step[2] = 1.0 - pow(b2, t);
 }
 
+// ---- finish: partial-row reduction + step tick + cross-GPU exchange in one launch -----------
+//
+// Block 0 does what elbo_reduce_kernel and step_tick_kernel do.  With world > 1 every block then
+// takes a slice of the exchanged vector x = [G_w | energy | grad[idx[*]]]: it stores the slice into
+// slot `rank` of every peer's receive buffer over NVLink, publishes its sequence number with a
+// system-scope release, waits until all `world` flags of its own buffer carry the number, and
+// adds the slots in rank order (identical rounding on every rank -> replicated parameters stay
+// bit-identical).  Receive buffers are double-buffered by sequence parity: a rank can be at most
+// one exchange ahead of the slowest one, because completing exchange s needs every rank's flag s.
+
+constexpr int kFinishThreads = 512;
+constexpr long long kSpinLimit = 4000000000ll;     // ~2 s of SM clocks
+
+template <typename real>
+struct FinishArgs {
+    const double* partials;
+    long long regions;
+    int K;
+    real* grad;
+    long long n_param;
+    double* step;
+    double b1, b2;
+    int world, rank;
+    long long n_idx;
+    const int* idx;
+    real* recv[LHVI_MAX_PEERS];
+    unsigned long long* flags[LHVI_MAX_PEERS];
+    unsigned long long* seq;
+    int* status;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(kFinishThreads)
+finish_kernel(const FinishArgs<real> a) {
+    __shared__ double s[(kFinishThreads / 32) * (LHVI_MAX_K + 1)];
+    __shared__ double res[LHVI_MAX_K + 1];
+    const int W = a.K + 1;
+    if (blockIdx.x == 0) {
+        double acc[LHVI_MAX_K + 1];
+        for (int i = 0; i < W; ++i) acc[i] = 0.0;
+        for (long long reg = 0; reg < a.regions; ++reg) {
+            const double* base = a.partials + reg * LHVI_PARTIAL_ROWS * W;
+            const int valid = (int)base[0];
+            for (int r = threadIdx.x; r < valid; r += blockDim.x)
+                for (int i = 0; i < W; ++i) acc[i] += base[(long long)(1 + r) * W + i];
+        }
+        block_sum_to(acc, W, s, res);
+        if (threadIdx.x < W) a.grad[a.n_param + threadIdx.x] = (real)res[threadIdx.x];
+        if (threadIdx.x == 0 && a.step != nullptr) {
+            const double t = a.step[0] + 1.0;
+            a.step[0] = t;
+            a.step[1] = 1.0 - pow(a.b1, t);
+            a.step[2] = 1.0 - pow(a.b2, t);
+        }
+        __syncthreads();
+    }
+    if (a.world <= 1) return;
+
+    const long long n_x = a.n_idx + W;
+    const long long chunk = (n_x + gridDim.x - 1) / gridDim.x;
+    const long long lo = blockIdx.x * chunk;
+    const long long hi = lo + chunk < n_x ? lo + chunk : n_x;
+    const unsigned long long seq = a.seq[blockIdx.x] + 1ull;
+    const size_t parity_base = (size_t)(seq & 1ull) * a.world * n_x;
+
+    for (long long j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+        const long long src = j < W ? a.n_param + j : (long long)a.idx[j - W];
+        const real v = a.grad[src];
+        const size_t dst = parity_base + (size_t)a.rank * n_x + j;
+        for (int p = 0; p < a.world; ++p) a.recv[p][dst] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int p = 0; p < a.world; ++p)
+            st_release_sys(a.flags[p] + (size_t)a.rank * gridDim.x + blockIdx.x, seq);
+    }
+    if (threadIdx.x < a.world) {
+        const unsigned long long* f = a.flags[a.rank] + (size_t)threadIdx.x * gridDim.x + blockIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > kSpinLimit) { *a.status = 1; break; }
+        }
+    }
+    __syncthreads();
+    const real* mine = a.recv[a.rank] + parity_base;
+    for (long long j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+        real sum = real(0);
+        for (int q = 0; q < a.world; ++q) sum += __ldcg(mine + (size_t)q * n_x + j);
+        const long long src = j < W ? a.n_param + j : (long long)a.idx[j - W];
+        a.grad[src] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) a.seq[blockIdx.x] = seq;
+}
+
 // ---- optimiser step ------------------------------------------------------------------------
 
 template <typename real>
@@ -48,13 +156,13 @@ struct StepArgs {
     const int* off;
     real* eta;
     real* tau;
-    const real* grad;
+    real* grad;
     real* m1;
     real* m2;
     real* wstate;
     const double* step;
     real lr, b1, b2, eps, var_floor;
-    int sgd;
+    int sgd, zero_grad;
 };
 
 template <typename real> struct PairVec;
@@ -112,6 +220,7 @@ param_step_kernel(const StepArgs<real> a) {
                     a.eta[i] = moved<real>(a.eta[i], a.grad[i], a.m1[i], a.m2[i], a, c1, c2);
                     real var = moved<real>(a.eta[i + 1], a.grad[i + 1], a.m1[i + 1], a.m2[i + 1], a, c1, c2);
                     a.eta[i + 1] = var < a.var_floor ? a.var_floor : var;
+                    if (a.zero_grad) { a.grad[i] = real(0); a.grad[i + 1] = real(0); }
                     continue;
                 }
                 V ve = *reinterpret_cast<V*>(a.eta + i);
@@ -133,6 +242,13 @@ param_step_kernel(const StepArgs<real> a) {
                 *reinterpret_cast<V*>(a.eta + i) = ve;
                 *reinterpret_cast<V*>(a.m1 + i) = vm;
                 *reinterpret_cast<V*>(a.m2 + i) = vu;
+                if (a.zero_grad) {
+                    V zero;
+                    real* zq = reinterpret_cast<real*>(&zero);
+#pragma unroll
+                    for (int p = 0; p < 2 * PER; ++p) zq[p] = real(0);
+                    *reinterpret_cast<V*>(a.grad + i) = zero;
+                }
             }
         } else {
             const int D = a.dim[v];
@@ -152,6 +268,8 @@ param_step_kernel(const StepArgs<real> a) {
                 for (int d = 0; d < D; ++d) z += M::exp(a.tau[row + d] - mx);
                 const real iz = real(1) / z;
                 for (int d = 0; d < D; ++d) a.eta[row + d] = M::exp(a.tau[row + d] - mx) * iz;
+                if (a.zero_grad)
+                    for (int d = 0; d < D; ++d) a.grad[row + d] = real(0);
             }
         }
     }
@@ -204,6 +322,95 @@ extern "C" int lhvi_elbo_reduce(const lhvi_model* m, int64_t rows, void* stream)
     return check_launch("elbo_reduce_kernel");
 }
 
+template <typename real>
+static int finish_t(const lhvi_model* m, long long regions, double* step, double b1, double b2,
+                    const lhvi_exchange* x, cudaStream_t s) {
+    FinishArgs<real> a;
+    a.partials = m->partials; a.regions = regions; a.K = m->K;
+    a.grad = (real*)m->grad; a.n_param = m->n_param;
+    a.step = step; a.b1 = b1; a.b2 = b2;
+    a.world = 1; a.rank = 0; a.n_idx = 0; a.idx = nullptr; a.seq = nullptr; a.status = nullptr;
+    for (int p = 0; p < LHVI_MAX_PEERS; ++p) { a.recv[p] = nullptr; a.flags[p] = nullptr; }
+    unsigned blocks = 1;
+    if (x != nullptr && x->world > 1) {
+        a.world = x->world; a.rank = x->rank; a.n_idx = x->n_idx; a.idx = x->idx;
+        a.seq = (unsigned long long*)x->seq; a.status = x->status;
+        for (int p = 0; p < x->world; ++p) {
+            a.recv[p] = (real*)x->recv[p];
+            a.flags[p] = (unsigned long long*)x->flags[p];
+        }
+        blocks = (unsigned)x->blocks;
+    }
+    finish_kernel<real><<<blocks, kFinishThreads, 0, s>>>(a);
+    return check_launch("finish_kernel");
+}
+
+extern "C" int lhvi_finish(const lhvi_model* m, int64_t rows, double* step, double b1, double b2,
+                           const lhvi_exchange* x, void* stream) {
+    if (!m || !m->partials || !m->grad || rows < 0) { set_error("lhvi_finish: null buffer or negative rows"); return LHVI_EINVAL; }
+    if (m->K < 1 || m->K > LHVI_MAX_K) { set_error("K=%d out of range 1..%d", m->K, LHVI_MAX_K); return LHVI_ELIMIT; }
+    if (rows % LHVI_PARTIAL_ROWS != 0) { set_error("lhvi_finish: rows must be a multiple of LHVI_PARTIAL_ROWS"); return LHVI_EINVAL; }
+    if (x != nullptr && x->world > 1) {
+        if (x->world > LHVI_MAX_PEERS) { set_error("lhvi_finish: world=%d exceeds LHVI_MAX_PEERS=%d", x->world, LHVI_MAX_PEERS); return LHVI_ELIMIT; }
+        if (x->rank < 0 || x->rank >= x->world) { set_error("lhvi_finish: rank %d outside world %d", x->rank, x->world); return LHVI_EINVAL; }
+        if (x->blocks < 1 || x->blocks > 32) { set_error("lhvi_finish: blocks=%d out of range 1..32", x->blocks); return LHVI_EINVAL; }
+        if (x->n_idx < 0 || (x->n_idx > 0 && !x->idx) || !x->seq || !x->status) { set_error("lhvi_finish: incomplete exchange descriptor"); return LHVI_EINVAL; }
+        for (int p = 0; p < x->world; ++p)
+            if (!x->recv[p] || !x->flags[p]) { set_error("lhvi_finish: peer %d has no mapped buffer", p); return LHVI_EINVAL; }
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long regions = rows / LHVI_PARTIAL_ROWS;
+    return m->dtype == LHVI_F64 ? finish_t<double>(m, regions, step, b1, b2, x, s)
+                                : finish_t<float>(m, regions, step, b1, b2, x, s);
+}
+
+// ---- peer-visible buffers (CUDA IPC) ---------------------------------------------------------
+
+static int cuda_fail(const char* what, cudaError_t e) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return LHVI_ECUDA;
+}
+
+extern "C" int lhvi_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle) {
+    if (bytes <= 0 || !ptr || !handle) { set_error("lhvi_peer_alloc: bad argument"); return LHVI_EINVAL; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == LHVI_IPC_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e != cudaSuccess) return cuda_fail("lhvi_peer_alloc: cudaMalloc", e);
+    e = cudaMemset(p, 0, (size_t)bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail("lhvi_peer_alloc", e); }
+    memcpy(handle, &h, sizeof(h));
+    *ptr = p;
+    return LHVI_OK;
+}
+
+extern "C" int lhvi_peer_open(const unsigned char* handle, void** ptr) {
+    if (!handle || !ptr) { set_error("lhvi_peer_open: bad argument"); return LHVI_EINVAL; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail("lhvi_peer_open: cudaIpcOpenMemHandle", e);
+    *ptr = p;
+    return LHVI_OK;
+}
+
+extern "C" int lhvi_peer_close(void* ptr) {
+    if (!ptr) return LHVI_OK;
+    cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    return e == cudaSuccess ? LHVI_OK : cuda_fail("lhvi_peer_close", e);
+}
+
+extern "C" int lhvi_peer_free(void* ptr) {
+    if (!ptr) return LHVI_OK;
+    cudaError_t e = cudaFree(ptr);
+    return e == cudaSuccess ? LHVI_OK : cuda_fail("lhvi_peer_free", e);
+}
+
 extern "C" int lhvi_step_tick(double* step, double b1, double b2, void* stream) {
     if (!step) { set_error("lhvi_step_tick: null step buffer"); return LHVI_EINVAL; }
     step_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step, b1, b2);
@@ -212,32 +419,32 @@ extern "C" int lhvi_step_tick(double* step, double b1, double b2, void* stream) 
 
 template <typename real>
 static int param_step_t(int K, int64_t n_vars, const uint8_t* kind, const int32_t* dim, const int32_t* off,
-                        void* eta, void* tau, const void* grad, int64_t n_param, void* m1, void* m2,
+                        void* eta, void* tau, void* grad, int64_t n_param, void* m1, void* m2,
                         void* wstate, const double* step, double lr, double b1, double b2, double eps,
-                        double var_floor, int sgd, cudaStream_t s) {
+                        double var_floor, int sgd, int zero_grad, cudaStream_t s) {
     StepArgs<real> a;
     a.K = K; a.n_vars = n_vars; a.n_param = n_param;
     a.kind = kind; a.dim = dim; a.off = off;
-    a.eta = (real*)eta; a.tau = (real*)tau; a.grad = (const real*)grad;
+    a.eta = (real*)eta; a.tau = (real*)tau; a.grad = (real*)grad;
     a.m1 = (real*)m1; a.m2 = (real*)m2; a.wstate = (real*)wstate; a.step = step;
     a.lr = (real)lr; a.b1 = (real)b1; a.b2 = (real)b2; a.eps = (real)eps; a.var_floor = (real)var_floor;
-    a.sgd = sgd;
+    a.sgd = sgd; a.zero_grad = zero_grad;
     param_step_kernel<real><<<grid_for(n_vars, 256), 256, 0, s>>>(a);
     return check_launch("param_step_kernel");
 }
 
 extern "C" int lhvi_param_step(int dtype, int K, int64_t n_vars, const uint8_t* var_kind,
                                const int32_t* var_dim, const int32_t* var_off, void* eta, void* tau,
-                               const void* grad, int64_t n_param, void* mom1, void* mom2, void* wstate,
+                               void* grad, int64_t n_param, void* mom1, void* mom2, void* wstate,
                                const double* step, double lr, double b1, double b2, double eps,
-                               double var_threshold, int sgd, void* stream) {
+                               double var_threshold, int sgd, int zero_grad, void* stream) {
     if (!eta || !tau || !grad || !mom1 || !mom2 || !wstate || !step) { set_error("lhvi_param_step: null buffer"); return LHVI_EINVAL; }
     if (n_vars > 0 && (!var_kind || !var_dim || !var_off)) { set_error("lhvi_param_step: null variable table"); return LHVI_EINVAL; }
     if (K < 1 || K > LHVI_MAX_K) { set_error("K=%d out of range 1..%d", K, LHVI_MAX_K); return LHVI_ELIMIT; }
     cudaStream_t s = (cudaStream_t)stream;
     return dtype == LHVI_F64
-        ? param_step_t<double>(K, n_vars, var_kind, var_dim, var_off, eta, tau, grad, n_param, mom1, mom2, wstate, step, lr, b1, b2, eps, var_threshold, sgd, s)
-        : param_step_t<float>(K, n_vars, var_kind, var_dim, var_off, eta, tau, grad, n_param, mom1, mom2, wstate, step, lr, b1, b2, eps, var_threshold, sgd, s);
+        ? param_step_t<double>(K, n_vars, var_kind, var_dim, var_off, eta, tau, grad, n_param, mom1, mom2, wstate, step, lr, b1, b2, eps, var_threshold, sgd, zero_grad, s)
+        : param_step_t<float>(K, n_vars, var_kind, var_dim, var_off, eta, tau, grad, n_param, mom1, mom2, wstate, step, lr, b1, b2, eps, var_threshold, sgd, zero_grad, s);
 }
 
 extern "C" int lhvi_mixture_belief(int dtype, int K, int64_t n, const int32_t* q_off, const int32_t* q_dim,

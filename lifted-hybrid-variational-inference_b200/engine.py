@@ -6,11 +6,15 @@ groups and the gradient buffer, and drives the CUDA kernels of ``liblhvi.so`` th
 C ABI (``include/lhvi.h``).  One iteration (reference ``ADAM_update`` body,
 ``VarInference.py:249-287``) is:
 
-    grad = 0
-    for every record group:  lhvi_factor_expect_grad   (node-entropy groups included)
-    lhvi_elbo_reduce                                    -> G_w[K], free energy
-    [all-reduce of grad | G_w | energy over NCCL when the records are sharded across GPUs]
-    lhvi_step_tick; lhvi_param_step                     -> new eta, tau, w, moments
+    for every record group:  lhvi_factor_expect_grad   (node-entropy groups included; the
+                                                        launches are independent and run on
+                                                        parallel branches of the CUDA graph)
+    lhvi_finish                                         -> G_w[K], free energy, step counter, and
+                                                        (records sharded over GPUs) the sum over
+                                                        ranks of [G_w | energy | gradients of the
+                                                        shared variables] through peer memory
+    lhvi_param_step                                     -> new eta, tau, w, moments; clears the
+                                                        gradient slots it consumed
 
 PyTorch is plumbing only (allocation, streams, torch.distributed).  There is no CPU path:
 constructing the engine without CUDA or without the built library raises.
@@ -18,12 +22,14 @@ constructing the engine without CUDA or without the built library raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import warnings
 
 import numpy as np
 import torch
 
 from . import _cabi
-from .dist import ShardPlan
+from .dist import PeerExchange, ShardPlan
 from .lowering import LoweredModel
 
 
@@ -65,8 +71,11 @@ class DeviceEngine:
         self.b1, self.b2, self.eps = 0.9, 0.999, 1e-8      # VarInference.py:223-225
         self.profile_group = None
         self.dom_events = []
-        self.use_graph = True          # replay one captured iteration instead of ~10 launches
+        self.use_graph = True          # replay one captured iteration instead of ~8 launches
+        self.parallel_groups = True    # independent group launches on parallel graph branches
         self._graphs = {}
+        self._side_streams = []
+        self._grad_clean = False       # True: every gradient slot is zero (param_step cleared them)
 
         self.plan = ShardPlan(process_group, enabled=shard)
         self.world, self.rank = self.plan.world, self.plan.rank
@@ -74,6 +83,32 @@ class DeviceEngine:
         self.reduce_grads = self.plan.active
 
         self._upload()
+        self.exchange = None           # "p2p" | "collective" when the records are sharded
+        self.peer = None
+        if self.plan.active:
+            self._setup_exchange()
+
+    def _setup_exchange(self):
+        """Exchange of [G_w | energy | shared-variable gradients] between the ranks: inside
+        lhvi_finish over NVLink peer memory when every rank can map its peers' buffers (one
+        node), else one all-reduce of the compact vector (LHVI_EXCHANGE=collective forces it)."""
+        K = self.K
+        idx = np.asarray(self.plan.shared_idx, dtype=np.int64)
+        if idx.size and idx.max() >= 2 ** 31:
+            raise ValueError("parameter vector too large for 32-bit exchange offsets")
+        self.xidx = self._dev(idx.astype(np.int32))
+        tail = np.arange(self.n_param, self.n_param + K + 1, dtype=np.int64)
+        self.xidx_all = self._dev(np.concatenate([tail, idx]))
+        self.xbuf = torch.zeros(int(idx.size) + K + 1, dtype=self.tdtype, device=self.device)
+        mode = os.environ.get("LHVI_EXCHANGE", "auto")
+        self.exchange = "collective"
+        if mode != "collective" and self.device.type == "cuda":
+            self.peer = PeerExchange.create(self.plan, self.lib, int(idx.size), K,
+                                            self.xidx.data_ptr(), self.tdtype, self.device)
+            if self.peer is not None:
+                self.exchange = "p2p"
+            elif mode == "p2p":
+                raise RuntimeError("lhvi: LHVI_EXCHANGE=p2p but the peers' buffers could not be mapped")
 
     # ---- buffers --------------------------------------------------------------------------
     def _dev(self, arr, dtype=None):
@@ -164,10 +199,19 @@ class DeviceEngine:
         self.wstate[K:2 * K].copy_(torch.as_tensor(e / e.sum()).to(self.tdtype))
 
     def get_state(self):
+        """(eta, tau, w_tau, w) on the host; with sharded records the ranks' pieces (owned
+        variables from their owner, shared ones are identical everywhere) are merged first."""
         K = self.K
+        self.check_exchange()
         ws = self.wstate.double().cpu().numpy()
-        return (self.eta.double().cpu().numpy(), self.tau.double().cpu().numpy(),
+        return (self.plan.merge(self.eta).double().cpu().numpy(),
+                self.plan.merge(self.tau).double().cpu().numpy(),
                 ws[:K].copy(), ws[K:2 * K].copy())
+
+    def check_exchange(self):
+        if self.peer is not None and self.peer.timed_out():
+            raise _cabi.LhviError("lhvi: a rank did not reach the gradient exchange within the "
+                                  "spin limit (peer exchange timed out)")
 
     def reset_moments(self):
         K = self.K
@@ -179,7 +223,8 @@ class DeviceEngine:
     def get_moments(self):
         K = self.K
         ws = self.wstate.double().cpu().numpy()
-        return (self.mom1.double().cpu().numpy(), self.mom2.double().cpu().numpy(),
+        return (self.plan.merge(self.mom1).double().cpu().numpy(),
+                self.plan.merge(self.mom2).double().cpu().numpy(),
                 ws[2 * K:3 * K].copy(), ws[3 * K:4 * K].copy(), float(self.step[0].item()))
 
     def set_moments(self, mom1, mom2, m_w, u_w, t):
@@ -195,45 +240,82 @@ class DeviceEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _launch_group(self, i, stream):
+        d = self.groups[i][0]
+        _cabi.check(self.lib.lhvi_factor_expect_grad(
+            C.byref(self.desc), C.byref(d), i * _cabi.LHVI_PARTIAL_ROWS, int(self.force_generic),
+            C.c_void_p(stream.cuda_stream)), self.lib)
+
+    def _launch_groups(self):
+        """One launch per record group.  The launches only share atomics into ``grad``, so
+        they are forked onto side streams (parallel branches once captured in a CUDA graph),
+        largest group first; with ``profile_group`` set they run in order on the current
+        stream with CUDA events around that group's launch (bench.py roofline)."""
+        main = torch.cuda.current_stream(self.device)
+        n = len(self.groups)
+        if self.profile_group is not None or not self.parallel_groups or n < 2:
+            for i in range(n):
+                timed = self.profile_group == i
+                if timed:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record(main)
+                self._launch_group(i, main)
+                if timed:
+                    ev[1].record(main)
+                    self.dom_events.append(ev)
+            return n
+        while len(self._side_streams) < n - 1:
+            self._side_streams.append(torch.cuda.Stream(device=self.device))
+        order = sorted(range(n), key=lambda i: -self.groups[i][2].n)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._launch_group(order[0], main)
+        for j, i in enumerate(order[1:]):
+            side = self._side_streams[j]
+            side.wait_event(fork)
+            self._launch_group(i, side)
+            join = torch.cuda.Event()
+            join.record(side)
+            main.wait_event(join)
+        return n
+
+    def _finish(self, tick, exchange):
+        lib, st = self.lib, self._stream()
+        x = C.byref(self.peer.desc) if (exchange and self.exchange == "p2p") else None
+        step = self.step.data_ptr() if tick else None
+        _cabi.check(lib.lhvi_finish(C.byref(self.desc), self.partial_rows, step, self.b1, self.b2, x, st), lib)
+        if exchange and self.exchange == "collective":
+            torch.index_select(self.grad, 0, self.xidx_all, out=self.xbuf)
+            self.plan.all_reduce(self.xbuf)
+            self.grad.index_copy_(0, self.xidx_all, self.xbuf)
+
     def grad_pass(self):
         """Fill ``self.grad`` = [parameter gradients | raw G_w | free energy] at the current
-        parameters (all-reduced over the process group when records are sharded)."""
-        lib, st = self.lib, self._stream()
+        parameters (summed over the process group when the records are sharded)."""
         self.grad.zero_()
-        launches = 0        # kernels of liblhvi.so only (torch's fill and the memsets are not counted)
-        for i, (d, _, _) in enumerate(self.groups):
-            timed = self.profile_group == i
-            if timed:       # CUDA events around one group's launch (bench.py roofline)
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                ev[0].record()
-            _cabi.check(lib.lhvi_factor_expect_grad(C.byref(self.desc), C.byref(d),
-                                                    i * _cabi.LHVI_PARTIAL_ROWS,
-                                                    int(self.force_generic), st), lib)
-            if timed:
-                ev[1].record()
-                self.dom_events.append(ev)
-            launches += 1
-        _cabi.check(lib.lhvi_elbo_reduce(C.byref(self.desc), self.partial_rows, st), lib)
-        launches += 1
+        self._grad_clean = False
+        launches = self._launch_groups()
+        self._finish(tick=False, exchange=False)
         if self.reduce_grads:
             self.plan.all_reduce(self.grad)
-        self.launches_per_pass = launches
+        self.launches_per_pass = launches + 1
         return self.grad
 
-    def param_step(self, lr, sgd=False):
+    def param_step(self, lr, sgd=False, zero_grad=False):
         lib, st = self.lib, self._stream()
-        if not sgd:
-            _cabi.check(lib.lhvi_step_tick(self.step.data_ptr(), self.b1, self.b2, st), lib)
         _cabi.check(lib.lhvi_param_step(
             self.dcode, self.K, self.n_vars, self.var_kind.data_ptr(), self.var_dim.data_ptr(),
             self.var_off.data_ptr(), self.eta.data_ptr(), self.tau.data_ptr(), self.grad.data_ptr(),
             self.n_param, self.mom1.data_ptr(), self.mom2.data_ptr(), self.wstate.data_ptr(),
             self.step.data_ptr(), float(lr), self.b1, self.b2, self.eps, self.var_threshold,
-            int(bool(sgd)), st), lib)
+            int(bool(sgd)), int(bool(zero_grad)), st), lib)
 
     def _iteration(self, lr, sgd):
-        self.grad_pass()
-        self.param_step(lr, sgd=sgd)
+        """One Jacobi iteration; expects clean gradient slots and leaves them clean."""
+        launches = self._launch_groups()
+        self._finish(tick=not sgd, exchange=self.plan.active)
+        self.param_step(lr, sgd=sgd, zero_grad=True)
+        self.launches_per_pass = launches + 1
 
     def _graph_for(self, lr, sgd):
         """CUDA graph of one iteration for these hyper-parameters (captured once).  The step
@@ -241,11 +323,15 @@ class DeviceEngine:
         key = (float(lr), bool(sgd), self.b1, self.b2, self.eps, self.var_threshold)
         graph = self._graphs.get(key)
         if graph is None:
-            self.grad_pass()                       # warm-up outside capture (lazy kernel setup)
+            # lazy kernel set-up (occupancy queries, module load) must happen outside capture;
+            # this pass has no side effects on the parameters
+            self.grad_pass()
+            self.grad.zero_()
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self._iteration(lr, sgd)
+            # capture records the launches without running them: nothing has changed yet
             self._graphs[key] = graph
         return graph
 
@@ -254,26 +340,34 @@ class DeviceEngine:
         n = int(n)
         if n <= 0:
             return
+        graph = None
         if self.use_graph and self.profile_group is None:
             try:
                 graph = self._graph_for(lr, sgd)
-            except Exception:                      # capture unsupported here (e.g. a collective)
+            except Exception as exc:               # capture unsupported here: same kernels, launched eagerly
+                warnings.warn(f"lhvi: CUDA-graph capture failed ({exc}); launching eagerly")
                 self.use_graph = False
-                graph = None
-            if graph is not None:
-                for _ in range(n):
-                    graph.replay()
-                return
+        if not self._grad_clean:
+            self.grad[:self.n_param].zero_()
+            self._grad_clean = True
         for _ in range(n):
-            self._iteration(lr, sgd)
+            if graph is not None:
+                graph.replay()
+            else:
+                self._iteration(lr, sgd)
 
     @property
     def launches_per_iteration(self):
-        return self.launches_per_pass + 2
+        """Kernels of liblhvi.so per iteration: the group launches, lhvi_finish, lhvi_param_step."""
+        return self.launches_per_pass + 1
+
+    def last_free_energy(self):
+        """Free energy computed by the most recent pass (at the parameters before its step)."""
+        return float(self.grad[self.n_param + self.K].item())
 
     def free_energy(self):
         self.grad_pass()
-        return float(self.grad[self.n_param + self.K].item())
+        return self.last_free_energy()
 
     def gradients(self):
         """Host copies of (raw parameter gradients [n_param], raw G_w [K], free energy)."""

@@ -1,8 +1,9 @@
-"""World-size-2 run of the sharding protocol on CPU (gloo): each rank takes its slice of the
-record groups (``ShardPlan`` / ``LoweredModel.shard``), the flat ``[grads | G_w | energy]``
-vector is all-reduced, every rank applies the same parameter step, and the replicas must
-match the single-process result.  The per-rank pass is the numpy oracle standing in for the
-CUDA kernels; the exchange object is the one the GPU engine uses."""
+"""World-size-2 run of the sharding protocol on CPU (gloo): ``ShardPlan`` partitions the
+records owner-computes style, each rank evaluates its records, the ranks all-reduce only the
+compact ``[G_w | energy | shared-variable gradients]`` vector, every rank steps the variables it
+owns plus the shared ones, and ``ShardPlan.merge`` assembles the state -- which must match the
+single-process result.  The per-rank pass is the numpy oracle standing in for the CUDA kernels;
+the plan / exchange / merge objects are the ones the GPU engine uses."""
 import os
 import socket
 import sys
@@ -37,19 +38,23 @@ def _worker(rank, world, port, out_dir):
         plan = ShardPlan()
         assert plan.world == world and plan.rank == rank
         mine = plan.shard(model)
+        assert "shared" in plan.describe()
+        shared = plan.shared_idx
         vi = NumpyVI(model)
         vi.eta[:], vi.tau[:], vi.w_tau = eta, tau, w_tau
         vi.refresh()
         K = model.K
         for _ in range(3):
             g, gw, e = grad_pass(mine, vi.eta, vi.w)
-            flat = torch.from_numpy(np.concatenate([g, gw, [e]]))
-            plan.all_reduce(flat)
-            flat = flat.numpy()
-            # identical step on every rank from the reduced vector
-            vi.gradients = lambda f=flat: (*tau_gradients(model, f[:-K - 1], f[-K - 1:-1], vi.eta, vi.w), f[-1])
+            x = torch.from_numpy(np.concatenate([gw, [e], g[shared]]))
+            plan.all_reduce(x)                       # the only per-iteration exchange
+            x = x.numpy()
+            g[shared] = x[K + 1:]
+            vi.gradients = lambda g=g, x=x: (*tau_gradients(model, g, x[:K], vi.eta, vi.w), x[K])
             vi.adam_step(0.1)
-        np.save(os.path.join(out_dir, f"eta_{rank}.npy"), vi.eta)
+        merged = plan.merge(torch.from_numpy(vi.eta.copy())).numpy()
+        np.save(os.path.join(out_dir, f"eta_{rank}.npy"), merged)
+        np.save(os.path.join(out_dir, f"shared_{rank}.npy"), vi.eta[shared])
         np.save(os.path.join(out_dir, f"wtau_{rank}.npy"), vi.w_tau)
     finally:
         dist.destroy_process_group()
@@ -70,5 +75,6 @@ def test_two_rank_protocol_matches_single_process(tmp_path):
     for r in range(world):
         np.testing.assert_allclose(np.load(tmp_path / f"eta_{r}.npy"), ref.eta, rtol=1e-10, atol=1e-12)
         np.testing.assert_allclose(np.load(tmp_path / f"wtau_{r}.npy"), ref.w_tau, rtol=1e-10, atol=1e-12)
-    # replicas are bit-identical to each other
+    # the merged state and the replicated shared variables are bit-identical across ranks
     assert np.array_equal(np.load(tmp_path / "eta_0.npy"), np.load(tmp_path / "eta_1.npy"))
+    assert np.array_equal(np.load(tmp_path / "shared_0.npy"), np.load(tmp_path / "shared_1.npy"))

@@ -104,6 +104,39 @@ def test_param_step_matches_oracle_sgd_and_adam(ns):
         np.testing.assert_allclose(w2, ref.w, rtol=1e-9)
 
 
+def test_queries_between_iterations_keep_the_gradient_buffer_consistent():
+    """iterate() clears the gradient slots inside the parameter step instead of a memset;
+    gradients() / free_energy() calls in between must not leak into the next iteration."""
+    syn = lhvi_b200.synthetic
+    model = syn.relational_hybrid(150, 4, 2, 3, seed=5, weighted=True)
+    eta, tau, w_tau = syn.random_state(model, 6)
+    ref = NumpyVI(model)
+    ref.eta[:], ref.tau[:], ref.w_tau = eta, tau, w_tau
+    ref.refresh()
+    eng = _engine_for(model)
+    eng.set_state(eta, tau, w_tau)
+    eng.reset_moments()
+    for n in (1, 2, 1):
+        g, gw, e = eng.gradients()
+        og, ogw, oe = grad_pass(model, ref.eta, ref.w)
+        np.testing.assert_allclose(e, oe, rtol=FP64_RTOL)
+        np.testing.assert_allclose(g, og, rtol=FP64_RTOL, atol=1e-10)
+        for _ in range(n):
+            fe = ref.adam_step(0.1)
+        eng.iterate(n, 0.1)
+        np.testing.assert_allclose(eng.last_free_energy(), fe, rtol=FP64_RTOL)
+        e2, _, wt2, _ = eng.get_state()
+        np.testing.assert_allclose(e2, ref.eta, rtol=1e-9, atol=1e-11)
+    # eager launches (no CUDA graph, sequential groups) give the same trajectory
+    eng2 = _engine_for(model)
+    eng2.use_graph = False
+    eng2.parallel_groups = False
+    eng2.set_state(eta, tau, w_tau)
+    eng2.reset_moments()
+    eng2.iterate(4, 0.1)
+    np.testing.assert_allclose(eng2.get_state()[0], ref.eta, rtol=1e-9, atol=1e-11)
+
+
 def test_belief_queries(ns):
     g, rvs = specs.hmln_hidden(ns)
     vi = lhvi_b200.VarInference.VarInference(g, 2, 3)
