@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--order", default="hub", choices=["hub", "entity"])
     ap.add_argument("--generic", action="store_true", help="force the generic kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-entities", type=int, default=20_000)
+    ap.add_argument("--cpu-sample-entities", type=int, default=200_000)
     return ap.parse_args()
 
 
@@ -72,9 +72,21 @@ def workload_config(a, n_records, parallelism=None):
 
 # ---- algorithmic bytes (DESIGN.md "Roofline accounting") -------------------------------------
 
-def group_bytes(g, K, s):
-    """Bytes one launch over record group ``g`` must move: the record columns once, plus per
-    hidden argument one parameter gather and one gradient write of K*P elements."""
+def is_streamed(g):
+    """Pure group with one hidden continuous argument in a hub run: served by the streaming
+    unary kernel from the folded columns (c0, l0, a0)."""
+    return (not g.node) and g.pure and g.nd == 0 and g.nc == 1 and g.ng == 0
+
+
+def group_bytes(g, K, s, hub=False):
+    """Algorithmic bytes one launch over record group ``g`` must move.
+
+    General groups (SURVEY section 8 d): the record columns once, plus per hidden argument one
+    parameter gather and one gradient write of K*P elements.  Streamed hub groups: the folded
+    record columns only -- (c0, l0, a0), the slot offset and the two lifted weights; the
+    variable's parameters and gradient are touched once per run, not per record."""
+    if hub and is_streamed(g):
+        return (3 * s + 4 + (2 * s if g.weighted else 0)) * g.n
     per = 0
     if not g.node:
         per += 4                                    # pot
@@ -92,6 +104,17 @@ def group_bytes(g, K, s):
 def variable_bytes(model, s):
     """Optimiser step: read grad, theta, m, v; write theta, m, v (7 * s per element)."""
     return 7 * s * model.n_param
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of this
+# workload at N=1 (profiles/r1_ncu_summary.md); keyed by the group description without its size
+TRAFFIC = {
+    "full nd=0 nc=2 ng=0 ne=0": 91.5e6 + 4.1e6,
+    "pure streamed nd=0 nc=1 ng=0 ne=1": 168.0e6 + 2.6e6,
+}
+NOTE = ("the full (two hidden arguments) kernel is bound by FP32/MUFU issue, not by HBM: ncu shows issue "
+        "slots ~69% busy, FMA and XU pipes ~50% each, DRAM ~0.8 TB/s; its fraction of the HBM roofline is "
+        "reported as asked but its limiter is instruction issue (profiles/r1_ncu_summary.md)")
 
 
 # ---- clocks ------------------------------------------------------------------------------------
@@ -218,9 +241,15 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # dominant kernel = launch over the group with the most algorithmic bytes on this rank
-    dom = max(range(len(eng.groups)), key=lambda i: group_bytes(eng.groups[i][2], a.K, s))
-    dom_group = eng.groups[dom][2]
+    def gbytes(i):
+        d, _, g = eng.groups[i]
+        return group_bytes(g, a.K, s, hub=bool(d.fold) and bool((d.hub_mask >> g.nd) & 1))
+
+    def gname(i):
+        d, _, g = eng.groups[i]
+        kind = "node" if g.node else ("pure" if g.pure else "full")
+        stream = " streamed" if (d.fold and (d.hub_mask >> g.nd) & 1) else ""
+        return f"{kind}{stream} nd={g.nd} nc={g.nc} ng={g.ng} ne={g.ne} n={g.n}"
 
     for _ in range(a.warmup):
         eng.iterate(1, lr)
@@ -235,14 +264,21 @@ def run_ours(a):
             eng.iterate(1, lr)
         ev1.record()
         barrier()
-        # same steps again, launched eagerly with CUDA events around the dominant kernel
-        eng.profile_group = dom
+        # the same steps again, launched one kernel after the other with CUDA events around every
+        # group's launch (each kernel timed alone -> burst peak applies)
+        eng.profile_group = "all"
         eng.dom_events = []
         for _ in range(a.steps):
             eng.iterate(1, lr)
         barrier()
     ms = ev0.elapsed_time(ev1)
-    dom_ms = float(np.mean([b.elapsed_time(e) for b, e in eng.dom_events])) if eng.dom_events else None
+    per_group = {}
+    for i, b, e in eng.dom_events:
+        per_group.setdefault(i, []).append(b.elapsed_time(e))
+    kernels = [{"group": gname(i), "ms": float(np.mean(v)), "bytes": gbytes(i),
+                "gbs": gbytes(i) / (float(np.mean(v)) * 1e-3) / 1e9} for i, v in sorted(per_group.items())]
+    dom = max(per_group, key=lambda i: np.mean(per_group[i])) if per_group else 0
+    dom_ms = float(np.mean(per_group[dom])) if per_group else None
     eng.profile_group = None
     launches = eng.launches_per_iteration * a.steps
 
@@ -293,15 +329,16 @@ def run_ours(a):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        dom_bytes = group_bytes(dom_group, a.K, s)
+        dom_bytes = gbytes(dom)
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else None
-        step_bytes = sum(group_bytes(g, a.K, s) for _, _, g in eng.groups) + variable_bytes(model, s)
+        step_bytes = sum(gbytes(i) for i in range(len(eng.groups))) + variable_bytes(eng.model, s)
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak if achieved else None, "traffic": None,
-            "kernel": f"factor kernel over group nd={dom_group.nd} nc={dom_group.nc} ng={dom_group.ng} "
-                      f"ne={dom_group.ne} pure={int(dom_group.pure)} ({dom_group.n} records on rank 0)",
+            "frac": achieved / peak if achieved else None, "traffic": TRAFFIC.get(gname(dom).split(" n=")[0]) if (world == 1 and a.entities == 1_000_000) else None,
+            "kernel": f"longest launch of the step: {gname(dom)} (rank 0)",
             "kernel_ms": dom_ms, "kernel_bytes": dom_bytes, "peak_source": peak_src,
+            "note": NOTE,
+            "kernels": kernels,
             "step_bytes": step_bytes, "step_achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
             "step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
         }

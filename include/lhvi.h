@@ -99,6 +99,14 @@ typedef struct lhvi_group {
     const void* wf;                /* [n]          W_f, weight on energy and g_w (node: energy scale) */
     const void* gam;               /* [(nd+nc)*n]  gamma, weight on each parameter gradient */
     const void* nscale;            /* [n]          node groups: parameter-gradient scale */
+    /* Optional streaming form of a pure group with exactly one hidden continuous argument
+       (nd=0, nc=1, ng=0, pure=1): the record's log-potential as a quadratic in that argument
+       with the point evidence already folded in, log psi(x) = c0 + l0 x + a0 x^2.
+       fold = [3][n_pad] (c0 | l0 | a0), n_pad a multiple of 1024 >= n; poff / wf / gam must
+       then be allocated with n_pad elements as well, records n..n_pad-1 carrying zero
+       coefficients and weights and the last record's offset.  NULL: not provided. */
+    const void* fold;
+    int64_t n_pad;
 } lhvi_group;
 
 /* Model-wide device buffers shared by every group launch. */

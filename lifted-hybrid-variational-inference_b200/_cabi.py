@@ -13,6 +13,7 @@ LHVI_MAX_AXES = 6
 LHVI_MAX_K = 8
 LHVI_MAX_T = 32
 LHVI_PARTIAL_ROWS = 1184
+LHVI_FOLD_TILE = 1024
 LHVI_MAX_PEERS = 16
 LHVI_IPC_HANDLE_BYTES = 64
 ABI_VERSION = 2
@@ -34,6 +35,7 @@ class LhviGroup(C.Structure):
         ("pot", C.c_void_p), ("poff", C.c_void_p),
         ("egval", C.c_void_p), ("egvar", C.c_void_p), ("ecval", C.c_void_p),
         ("wf", C.c_void_p), ("gam", C.c_void_p), ("nscale", C.c_void_p),
+        ("fold", C.c_void_p), ("n_pad", C.c_int64),
     ]
 
 

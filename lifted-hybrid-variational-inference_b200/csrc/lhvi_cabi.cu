@@ -45,6 +45,10 @@ static int validate(const lhvi_model* m, const lhvi_group* g, int64_t row0) {
         set_error("factor group without pot/ptab");
         return LHVI_EINVAL;
     }
+    if (g->fold) {
+        if (g->node || !g->pure || g->nd != 0 || g->nc != 1 || g->ng != 0) { set_error("fold columns are only defined for pure groups with one hidden continuous argument"); return LHVI_EINVAL; }
+        if (g->n_pad < g->n || g->n_pad % 1024 != 0) { set_error("fold columns: n_pad=%lld must be a multiple of 1024 and >= n=%lld", (long long)g->n_pad, (long long)g->n); return LHVI_EINVAL; }
+    }
     return LHVI_OK;
 }
 

@@ -125,6 +125,8 @@ struct GroupView {
     const real* wf;
     const real* gam;
     const real* nscale;
+    const real* fold;
+    long long n_pad;
     // model
     int K, T;
     const real* quad;
@@ -146,6 +148,7 @@ inline GroupView<real> make_view(const lhvi_model* m, const lhvi_group* g, int64
     v.egval = (const real*)g->egval; v.egvar = (const real*)g->egvar;
     v.ecval = (const real*)g->ecval; v.wf = (const real*)g->wf;
     v.gam = (const real*)g->gam; v.nscale = (const real*)g->nscale;
+    v.fold = (const real*)g->fold; v.n_pad = g->n_pad;
     v.K = m->K; v.T = m->T;
     v.quad = (const real*)m->quad; v.ptab = (const real*)m->ptab;
     v.eta = (const real*)m->eta; v.w = (const real*)m->w;

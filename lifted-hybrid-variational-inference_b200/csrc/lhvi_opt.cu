@@ -50,6 +50,7 @@ __global__ void step_tick_kernel(double* step, double b1, double b2) {
 // one exchange ahead of the slowest one, because completing exchange s needs every rank's flag s.
 
 constexpr int kFinishThreads = 512;
+constexpr int kFinishRegions = 64;
 constexpr long long kSpinLimit = 4000000000ll;     // ~2 s of SM clocks
 
 template <typename real>
@@ -87,9 +88,28 @@ finish_kernel(const FinishArgs<real> a) {
     __shared__ double res[LHVI_MAX_K + 1];
     const int W = a.K + 1;
     if (blockIdx.x == 0) {
+        // all region headers first (one round trip), then one flat pass over the valid rows
+        __shared__ int s_start[kFinishRegions + 1];
+        const int regions = (int)(a.regions < kFinishRegions ? a.regions : kFinishRegions);
+        if (threadIdx.x < regions)
+            s_start[threadIdx.x + 1] = (int)a.partials[(long long)threadIdx.x * LHVI_PARTIAL_ROWS * W];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_start[0] = 0;
+            for (int i = 0; i < regions; ++i) s_start[i + 1] += s_start[i];
+        }
+        __syncthreads();
         double acc[LHVI_MAX_K + 1];
         for (int i = 0; i < W; ++i) acc[i] = 0.0;
-        for (long long reg = 0; reg < a.regions; ++reg) {
+        const int total = s_start[regions];
+        for (int f = threadIdx.x; f < total; f += blockDim.x) {
+            int reg = 0;
+            while (f >= s_start[reg + 1]) ++reg;
+            const double* row = a.partials + ((long long)reg * LHVI_PARTIAL_ROWS + 1 + (f - s_start[reg])) * W;
+            for (int i = 0; i < W; ++i) acc[i] += row[i];
+        }
+        // more regions than the header table holds: the rest one by one
+        for (long long reg = regions; reg < a.regions; ++reg) {
             const double* base = a.partials + reg * LHVI_PARTIAL_ROWS * W;
             const int valid = (int)base[0];
             for (int r = threadIdx.x; r < valid; r += blockDim.x)
@@ -98,10 +118,10 @@ finish_kernel(const FinishArgs<real> a) {
         block_sum_to(acc, W, s, res);
         if (threadIdx.x < W) a.grad[a.n_param + threadIdx.x] = (real)res[threadIdx.x];
         if (threadIdx.x == 0 && a.step != nullptr) {
-            const double t = a.step[0] + 1.0;
-            a.step[0] = t;
-            a.step[1] = 1.0 - pow(a.b1, t);
-            a.step[2] = 1.0 - pow(a.b2, t);
+            // b^t as a running product (b^(t-1) = 1 - step[.]): no pow() on the critical path
+            a.step[0] = a.step[0] + 1.0;
+            a.step[1] = 1.0 - (1.0 - a.step[1]) * a.b1;
+            a.step[2] = 1.0 - (1.0 - a.step[2]) * a.b2;
         }
         __syncthreads();
     }

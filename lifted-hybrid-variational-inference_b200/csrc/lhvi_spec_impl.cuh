@@ -545,6 +545,19 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
                 }
             }
 
+            // w_k' times the normalisers of every axis: the starting value of the belief products
+            real pk0[K];
+#pragma unroll
+            for (int k2 = 0; k2 < K; ++k2) {
+                pk0[k2] = wk[k2];
+                if constexpr (FL != kPure) {
+#pragma unroll
+                    for (int a = 0; a < NC; ++a) pk0[k2] *= nrm[a][k2];
+#pragma unroll
+                    for (int j = 0; j < NG; ++j) pk0[k2] *= egn[j];
+                }
+            }
+
             real Eks[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
@@ -559,12 +572,14 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
                         c.x[a][t] = dx + mu[a][k];
                         if constexpr (FL != kPure) {
 #pragma unroll
+                            // densities without their normalisers 1 / (sqrt(2pi) var): those depend
+                            // on (argument, component) only and are folded into pk once per record
                             for (int k2 = 0; k2 < K; ++k2) {
                                 if (k2 == k) {
-                                    c.q[a][k2][t] = eq[t] * nrm[a][k2];      // exp(-xi^2) / (sqrt(2pi) var)
+                                    c.q[a][k2][t] = eq[t];                   // exp(-xi^2)
                                 } else {
                                     const real u = dx + (mu[a][k] - mu[a][k2]);
-                                    c.q[a][k2][t] = F::exp_scaled(hvar[a][k2] * (u * u)) * nrm[a][k2];
+                                    c.q[a][k2][t] = F::exp_scaled(hvar[a][k2] * (u * u));
                                 }
                             }
                         }
@@ -575,26 +590,23 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
 #pragma unroll
                     for (int t = 0; t < T; ++t) {
                         c.x[NC + j][t] = egs[j] * xi[t] + egval[j];
-                        const real qe = eq[t] * egn[j];
 #pragma unroll
-                        for (int k2 = 0; k2 < K; ++k2) c.q[NC + j][k2][t] = qe;
+                        for (int k2 = 0; k2 < K; ++k2) c.q[NC + j][k2][t] = eq[t];
                     }
                 }
                 real pk[K];
 #pragma unroll
-                for (int k2 = 0; k2 < K; ++k2) pk[k2] = wk[k2];
+                for (int k2 = 0; k2 < K; ++k2) pk[k2] = pk0[k2];
 
 #pragma unroll
                 for (int a = 0; a < NC; ++a) { c.m1[a] = real(0); c.m2[a] = real(0); }
                 c.qmin = real(0);
                 // every belief on this grid is at least the own-component term, so float products
                 // cannot have underflowed if that term is comfortably representable
-                real own = wk[k];
+                real own = pk0[k];
                 if constexpr (FL != kPure) {
 #pragma unroll
-                    for (int a = 0; a < NC; ++a) own *= eq_min * nrm[a][k];
-#pragma unroll
-                    for (int j = 0; j < NG; ++j) own *= eq_min * egn[j];
+                    for (int a = 0; a < NA; ++a) own *= eq_min;
                 }
                 real Ek = Walk<real, K, T, NC, NG, NE, FL, false, 0>::run(c, pk, real(1), cst0, lin0);
                 if (c.qmin < F::kQFloor || own < F::kBFloor) {
@@ -643,7 +655,9 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
                 // per-thread running sum while the hub variable stays the same
                 if (active) {
                     if (key[a] != hub_key) {
-                        if (hub_key >= 0) flush_hub(hub_key, hub_acc);
+                        // every thread of the block passes this boundary within one tile: straight
+                        // to global REDs (pipelined in L2) instead of ~1500 contended shared atomics
+                        if (hub_key >= 0) red_vec<NV>(g.grad + hub_key, hub_acc);
                         hub_key = key[a];
 #pragma unroll
                         for (int i = 0; i < NV; ++i) hub_acc[i] = real(0);
@@ -860,7 +874,7 @@ pure_unary_kernel(const GroupView<real> g, const SpecLaunch L) {
             const int key = c_off[j];
             if (key < 0) continue;                       // past the end of the chunk
             if (key != run_key) {
-                if (run_key >= 0) flush(run_key, run_acc);
+                if (run_key >= 0) red_vec<NV>(g.grad + run_key, run_acc);     // see factor_spec_kernel
                 run_key = key;
 #pragma unroll
                 for (int i = 0; i < NV; ++i) run_acc[i] = real(0);
@@ -1006,6 +1020,388 @@ static int launch_pure_unary(const lhvi_model* m, const lhvi_group* g, int64_t r
                : go(pure_unary_kernel<real, K, T, NE, false, false>);
 }
 
+// ---- folded unary records: a streaming reduction ---------------------------------------------------
+//
+// Input: the fold columns of lhvi_group (log psi(x) = c0 + l0 x + a0 x^2 per record, evidence already
+// folded in).  E_k[log psi], E_k[log psi (x-mu)] and E_k[log psi ((x-mu)^2 - var)] are *linear* in
+// (c0, l0, a0) with coefficients that depend on the variable only, so inside a run of records on
+// the same variable a thread just accumulates the gamma- and W_f-weighted sums of the coefficients
+// (re-expanded around the belief mean so that the sums stay small: 9 FMAs per record) and applies
+// the per-component formulas once per run, in double.  Every record is still read and folded in
+// every iteration -- nothing is cached across iterations.
+//
+// The reference integrates log(psi + 1e-100); a record whose quadratic could reach the floor on
+// the run's node interval (lower bound A - |B| R - |C| R^2 below the threshold) is excluded from
+// the sums and evaluated node by node with the literal formula.
+//
+// The quadrature rule enters through its even moments M0, M2, M4 (the rule is symmetric, the host
+// checks it), so T is a run-time value here.
+
+constexpr int kFoldThreads = 256;
+constexpr int kFoldTile = kFoldThreads * kQuad;
+static_assert(kFoldTile == 1024, "lhvi.h documents n_pad as a multiple of 1024");
+
+// literal evaluation of one record (floor possibly active); adds into acc / rg
+template <typename real, int K>
+__device__ __noinline__ void fold_slow_record(const real* __restrict__ slot, const real* s_quad, int T,
+                                              const real* s_w, double c0, double l0, double a0,
+                                              double wf, double gam, double* acc, double* rg) {
+    double esum = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const double mu = (double)slot[2 * k], var = (double)slot[2 * k + 1];
+        const double sd = ::sqrt(2.0 * var);
+        double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+        for (int t = 0; t < T; ++t) {
+            const double xi = (double)s_quad[t], om = (double)s_quad[T + t];
+            const double x = sd * xi + mu;
+            const double lq = ::log(::exp(c0 + x * (l0 + a0 * x)) + kEps);
+            e0 += om * lq;
+            e1 += om * xi * lq;
+            e2 += om * xi * xi * lq;
+        }
+        acc[k] -= wf * e0;
+        esum += (double)s_w[k] * e0;
+        rg[2 * k] -= gam * (sd * e1) / var;
+        rg[2 * k + 1] -= gam * (e2 - 0.5 * e0) / var;
+    }
+    acc[K] -= wf * esum;
+}
+
+template <typename real, int K>
+struct FoldShared {
+    real quad[2 * LHVI_MAX_T];
+    double mom[4];                     // M0, M2, M4, max |xi|
+    real w[K];
+    int tag[kCacheSlots];
+    real val[kCacheSlots][2 * K];
+};
+
+template <typename real> struct RunStart { real xbar, R; };
+
+// expansion point (belief mean) and node radius of a variable's run
+template <typename real, int K>
+__device__ __noinline__ RunStart<real> fold_begin_run(const real* __restrict__ eta, int key,
+                                                      const FoldShared<real, K>* sh) {
+    constexpr int NV = 2 * K;
+    real slot[NV];
+    load_vec<NV>(eta + key, slot);
+    real m = real(0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) m += sh->w[k] * slot[2 * k];
+    const real xi_max = (real)sh->mom[3];
+    real rad = real(0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const real d = fabs(slot[2 * k] - m) + Fast<real>::sqrt(real(2) * slot[2 * k + 1]) * xi_max;
+        rad = d > rad ? d : rad;
+    }
+    RunStart<real> out;
+    out.xbar = m;
+    out.R = rad * real(1.0001);
+    return out;
+}
+
+// close a run: per-component formulas on the accumulated sums (in double), gradient out through
+// the block's shared cache (hubs) or vector REDs
+template <typename real, int K, bool USE_CACHE>
+__device__ __forceinline__ void fold_close_run(const real* __restrict__ eta, real* grad, int key, real xbar,
+                                            real sg0, real sg1, real sg2, real sw0, real sw1, real sw2,
+                                            FoldShared<real, K>* sh, double* acc, double* rg) {
+    constexpr int NV = 2 * K;
+    constexpr int kSlotElems = NV <= 2 ? 2 : ((NV + 3) / 4) * 4;
+    real slot[NV];
+    load_vec<NV>(eta + key, slot);
+    const double M0 = sh->mom[0], M2 = sh->mom[1], M4 = sh->mom[2];
+    const double G0 = (double)sg0, G1 = (double)sg1, G2 = (double)sg2;
+    const double W0 = (double)sw0, W1 = (double)sw1, W2 = (double)sw2;
+    real v[NV];
+    double esum = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double mu = (double)slot[2 * k], var = (double)slot[2 * k + 1];
+        const double d = mu - (double)xbar, s2 = 2.0 * var;
+        // q(mu + s xi) = A + B xi + C xi^2 (s = sqrt(2 var)); the W_f-weighted sum needs E[q] only
+        const double Aw = W0 + d * (W1 + W2 * d), Cw = W2 * s2;
+        const double Ek = M0 * Aw + M2 * Cw;
+        acc[k] -= Ek;
+        esum += (double)sh->w[k] * Ek;
+        const double Ag = G0 + d * (G1 + G2 * d), Bg = G1 + 2.0 * G2 * d, Cg = G2 * s2;
+        const double e0 = M0 * Ag + M2 * Cg;
+        const double e2 = M2 * Ag + M4 * Cg;
+        // sum w xi q = s M2 Bg, so g_mu = -(s * s M2 Bg) / var = -2 M2 Bg ; g_var = -(e2 - e0 / 2) / var
+        double gm = -2.0 * M2 * Bg, gv = -(e2 - 0.5 * e0) / var;
+        if (rg != nullptr) {           // records of this run that took the literal path
+            gm += rg[2 * k];
+            gv += rg[2 * k + 1];
+            rg[2 * k] = 0.0;
+            rg[2 * k + 1] = 0.0;
+        }
+        v[2 * k] = (real)gm;
+        v[2 * k + 1] = (real)gv;
+    }
+    acc[K] -= esum;
+    if constexpr (USE_CACHE) {
+        const int slot_i = (key / kSlotElems) & (kCacheSlots - 1);
+        const int old = atomicCAS(&sh->tag[slot_i], -1, key);
+        if (old == -1 || old == key) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) atomicAdd(&sh->val[slot_i][i], v[i]);
+            return;
+        }
+    }
+    red_vec<NV>(grad + key, v);
+}
+
+// per-thread state of the current run: expansion point, node radius, weighted coefficient sums
+template <typename real>
+struct FoldState {
+    int run_key;
+    real xbar, R;
+    real sg0, sg1, sg2;      // gamma-weighted sums of (A', B', C')
+    real sw0, sw1, sw2;      // W_f-weighted sums
+};
+
+template <typename real>
+struct FoldCols {
+    const real* c0;
+    const real* l0;
+    const real* a0;
+    const int* off;
+    const real* wf;
+    const real* gam;
+    const real* eta;
+    real* grad;
+    int T;
+};
+
+// natural-log units: below these the floor is visible at the working precision
+template <typename real> __device__ __forceinline__ constexpr real fold_floor() {
+    // log(e^q + 1e-100) - q = log1p(e^(-230.26 - q)) reaches half an ulp of q at q = -219 (float)
+    // and q = -198 (double)
+    return sizeof(real) == 4 ? real(-216.0) : real(-195.0);
+}
+
+// accumulators of the uncommon path; they live in local memory and are touched only there
+template <int K>
+struct FoldSlowAcc {
+    double acc[K + 1];
+    double rg[2 * K];
+};
+
+// The uncommon tile: a run ends inside it, or a record may touch the floor.  Processes the four
+// records of this thread one by one from global memory; kept out of line (and its state passed
+// through memory) so that the streaming loop keeps everything in registers.
+template <typename real, int K, bool WEIGHTED, bool USE_CACHE>
+__device__ __noinline__ void fold_slow_tile(const FoldCols<real>* c, long long r, FoldState<real>* st,
+                                            FoldShared<real, K>* sh, FoldSlowAcc<K>* sa, bool first) {
+    if (first) {
+        for (int i = 0; i <= K; ++i) sa->acc[i] = 0.0;
+        for (int i = 0; i < 2 * K; ++i) sa->rg[i] = 0.0;
+    }
+#pragma unroll 1
+    for (int j = 0; j < kQuad; ++j) {
+        const int key = c->off[r + j];
+        if (key != st->run_key) {
+            // a run ending mid-chunk ends for every thread of the block within two tiles: these
+            // closes go straight to global REDs (pipelined in L2) -- through the shared cache they
+            // would be ~1500 same-address shared atomics in a row and stall the block for ~50 us
+            if (st->run_key >= 0)
+                fold_close_run<real, K, false>(c->eta, c->grad, st->run_key, st->xbar, st->sg0, st->sg1, st->sg2,
+                                               st->sw0, st->sw1, st->sw2, sh, sa->acc, sa->rg);
+            st->sg0 = st->sg1 = st->sg2 = st->sw0 = st->sw1 = st->sw2 = real(0);
+            const RunStart<real> b = fold_begin_run<real, K>(c->eta, key, sh);
+            st->run_key = key;
+            st->xbar = b.xbar;
+            st->R = b.R;
+        }
+        const real c0 = c->c0[r + j], l0 = c->l0[r + j], a0 = c->a0[r + j];
+        const real wf = WEIGHTED ? c->wf[r + j] : real(1);
+        const real gam = WEIGHTED ? c->gam[r + j] : real(1);
+        const real Bp = l0 + real(2) * a0 * st->xbar;
+        const real Ap = c0 + st->xbar * (l0 + a0 * st->xbar);
+        const real low = Ap - (fabs(Bp) + fabs(a0) * st->R) * st->R;
+        if (low < fold_floor<real>()) {
+            fold_slow_record<real, K>(c->eta + key, sh->quad, c->T, sh->w, (double)c0, (double)l0, (double)a0,
+                                      (double)wf, (double)gam, sa->acc, sa->rg);
+        } else {
+            st->sg0 += gam * Ap; st->sg1 += gam * Bp; st->sg2 += gam * a0;
+            st->sw0 += wf * Ap;  st->sw1 += wf * Bp;  st->sw2 += wf * a0;
+        }
+    }
+}
+
+template <typename real, int K, bool WEIGHTED, bool USE_CACHE>
+__global__ void __launch_bounds__(kFoldThreads, 4)
+unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
+    constexpr int NV = 2 * K;
+
+    __shared__ FoldShared<real, K> sh;
+    __shared__ double s_scratch[(kFoldThreads / 32) * (K + 1)];
+    const int T = g.T;
+    for (int i = threadIdx.x; i < 2 * T; i += blockDim.x) sh.quad[i] = g.quad[i];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) sh.w[i] = g.w[i];
+    for (int i = threadIdx.x; i < kCacheSlots; i += blockDim.x) sh.tag[i] = -1;
+    for (int i = threadIdx.x; i < kCacheSlots * NV; i += blockDim.x) (&sh.val[0][0])[i] = real(0);
+    if (threadIdx.x == 0) {
+        double m0 = 0.0, m2 = 0.0, m4 = 0.0, xm = 0.0;
+        for (int t = 0; t < T; ++t) {
+            const double x = (double)g.quad[t], om = (double)g.quad[T + t];
+            m0 += om; m2 += om * x * x; m4 += om * x * x * x * x;
+            xm = ::fmax(xm, ::fabs(x));
+        }
+        sh.mom[0] = m0; sh.mom[1] = m2; sh.mom[2] = m4; sh.mom[3] = xm;
+    }
+    __syncthreads();
+
+    // 32-bit record indices (n_pad < 2^31 is checked at launch)
+    const unsigned lo = blockIdx.x * (unsigned)L.chunk;
+    const unsigned hi = (long long)lo + L.chunk < g.n_pad ? lo + (unsigned)L.chunk : (unsigned)g.n_pad;
+    const real* __restrict__ col0 = g.fold;
+    const real* __restrict__ col1 = g.fold + g.n_pad;
+    const real* __restrict__ col2 = g.fold + 2 * g.n_pad;
+
+    FoldSlowAcc<K> sa;                   // written by the uncommon path only
+    bool slow_used = false;
+
+    // open the run of this thread's first record, so that the first tile is an ordinary one
+    unsigned r = lo + threadIdx.x * kQuad;
+    int run_key = -1;
+    real xbar = real(0), R = real(0);
+    if (r < hi) {
+        run_key = g.poff[r];
+        const RunStart<real> b = fold_begin_run<real, K>(g.eta, run_key, &sh);
+        xbar = b.xbar;
+        R = b.R;
+    }
+    real sg0 = real(0), sg1 = real(0), sg2 = real(0);
+    real sw0 = real(0), sw1 = real(0), sw2 = real(0);
+
+    // The loads are kept in flight by occupancy (4 blocks x 8 warps per SM, six 512-byte requests
+    // per warp and tile) rather than by a second set of column registers.
+#pragma unroll 1
+    for (; r < hi; r += kFoldTile) {
+        real q_c0[kQuad], q_l0[kQuad], q_a0[kQuad], q_wf[kQuad], q_gam[kQuad];
+        int q_off[kQuad];
+        load_quad<int>(g.poff + r, q_off);
+        load_quad<real>(col0 + r, q_c0);
+        load_quad<real>(col1 + r, q_l0);
+        load_quad<real>(col2 + r, q_a0);
+        if constexpr (WEIGHTED) { load_quad<real>(g.wf + r, q_wf); load_quad<real>(g.gam + r, q_gam); }
+
+        // accumulate speculatively (which also keeps every load ahead of the branch), commit if
+        // the whole quad belongs to the open run and stays clear of the floor
+        bool fast = true;
+        real t0 = sg0, t1 = sg1, t2 = sg2, u0 = sw0, u1 = sw1, u2 = sw2;
+#pragma unroll
+        for (int j = 0; j < kQuad; ++j) {
+            const real a0 = q_a0[j];
+            const real Bp = q_l0[j] + (a0 + a0) * xbar;
+            const real Ap = q_c0[j] + xbar * (q_l0[j] + a0 * xbar);
+            const real low = Ap - (fabs(Bp) + fabs(a0) * R) * R;
+            fast = fast && q_off[j] == run_key && !(low < fold_floor<real>());
+            const real wf = WEIGHTED ? q_wf[j] : real(1);
+            const real gam = WEIGHTED ? q_gam[j] : real(1);
+            t0 += gam * Ap; t1 += gam * Bp; t2 += gam * a0;
+            u0 += wf * Ap;  u1 += wf * Bp;  u2 += wf * a0;
+        }
+        if (fast) {
+            sg0 = t0; sg1 = t1; sg2 = t2; sw0 = u0; sw1 = u1; sw2 = u2;
+        } else {
+            FoldCols<real> cols;
+            cols.c0 = col0; cols.l0 = col1; cols.a0 = col2;
+            cols.off = g.poff; cols.wf = g.wf; cols.gam = g.gam; cols.eta = g.eta; cols.grad = g.grad; cols.T = T;
+            FoldState<real> st;
+            st.run_key = run_key; st.xbar = xbar; st.R = R;
+            st.sg0 = sg0; st.sg1 = sg1; st.sg2 = sg2; st.sw0 = sw0; st.sw1 = sw1; st.sw2 = sw2;
+            fold_slow_tile<real, K, WEIGHTED, USE_CACHE>(&cols, (long long)r, &st, &sh, &sa, !slow_used);
+            slow_used = true;
+            run_key = st.run_key; xbar = st.xbar; R = st.R;
+            sg0 = st.sg0; sg1 = st.sg1; sg2 = st.sg2; sw0 = st.sw0; sw1 = st.sw1; sw2 = st.sw2;
+        }
+    }
+
+    // ---- close the open runs.  The formulas are linear in the sums, so a warp whose lanes all sit
+    // in the same run (and whose expansion point is therefore the same) adds the sums up first
+    // and lets one lane apply them.
+    double acc[K + 1];
+#pragma unroll
+    for (int i = 0; i <= K; ++i) acc[i] = 0.0;
+    {
+        const int lane = threadIdx.x & 31;
+        const int k0 = __shfl_sync(0xffffffffu, run_key, 0);
+        const bool uniform = __all_sync(0xffffffffu, run_key == k0);
+        if (uniform) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sg0 += __shfl_xor_sync(0xffffffffu, sg0, o);
+                sg1 += __shfl_xor_sync(0xffffffffu, sg1, o);
+                sg2 += __shfl_xor_sync(0xffffffffu, sg2, o);
+                sw0 += __shfl_xor_sync(0xffffffffu, sw0, o);
+                sw1 += __shfl_xor_sync(0xffffffffu, sw1, o);
+                sw2 += __shfl_xor_sync(0xffffffffu, sw2, o);
+            }
+            double rgs[NV];
+            const bool any_slow = __any_sync(0xffffffffu, slow_used);
+            if (any_slow) {               // literal-path gradients of this run, summed over the warp
+#pragma unroll
+                for (int i = 0; i < NV; ++i) rgs[i] = warp_sum(slow_used ? sa.rg[i] : 0.0);
+            }
+            if (lane == 0 && run_key >= 0)
+                fold_close_run<real, K, USE_CACHE>(g.eta, g.grad, run_key, xbar, sg0, sg1, sg2, sw0, sw1, sw2, &sh, acc,
+                                                   any_slow ? rgs : nullptr);
+        } else if (run_key >= 0) {
+            fold_close_run<real, K, USE_CACHE>(g.eta, g.grad, run_key, xbar, sg0, sg1, sg2, sw0, sw1, sw2, &sh, acc,
+                                               slow_used ? sa.rg : nullptr);
+        }
+        if (slow_used) {
+#pragma unroll
+            for (int i = 0; i <= K; ++i) acc[i] += sa.acc[i];
+        }
+    }
+
+    publish_partials(acc, K + 1, s_scratch, g.partials);
+
+    if constexpr (USE_CACHE) {
+        for (int slot = threadIdx.x; slot < kCacheSlots; slot += blockDim.x) {
+            const int tag = sh.tag[slot];
+            if (tag >= 0) {
+                real v[NV];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) v[j] = sh.val[slot][j];
+                red_vec<NV>(g.grad + tag, v);
+            }
+        }
+    }
+}
+
+template <typename real, int K>
+static int launch_unary_fold(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStream_t s) {
+    const GroupView<real> v = make_view<real>(m, g, row0);
+    const bool weighted = g->weighted != 0;
+    const bool hub = ((g->hub_mask >> g->nd) & 1) != 0;
+    auto go = [&](auto kernel) {
+        static int resident = 0;
+        if (resident == 0) {
+            int per_sm = 0, sms = 0, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFoldThreads, 0);
+            resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+        }
+        if (v.n_pad >= (1ll << 31)) { set_error("unary_fold_kernel: more than 2^31 records in one group"); return (int)LHVI_ELIMIT; }
+        const long long tiles = v.n_pad / kFoldTile;
+        long long blocks = tiles < resident ? tiles : resident;
+        if (blocks > LHVI_PARTIAL_ROWS - 1) blocks = LHVI_PARTIAL_ROWS - 1;
+        SpecLaunch L;
+        L.chunk = (tiles + blocks - 1) / blocks * kFoldTile;
+        blocks = (v.n_pad + L.chunk - 1) / L.chunk;
+        kernel<<<(unsigned)blocks, kFoldThreads, 0, s>>>(v, L);
+        return check_launch("unary_fold_kernel");
+    };
+    if (weighted) return hub ? go(unary_fold_kernel<real, K, true, true>) : go(unary_fold_kernel<real, K, true, false>);
+    return hub ? go(unary_fold_kernel<real, K, false, true>) : go(unary_fold_kernel<real, K, false, false>);
+}
+
 // ---- dispatch ----------------------------------------------------------------------------------
 
 template <typename real, int K, int T, int NC, int NG, int NE, int FL, bool WEIGHTED, int HUB>
@@ -1066,6 +1462,10 @@ int launch_kt(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStream
     if (g->pure) {
         const int code = g->nc * 10 + g->ne;
         if (g->ng != 0) return 1;
+        // the streaming kernel pays off for long runs of records on one variable (hub groups); a
+        // group of distinct variables closes a run per record and is better served below
+        if (g->fold != nullptr && g->nc == 1 && (((g->hub_mask >> g->nd) & 1) != 0 || m->T != T))
+            return launch_unary_fold<real, K>(m, g, row0, s);
         switch (code) {
             case 10: { const int rc = launch_pure_unary<real, K, T, 0>(m, g, row0, s); if (rc <= 0) return rc; break; }
             case 11: { const int rc = launch_pure_unary<real, K, T, 1>(m, g, row0, s); if (rc <= 0) return rc; break; }

@@ -30,7 +30,7 @@ import torch
 
 from . import _cabi
 from .dist import PeerExchange, ShardPlan
-from .lowering import LoweredModel
+from .lowering import LoweredModel, fold_unary
 
 
 def hermgauss_scaled(T):
@@ -140,6 +140,9 @@ class DeviceEngine:
         self.wstate[K:2 * K] = 1.0 / K
         self.step = z(4, torch.float64)
 
+        # the streaming unary kernel uses only the even moments of the quadrature rule
+        self.symmetric_rule = bool(abs(np.dot(qw, qx)) < 1e-13 and abs(np.dot(qw, qx ** 3)) < 1e-13)
+
         self.groups = []      # (descriptor struct, tensors kept alive, RecordGroup)
         for g in self.model.groups:
             keep = {}
@@ -151,19 +154,31 @@ class DeviceEngine:
             d.hub_mask = hub_mask(g)
             d.pure = int(g.pure)
 
-            def put(name, arr, dt):
+            fold = fold_unary(g, m.ptab) if (self.symmetric_rule and g.n > 0) else None
+            tile = _cabi.LHVI_FOLD_TILE
+            n_pad = (g.n + tile - 1) // tile * tile if fold is not None else g.n
+
+            def put(name, arr, dt, pad=None):
                 if arr.size == 0:
                     return None
+                if pad is not None and n_pad > g.n:          # single-column arrays of a folded group
+                    arr = np.concatenate([arr.reshape(-1), np.full(n_pad - g.n, pad, dtype=arr.dtype)])
                 keep[name] = self._dev(arr, dt)
                 return keep[name].data_ptr()
+            padded = fold is not None
             d.pot = None if g.node else put("pot", g.pot, torch.int32)
-            d.poff = put("poff", g.poff, torch.int32)
+            d.poff = put("poff", g.poff, torch.int32, pad=g.poff[0, -1] if padded else None)
             d.egval = put("egval", g.egval, self.tdtype)
             d.egvar = put("egvar", g.egvar, self.tdtype)
             d.ecval = put("ecval", g.ecval, self.tdtype)
-            d.wf = put("wf", g.wf, self.tdtype) if g.weighted else None
-            d.gam = put("gam", g.gam, self.tdtype) if g.weighted else None
+            d.wf = put("wf", g.wf, self.tdtype, pad=0.0 if padded else None) if g.weighted else None
+            d.gam = put("gam", g.gam, self.tdtype, pad=0.0 if padded else None) if g.weighted else None
             d.nscale = put("nscale", g.nscale, self.tdtype) if g.node else None
+            d.fold, d.n_pad = None, 0
+            if padded:
+                cols = np.zeros((3, n_pad))
+                cols[:, :g.n] = fold
+                d.fold, d.n_pad = put("fold", cols, self.tdtype), n_pad
             self.groups.append((d, keep, g))
 
         rows = max(1, len(self.groups)) * _cabi.LHVI_PARTIAL_ROWS
@@ -255,14 +270,14 @@ class DeviceEngine:
         n = len(self.groups)
         if self.profile_group is not None or not self.parallel_groups or n < 2:
             for i in range(n):
-                timed = self.profile_group == i
+                timed = self.profile_group == i or self.profile_group == "all"
                 if timed:
                     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                     ev[0].record(main)
                 self._launch_group(i, main)
                 if timed:
                     ev[1].record(main)
-                    self.dom_events.append(ev)
+                    self.dom_events.append((i, ev[0], ev[1]))
             return n
         while len(self._side_streams) < n - 1:
             self._side_streams.append(torch.cuda.Stream(device=self.device))

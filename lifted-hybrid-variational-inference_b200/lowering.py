@@ -306,6 +306,37 @@ class PotentialTable:
         return np.concatenate(self.chunks) if self.chunks else np.zeros(1)
 
 
+def fold_unary(g: RecordGroup, ptab: np.ndarray):
+    """Streaming form of a pure group with one hidden continuous argument: per record the
+    quadratic ``log psi(x) = c0 + l0 x + a0 x^2`` in that argument with the point evidence
+    substituted (coefficient layout of ``ptab``: c, b[nct], upper-triangular A row-major;
+    canonical argument order [hidden | evidence...]).  Returns ``[3, n]`` float64 or ``None``
+    when the group has another shape."""
+    if g.node or not g.pure or g.nd != 0 or g.nc != 1 or g.ng != 0:
+        return None
+    nct = 1 + g.ne
+    ncoef = ncoef_for(nct)
+    coef = ptab[g.pot.astype(np.int64)[:, None] + np.arange(ncoef)[None, :]]      # [n, ncoef]
+    ev = g.ecval                                                                   # [ne, n]
+    c0 = coef[:, 0].copy()
+    l0 = coef[:, 1].copy()
+    for e in range(g.ne):
+        c0 += coef[:, 2 + e] * ev[e]
+    p = 1 + nct
+    a0 = None
+    for i in range(nct):
+        for j in range(i, nct):
+            a = coef[:, p]
+            p += 1
+            if i == 0 and j == 0:
+                a0 = a.copy()
+            elif i == 0:
+                l0 += a * ev[j - 1]
+            else:
+                c0 += a * ev[i - 1] * ev[j - 1]
+    return np.stack([c0, l0, a0])
+
+
 # ----------------------------------------------------------------------------------------
 # graphs -> record groups
 # ----------------------------------------------------------------------------------------

@@ -54,3 +54,27 @@ def test_shard_partitions_records():
     np.testing.assert_allclose(sum(p[0] for p in parts), full[0], rtol=1e-11, atol=1e-12)
     np.testing.assert_allclose(sum(p[1] for p in parts), full[1], rtol=1e-11)
     np.testing.assert_allclose(sum(p[2] for p in parts), full[2], rtol=1e-11)
+
+
+def test_fold_unary_matches_the_coefficient_blocks():
+    """lowering.fold_unary: c0 + l0 x + a0 x^2 equals the ptab quadratic with the record's point
+    evidence substituted, for every pure one-argument group of the relational model."""
+    syn, low = lhvi_b200.synthetic, lhvi_b200.lowering
+    model = syn.relational_hybrid(40, 3, 2, 3, seed=9, weighted=True)
+    rng = np.random.default_rng(0)
+    seen = 0
+    for g in model.groups:
+        fold = low.fold_unary(g, model.ptab)
+        if g.node or not g.pure or g.nc != 1:
+            assert fold is None
+            continue
+        seen += 1
+        assert fold.shape == (3, g.n)
+        ncoef = low.ncoef_for(1 + g.ne)
+        for r in rng.choice(g.n, size=min(g.n, 25), replace=False):
+            coef = model.ptab[g.pot[r]:g.pot[r] + ncoef]
+            for x in (-2.3, 0.0, 1.7):
+                want = low.eval_quadratic(coef, [x] + [g.ecval[e, r] for e in range(g.ne)])
+                got = fold[0, r] + fold[1, r] * x + fold[2, r] * x * x
+                assert abs(want - got) <= 1e-12 * max(1.0, abs(want))
+    assert seen >= 2
