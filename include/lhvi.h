@@ -5,7 +5,8 @@
  *   - takes raw DEVICE pointers and plain sizes (no framework types),
  *   - is asynchronous on the CUDA stream passed as `stream` (a cudaStream_t cast to void*,
  *     NULL = legacy default stream),
- *   - never allocates, frees or synchronises: the caller owns every buffer,
+ *   - never allocates, frees or synchronises: the caller owns every buffer (the only exception is
+ *     the explicit lhvi_peer_* life cycle of the cross-GPU exchange buffers),
  *   - returns 0 on success or a negative LHVI_E* code; lhvi_last_error() then holds a
  *     human-readable message (thread-local).
  *

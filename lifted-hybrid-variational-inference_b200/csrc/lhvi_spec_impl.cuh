@@ -1253,9 +1253,11 @@ unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
     }
     __syncthreads();
 
-    // 32-bit record indices (n_pad < 2^31 is checked at launch)
-    const unsigned lo = blockIdx.x * (unsigned)L.chunk;
-    const unsigned hi = (long long)lo + L.chunk < g.n_pad ? lo + (unsigned)L.chunk : (unsigned)g.n_pad;
+    // 32-bit record indices (n_pad < 2^31 is checked at launch).  L.chunk holds the number of
+    // tiles: block b takes tiles [tiles b / B, tiles (b + 1) / B), so that block sizes differ by
+    // at most one tile and every SM (4 resident blocks) streams the same number of bytes.
+    const unsigned lo = (unsigned)(L.chunk * blockIdx.x / gridDim.x) * kFoldTile;
+    const unsigned hi = (unsigned)(L.chunk * (blockIdx.x + 1) / gridDim.x) * kFoldTile;
     const real* __restrict__ col0 = g.fold;
     const real* __restrict__ col1 = g.fold + g.n_pad;
     const real* __restrict__ col2 = g.fold + 2 * g.n_pad;
@@ -1393,8 +1395,7 @@ static int launch_unary_fold(const lhvi_model* m, const lhvi_group* g, int64_t r
         long long blocks = tiles < resident ? tiles : resident;
         if (blocks > LHVI_PARTIAL_ROWS - 1) blocks = LHVI_PARTIAL_ROWS - 1;
         SpecLaunch L;
-        L.chunk = (tiles + blocks - 1) / blocks * kFoldTile;
-        blocks = (v.n_pad + L.chunk - 1) / L.chunk;
+        L.chunk = tiles;
         kernel<<<(unsigned)blocks, kFoldThreads, 0, s>>>(v, L);
         return check_launch("unary_fold_kernel");
     };
