@@ -1037,6 +1037,9 @@ static int launch_pure_unary(const lhvi_model* m, const lhvi_group* g, int64_t r
 // The quadrature rule enters through its even moments M0, M2, M4 (the rule is symmetric, the host
 // checks it), so T is a run-time value here.
 
+#ifndef LHVI_FOLD_BLOCKS
+#define LHVI_FOLD_BLOCKS 4
+#endif
 constexpr int kFoldThreads = 256;
 constexpr int kFoldTile = kFoldThreads * kQuad;
 static_assert(kFoldTile == 1024, "lhvi.h documents n_pad as a multiple of 1024");
@@ -1161,14 +1164,12 @@ struct FoldState {
     real sw0, sw1, sw2;      // W_f-weighted sums
 };
 
+// what the uncommon path needs besides the state: the tile's records (already loaded by the
+// caller, handed over through memory) and the model pointers
 template <typename real>
 struct FoldCols {
-    const real* c0;
-    const real* l0;
-    const real* a0;
-    const int* off;
-    const real* wf;
-    const real* gam;
+    real c0[kQuad], l0[kQuad], a0[kQuad], wf[kQuad], gam[kQuad];
+    int off[kQuad];
     const real* eta;
     real* grad;
     int T;
@@ -1192,7 +1193,7 @@ struct FoldSlowAcc {
 // records of this thread one by one from global memory; kept out of line (and its state passed
 // through memory) so that the streaming loop keeps everything in registers.
 template <typename real, int K, bool WEIGHTED, bool USE_CACHE>
-__device__ __noinline__ void fold_slow_tile(const FoldCols<real>* c, long long r, FoldState<real>* st,
+__device__ __noinline__ void fold_slow_tile(const FoldCols<real>* c, FoldState<real>* st,
                                             FoldShared<real, K>* sh, FoldSlowAcc<K>* sa, bool first) {
     if (first) {
         for (int i = 0; i <= K; ++i) sa->acc[i] = 0.0;
@@ -1200,7 +1201,7 @@ __device__ __noinline__ void fold_slow_tile(const FoldCols<real>* c, long long r
     }
 #pragma unroll 1
     for (int j = 0; j < kQuad; ++j) {
-        const int key = c->off[r + j];
+        const int key = c->off[j];
         if (key != st->run_key) {
             // a run ending mid-chunk ends for every thread of the block within two tiles: these
             // closes go straight to global REDs (pipelined in L2) -- through the shared cache they
@@ -1214,9 +1215,9 @@ __device__ __noinline__ void fold_slow_tile(const FoldCols<real>* c, long long r
             st->xbar = b.xbar;
             st->R = b.R;
         }
-        const real c0 = c->c0[r + j], l0 = c->l0[r + j], a0 = c->a0[r + j];
-        const real wf = WEIGHTED ? c->wf[r + j] : real(1);
-        const real gam = WEIGHTED ? c->gam[r + j] : real(1);
+        const real c0 = c->c0[j], l0 = c->l0[j], a0 = c->a0[j];
+        const real wf = WEIGHTED ? c->wf[j] : real(1);
+        const real gam = WEIGHTED ? c->gam[j] : real(1);
         const real Bp = l0 + real(2) * a0 * st->xbar;
         const real Ap = c0 + st->xbar * (l0 + a0 * st->xbar);
         const real low = Ap - (fabs(Bp) + fabs(a0) * st->R) * st->R;
@@ -1231,7 +1232,7 @@ __device__ __noinline__ void fold_slow_tile(const FoldCols<real>* c, long long r
 }
 
 template <typename real, int K, bool WEIGHTED, bool USE_CACHE>
-__global__ void __launch_bounds__(kFoldThreads, 4)
+__global__ void __launch_bounds__(kFoldThreads, LHVI_FOLD_BLOCKS)
 unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
     constexpr int NV = 2 * K;
 
@@ -1310,12 +1311,17 @@ unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
             sg0 = t0; sg1 = t1; sg2 = t2; sw0 = u0; sw1 = u1; sw2 = u2;
         } else {
             FoldCols<real> cols;
-            cols.c0 = col0; cols.l0 = col1; cols.a0 = col2;
-            cols.off = g.poff; cols.wf = g.wf; cols.gam = g.gam; cols.eta = g.eta; cols.grad = g.grad; cols.T = T;
+#pragma unroll
+            for (int j = 0; j < kQuad; ++j) {
+                cols.c0[j] = q_c0[j]; cols.l0[j] = q_l0[j]; cols.a0[j] = q_a0[j]; cols.off[j] = q_off[j];
+                cols.wf[j] = WEIGHTED ? q_wf[j] : real(1);
+                cols.gam[j] = WEIGHTED ? q_gam[j] : real(1);
+            }
+            cols.eta = g.eta; cols.grad = g.grad; cols.T = T;
             FoldState<real> st;
             st.run_key = run_key; st.xbar = xbar; st.R = R;
             st.sg0 = sg0; st.sg1 = sg1; st.sg2 = sg2; st.sw0 = sw0; st.sw1 = sw1; st.sw2 = sw2;
-            fold_slow_tile<real, K, WEIGHTED, USE_CACHE>(&cols, (long long)r, &st, &sh, &sa, !slow_used);
+            fold_slow_tile<real, K, WEIGHTED, USE_CACHE>(&cols, &st, &sh, &sa, !slow_used);
             slow_used = true;
             run_key = st.run_key; xbar = st.xbar; R = st.R;
             sg0 = st.sg0; sg1 = st.sg1; sg2 = st.sg2; sw0 = st.sw0; sw1 = st.sw1; sw2 = st.sw2;
