@@ -29,6 +29,7 @@
  *                             (VarInference.py:256-287), or the plain SGD step (:302-329).
  *   lhvi_mixture_belief       belief(x, rv) for a batch of (variable, x) queries
  *                             (VarInference.py:333-353).
+ *   lhvi_mixture_map          map(rv) for a batch of variables (VarInference.py:355-376).
  *   lhvi_finish               lhvi_elbo_reduce + lhvi_step_tick in one launch, and -- when the
  *                             records are sharded over several GPUs -- the sum over ranks of
  *                             G_w, the free energy and the gradients of the variables that
@@ -216,6 +217,14 @@ int lhvi_param_step(int dtype, int K, int64_t n_vars, const uint8_t* var_kind,
 int lhvi_mixture_belief(int dtype, int K, int64_t n, const int32_t* q_off, const int32_t* q_dim,
                         const uint8_t* q_kind, const void* x, const void* eta, const void* w,
                         void* out, void* stream);
+
+/*
+ * MAP of n variables' marginal beliefs (VarInference.py:355-376): for a continuous variable the
+ * arg-max of sum_k w_k q_k(x) reached from the best component mean by safeguarded Newton ascent
+ * (the reference uses scipy BFGS from the same start); for a discrete one the arg-max state index.
+ */
+int lhvi_mixture_map(int dtype, int K, int64_t n, const int32_t* q_off, const int32_t* q_dim,
+                     const uint8_t* q_kind, const void* eta, const void* w, void* out, void* stream);
 
 #ifdef __cplusplus
 }

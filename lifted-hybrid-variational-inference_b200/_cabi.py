@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblhvi.so"
 
 SYMBOLS = ("lhvi_last_error", "lhvi_abi_version", "lhvi_has_specialisation",
            "lhvi_factor_expect_grad", "lhvi_elbo_reduce", "lhvi_step_tick",
-           "lhvi_param_step", "lhvi_mixture_belief", "lhvi_finish",
+           "lhvi_param_step", "lhvi_mixture_belief", "lhvi_mixture_map", "lhvi_finish",
            "lhvi_peer_alloc", "lhvi_peer_open", "lhvi_peer_close", "lhvi_peer_free")
 
 
@@ -102,6 +102,9 @@ def load(build_if_missing: bool = False):
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
                                     C.c_double, C.c_int, C.c_int, C.c_void_p]
+    lib.lhvi_mixture_map.restype = C.c_int
+    lib.lhvi_mixture_map.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lhvi_finish.restype = C.c_int
     lib.lhvi_finish.argtypes = [C.POINTER(LhviModel), C.c_int64, C.c_void_p, C.c_double, C.c_double,
                                 C.POINTER(LhviExchange), C.c_void_p]

@@ -95,6 +95,7 @@ class VIBase:
         self._model = None
         self._pushed = None
         self._grad_cache = None
+        self._map_cache = None
 
     # hooks the three engines specialise
     def _handles(self):
@@ -341,16 +342,24 @@ class VIBase:
             raise ValueError(f"{x!r} is not in the variable's domain")
         return float(self.beliefs([x], [rv])[0])
 
+    def map_all(self):
+        """MAP of every hidden variable in one device launch: ``{handle: value}`` (discrete
+        values are domain values).  ``map(rv)`` serves itself from this table, so the usual
+        ``for rv in g.rvs: infer.map(rv)`` loop of the reference's demos costs one launch."""
+        self._push()
+        if self._map_cache is not None and self._map_cache[0] == self._pushed:
+            return self._map_cache[1]
+        m = self._model
+        res = self._engine.mixture_map().double().cpu().numpy()
+        table = {}
+        for h, i in m.index.items():
+            table[h] = float(res[i]) if m.var_kind[i] == 0 else h.domain.values[int(res[i])]
+        self._map_cache = (self._pushed, table)
+        return table
+
     def map(self, rv):
         """MAP value of one variable's marginal belief (VarInference.py:355-376)."""
         h = self._handle_of(rv)
         if h.value is not None:
             return rv.value
-        eta = self.eta[h]
-        if h.domain.continuous:
-            cand = eta[:, 0]
-            dens = [(self.w * norm_pdf(x, eta[:, 0], eta[:, 1])).sum() for x in cand]
-            x0 = cand[int(np.argmax(dens))]
-            return float(mixture_mode(self.w, eta[None, :, 0], eta[None, :, 1], np.array([x0]))[0])
-        p = (self.w[:, None] * eta).sum(axis=0)
-        return h.domain.values[int(np.argmax(p))]
+        return self.map_all()[h]

@@ -318,6 +318,68 @@ mixture_belief_kernel(int K, long long n, const int* __restrict__ q_off, const i
     }
 }
 
+// ---- batched MAP queries ----------------------------------------------------------------------
+// Continuous variable: start at the component mean with the largest belief, then safeguarded
+// Newton ascent on the one-dimensional mixture (the reference starts at the same point and calls
+// scipy's BFGS, VarInference.py:355-376).  Discrete variable: arg-max state of the mixture marginal.
+// Always evaluated in double: the cost is negligible next to one iteration.
+
+template <typename real>
+__device__ double mixture_density(const real* __restrict__ p, const real* __restrict__ w, int K, double x) {
+    double b = 0.0;
+    for (int k = 0; k < K; ++k) b += (double)w[k] * norm_pdf_d(x, (double)p[2 * k], (double)p[2 * k + 1]);
+    return b;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(128)
+mixture_map_kernel(int K, long long n, const int* __restrict__ q_off, const int* __restrict__ q_dim,
+                   const uint8_t* __restrict__ q_kind, const real* __restrict__ eta, const real* __restrict__ w,
+                   real* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const real* p = eta + q_off[i];
+        if (q_kind[i] != 0) {
+            const int D = q_dim[i];
+            int best = 0;
+            double best_v = -1.0;
+            for (int d = 0; d < D; ++d) {
+                double v = 0.0;
+                for (int k = 0; k < K; ++k) v += (double)w[k] * (double)p[k * D + d];
+                if (v > best_v) { best_v = v; best = d; }
+            }
+            out[i] = (real)best;
+            continue;
+        }
+        double x = (double)p[0], fx = mixture_density<real>(p, w, K, x);
+        for (int k = 1; k < K; ++k) {
+            const double v = mixture_density<real>(p, w, K, (double)p[2 * k]);
+            if (v > fx) { fx = v; x = (double)p[2 * k]; }
+        }
+        for (int it = 0; it < 60; ++it) {
+            double g1 = 0.0, g2 = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const double mu = (double)p[2 * k], var = (double)p[2 * k + 1];
+                const double d = x - mu, pk = (double)w[k] * norm_pdf_d(x, mu, var);
+                g1 -= pk * d / var;
+                g2 += pk * (d * d / (var * var) - 1.0 / var);
+            }
+            double step = g2 < 0.0 ? -g1 / g2 : (g1 > 0.0 ? 0.1 : (g1 < 0.0 ? -0.1 : 0.0));
+            double fc = fx;
+            for (int bt = 0; bt < 30; ++bt) {                 // never accept a lower density
+                fc = mixture_density<real>(p, w, K, x + step);
+                if (!(fc < fx)) break;
+                step *= 0.5;
+            }
+            if (fc < fx) break;
+            x += step;
+            fx = fc;
+            if (fabs(step) < 1e-13) break;
+        }
+        out[i] = (real)x;
+    }
+}
+
 static unsigned grid_for(long long n, int threads) {
     long long b = (n + threads - 1) / threads;
     if (b < 1) b = 1;
@@ -479,4 +541,17 @@ extern "C" int lhvi_mixture_belief(int dtype, int K, int64_t n, const int32_t* q
     else
         mixture_belief_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(K, n, q_off, q_dim, q_kind, (const float*)x, (const float*)eta, (const float*)w, (float*)out);
     return check_launch("mixture_belief_kernel");
+}
+
+extern "C" int lhvi_mixture_map(int dtype, int K, int64_t n, const int32_t* q_off, const int32_t* q_dim,
+                                const uint8_t* q_kind, const void* eta, const void* w, void* out, void* stream) {
+    if (n == 0) return LHVI_OK;
+    if (!q_off || !q_dim || !q_kind || !eta || !w || !out) { set_error("lhvi_mixture_map: null buffer"); return LHVI_EINVAL; }
+    if (K < 1 || K > LHVI_MAX_K) { set_error("K=%d out of range 1..%d", K, LHVI_MAX_K); return LHVI_ELIMIT; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == LHVI_F64)
+        mixture_map_kernel<double><<<grid_for(n, 128), 128, 0, s>>>(K, n, q_off, q_dim, q_kind, (const double*)eta, (const double*)w, (double*)out);
+    else
+        mixture_map_kernel<float><<<grid_for(n, 128), 128, 0, s>>>(K, n, q_off, q_dim, q_kind, (const float*)eta, (const float*)w, (float*)out);
+    return check_launch("mixture_map_kernel");
 }

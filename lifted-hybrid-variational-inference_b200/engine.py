@@ -403,3 +403,23 @@ class DeviceEngine:
             self.dcode, self.K, n, off.data_ptr(), dim.data_ptr(), kind.data_ptr(), xs.data_ptr(),
             self.eta.data_ptr(), self.w.data_ptr(), out.data_ptr(), self._stream()), self.lib)
         return out
+
+    def mixture_map(self, q_off=None, q_dim=None, q_kind=None):
+        """Batched ``map`` (VarInference.py:355-376) of the given slots (default: every hidden
+        variable of the model, in slot-table order): continuous -> MAP position, discrete ->
+        arg-max state index.  With sharded records the state is merged first."""
+        m = self.full_model
+        if q_off is None:
+            q_off, q_dim, q_kind = m.var_off, m.var_dim, m.var_kind
+        n = len(q_off)
+        out = torch.empty(n, dtype=self.tdtype, device=self.device)
+        if n == 0:
+            return out
+        off = self._dev(np.asarray(q_off, dtype=np.int32))
+        dim = self._dev(np.asarray(q_dim, dtype=np.int32))
+        kind = self._dev(np.asarray(q_kind, dtype=np.uint8))
+        eta = self.plan.merge(self.eta)
+        _cabi.check(self.lib.lhvi_mixture_map(
+            self.dcode, self.K, n, off.data_ptr(), dim.data_ptr(), kind.data_ptr(),
+            eta.data_ptr(), self.w.data_ptr(), out.data_ptr(), self._stream()), self.lib)
+        return out

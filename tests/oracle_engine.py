@@ -69,6 +69,24 @@ class OracleEngine:
         return torch.as_tensor(out)
 
 
+    def mixture_map(self, q_off=None, q_dim=None, q_kind=None):
+        from lhvi_b200._vi_base import mixture_mode
+        m, K = self.model, self.K
+        if q_off is None:
+            q_off, q_dim, q_kind = m.var_off, m.var_dim, m.var_kind
+        out = np.zeros(len(q_off))
+        for i, (o, d, kd) in enumerate(zip(q_off, q_dim, q_kind)):
+            if kd == 0:
+                p = self.vi.eta[o:o + 2 * K].reshape(K, 2)
+                dens = [(self.vi.w * norm_pdf_ref(x, p[:, 0], p[:, 1])).sum() for x in p[:, 0]]
+                x0 = p[int(np.argmax(dens)), 0]
+                out[i] = mixture_mode(self.vi.w, p[None, :, 0], p[None, :, 1], np.array([x0]))[0]
+            else:
+                p = self.vi.eta[o:o + K * d].reshape(K, d)
+                out[i] = int(np.argmax((self.vi.w[:, None] * p).sum(axis=0)))
+        return torch.as_tensor(out)
+
+
 def use_oracle_engine(vi):
     vi._make_engine = lambda model: OracleEngine(model, var_threshold=vi.var_threshold)
     vi._sync = lambda: None

@@ -150,6 +150,35 @@ def test_belief_queries(ns):
                 assert np.isclose(vi.belief(x, rv), vi.rvs_belief((x,), (rv,)), rtol=1e-12)
 
 
+def test_batched_map_finds_the_mixture_modes(ns):
+    """lhvi_mixture_map against a dense scan + scipy refinement of every variable's mixture
+    (the reference calls scipy.optimize.minimize per variable, VarInference.py:355-376)."""
+    from scipy.optimize import minimize_scalar
+    g, rvs = specs.hmln_hidden(ns)
+    vi = lhvi_b200.VarInference.VarInference(g, 3, 3)
+    np.random.seed(8)
+    with contextlib.redirect_stdout(io.StringIO()):
+        vi.run(4, lr=0.3, is_log=False)
+    table = vi.map_all()
+    assert set(table) == {rv for rv in rvs if rv.value is None}
+    for rv in rvs:
+        if rv.value is not None:
+            assert vi.map(rv) == rv.value
+            continue
+        if not rv.domain.continuous:
+            marg = [vi.belief(x, rv) for x in rv.domain.values]
+            assert vi.map(rv) == rv.domain.values[int(np.argmax(marg))]
+            continue
+        eta = vi.eta[rv]
+        f = lambda x: -float(vi.rvs_belief((x,), (rv,)))
+        # the reference's answer: local optimum reached from the best component mean
+        x0 = eta[int(np.argmax([-f(m) for m in eta[:, 0]])), 0]
+        res = minimize_scalar(f, bracket=(x0 - 1e-3, x0 + 1e-3), tol=1e-12)
+        got = vi.map(rv)
+        assert -f(got) >= -f(x0) - 1e-15
+        assert abs(got - res.x) < 1e-5 or abs(f(got) - res.fun) < 1e-12
+
+
 @pytest.mark.parametrize("dtype,tol", [("float64", 1e-9), ("float32", 5e-5)])
 def test_generated_models_against_oracle(dtype, tol):
     syn = lhvi_b200.synthetic
