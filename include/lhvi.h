@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define LHVI_ABI_VERSION 2
+#define LHVI_ABI_VERSION 3
 
 /* element type of every `void*` buffer of reals */
 #define LHVI_F32 0
@@ -72,6 +72,7 @@ extern "C" {
 #define LHVI_MAX_NODES 64    /* sum over axes of quadrature nodes / states */
 #define LHVI_MAX_GACC 256    /* sum over hidden arguments of K * (2 | D) */
 #define LHVI_PARTIAL_ROWS 1184   /* rows of `partials` reserved per launch: 1 header + 1183 data */
+#define LHVI_RUN_MAX_HUBS 16 /* distinct hub variables of a run-major group (lhvi_group::run_*) */
 #define LHVI_MAX_PEERS 16    /* GPUs of one NVLink domain taking part in lhvi_finish's exchange */
 #define LHVI_IPC_HANDLE_BYTES 64
 
@@ -109,12 +110,29 @@ typedef struct lhvi_group {
        coefficients and weights and the last record's offset.  NULL: not provided. */
     const void* fold;
     int64_t n_pad;
+    /* Optional run-major form of a full group with two hidden continuous arguments (nd=0, nc=2,
+       ng=0, node=0, pure=0) of which argument `run_hub_arg` (0 or 1) takes at most
+       LHVI_RUN_MAX_HUBS distinct values: the records (every column above) are sorted by the
+       *other* hidden argument, run i = records run_start[i] .. run_start[i+1]-1 all have that
+       argument at parameter offset run_key[i]; run_hid[r] indexes hub_keys (the distinct offsets
+       of the hub argument).  A long run may be split into several runs with the same key.
+       run_start == NULL: not provided. */
+    const int32_t* run_start;      /* [n_runs + 1] */
+    const int32_t* run_key;        /* [n_runs] */
+    const int32_t* run_hid;        /* [n] */
+    const int32_t* hub_keys;       /* [n_hubs] */
+    int64_t n_runs;
+    int32_t n_hubs;
+    int32_t run_hub_arg;
 } lhvi_group;
 
 /* Model-wide device buffers shared by every group launch. */
 typedef struct lhvi_model {
     int32_t dtype;                 /* LHVI_F32 | LHVI_F64 */
     int32_t K, T;                  /* mixture components, quadrature points */
+    int32_t rule_symmetric;        /* 1: quad is exactly mirror-symmetric (x_t = -x_{T-1-t}, equal weights,
+                                      x = 0 in the middle of an odd rule), as numpy's hermgauss returns it;
+                                      the specialised kernels require it (0: generic kernel) */
     int64_t n_param;               /* elements of eta / grad parameter part */
     const void* quad;              /* [2T]  Gauss-Hermite nodes, then weights / sqrt(pi) */
     const void* ptab;              /* coefficient table */

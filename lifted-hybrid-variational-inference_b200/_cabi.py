@@ -15,8 +15,9 @@ LHVI_MAX_T = 32
 LHVI_PARTIAL_ROWS = 1184
 LHVI_FOLD_TILE = 1024
 LHVI_MAX_PEERS = 16
+LHVI_RUN_MAX_HUBS = 16
 LHVI_IPC_HANDLE_BYTES = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblhvi.so")
 
@@ -36,12 +37,14 @@ class LhviGroup(C.Structure):
         ("egval", C.c_void_p), ("egvar", C.c_void_p), ("ecval", C.c_void_p),
         ("wf", C.c_void_p), ("gam", C.c_void_p), ("nscale", C.c_void_p),
         ("fold", C.c_void_p), ("n_pad", C.c_int64),
+        ("run_start", C.c_void_p), ("run_key", C.c_void_p), ("run_hid", C.c_void_p), ("hub_keys", C.c_void_p),
+        ("n_runs", C.c_int64), ("n_hubs", C.c_int32), ("run_hub_arg", C.c_int32),
     ]
 
 
 class LhviModel(C.Structure):
     _fields_ = [
-        ("dtype", C.c_int32), ("K", C.c_int32), ("T", C.c_int32),
+        ("dtype", C.c_int32), ("K", C.c_int32), ("T", C.c_int32), ("rule_symmetric", C.c_int32),
         ("n_param", C.c_int64),
         ("quad", C.c_void_p), ("ptab", C.c_void_p), ("eta", C.c_void_p), ("w", C.c_void_p),
         ("grad", C.c_void_p), ("partials", C.c_void_p),

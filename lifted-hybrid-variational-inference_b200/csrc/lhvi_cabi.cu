@@ -49,6 +49,11 @@ static int validate(const lhvi_model* m, const lhvi_group* g, int64_t row0) {
         if (g->node || !g->pure || g->nd != 0 || g->nc != 1 || g->ng != 0) { set_error("fold columns are only defined for pure groups with one hidden continuous argument"); return LHVI_EINVAL; }
         if (g->n_pad < g->n || g->n_pad % 1024 != 0) { set_error("fold columns: n_pad=%lld must be a multiple of 1024 and >= n=%lld", (long long)g->n_pad, (long long)g->n); return LHVI_EINVAL; }
     }
+    if (g->run_start) {
+        if (g->node || g->pure || g->nd != 0 || g->nc != 2 || g->ng != 0) { set_error("run-major columns are only defined for full groups with two hidden continuous arguments"); return LHVI_EINVAL; }
+        if (!g->run_key || !g->run_hid || !g->hub_keys) { set_error("run-major group without run_key/run_hid/hub_keys"); return LHVI_EINVAL; }
+        if (g->n_runs < 1 || g->n_hubs < 1 || g->run_hub_arg < 0 || g->run_hub_arg > 1) { set_error("run-major group: n_runs=%lld n_hubs=%d run_hub_arg=%d", (long long)g->n_runs, g->n_hubs, g->run_hub_arg); return LHVI_EINVAL; }
+    }
     return LHVI_OK;
 }
 

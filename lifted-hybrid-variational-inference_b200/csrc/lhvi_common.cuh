@@ -127,6 +127,11 @@ struct GroupView {
     const real* nscale;
     const real* fold;
     long long n_pad;
+    const int* run_start;
+    const int* run_key;
+    const int* run_hid;
+    const int* hub_keys;
+    long long n_runs;
     // model
     int K, T;
     const real* quad;
@@ -149,6 +154,8 @@ inline GroupView<real> make_view(const lhvi_model* m, const lhvi_group* g, int64
     v.ecval = (const real*)g->ecval; v.wf = (const real*)g->wf;
     v.gam = (const real*)g->gam; v.nscale = (const real*)g->nscale;
     v.fold = (const real*)g->fold; v.n_pad = g->n_pad;
+    v.run_start = g->run_start; v.run_key = g->run_key; v.run_hid = g->run_hid;
+    v.hub_keys = g->hub_keys; v.n_runs = g->n_runs;
     v.K = m->K; v.T = m->T;
     v.quad = (const real*)m->quad; v.ptab = (const real*)m->ptab;
     v.eta = (const real*)m->eta; v.w = (const real*)m->w;

@@ -1,0 +1,369 @@
+// Run-major kernel for full records with two hidden continuous arguments of which one takes only
+// a few distinct values in the group (the "hub" argument: the group-level variables of a
+// relational model).  Included by lhvi_spec_impl.cuh.
+//
+// Layout (lhvi_group::run_*): the records are sorted by their *other* hidden argument (the run
+// argument), so that all records of one run variable are contiguous; run_start / run_key give the
+// runs, run_hid the record's hub as an index into hub_keys.  One thread owns one run at a time:
+//   - the run variable's axis tables (nodes, cross densities, normalisers: 6 of the 9 exponentials
+//     per component pair) are built once per run and kept in registers,
+//   - the axis tables of *every* hub of the group sit in shared memory, built once per block,
+//   - the run variable's gradient is summed in registers and leaves with one vector RED per run,
+//   - hub gradients are summed in thread-private shared-memory slots ([hub][value][thread]: no
+//     conflicts, no atomics, no shuffles) and reduced once per block.
+// What remains per record and component is the 3 x 3 grid of log-beliefs (Walk) and the closed-form
+// moments of the quadratic log-potential -- about half of the instructions of the record-major
+// kernel.  Floors are handled as there: optimistic walk, literal redo when a bound trips.
+#pragma once
+
+namespace lhvi {
+
+constexpr int kRunMaxHubs = LHVI_RUN_MAX_HUBS;
+
+struct RunLaunch {
+    int n_hubs;
+};
+
+template <typename real, int K, int T, int NE, bool WEIGHTED, int HUBPOS>
+__global__ void __launch_bounds__(kSpecThreads, 2)
+factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
+    using F = Fast<real>;
+    constexpr int NC = 2, NG = 0, NCT = 2 + NE, NV = 2 * K;
+    using C = Ctx<real, K, T, NC, NG, NE>;
+    constexpr int NQ = C::NQ;
+    constexpr int TP = (T + 3) / 4 * 4;
+    constexpr int RA = 1 - HUBPOS;                  // canonical position of the run argument
+    static_assert(K <= 4, "hub normalisers are stored four to a row");
+
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    real* s_acc = reinterpret_cast<real*>(s_dyn);   // [n_hubs][NV][kSpecThreads] thread-private sums
+
+    __shared__ real s_quad[2 * T];
+    __shared__ real s_eq[T];
+    __shared__ real s_w[K];
+    __shared__ real s_mom[5];
+    __shared__ __align__(16) real s_hq[kRunMaxHubs][K][K][TP];   // q_{k2}(x_{k,t}) of every hub
+    __shared__ __align__(16) real s_hnrm[kRunMaxHubs][4];        // 1 / (sqrt(2 pi) var_k2)
+    __shared__ __align__(16) real s_hms[kRunMaxHubs][K][2];      // mu_k, sqrt(2 var_k)
+    __shared__ real s_hinv[kRunMaxHubs][K];                      // 1 / var_k
+    __shared__ int s_hkey[kRunMaxHubs];
+    __shared__ double s_scratch[(kSpecThreads / 32) * (K + 1)];
+
+    const int tid = threadIdx.x;
+    const int H = L.n_hubs;
+    for (int i = tid; i < 2 * T; i += blockDim.x) s_quad[i] = g.quad[i];
+    for (int i = tid; i < T; i += blockDim.x) s_eq[i] = (real)::exp(-(double)g.quad[i] * (double)g.quad[i]);
+    for (int i = tid; i < K; i += blockDim.x) s_w[i] = g.w[i];
+    for (int i = tid; i < H; i += blockDim.x) s_hkey[i] = g.hub_keys[i];
+    for (int i = tid; i < H * NV * kSpecThreads; i += blockDim.x) s_acc[i] = real(0);
+    if (tid == 0) {
+        real M0 = real(0), M2 = real(0), M4 = real(0), xm = real(0);
+        for (int t = 0; t < T; ++t) {
+            const real x = g.quad[t], om = g.quad[T + t];
+            M0 += om;
+            M2 += om * x * x;
+            M4 += om * x * x * x * x;
+            xm = fabs(x) > xm ? fabs(x) : xm;
+        }
+        s_mom[0] = M0 * M0;            // sum W            (two axes)
+        s_mom[1] = M0 * M2;            // sum W xi_a^2
+        s_mom[2] = M0 * M4;            // sum W xi_a^4
+        s_mom[3] = M2 * M2;            // sum W xi_a^2 xi_b^2
+        s_mom[4] = xm;
+    }
+    __syncthreads();
+    // axis tables of every hub
+    for (int idx = tid; idx < H * K * K * T; idx += blockDim.x) {
+        const int h = idx / (K * K * T), k = (idx / (K * T)) % K, k2 = (idx / T) % K, t = idx % T;
+        const int key = s_hkey[h];
+        real q = s_eq[t];
+        if (k2 != k) {
+            const real mu_k = g.eta[key + 2 * k], var_k = g.eta[key + 2 * k + 1];
+            const real mu_2 = g.eta[key + 2 * k2], var_2 = g.eta[key + 2 * k2 + 1];
+            const real u = F::sqrt(real(2) * var_k) * s_quad[t] + (mu_k - mu_2);
+            q = F::exp_scaled(real(-0.5) * F::kExpScale * F::rcp(var_2) * (u * u));
+        }
+        s_hq[h][k][k2][t] = q;
+    }
+    for (int idx = tid; idx < H * K; idx += blockDim.x) {
+        const int h = idx / K, k = idx % K;
+        const int key = s_hkey[h];
+        const real mu_k = g.eta[key + 2 * k], var_k = g.eta[key + 2 * k + 1];
+        const real inv = F::rcp(var_k);
+        s_hnrm[h][k] = inv * real(1.0 / kSqrt2Pi);
+        s_hms[h][k][0] = mu_k;
+        s_hms[h][k][1] = F::sqrt(real(2) * var_k);
+        s_hinv[h][k] = inv;
+    }
+    __syncthreads();
+
+    C c;
+    real eq[T], xi[T], wk[K];
+    real eq_min = real(1);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        xi[t] = s_quad[t];
+        c.w0[t] = s_quad[T + t];
+        c.w1[t] = c.w0[t] * xi[t];
+        c.w2[t] = c.w1[t] * xi[t];
+        eq[t] = s_eq[t];
+        eq_min = eq[t] < eq_min ? eq[t] : eq_min;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) wk[k] = s_w[k];
+    c.eta = g.eta;
+    c.s_w = s_w;
+    const volatile real* v_mom = s_mom;
+
+    double acc[K + 1];
+#pragma unroll
+    for (int i = 0; i <= K; ++i) acc[i] = 0.0;
+
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long run = (long long)blockIdx.x * blockDim.x + tid; run < g.n_runs; run += stride) {
+        const int keyE = __ldg(g.run_key + run);
+        const int r0 = __ldg(g.run_start + run), r1 = __ldg(g.run_start + run + 1);
+        {   // warm L1 with the next run's first records and slot
+            const long long nxt = run + stride;
+            if (nxt < g.n_runs) {
+                const int rn = __ldg(g.run_start + nxt);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(g.pot + rn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(g.run_hid + rn));
+                if constexpr (WEIGHTED) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.wf + rn));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.gam + rn));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.gam + g.n + rn));
+                }
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(g.eta + __ldg(g.run_key + nxt)));
+            }
+        }
+
+        // ---- the run variable: parameters and axis tables, once per run
+        real muE[K], sdE[K], invE[K], nrmE[K], hvE[K];
+        {
+            real slot[NV];
+            load_vec<NV>(g.eta + keyE, slot);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                muE[k] = slot[2 * k];
+                invE[k] = F::rcp(slot[2 * k + 1]);
+                hvE[k] = real(-0.5) * F::kExpScale * invE[k];
+                nrmE[k] = invE[k] * real(1.0 / kSqrt2Pi);
+                sdE[k] = F::sqrt(real(2) * slot[2 * k + 1]);
+            }
+        }
+        real qE[K][K][T];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const real dx = sdE[k] * xi[t];
+#pragma unroll
+                for (int k2 = 0; k2 < K; ++k2) {
+                    if (k2 == k) {
+                        qE[k][k2][t] = eq[t];
+                    } else {
+                        const real u = dx + (muE[k] - muE[k2]);
+                        qE[k][k2][t] = F::exp_scaled(hvE[k2] * (u * u));
+                    }
+                }
+            }
+        real G1[K], G2[K], af[K + 1];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { G1[k] = real(0); G2[k] = real(0); }
+#pragma unroll
+        for (int i = 0; i <= K; ++i) af[i] = real(0);
+        c.pt.poff[0] = keyE;
+
+        // ---- its records
+#pragma unroll 1
+        for (int r = r0; r < r1; ++r) {
+            const int pot = __ldg(g.pot + r);
+            const int h = __ldg(g.run_hid + r);
+            real wf = real(1), gamE = real(1), gamH = real(1);
+            if constexpr (WEIGHTED) {
+                wf = __ldg(g.wf + r);
+                gamE = __ldg(g.gam + (long long)RA * g.n + r);
+                gamH = __ldg(g.gam + (long long)HUBPOS * g.n + r);
+            }
+            // quadratic log-potential reduced by the point evidence, then renumbered to walk order
+            // (axis 0 = run argument, axis 1 = hub argument)
+            real cst0, lin0[NQ];
+            {
+                const real* cf = g.ptab + pot;
+                constexpr real to_unit = real(1) / F::kUnit;
+                real lc[NCT], Ac[NCT][NCT];
+                cst0 = __ldg(cf) * to_unit;
+#pragma unroll
+                for (int i = 0; i < NCT; ++i) lc[i] = __ldg(cf + 1 + i) * to_unit;
+                int p = 1 + NCT;
+#pragma unroll
+                for (int i = 0; i < NCT; ++i)
+#pragma unroll
+                    for (int j = i; j < NCT; ++j) Ac[i][j] = __ldg(cf + p++) * to_unit;
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const int j = 2 + e;
+                    const real xv = __ldg(g.ecval + (long long)e * g.n + r);
+                    cst0 += xv * (lc[j] + Ac[j][j] * xv);
+#pragma unroll
+                    for (int i = 0; i < j; ++i) lc[i] += Ac[i][j] * xv;
+#pragma unroll
+                    for (int i = j + 1; i < NCT; ++i) lc[i] += Ac[j][i] * xv;
+                }
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) lin0[j] = real(0);
+                lin0[0] = lc[RA];
+                lin0[1] = lc[HUBPOS];
+#pragma unroll
+                for (int i = 0; i < NQ; ++i)
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j) c.A[i][j] = real(0);
+                c.A[0][0] = Ac[RA][RA];
+                c.A[1][1] = Ac[HUBPOS][HUBPOS];
+                c.A[0][1] = Ac[0][1];
+            }
+
+            real pk0[K];
+#pragma unroll
+            for (int k2 = 0; k2 < K; ++k2) pk0[k2] = wk[k2] * nrmE[k2] * s_hnrm[h][k2];
+
+            real e_sum = real(0);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+#pragma unroll
+                for (int k2 = 0; k2 < K; ++k2)
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        c.q[0][k2][t] = qE[k][k2][t];
+                        c.q[1][k2][t] = s_hq[h][k][k2][t];
+                    }
+                const real muH = s_hms[h][k][0], sdH = s_hms[h][k][1];
+                real pk[K];
+#pragma unroll
+                for (int k2 = 0; k2 < K; ++k2) pk[k2] = pk0[k2];
+                c.m1[0] = c.m1[1] = c.m2[0] = c.m2[1] = real(0);
+                c.qmin = real(0);
+                const real own = pk0[k] * eq_min * eq_min;
+                real Ek = Walk<real, K, T, NC, NG, NE, kFull, false, 0>::run(c, pk, real(1), cst0, lin0);
+                bool redo = own < F::kBFloor;
+                {
+                    // closed-form quadrature sums of log psi (see factor_spec_kernel)
+                    const real h0 = c.A[0][0] * muE[k], h1 = c.A[1][1] * muH;
+                    const real x01 = c.A[0][1] * muH;
+                    const real D0 = lin0[0] + (h0 + h0) + x01;
+                    const real D1 = lin0[1] + (h1 + h1) + c.A[0][1] * muE[k];
+                    const real P = cst0 + muE[k] * (lin0[0] + h0 + x01) + muH * (lin0[1] + h1);
+                    const real R0 = c.A[0][0] * sdE[k] * sdE[k], R1 = c.A[1][1] * sdH * sdH;
+                    const real Q0 = sdE[k] * D0, Q1 = sdH * D1;
+                    const real xm = v_mom[4];
+                    const real absR = fabs(R0) + fabs(R1) + fabs(c.A[0][1]) * sdE[k] * sdH;
+                    redo = redo || (P - xm * (fabs(Q0) + fabs(Q1) + xm * absR)) < F::kQFloor;
+                    const real cm0 = v_mom[0], cm2 = v_mom[1], cm4 = v_mom[2], cm22 = v_mom[3];
+                    const real base = cm2 * P;
+                    Ek += cm0 * P + cm2 * (R0 + R1);
+                    c.m1[0] += cm2 * Q0;
+                    c.m1[1] += cm2 * Q1;
+                    c.m2[0] += base + cm4 * R0 + cm22 * R1;
+                    c.m2[1] += base + cm4 * R1 + cm22 * R0;
+                }
+                if (redo) {
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        c.x[0][t] = sdE[k] * xi[t] + muE[k];
+                        c.x[1][t] = sdH * xi[t] + muH;
+                    }
+                    c.m1[0] = c.m1[1] = c.m2[0] = c.m2[1] = real(0);
+                    c.pt.poff[1] = s_hkey[h];
+                    Ek = Walk<real, K, T, NC, NG, NE, kFull, true, 0>::run(c, pk, real(1), cst0, lin0);
+                }
+                Ek *= F::kUnit;
+                // raw sums; the factors -sdev kUnit / var and -1 / var are applied once at the end
+                G1[k] += gamE * c.m1[0];
+                G2[k] += gamE * (c.m2[0] * F::kUnit - real(0.5) * Ek);
+                real* ap = s_acc + ((h * NV + 2 * k) * kSpecThreads + tid);
+                ap[0] += gamH * c.m1[1];
+                ap[kSpecThreads] += gamH * (c.m2[1] * F::kUnit - real(0.5) * Ek);
+                af[k] += wf * Ek;
+                e_sum += wk[k] * Ek;
+            }
+            af[K] += wf * e_sum;
+        }
+
+        // ---- end of the run: the run variable's gradient, one vector RED
+        real gvE[NV];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            gvE[2 * k] = -(sdE[k] * F::kUnit * G1[k]) * invE[k];
+            gvE[2 * k + 1] = -G2[k] * invE[k];
+        }
+        if (r1 > r0) red_vec<NV>(g.grad + keyE, gvE);
+#pragma unroll
+        for (int i = 0; i <= K; ++i) acc[i] -= (double)af[i];
+    }
+
+    publish_partials(acc, K + 1, s_scratch, g.partials);      // ends with a barrier
+
+    // ---- hub gradients: sum the thread-private slots, one warp per hub at a time
+    {
+        const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+        for (int h = warp; h < H; h += nwarps) {
+            real v[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                real s = real(0);
+                const real* src = s_acc + (h * NV + i) * kSpecThreads;
+#pragma unroll
+                for (int j = 0; j < kSpecThreads / 32; ++j) s += src[lane + 32 * j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                v[i] = s;
+            }
+            if (lane == 0) {
+                bool any = false;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    v[2 * k] = -(s_hms[h][k][1] * F::kUnit * v[2 * k]) * s_hinv[h][k];
+                    v[2 * k + 1] = -v[2 * k + 1] * s_hinv[h][k];
+                    any = any || v[2 * k] != real(0) || v[2 * k + 1] != real(0);
+                }
+                if (any) red_vec<NV>(g.grad + s_hkey[h], v);
+            }
+        }
+    }
+}
+
+template <typename real, int K, int T, int NE>
+static int launch_run(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStream_t s) {
+    const GroupView<real> v = make_view<real>(m, g, row0);
+    if (g->n_hubs < 1 || g->n_hubs > kRunMaxHubs) return 1;
+    const size_t dyn = (size_t)g->n_hubs * 2 * K * kSpecThreads * sizeof(real);
+    if (dyn > 96 * 1024) return 1;
+    if (g->n >= (1ll << 31)) { set_error("factor_run_kernel: more than 2^31 records in one group"); return (int)LHVI_ELIMIT; }
+    auto go = [&](auto kernel) {
+        // (every instantiation has the same function-pointer type, so nothing here may be cached
+        // in a static of this generic lambda; the calls are host-side and the launches are replayed
+        // from a CUDA graph anyway)
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024));
+        if (e != cudaSuccess) { set_error("factor_run_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)LHVI_ECUDA; }
+        int dev = 0, per_sm = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSpecThreads, dyn);
+        long long resident = (long long)(per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+        long long blocks = (g->n_runs + kSpecThreads - 1) / kSpecThreads;
+        if (blocks > resident) blocks = resident;
+        if (blocks > LHVI_PARTIAL_ROWS - 1) blocks = LHVI_PARTIAL_ROWS - 1;
+        if (blocks < 1) blocks = 1;
+        RunLaunch L;
+        L.n_hubs = g->n_hubs;
+        kernel<<<(unsigned)blocks, kSpecThreads, dyn, s>>>(v, L);
+        return check_launch("factor_run_kernel");
+    };
+    const bool weighted = g->weighted != 0;
+    if (g->run_hub_arg == 0)
+        return weighted ? go(factor_run_kernel<real, K, T, NE, true, 0>) : go(factor_run_kernel<real, K, T, NE, false, 0>);
+    return weighted ? go(factor_run_kernel<real, K, T, NE, true, 1>) : go(factor_run_kernel<real, K, T, NE, false, 1>);
+}
+
+}  // namespace lhvi

@@ -17,7 +17,7 @@ bool spec_available(const lhvi_model* m, const lhvi_group* g) {
     if (g->nd != 0 || m->K < 1 || m->K > 3) return false;
     // the streaming unary kernel takes T at run time (it only needs the rule's even moments)
     if (g->fold && g->pure && !g->node && g->nc == 1 && g->ng == 0) return true;
-    if (m->T != 3) return false;
+    if (m->T != 3 || !m->rule_symmetric) return false;
     if (g->node) return (g->nc == 1 && g->ng == 0 && g->ne == 0) || (g->nc == 0 && g->ng == 1 && g->ne == 0);
     if (g->pure) {
         if (g->ng != 0) return false;

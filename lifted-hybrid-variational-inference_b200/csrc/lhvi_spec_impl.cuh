@@ -188,12 +188,14 @@ template <typename real, int K, int T, int NC, int NG, int NE, int FL, bool CHEC
 struct Walk {
     using C = Ctx<real, K, T, NC, NG, NE>;
     using F = Fast<real>;
+    // the unchecked full walk integrates log b only (log psi has closed-form moments, see the kernel)
+    static constexpr bool WITH_PSI = FL == kPure || (FL == kFull && CHECKED);
     // returns sum over the inner axes of (prod inner omega) * F ; Wout = prod of outer omegas
     static __device__ __forceinline__ real run(C& c, const real (&pk)[K], real Wout, real cst,
                                                const real (&lin)[C::NQ]) {
         if constexpr (AX == C::NA) {
             real lpsi = cst, lb = real(0);
-            if constexpr (FL != kNode) {
+            if constexpr (WITH_PSI) {
                 if constexpr (CHECKED) lpsi = checked_log_psi<real>(cst);
                 else c.qmin = F::min(c.qmin, cst);
             }
@@ -209,9 +211,10 @@ struct Walk {
             }
             if constexpr (FL == kNode) return lb;
             else if constexpr (FL == kPure) return lpsi;
-            else return lpsi - lb;
+            else if constexpr (CHECKED) return lpsi - lb;
+            else return -lb;
         } else {
-            real s0 = real(0), s1 = real(0), s2 = real(0);
+            real R[T];
 #pragma unroll
             for (int t = 0; t < T; ++t) {
                 real pk2[K];
@@ -222,22 +225,41 @@ struct Walk {
 #pragma unroll
                     for (int k2 = 0; k2 < K; ++k2) pk2[k2] = pk[k2];
                 }
-                const real xv = c.x[AX][t];
                 real cst2 = cst;
                 real lin2[C::NQ];
 #pragma unroll
                 for (int j = 0; j < C::NQ; ++j) lin2[j] = lin[j];
-                if constexpr (FL != kNode) {
+                if constexpr (WITH_PSI) {
+                    const real xv = c.x[AX][t];
                     cst2 = cst + xv * (lin[AX] + c.A[AX][AX] * xv);
 #pragma unroll
                     for (int j = AX + 1; j < C::NA; ++j) lin2[j] = lin[j] + c.A[AX][j] * xv;
                 }
-                if constexpr (CHECKED) c.pt.x[AX] = xv;
-                const real R = Walk<real, K, T, NC, NG, NE, FL, CHECKED, AX + 1>::run(c, pk2, Wout * c.w0[t], cst2, lin2);
-                s0 += c.w0[t] * R;
-                if constexpr (AX < NC) {
-                    s1 += c.w1[t] * R;
-                    s2 += c.w2[t] * R;
+                if constexpr (CHECKED) c.pt.x[AX] = c.x[AX][t];
+                R[t] = Walk<real, K, T, NC, NG, NE, FL, CHECKED, AX + 1>::run(c, pk2, Wout * c.w0[t], cst2, lin2);
+            }
+            real s0 = real(0), s1 = real(0), s2 = real(0);
+            if constexpr (!CHECKED) {
+                // the rule is mirror-symmetric (xi_t = -xi_{T-1-t}, equal weights, xi = 0 in the middle
+                // of an odd rule; lhvi_model::rule_symmetric): pair the mirror nodes
+#pragma unroll
+                for (int t = 0; t < T / 2; ++t) {
+                    const real sm = R[t] + R[T - 1 - t];
+                    s0 += c.w0[t] * sm;
+                    if constexpr (AX < NC) {
+                        s1 += c.w1[T - 1 - t] * (R[T - 1 - t] - R[t]);
+                        s2 += c.w2[t] * sm;
+                    }
+                }
+                if constexpr ((T & 1) != 0) s0 += c.w0[T / 2] * R[T / 2];
+            } else {
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    s0 += c.w0[t] * R[t];
+                    if constexpr (AX < NC) {
+                        s1 += c.w1[t] * R[t];
+                        s2 += c.w2[t] * R[t];
+                    }
                 }
             }
             if constexpr (AX < NC) {
@@ -269,6 +291,12 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
     __shared__ int s_tag[kCacheSlots];
     __shared__ real s_val[kCacheSlots][NV];
     __shared__ double s_scratch[(kSpecThreads / 32) * (K + 1)];
+    // axis table of the hub variable the block is working on (full records with a hub argument):
+    // cross densities q_{k2}(x_{k,t}) and the per-component scalars, built once per hub and block
+    constexpr bool kHubTab = FL == kFull && HUB >= 0;
+    constexpr int TP = (T + 3) / 4 * 4;
+    __shared__ __align__(16) real s_hq[kHubTab ? K : 1][kHubTab ? K : 1][TP];
+    __shared__ real s_hpar[5][K];          // mu, var, hvar, nrm, sdev
 
     for (int i = threadIdx.x; i < 2 * T; i += blockDim.x) s_quad[i] = g.quad[i];
     for (int i = threadIdx.x; i < T; i += blockDim.x) s_eq[i] = (real)::exp(-(double)g.quad[i] * (double)g.quad[i]);
@@ -293,6 +321,35 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
     for (int k = 0; k < K; ++k) wk[k] = s_w[k];
     c.eta = g.eta;
     c.s_w = s_w;
+
+    // Full records: log psi is a quadratic, so its quadrature sums are closed forms in the rule's
+    // even moments (the rule is mirror-symmetric, odd moments vanish) -- only -log b is walked.
+    //   sum W = M0^NA, sum W xi_a^2 = M0^(NA-1) M2, sum W xi_a^4 = M0^(NA-1) M4,
+    //   sum W xi_a^2 xi_b^2 = M0^(NA-2) M2^2
+    __shared__ real s_mom[5];              // cm0, cm2, cm4, cm22, max |xi| (computed once per block)
+    if constexpr (FL == kFull) {
+        if (threadIdx.x == 0) {
+            real M0 = real(0), M2 = real(0), M4 = real(0), xm = real(0);
+            for (int t = 0; t < T; ++t) {
+                const real x = s_quad[t], om = s_quad[T + t];
+                M0 += om;
+                M2 += om * x * x;
+                M4 += om * x * x * x * x;
+                xm = fabs(x) > xm ? fabs(x) : xm;
+            }
+            real p2 = real(1);                 // M0^(NA-2)
+            for (int a = 0; a + 2 < NA; ++a) p2 *= M0;
+            const real p1 = NA >= 2 ? p2 * M0 : real(1);
+            s_mom[0] = p1 * M0;
+            s_mom[1] = p1 * M2;
+            s_mom[2] = p1 * M4;
+            s_mom[3] = NA >= 2 ? p2 * M2 * M2 : real(0);
+            s_mom[4] = xm;
+        }
+        __syncthreads();
+    }
+    const volatile real* v_mom = s_mom;     // re-read where used rather than recomputed per record
+    int tab_key = -1;                      // hub variable whose table sits in s_hq / s_hpar
 
     double acc[K + 1];
 #pragma unroll
@@ -350,6 +407,35 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
     // non-hub parameter slots are prefetched into L1 one tile ahead, which needs their offsets
     // two tiles ahead (f_poff)
     constexpr bool kSlotPrefetch = FL == kFull;
+    // ... and from there into shared memory with cp.async (one tile ahead, double-buffered, laid
+    // out [buffer][argument][16-byte chunk][thread] so that the reads are conflict-free): the gather
+    // latency of the non-hub slots is then off the record's critical path without costing registers
+    constexpr int kStageArgs = FL == kFull ? NC - (HUB >= 0 ? 1 : 0) : 0;
+    constexpr int kSlotBytes = kSlotElems * (int)sizeof(real);
+    constexpr int kChunkBytes = kSlotBytes < 16 ? kSlotBytes : 16;
+    constexpr int kChunks = kSlotBytes / kChunkBytes;
+    constexpr bool kStage = kStageArgs > 0 && 2 * kStageArgs * kSlotBytes * kSpecThreads <= 32768;
+    __shared__ __align__(16) unsigned char s_stage[kStage ? 2 * kStageArgs * kSlotBytes * kSpecThreads : 16];
+    auto stage_slots = [&](int buf, const int (&off)[NCS]) {
+        if constexpr (kStage) {
+            int sa = 0;
+#pragma unroll
+            for (int a = 0; a < NC; ++a) {
+                if (a == HUB) continue;
+                if (off[a] >= 0) {
+#pragma unroll
+                    for (int ch = 0; ch < kChunks; ++ch) {
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(
+                            s_stage + ((((buf * kStageArgs + sa) * kChunks + ch) * kSpecThreads + threadIdx.x) * kChunkBytes));
+                        const char* src = reinterpret_cast<const char*>(g.eta + off[a]) + ch * kChunkBytes;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(kChunkBytes) : "memory");
+                    }
+                }
+                ++sa;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    };
 #pragma unroll
     for (int a = 0; a < NCS; ++a) { c_poff[a] = -1; n_poff[a] = -1; f_poff[a] = -1; }
     if (lo + threadIdx.x < hi) {
@@ -362,6 +448,15 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
             for (int a = 0; a < NC; ++a) f_poff[a] = __ldcs(g.poff + a * g.n + lo + blockDim.x + threadIdx.x);
         }
     }
+    stage_slots(0, c_poff);
+    int stage_buf = 0;                     // buffer holding the current tile's slots
+
+    // hub variable of the tile's first record (the same load in every thread: block-uniform)
+    constexpr int HUBI = HUB >= 0 ? HUB : 0;
+    int c_tkey = -1, n_tkey = -1;
+    if constexpr (kHubTab) {
+        if (lo < hi) c_tkey = __ldg(g.poff + HUBI * g.n + lo);
+    }
 
     for (long long base = lo; base < hi; base += blockDim.x) {
         const long long r = base + threadIdx.x;
@@ -370,12 +465,45 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
             const long long r1 = r + blockDim.x;
             LHVI_FETCH(r1, n_pot, n_poff, n_egv, n_egs, n_ec, n_wf, n_gam);
         }
+        if constexpr (kHubTab) {
+            if (base + blockDim.x < hi) n_tkey = __ldg(g.poff + HUBI * g.n + base + blockDim.x);
+            if (c_tkey != tab_key) {
+                __syncthreads();                     // every thread is done with the old table
+                const int idx = threadIdx.x;
+                if (idx < K * K * T) {
+                    const int k = idx / (K * T), k2 = (idx / T) % K, t = idx % T;
+                    real q = s_eq[t];                // own component: exp(-xi^2)
+                    if (k2 != k) {
+                        const real mu_k = g.eta[c_tkey + 2 * k], var_k = g.eta[c_tkey + 2 * k + 1];
+                        const real mu_2 = g.eta[c_tkey + 2 * k2], var_2 = g.eta[c_tkey + 2 * k2 + 1];
+                        const real u = F::sqrt(real(2) * var_k) * s_quad[t] + (mu_k - mu_2);
+                        q = F::exp_scaled(real(-0.5) * F::kExpScale * F::rcp(var_2) * (u * u));
+                    }
+                    s_hq[k][k2][t] = q;
+                }
+                if (idx < K) {
+                    const real mu_k = g.eta[c_tkey + 2 * idx], var_k = g.eta[c_tkey + 2 * idx + 1];
+                    const real inv = F::rcp(var_k);
+                    s_hpar[0][idx] = mu_k;
+                    s_hpar[1][idx] = var_k;
+                    s_hpar[2][idx] = real(-0.5) * F::kExpScale * inv;
+                    s_hpar[3][idx] = inv * real(1.0 / kSqrt2Pi);
+                    s_hpar[4][idx] = F::sqrt(real(2) * var_k);
+                }
+                __syncthreads();
+                tab_key = c_tkey;
+            }
+        }
         if constexpr (kSlotPrefetch) {
             // f_poff holds the offsets of tile +1 (loaded one tile ago): warm L1 with those slots
+            if constexpr (kStage) {
+                stage_slots(stage_buf ^ 1, f_poff);
+            } else {
 #pragma unroll
-            for (int a = 0; a < NC; ++a) {
-                if (a != HUB && f_poff[a] >= 0)
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.eta + f_poff[a]));
+                for (int a = 0; a < NC; ++a) {
+                    if (a != HUB && f_poff[a] >= 0)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(g.eta + f_poff[a]));
+                }
             }
             const long long r2 = r + 2 * (long long)blockDim.x;
 #pragma unroll
@@ -488,12 +616,59 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
                 for (int a = 0; a < NC; ++a) gam_r[a] = __ldcs(g.gam + a * g.n + r);
             }
             real mu[NCS][K], var[NCS][K], hvar[NCS][K], nrm[NCS][K];
+            // the record's hub variable is the one tabulated in shared memory (always, except for
+            // the records of a tile in which the hub changes)
+            const bool use_tab = kHubTab && c_poff[HUBI] == tab_key;
 #pragma unroll
             for (int a = 0; a < NC; ++a) {
                 key[a] = c_poff[a];
                 c.pt.poff[a] = key[a];
-                real slot[NV];
-                load_vec<NV>(g.eta + key[a], slot);
+                if (kHubTab && a == HUB && use_tab) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        mu[a][k] = s_hpar[0][k];
+                        var[a][k] = s_hpar[1][k];
+                        hvar[a][k] = s_hpar[2][k];
+                        nrm[a][k] = s_hpar[3][k];
+                    }
+                    continue;
+                }
+                real slot[kSlotElems];
+                if constexpr (kStage) {
+                    if (a != HUB) {
+                        // this tile's group of copies was committed one tile ago (one newer group may be pending)
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                        const int sa = a - (HUB >= 0 && a > HUB ? 1 : 0);
+#pragma unroll
+                        for (int ch = 0; ch < kChunks; ++ch) {
+                            const unsigned char* src =
+                                s_stage + ((((stage_buf * kStageArgs + sa) * kChunks + ch) * kSpecThreads + threadIdx.x) * kChunkBytes);
+                            constexpr int EPC = kChunkBytes / (int)sizeof(real);     // elements per chunk
+                            if constexpr (kChunkBytes == 16) {
+                                const float4 t = *reinterpret_cast<const float4*>(src);
+                                if constexpr (sizeof(real) == 4) {
+                                    slot[ch * EPC + 0] = t.x; slot[ch * EPC + 1] = t.y; slot[ch * EPC + 2] = t.z; slot[ch * EPC + 3] = t.w;
+                                } else {
+                                    const double2 d = *reinterpret_cast<const double2*>(&t);
+                                    slot[ch * EPC + 0] = d.x; slot[ch * EPC + 1] = d.y;
+                                }
+                            } else {
+                                const float2 t = *reinterpret_cast<const float2*>(src);
+                                slot[0] = t.x; slot[1] = t.y;
+                            }
+                        }
+                    } else {
+                        real tmp[NV];
+                        load_vec<NV>(g.eta + key[a], tmp);
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) slot[i] = tmp[i];
+                    }
+                } else {
+                    real tmp[NV];
+                    load_vec<NV>(g.eta + key[a], tmp);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) slot[i] = tmp[i];
+                }
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     mu[a][k] = slot[2 * k];
@@ -565,11 +740,19 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
                 real sdev[NCS];
 #pragma unroll
                 for (int a = 0; a < NC; ++a) {
+                    if (kHubTab && a == HUB && use_tab) {
+                        sdev[a] = s_hpar[4][k];
+#pragma unroll
+                        for (int k2 = 0; k2 < K; ++k2)
+#pragma unroll
+                            for (int t = 0; t < T; ++t) c.q[a][k2][t] = s_hq[k][k2][t];
+                        continue;
+                    }
                     sdev[a] = F::sqrt(real(2) * var[a][k]);
 #pragma unroll
                     for (int t = 0; t < T; ++t) {
                         const real dx = sdev[a] * xi[t];
-                        c.x[a][t] = dx + mu[a][k];
+                        if constexpr (FL == kPure) c.x[a][t] = dx + mu[a][k];
                         if constexpr (FL != kPure) {
 #pragma unroll
                             // densities without their normalisers 1 / (sqrt(2pi) var): those depend
@@ -589,7 +772,7 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
                 for (int j = 0; j < NG; ++j) {
 #pragma unroll
                     for (int t = 0; t < T; ++t) {
-                        c.x[NC + j][t] = egs[j] * xi[t] + egval[j];
+                        if constexpr (FL == kPure) c.x[NC + j][t] = egs[j] * xi[t] + egval[j];
 #pragma unroll
                         for (int k2 = 0; k2 < K; ++k2) c.q[NC + j][k2][t] = eq[t];
                     }
@@ -609,10 +792,68 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
                     for (int a = 0; a < NA; ++a) own *= eq_min;
                 }
                 real Ek = Walk<real, K, T, NC, NG, NE, FL, false, 0>::run(c, pk, real(1), cst0, lin0);
-                if (c.qmin < F::kQFloor || own < F::kBFloor) {
+                bool redo = own < F::kBFloor;
+                if constexpr (FL == kFull) {
+                    // closed-form quadrature sums of log psi over the grid centred at cen with
+                    // half-widths sc: log psi = P + sum_a Q_a xi_a + sum_a R_aa xi_a^2 + cross terms
+                    real cen[NA > 0 ? NA : 1], sc[NA > 0 ? NA : 1], Dv[NA > 0 ? NA : 1];
+#pragma unroll
+                    for (int a = 0; a < NC; ++a) { cen[a] = mu[a][k]; sc[a] = sdev[a]; }
+#pragma unroll
+                    for (int j = 0; j < NG; ++j) { cen[NC + j] = egval[j]; sc[NC + j] = egs[j]; }
+                    real P = cst0;
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) {
+                        const real h = c.A[a][a] * cen[a];
+                        Dv[a] = lin0[a] + (h + h);
+                        P += cen[a] * (lin0[a] + h);
+                    }
+#pragma unroll
+                    for (int a = 0; a < NA; ++a)
+#pragma unroll
+                        for (int b = a + 1; b < NA; ++b) {
+                            const real ab = c.A[a][b] * cen[b];
+                            Dv[a] += ab;
+                            Dv[b] += c.A[a][b] * cen[a];
+                            P += ab * cen[a];
+                        }
+                    real Raa[NA > 0 ? NA : 1], Rsum = real(0), absQ = real(0), absR = real(0);
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) {
+                        Raa[a] = c.A[a][a] * sc[a] * sc[a];
+                        Rsum += Raa[a];
+                        absQ += fabs(sc[a] * Dv[a]);
+                        absR += fabs(Raa[a]);
+                    }
+#pragma unroll
+                    for (int a = 0; a < NA; ++a)
+#pragma unroll
+                        for (int b = a + 1; b < NA; ++b) absR += fabs(c.A[a][b]) * sc[a] * sc[b];
+                    // lower bound of log psi on the grid: can the 1e-100 floor be active?
+                    const real xi_max = v_mom[4];
+                    redo = redo || (P - xi_max * (absQ + xi_max * absR)) < F::kQFloor;
+                    const real cm0 = v_mom[0], cm2 = v_mom[1], cm4 = v_mom[2], cm22 = v_mom[3];
+                    Ek += cm0 * P + cm2 * Rsum;
+#pragma unroll
+                    for (int a = 0; a < NC; ++a) {
+                        c.m1[a] += cm2 * (sc[a] * Dv[a]);
+                        c.m2[a] += cm2 * P + cm4 * Raa[a] + cm22 * (Rsum - Raa[a]);
+                    }
+                } else {
+                    redo = redo || c.qmin < F::kQFloor;
+                }
+                if (redo) {
                     // a floor may be active on this grid: redo it with the literal formulas
 #pragma unroll
-                    for (int a = 0; a < NC; ++a) { c.m1[a] = real(0); c.m2[a] = real(0); }
+                    for (int a = 0; a < NC; ++a) {
+                        c.m1[a] = real(0); c.m2[a] = real(0);
+#pragma unroll
+                        for (int t = 0; t < T; ++t) c.x[a][t] = sdev[a] * xi[t] + mu[a][k];
+                    }
+#pragma unroll
+                    for (int j = 0; j < NG; ++j)
+#pragma unroll
+                        for (int t = 0; t < T; ++t) c.x[NC + j][t] = egs[j] * xi[t] + egval[j];
                     Ek = Walk<real, K, T, NC, NG, NE, FL, true, 0>::run(c, pk, real(1), cst0, lin0);
                 }
                 Ek *= F::kUnit;
@@ -701,6 +942,8 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
         c_pot = n_pot;
         c_wf = n_wf;
         c_gam = n_gam;
+        c_tkey = n_tkey;
+        stage_buf ^= 1;
 #pragma unroll
         for (int a = 0; a < NCS; ++a) c_poff[a] = n_poff[a];
 #pragma unroll
@@ -1409,6 +1652,10 @@ static int launch_unary_fold(const lhvi_model* m, const lhvi_group* g, int64_t r
     return hub ? go(unary_fold_kernel<real, K, false, true>) : go(unary_fold_kernel<real, K, false, false>);
 }
 
+}  // namespace lhvi
+#include "lhvi_run_impl.cuh"
+namespace lhvi {
+
 // ---- dispatch ----------------------------------------------------------------------------------
 
 template <typename real, int K, int T, int NC, int NG, int NE, int FL, bool WEIGHTED, int HUB>
@@ -1487,6 +1734,10 @@ int launch_kt(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStream
         }
     }
     const int code = g->nc * 100 + g->ng * 10 + g->ne;
+    if (g->run_start != nullptr && (code == 200 || code == 201)) {
+        const int rc = code == 200 ? launch_run<real, K, T, 0>(m, g, row0, s) : launch_run<real, K, T, 1>(m, g, row0, s);
+        if (rc <= 0) return rc;          // 1: not eligible (too many hubs), use the record-major kernel
+    }
     switch (code) {
 #define X(NC_, NG_, NE_) case NC_ * 100 + NG_ * 10 + NE_: return launch_one<real, K, T, NC_, NG_, NE_, kFull>(m, g, row0, s);
         LHVI_SPEC_FULL(X)

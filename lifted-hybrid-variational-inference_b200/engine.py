@@ -52,9 +52,39 @@ def hub_mask(g):
     return mask
 
 
+RUN_SPLIT = 64          # a longer run is split (one thread walks a run)
+RUN_ACC_BYTES = 96 * 1024
+
+
+def run_layout(g, K, elem_bytes):
+    """Run-major form of a full group with two hidden continuous arguments, one of which takes
+    few distinct values (lhvi.h, lhvi_group::run_*): returns (sorted group, run_start, run_key,
+    run_hid, hub_keys, hub_arg) or None when the group does not qualify."""
+    if g.node or g.pure or g.nd != 0 or g.nc != 2 or g.ng != 0 or g.ne > 1 or g.n < 2:
+        return None
+    uniq = [np.unique(g.poff[a]) for a in (0, 1)]
+    hub_arg = 0 if uniq[0].size < uniq[1].size else 1
+    hubs = uniq[hub_arg]
+    if hubs.size > _cabi.LHVI_RUN_MAX_HUBS or hubs.size * 2 * K * 256 * elem_bytes > RUN_ACC_BYTES:
+        return None
+    run_arg = 1 - hub_arg
+    if g.n < 1.5 * uniq[run_arg].size:          # hardly any run: the record-major kernel is as good
+        return None
+    order = np.argsort(g.poff[run_arg], kind="stable")
+    sg = g.take(order)
+    keys = sg.poff[run_arg]
+    starts = np.concatenate([[0], np.flatnonzero(keys[1:] != keys[:-1]) + 1, [sg.n]])
+    if np.diff(starts).max() > RUN_SPLIT:
+        pieces = [np.arange(a, b, RUN_SPLIT) for a, b in zip(starts[:-1], starts[1:])]
+        starts = np.concatenate(pieces + [[sg.n]])
+    run_key = keys[starts[:-1]]
+    hid = np.searchsorted(hubs, sg.poff[hub_arg])
+    return sg, starts.astype(np.int32), run_key.astype(np.int32), hid.astype(np.int32), hubs.astype(np.int32), hub_arg
+
+
 class DeviceEngine:
     def __init__(self, model: LoweredModel, dtype="float64", device=None, var_threshold=0.1,
-                 process_group=None, shard=True, force_generic=False):
+                 process_group=None, shard=True, force_generic=False, run_major=True):
         if not torch.cuda.is_available():
             raise RuntimeError(
                 "lhvi: no CUDA device visible. The variational-inference update loop runs only "
@@ -68,6 +98,7 @@ class DeviceEngine:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.var_threshold = float(var_threshold)
         self.force_generic = bool(force_generic)
+        self.run_major = bool(run_major)     # False: keep every group record-major (tests)
         self.b1, self.b2, self.eps = 0.9, 0.999, 1e-8      # VarInference.py:223-225
         self.profile_group = None
         self.dom_events = []
@@ -142,11 +173,18 @@ class DeviceEngine:
 
         # the streaming unary kernel uses only the even moments of the quadrature rule
         self.symmetric_rule = bool(abs(np.dot(qw, qx)) < 1e-13 and abs(np.dot(qw, qx ** 3)) < 1e-13)
+        # exact mirror symmetry (what hermgauss returns): the specialised walk pairs the mirror nodes
+        self.mirror_rule = bool(np.array_equal(qx, -qx[::-1]) and np.array_equal(qw, qw[::-1])
+                                and (self.T % 2 == 0 or qx[self.T // 2] == 0.0))
 
         self.groups = []      # (descriptor struct, tensors kept alive, RecordGroup)
+        esize = 8 if self.dtype_name == "float64" else 4
         for g in self.model.groups:
             keep = {}
             d = _cabi.LhviGroup()
+            runs = run_layout(g, K, esize) if (self.run_major and self.mirror_rule and self.T == 3 and K <= 3) else None
+            if runs is not None:
+                g = runs[0]
             d.nd, d.nc, d.ng, d.ne = g.nd, g.nc, g.ng, g.ne
             for i in range(_cabi.LHVI_MAX_AXES):
                 d.dims[i] = int(g.dims[i]) if i < len(g.dims) else 0
@@ -179,6 +217,13 @@ class DeviceEngine:
                 cols = np.zeros((3, n_pad))
                 cols[:, :g.n] = fold
                 d.fold, d.n_pad = put("fold", cols, self.tdtype), n_pad
+            d.run_start, d.n_runs, d.n_hubs, d.run_hub_arg = None, 0, 0, 0
+            if runs is not None:
+                _, starts, run_key, hid, hubs, hub_arg = runs
+                for name, arr in (("run_start", starts), ("run_key", run_key), ("run_hid", hid), ("hub_keys", hubs)):
+                    keep[name] = self._dev(arr, torch.int32)
+                    setattr(d, name, keep[name].data_ptr())
+                d.n_runs, d.n_hubs, d.run_hub_arg = int(run_key.size), int(hubs.size), int(hub_arg)
             self.groups.append((d, keep, g))
 
         rows = max(1, len(self.groups)) * _cabi.LHVI_PARTIAL_ROWS
@@ -187,6 +232,7 @@ class DeviceEngine:
 
         md = _cabi.LhviModel()
         md.dtype, md.K, md.T, md.n_param = self.dcode, K, self.T, n_param
+        md.rule_symmetric = int(self.mirror_rule)
         md.quad, md.ptab = self.quad.data_ptr(), self.ptab.data_ptr()
         md.eta, md.w = self.eta.data_ptr(), self.wstate[K:2 * K].data_ptr()
         md.grad, md.partials = self.grad.data_ptr(), self.partials.data_ptr()

@@ -197,6 +197,81 @@ def test_generated_models_against_oracle(dtype, tol):
         np.testing.assert_allclose(grad, og, rtol=tol, atol=tol * np.abs(og).max())
 
 
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-9), ("float32", 5e-5)])
+@pytest.mark.parametrize("K", [1, 2, 3])
+def test_run_major_kernel_matches_record_major_and_oracle(dtype, tol, K):
+    """Full records with a few-valued (hub) argument run through the run-major kernel
+    (lhvi_group::run_*): same sums as the record-major kernel and the oracle, for both positions
+    of the hub argument, ragged runs, runs longer than the split length, weighted and not."""
+    import dataclasses
+    syn = lhvi_b200.synthetic
+    rng = np.random.default_rng(5)
+    for weighted, swap in ((True, False), (False, True)):
+        model = syn.relational_hybrid(400, 7, K, 3, seed=3, weighted=weighted, observed_frac=0.5)
+        groups = []
+        for g in model.groups:
+            if not g.node and not g.pure and g.nc == 2:
+                keep = np.flatnonzero(rng.random(g.n) < 0.6)            # ragged runs
+                g = g.take(keep)
+                if weighted:
+                    g = dataclasses.replace(g, wf=rng.uniform(0.5, 3.0, g.n),
+                                            gam=rng.integers(0, 4, size=(2, g.n)).astype(np.float64))
+                if swap:                                               # hub argument first
+                    blocks = {}
+                    pot = g.pot.copy()
+                    for b in np.unique(g.pot):
+                        blocks[b] = b
+                    ptab = model.ptab.copy()
+                    for b in np.unique(g.pot):                         # c, l0, l1, A00, A01, A11 -> swap roles
+                        c, l0, l1, a00, a01, a11 = ptab[b:b + 6]
+                        ptab = np.concatenate([ptab, [c, l1, l0, a11, a01, a00]])
+                        pot[g.pot == b] = ptab.size - 6
+                    model = dataclasses.replace(model, ptab=ptab)
+                    g = dataclasses.replace(g, pot=pot.astype(np.int32), poff=g.poff[::-1].copy(), gam=g.gam[::-1].copy())
+            groups.append(g)
+        model = dataclasses.replace(model, groups=groups)
+        eta, tau, w_tau = syn.random_state(model, 1)
+        w = np.full(K, 1.0 / K)
+        og, ogw, oe = grad_pass(model, eta, w)
+        outs = []
+        for run_major in (True, False):
+            eng = _engine_for(model, dtype, run_major=run_major)
+            used = [bool(d.run_start) for d, _, _ in eng.groups]
+            assert any(used) == run_major
+            eng.set_state(eta, tau, w_tau)
+            outs.append(eng.gradients())
+        for grad, g_w, energy in outs:
+            np.testing.assert_allclose(energy, oe, rtol=tol)
+            np.testing.assert_allclose(g_w, ogw, rtol=tol, atol=tol * np.abs(ogw).max())
+            np.testing.assert_allclose(grad, og, rtol=tol, atol=tol * np.abs(og).max())
+
+
+def test_run_major_kernel_floors():
+    """Deep-tail potentials and far-apart components on a hub model: the run-major kernel must
+    take the literal path (log(psi + 1e-100), log(b + 1e-100) in double) like the reference."""
+    syn = lhvi_b200.synthetic
+    K = 2
+    model = syn.relational_hybrid(200, 4, K, 3, seed=1, observed_frac=0.4)
+    eta, tau, w_tau = syn.random_state(model, 0)
+    cont = model.var_off.astype(np.int64)
+    eta[cont] = -40.0
+    eta[cont + 2] = 45.0
+    eta[cont + 1] = 0.1
+    eta[cont + 3] = 0.1
+    w_tau = np.array([-60.0, 0.0])
+    e = np.e ** w_tau
+    og, ogw, oe = grad_pass(model, eta, e / e.sum())
+    for dtype, tol in (("float64", 1e-9), ("float32", 1e-4)):
+        eng = _engine_for(model, dtype)
+        assert any(bool(d.run_start) for d, _, _ in eng.groups)
+        eng.set_state(eta, tau, w_tau)
+        grad, g_w, energy = eng.gradients()
+        assert np.isfinite(grad).all() and np.isfinite(g_w).all()
+        np.testing.assert_allclose(energy, oe, rtol=tol)
+        np.testing.assert_allclose(g_w, ogw, rtol=tol, atol=tol * np.abs(ogw).max())
+        np.testing.assert_allclose(grad, og, rtol=tol * 10, atol=tol * np.abs(og).max())
+
+
 def test_fp32_underflow_fallback():
     """Far-apart mixture components: float pdfs underflow to zero, the kernel must redo those
     points in double like the reference's log(b + 1e-100)."""

@@ -1,0 +1,3 @@
+import json,sys
+d=json.load(open(sys.argv[1]));print("ms/step",d["ms_per_step"],"it/s",d["value"],"e2e",d["e2e"]["value"])
+for k in d["roofline"]["kernels"]: print("  ",k["group"],round(k["ms"]*1e3,1),"us",round(k["gbs"]),"GB/s")
