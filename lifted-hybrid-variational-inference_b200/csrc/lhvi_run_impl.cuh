@@ -44,8 +44,7 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
     __shared__ real s_mom[5];
     __shared__ __align__(16) real s_hq[kRunMaxHubs][K][K][TP];   // q_{k2}(x_{k,t}) of every hub
     __shared__ __align__(16) real s_hnrm[kRunMaxHubs][4];        // 1 / (sqrt(2 pi) var_k2)
-    __shared__ __align__(16) real s_hms[kRunMaxHubs][K][2];      // mu_k, sqrt(2 var_k)
-    __shared__ real s_hinv[kRunMaxHubs][K];                      // 1 / var_k
+    __shared__ __align__(16) real s_hms[kRunMaxHubs][K][4];      // mu_k, sqrt(2 var_k), 2 var_k, 1 / var_k
     __shared__ int s_hkey[kRunMaxHubs];
     __shared__ double s_scratch[(kSpecThreads / 32) * (K + 1)];
 
@@ -93,7 +92,8 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
         s_hnrm[h][k] = inv * real(1.0 / kSqrt2Pi);
         s_hms[h][k][0] = mu_k;
         s_hms[h][k][1] = F::sqrt(real(2) * var_k);
-        s_hinv[h][k] = inv;
+        s_hms[h][k][2] = real(2) * var_k;
+        s_hms[h][k][3] = inv;
     }
     __syncthreads();
 
@@ -113,7 +113,8 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
     for (int k = 0; k < K; ++k) wk[k] = s_w[k];
     c.eta = g.eta;
     c.s_w = s_w;
-    const volatile real* v_mom = s_mom;
+    const real cm0 = s_mom[0], cm2 = s_mom[1], cm22 = s_mom[3], cmd = s_mom[2] - s_mom[3], xm = s_mom[4];
+    auto own_floor = [](real own) { return own < F::kBFloor; };
 
     double acc[K + 1];
 #pragma unroll
@@ -139,7 +140,7 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
         }
 
         // ---- the run variable: parameters and axis tables, once per run
-        real muE[K], sdE[K], invE[K], nrmE[K], hvE[K];
+        real muE[K], sdE[K], invE[K], nrmE[K], hvE[K], tvE[K];
         {
             real slot[NV];
             load_vec<NV>(g.eta + keyE, slot);
@@ -149,7 +150,8 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
                 invE[k] = F::rcp(slot[2 * k + 1]);
                 hvE[k] = real(-0.5) * F::kExpScale * invE[k];
                 nrmE[k] = invE[k] * real(1.0 / kSqrt2Pi);
-                sdE[k] = F::sqrt(real(2) * slot[2 * k + 1]);
+                tvE[k] = real(2) * slot[2 * k + 1];
+                sdE[k] = F::sqrt(tvE[k]);
             }
         }
         real qE[K][K][T];
@@ -175,25 +177,33 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
         for (int i = 0; i <= K; ++i) af[i] = real(0);
         c.pt.poff[0] = keyE;
 
-        // ---- its records
+        // ---- its records (columns fetched one record ahead)
+        int n_pot = 0, n_h = 0;
+        real n_wf = real(1), n_gE = real(1), n_gH = real(1);
+#define LHVI_RUN_FETCH(RR)                                                        \
+        do {                                                                      \
+            n_pot = __ldg(g.pot + (RR));                                          \
+            n_h = __ldg(g.run_hid + (RR));                                        \
+            if constexpr (WEIGHTED) {                                             \
+                n_wf = __ldg(g.wf + (RR));                                        \
+                n_gE = __ldg(g.gam + (long long)RA * g.n + (RR));                 \
+                n_gH = __ldg(g.gam + (long long)HUBPOS * g.n + (RR));             \
+            }                                                                     \
+        } while (0)
+        if (r0 < r1) LHVI_RUN_FETCH(r0);
 #pragma unroll 1
         for (int r = r0; r < r1; ++r) {
-            const int pot = __ldg(g.pot + r);
-            const int h = __ldg(g.run_hid + r);
-            real wf = real(1), gamE = real(1), gamH = real(1);
-            if constexpr (WEIGHTED) {
-                wf = __ldg(g.wf + r);
-                gamE = __ldg(g.gam + (long long)RA * g.n + r);
-                gamH = __ldg(g.gam + (long long)HUBPOS * g.n + r);
-            }
-            // quadratic log-potential reduced by the point evidence, then renumbered to walk order
-            // (axis 0 = run argument, axis 1 = hub argument)
-            real cst0, lin0[NQ];
+            const int pot = n_pot, h = n_h;
+            const real wf = n_wf, gamE = n_gE, gamH = n_gH;
+            if (r + 1 < r1) LHVI_RUN_FETCH(r + 1);
+            // quadratic log-potential reduced by the point evidence, in walk order (axis 0 = run
+            // argument, axis 1 = hub argument): c0 + l0 x0 + l1 x1 + a00 x0^2 + a01 x0 x1 + a11 x1^2
+            real c0, l0, l1, a00, a01, a11;
             {
                 const real* cf = g.ptab + pot;
                 constexpr real to_unit = real(1) / F::kUnit;
                 real lc[NCT], Ac[NCT][NCT];
-                cst0 = __ldg(cf) * to_unit;
+                c0 = __ldg(cf) * to_unit;
 #pragma unroll
                 for (int i = 0; i < NCT; ++i) lc[i] = __ldg(cf + 1 + i) * to_unit;
                 int p = 1 + NCT;
@@ -205,23 +215,14 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
                 for (int e = 0; e < NE; ++e) {
                     const int j = 2 + e;
                     const real xv = __ldg(g.ecval + (long long)e * g.n + r);
-                    cst0 += xv * (lc[j] + Ac[j][j] * xv);
+                    c0 += xv * (lc[j] + Ac[j][j] * xv);
 #pragma unroll
                     for (int i = 0; i < j; ++i) lc[i] += Ac[i][j] * xv;
 #pragma unroll
                     for (int i = j + 1; i < NCT; ++i) lc[i] += Ac[j][i] * xv;
                 }
-#pragma unroll
-                for (int j = 0; j < NQ; ++j) lin0[j] = real(0);
-                lin0[0] = lc[RA];
-                lin0[1] = lc[HUBPOS];
-#pragma unroll
-                for (int i = 0; i < NQ; ++i)
-#pragma unroll
-                    for (int j = 0; j < NQ; ++j) c.A[i][j] = real(0);
-                c.A[0][0] = Ac[RA][RA];
-                c.A[1][1] = Ac[HUBPOS][HUBPOS];
-                c.A[0][1] = Ac[0][1];
+                l0 = lc[RA]; l1 = lc[HUBPOS];
+                a00 = Ac[RA][RA]; a11 = Ac[HUBPOS][HUBPOS]; a01 = Ac[0][1];
             }
 
             real pk0[K];
@@ -231,64 +232,114 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
             real e_sum = real(0);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
+                real qH[K][T];
 #pragma unroll
                 for (int k2 = 0; k2 < K; ++k2)
 #pragma unroll
-                    for (int t = 0; t < T; ++t) {
-                        c.q[0][k2][t] = qE[k][k2][t];
-                        c.q[1][k2][t] = s_hq[h][k][k2][t];
+                    for (int t = 0; t < T; ++t) qH[k2][t] = s_hq[h][k][k2][t];
+                const real muH = s_hms[h][k][0], sdH = s_hms[h][k][1], tvH = s_hms[h][k][2];
+                const real e = muE[k], sE = sdE[k];
+
+                // ---- log b on the T x T grid; mirror nodes are paired on both axes.  Per outer node:
+                // S = sum_t2 w0 L, HS / HD = the weighted pair sums / differences of the inner axis
+                real S[T], HS[T], HD[T];
+#pragma unroll
+                for (int t1 = 0; t1 < T; ++t1) {
+                    real pk2[K], Lg[T];
+#pragma unroll
+                    for (int k2 = 0; k2 < K; ++k2) pk2[k2] = pk0[k2] * qE[k][k2][t1];
+#pragma unroll
+                    for (int t2 = 0; t2 < T; ++t2) {
+                        real b = pk2[0] * qH[0][t2];
+#pragma unroll
+                        for (int k2 = 1; k2 < K; ++k2) b += pk2[k2] * qH[k2][t2];
+                        Lg[t2] = F::log_belief(b);
                     }
-                const real muH = s_hms[h][k][0], sdH = s_hms[h][k][1];
-                real pk[K];
+                    real s0 = real(0), hs = real(0), hd = real(0);
+                    if constexpr (T == 3) {              // one pair: its weights are applied at the end
+                        hs = Lg[0] + Lg[2];
+                        hd = Lg[2] - Lg[0];
+                        s0 = c.w0[0] * hs + c.w0[1] * Lg[1];
+                    } else {
 #pragma unroll
-                for (int k2 = 0; k2 < K; ++k2) pk[k2] = pk0[k2];
-                c.m1[0] = c.m1[1] = c.m2[0] = c.m2[1] = real(0);
-                c.qmin = real(0);
-                const real own = pk0[k] * eq_min * eq_min;
-                real Ek = Walk<real, K, T, NC, NG, NE, kFull, false, 0>::run(c, pk, real(1), cst0, lin0);
-                bool redo = own < F::kBFloor;
-                {
-                    // closed-form quadrature sums of log psi (see factor_spec_kernel)
-                    const real h0 = c.A[0][0] * muE[k], h1 = c.A[1][1] * muH;
-                    const real x01 = c.A[0][1] * muH;
-                    const real D0 = lin0[0] + (h0 + h0) + x01;
-                    const real D1 = lin0[1] + (h1 + h1) + c.A[0][1] * muE[k];
-                    const real P = cst0 + muE[k] * (lin0[0] + h0 + x01) + muH * (lin0[1] + h1);
-                    const real R0 = c.A[0][0] * sdE[k] * sdE[k], R1 = c.A[1][1] * sdH * sdH;
-                    const real Q0 = sdE[k] * D0, Q1 = sdH * D1;
-                    const real xm = v_mom[4];
-                    const real absR = fabs(R0) + fabs(R1) + fabs(c.A[0][1]) * sdE[k] * sdH;
-                    redo = redo || (P - xm * (fabs(Q0) + fabs(Q1) + xm * absR)) < F::kQFloor;
-                    const real cm0 = v_mom[0], cm2 = v_mom[1], cm4 = v_mom[2], cm22 = v_mom[3];
-                    const real base = cm2 * P;
-                    Ek += cm0 * P + cm2 * (R0 + R1);
-                    c.m1[0] += cm2 * Q0;
-                    c.m1[1] += cm2 * Q1;
-                    c.m2[0] += base + cm4 * R0 + cm22 * R1;
-                    c.m2[1] += base + cm4 * R1 + cm22 * R0;
+                        for (int t2 = 0; t2 < T / 2; ++t2) {
+                            const real sm = Lg[t2] + Lg[T - 1 - t2];
+                            s0 += c.w0[t2] * sm;
+                            hs += c.w2[t2] * sm;
+                            hd += c.w1[T - 1 - t2] * (Lg[T - 1 - t2] - Lg[t2]);
+                        }
+                        if constexpr ((T & 1) != 0) s0 += c.w0[T / 2] * Lg[T / 2];
+                    }
+                    S[t1] = s0; HS[t1] = hs; HD[t1] = hd;
                 }
+                real Elb = real(0), e1 = real(0), e2 = real(0), g1 = real(0), g2 = real(0);
+#pragma unroll
+                for (int t1 = 0; t1 < T / 2; ++t1) {
+                    const real sm = S[t1] + S[T - 1 - t1];
+                    Elb += c.w0[t1] * sm;
+                    e2 += c.w2[t1] * sm;
+                    e1 += c.w1[T - 1 - t1] * (S[T - 1 - t1] - S[t1]);
+                    g1 += c.w0[t1] * (HD[t1] + HD[T - 1 - t1]);
+                    g2 += c.w0[t1] * (HS[t1] + HS[T - 1 - t1]);
+                }
+                if constexpr ((T & 1) != 0) {
+                    Elb += c.w0[T / 2] * S[T / 2];
+                    g1 += c.w0[T / 2] * HD[T / 2];
+                    g2 += c.w0[T / 2] * HS[T / 2];
+                }
+                if constexpr (T == 3) { g1 *= c.w1[2]; g2 *= c.w2[0]; }
+
+                // ---- closed-form quadrature sums of log psi (see factor_spec_kernel)
+                const real h0 = a00 * e, h1 = a11 * muH, x01 = a01 * muH;
+                const real t0 = (l0 + h0) + x01, t1 = l1 + h1;
+                const real P = e * t0 + (muH * t1 + c0);
+                const real Q0 = sE * (t0 + h0), Q1 = sdH * (a01 * e + (t1 + h1));
+                const real R0 = a00 * tvE[k], R1 = a11 * tvH, Rs = R0 + R1;
+                const real absR = fabs(a01) * (sE * sdH) + (fabs(R0) + fabs(R1));
+                const bool redo = own_floor(pk0[k] * eq_min * eq_min) ||
+                                  (P - xm * ((fabs(Q0) + fabs(Q1)) + xm * absR)) < F::kQFloor;
+                const real base2 = cm2 * P + cm22 * Rs;
+                real Ek = (cm0 * P + cm2 * Rs) - Elb;
+                real m1E = cm2 * Q0 - e1, m1H = cm2 * Q1 - g1;
+                real m2E = (cmd * R0 + base2) - e2, m2H = (cmd * R1 + base2) - g2;
                 if (redo) {
+                    // a floor may be active on this grid: redo it with the literal formulas
+                    real pk[K], lin0[NQ];
+#pragma unroll
+                    for (int k2 = 0; k2 < K; ++k2) pk[k2] = pk0[k2];
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j) lin0[j] = real(0);
+                    lin0[0] = l0; lin0[1] = l1;
+#pragma unroll
+                    for (int i = 0; i < NQ; ++i)
+#pragma unroll
+                        for (int j = 0; j < NQ; ++j) c.A[i][j] = real(0);
+                    c.A[0][0] = a00; c.A[1][1] = a11; c.A[0][1] = a01;
 #pragma unroll
                     for (int t = 0; t < T; ++t) {
-                        c.x[0][t] = sdE[k] * xi[t] + muE[k];
+                        c.x[0][t] = sE * xi[t] + e;
                         c.x[1][t] = sdH * xi[t] + muH;
+#pragma unroll
+                        for (int k2 = 0; k2 < K; ++k2) { c.q[0][k2][t] = real(0); c.q[1][k2][t] = real(0); }
                     }
                     c.m1[0] = c.m1[1] = c.m2[0] = c.m2[1] = real(0);
                     c.pt.poff[1] = s_hkey[h];
-                    Ek = Walk<real, K, T, NC, NG, NE, kFull, true, 0>::run(c, pk, real(1), cst0, lin0);
+                    Ek = Walk<real, K, T, NC, NG, NE, kFull, true, 0>::run(c, pk, real(1), c0, lin0);
+                    m1E = c.m1[0]; m1H = c.m1[1]; m2E = c.m2[0]; m2H = c.m2[1];
                 }
                 Ek *= F::kUnit;
                 // raw sums; the factors -sdev kUnit / var and -1 / var are applied once at the end
-                G1[k] += gamE * c.m1[0];
-                G2[k] += gamE * (c.m2[0] * F::kUnit - real(0.5) * Ek);
+                G1[k] += gamE * m1E;
+                G2[k] += gamE * (m2E * F::kUnit - real(0.5) * Ek);
                 real* ap = s_acc + ((h * NV + 2 * k) * kSpecThreads + tid);
-                ap[0] += gamH * c.m1[1];
-                ap[kSpecThreads] += gamH * (c.m2[1] * F::kUnit - real(0.5) * Ek);
+                ap[0] += gamH * m1H;
+                ap[kSpecThreads] += gamH * (m2H * F::kUnit - real(0.5) * Ek);
                 af[k] += wf * Ek;
                 e_sum += wk[k] * Ek;
             }
             af[K] += wf * e_sum;
         }
+#undef LHVI_RUN_FETCH
 
         // ---- end of the run: the run variable's gradient, one vector RED
         real gvE[NV];
@@ -323,8 +374,8 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
                 bool any = false;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    v[2 * k] = -(s_hms[h][k][1] * F::kUnit * v[2 * k]) * s_hinv[h][k];
-                    v[2 * k + 1] = -v[2 * k + 1] * s_hinv[h][k];
+                    v[2 * k] = -(s_hms[h][k][1] * F::kUnit * v[2 * k]) * s_hms[h][k][3];
+                    v[2 * k + 1] = -v[2 * k + 1] * s_hms[h][k][3];
                     any = any || v[2 * k] != real(0) || v[2 * k + 1] != real(0);
                 }
                 if (any) red_vec<NV>(g.grad + s_hkey[h], v);

