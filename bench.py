@@ -225,6 +225,9 @@ def run_ours(a):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     syn = lhvi_b200.synthetic

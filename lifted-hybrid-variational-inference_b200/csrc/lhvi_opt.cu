@@ -75,6 +75,10 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -141,10 +145,12 @@ finish_kernel(const FinishArgs<real> a) {
         for (int p = 0; p < a.world; ++p) a.recv[p][dst] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    // one thread per peer publishes the sequence number: each fences (cumulative over the block's
+    // stores, which the barrier ordered before it) and then stores its flag, so the world - 1 NVLink
+    // round trips overlap instead of queueing behind one thread's release stores
+    if (threadIdx.x < a.world) {
         __threadfence_system();
-        for (int p = 0; p < a.world; ++p)
-            st_release_sys(a.flags[p] + (size_t)a.rank * gridDim.x + blockIdx.x, seq);
+        st_relaxed_sys(a.flags[threadIdx.x] + (size_t)a.rank * gridDim.x + blockIdx.x, seq);
     }
     if (threadIdx.x < a.world) {
         const unsigned long long* f = a.flags[a.rank] + (size_t)threadIdx.x * gridDim.x + blockIdx.x;

@@ -1477,6 +1477,49 @@ __device__ __noinline__ void fold_slow_tile(const FoldCols<real>* c, FoldState<r
     }
 }
 
+// Close the open runs of a whole warp.  The formulas are linear in the sums, so a warp whose lanes
+// all sit in the same run (and whose expansion point is therefore the same) adds the sums up first
+// and lets one lane apply them.  Out of line, state through memory: the streaming loop keeps its
+// registers.  G_w / energy go to sa->acc; the sums and sa->rg are cleared.
+template <typename real, int K, bool USE_CACHE>
+__device__ __noinline__ void fold_close_warp(const real* __restrict__ eta, real* grad, FoldState<real>* st,
+                                             FoldShared<real, K>* sh, FoldSlowAcc<K>* sa, bool slow_used) {
+    constexpr int NV = 2 * K;
+    const int lane = threadIdx.x & 31;
+    const int run_key = st->run_key;
+    real sg0 = st->sg0, sg1 = st->sg1, sg2 = st->sg2, sw0 = st->sw0, sw1 = st->sw1, sw2 = st->sw2;
+    const int k0 = __shfl_sync(0xffffffffu, run_key, 0);
+    const bool uniform = __all_sync(0xffffffffu, run_key == k0);
+    if (uniform) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sg0 += __shfl_xor_sync(0xffffffffu, sg0, o);
+            sg1 += __shfl_xor_sync(0xffffffffu, sg1, o);
+            sg2 += __shfl_xor_sync(0xffffffffu, sg2, o);
+            sw0 += __shfl_xor_sync(0xffffffffu, sw0, o);
+            sw1 += __shfl_xor_sync(0xffffffffu, sw1, o);
+            sw2 += __shfl_xor_sync(0xffffffffu, sw2, o);
+        }
+        double rgs[NV];
+        const bool any_slow = __any_sync(0xffffffffu, slow_used);
+        if (any_slow) {               // literal-path gradients of this run, summed over the warp
+#pragma unroll
+            for (int i = 0; i < NV; ++i) rgs[i] = warp_sum(slow_used ? sa->rg[i] : 0.0);
+        }
+        if (lane == 0 && run_key >= 0)
+            fold_close_run<real, K, USE_CACHE>(eta, grad, run_key, st->xbar, sg0, sg1, sg2, sw0, sw1, sw2, sh, sa->acc,
+                                               any_slow ? rgs : nullptr);
+        if (slow_used) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) sa->rg[i] = 0.0;
+        }
+    } else if (run_key >= 0) {
+        fold_close_run<real, K, USE_CACHE>(eta, grad, run_key, st->xbar, sg0, sg1, sg2, sw0, sw1, sw2, sh, sa->acc,
+                                           slow_used ? sa->rg : nullptr);
+    }
+    st->sg0 = st->sg1 = st->sg2 = st->sw0 = st->sw1 = st->sw2 = real(0);
+}
+
 template <typename real, int K, bool WEIGHTED, bool USE_CACHE>
 __global__ void __launch_bounds__(kFoldThreads, LHVI_FOLD_BLOCKS)
 unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
@@ -1509,8 +1552,11 @@ unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
     const real* __restrict__ col1 = g.fold + g.n_pad;
     const real* __restrict__ col2 = g.fold + 2 * g.n_pad;
 
-    FoldSlowAcc<K> sa;                   // written by the uncommon path only
-    bool slow_used = false;
+    FoldSlowAcc<K> sa;                   // written by the uncommon paths only (local memory)
+    for (int i = 0; i <= K; ++i) sa.acc[i] = 0.0;
+    for (int i = 0; i < 2 * K; ++i) sa.rg[i] = 0.0;
+    bool slow_used = false;              // sa.rg may be non-zero
+    bool sa_used = false;                // sa.acc may be non-zero
 
     // open the run of this thread's first record, so that the first tile is an ordinary one
     unsigned r = lo + threadIdx.x * kQuad;
@@ -1536,6 +1582,24 @@ unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
         load_quad<real>(col1 + r, q_l0);
         load_quad<real>(col2 + r, q_a0);
         if constexpr (WEIGHTED) { load_quad<real>(g.wf + r, q_wf); load_quad<real>(g.gam + r, q_gam); }
+
+        // a whole warp leaving its runs at this quad (the block's range crosses into the next hub's
+        // records) closes them together: one close and one flush per warp instead of 32 closes and
+        // 64 same-address REDs (the per-thread path made the boundary blocks ~12 us late)
+        if (__any_sync(0xffffffffu, q_off[0] != run_key)) {
+            if (__all_sync(0xffffffffu, q_off[0] != run_key)) {
+                FoldState<real> st;
+                st.run_key = run_key; st.xbar = xbar; st.R = R;
+                st.sg0 = sg0; st.sg1 = sg1; st.sg2 = sg2; st.sw0 = sw0; st.sw1 = sw1; st.sw2 = sw2;
+                fold_close_warp<real, K, USE_CACHE>(g.eta, g.grad, &st, &sh, &sa, slow_used);
+                sa_used = true;
+                sg0 = sg1 = sg2 = sw0 = sw1 = sw2 = real(0);
+                run_key = q_off[0];
+                const RunStart<real> b = fold_begin_run<real, K>(g.eta, run_key, &sh);
+                xbar = b.xbar;
+                R = b.R;
+            }
+        }
 
         // accumulate speculatively (which also keeps every load ahead of the branch), commit if
         // the whole quad belongs to the open run and stays clear of the floor
@@ -1567,8 +1631,9 @@ unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
             FoldState<real> st;
             st.run_key = run_key; st.xbar = xbar; st.R = R;
             st.sg0 = sg0; st.sg1 = sg1; st.sg2 = sg2; st.sw0 = sw0; st.sw1 = sw1; st.sw2 = sw2;
-            fold_slow_tile<real, K, WEIGHTED, USE_CACHE>(&cols, &st, &sh, &sa, !slow_used);
+            fold_slow_tile<real, K, WEIGHTED, USE_CACHE>(&cols, &st, &sh, &sa, false);
             slow_used = true;
+            sa_used = true;
             run_key = st.run_key; xbar = st.xbar; R = st.R;
             sg0 = st.sg0; sg1 = st.sg1; sg2 = st.sg2; sw0 = st.sw0; sw1 = st.sw1; sw2 = st.sw2;
         }
@@ -1607,7 +1672,7 @@ unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
             fold_close_run<real, K, USE_CACHE>(g.eta, g.grad, run_key, xbar, sg0, sg1, sg2, sw0, sw1, sw2, &sh, acc,
                                                slow_used ? sa.rg : nullptr);
         }
-        if (slow_used) {
+        if (sa_used) {
 #pragma unroll
             for (int i = 0; i <= K; ++i) acc[i] += sa.acc[i];
         }

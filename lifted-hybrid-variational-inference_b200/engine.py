@@ -30,7 +30,7 @@ import torch
 
 from . import _cabi
 from .dist import PeerExchange, ShardPlan
-from .lowering import LoweredModel, fold_unary
+from .lowering import LoweredModel, RecordGroup, fold_unary
 
 
 def hermgauss_scaled(T):
@@ -52,8 +52,42 @@ def hub_mask(g):
     return mask
 
 
+FOLD_ALIGN_MIN_TILES = 4   # runs of a streamed group at least this long are padded to whole tiles
+
+
+def align_runs(g, null_pot, tile):
+    """Pad the long runs (records on one variable) of a streamed unary group to whole tiles with
+    null records -- coefficient block ``null_pot`` (log psi = 0), zero weights, zero evidence, the
+    run's own offset -- so that a hub boundary never falls inside a tile of the streaming kernel
+    (a split tile sends its threads through the per-thread path: 4-8 us per launch).  The padded
+    group is an ordinary group: every kernel, the generic one included, sums the same values."""
+    key = g.poff[0]
+    starts = np.concatenate([[0], np.flatnonzero(key[1:] != key[:-1]) + 1, [g.n]])
+    lens = np.diff(starts)
+    plen = np.where(lens >= FOLD_ALIGN_MIN_TILES * tile, (lens + tile - 1) // tile * tile, lens)
+    total = int(plen.sum())
+    plen[-1] += (total + tile - 1) // tile * tile - total          # the tail, as before
+    if int(plen.sum()) == g.n:
+        return g
+    dst0 = np.cumsum(plen) - plen
+    pos = np.repeat(dst0 - starts[:-1], lens) + np.arange(g.n)      # where each record goes
+    n2 = int(plen.sum())
+
+    def spread(arr, fill):
+        out = np.full(arr.shape[:-1] + (n2,), fill, dtype=arr.dtype)
+        out[..., pos] = arr
+        return out
+    poff = np.repeat(key[starts[:-1]], plen)[None, :].astype(g.poff.dtype)
+    return RecordGroup(g.nd, g.nc, g.ng, g.ne, g.dims, g.node, spread(g.pot, null_pot), poff,
+                       spread(g.egval, 0.0), spread(g.egvar, 1.0), spread(g.ecval, 0.0),
+                       spread(g.wf, 0.0), spread(g.gam, 0.0), spread(g.nscale, 0.0), g.weighted, g.pure)
+
+
 RUN_SPLIT = 64          # a longer run is split (one thread walks a run)
 RUN_ACC_BYTES = 96 * 1024
+
+
+RUN_THREAD_SLOTS = 148 * 2 * 256     # resident threads of the run-major kernel on one B200
 
 
 def run_layout(g, K, elem_bytes):
@@ -74,8 +108,11 @@ def run_layout(g, K, elem_bytes):
     sg = g.take(order)
     keys = sg.poff[run_arg]
     starts = np.concatenate([[0], np.flatnonzero(keys[1:] != keys[:-1]) + 1, [sg.n]])
-    if np.diff(starts).max() > RUN_SPLIT:
-        pieces = [np.arange(a, b, RUN_SPLIT) for a, b in zip(starts[:-1], starts[1:])]
+    # one thread walks a run: cap the run length, and when the group is small (a rank's shard of a
+    # strong-scaled model) cut the runs further so that every resident thread has one
+    split = int(min(RUN_SPLIT, max(2, -(-sg.n // RUN_THREAD_SLOTS))))
+    if np.diff(starts).max() > split:
+        pieces = [np.arange(a, b, split) for a, b in zip(starts[:-1], starts[1:])]
         starts = np.concatenate(pieces + [[sg.n]])
     run_key = keys[starts[:-1]]
     hid = np.searchsorted(hubs, sg.poff[hub_arg])
@@ -154,7 +191,7 @@ class DeviceEngine:
         self.n_param = n_param
         qx, qw = hermgauss_scaled(self.T)
         self.quad = self._dev(np.concatenate([qx, qw]), self.tdtype)
-        self.ptab = self._dev(m.ptab, self.tdtype)
+        ptab_host = np.asarray(m.ptab, dtype=np.float64)
         self.var_kind = self._dev(m.var_kind.astype(np.uint8))
         self.var_dim = self._dev(m.var_dim.astype(np.int32))
         self.var_off = self._dev(m.var_off.astype(np.int32))
@@ -179,8 +216,10 @@ class DeviceEngine:
 
         self.groups = []      # (descriptor struct, tensors kept alive, RecordGroup)
         esize = 8 if self.dtype_name == "float64" else 4
+        null_pot = {}           # nct -> offset of an all-zero coefficient block appended to ptab
         for g in self.model.groups:
             keep = {}
+            g_report = g        # what bench.py and callers see: the group as lowered
             d = _cabi.LhviGroup()
             runs = run_layout(g, K, esize) if (self.run_major and self.mirror_rule and self.T == 3 and K <= 3) else None
             if runs is not None:
@@ -192,8 +231,17 @@ class DeviceEngine:
             d.hub_mask = hub_mask(g)
             d.pure = int(g.pure)
 
-            fold = fold_unary(g, m.ptab) if (self.symmetric_rule and g.n > 0) else None
             tile = _cabi.LHVI_FOLD_TILE
+            streamed = (self.symmetric_rule and g.n > 0 and not g.node and g.pure and g.nd == 0 and g.nc == 1
+                        and g.ng == 0 and K <= 3 and bool((hub_mask(g) >> g.nd) & 1))
+            if streamed:
+                nct = g.nc + g.ne
+                if nct not in null_pot:
+                    null_pot[nct] = ptab_host.size
+                    ptab_host = np.concatenate([ptab_host, np.zeros((nct + 1) * (nct + 2) // 2)])
+                g = align_runs(g, null_pot[nct], tile)
+                d.n = int(g.n)
+            fold = fold_unary(g, ptab_host) if (self.symmetric_rule and g.n > 0) else None
             n_pad = (g.n + tile - 1) // tile * tile if fold is not None else g.n
 
             def put(name, arr, dt, pad=None):
@@ -224,8 +272,9 @@ class DeviceEngine:
                     keep[name] = self._dev(arr, torch.int32)
                     setattr(d, name, keep[name].data_ptr())
                 d.n_runs, d.n_hubs, d.run_hub_arg = int(run_key.size), int(hubs.size), int(hub_arg)
-            self.groups.append((d, keep, g))
+            self.groups.append((d, keep, g_report))
 
+        self.ptab = self._dev(ptab_host, self.tdtype)
         rows = max(1, len(self.groups)) * _cabi.LHVI_PARTIAL_ROWS
         self.partial_rows = rows
         self.partials = z(rows * (K + 1), torch.float64)
