@@ -38,6 +38,8 @@
  *                             these are still its `energy -= ...` / `g_w[k] -= ...` /
  *                             `g_mu -= ...` sums (VarInference.py:72,88,120-129), split by rank.
  *   lhvi_peer_*               life cycle of the peer-visible exchange buffers (CUDA IPC).
+ *   lhvi_state_pack/unpack    the compact per-variable parameter arrays of the reference
+ *                             (eta[rv], VarInference.py:197-213) <-> the padded device slots.
  *
  * Data layout: a flat parameter vector with one slot per hidden variable
  * (continuous: K x (mu, var) interleaved; discrete: K x D row-major probabilities), a
@@ -243,6 +245,17 @@ int lhvi_mixture_belief(int dtype, int K, int64_t n, const int32_t* q_off, const
  */
 int lhvi_mixture_map(int dtype, int K, int64_t n, const int32_t* q_off, const int32_t* q_dim,
                      const uint8_t* q_kind, const void* eta, const void* w, void* out, void* stream);
+
+/*
+ * The state a reference caller holds between ADAM_update calls is eta[rv] as K x 2 / K x D arrays
+ * (VarInference.py:197-213), i.e. without the padding of the device slots.  These two calls move
+ * between that compact layout and the slot layout: packed[i] = state[map[i]] (pack) and
+ * state[map[i]] = packed[i] (unpack) for i < n; `map` [n] holds the element offsets of the used
+ * slot elements in ascending order (device).  A host transfers `packed` instead of the padded
+ * vector (25 % fewer bytes at K = 3).
+ */
+int lhvi_state_pack(int dtype, int64_t n, const int32_t* map, const void* state, void* packed, void* stream);
+int lhvi_state_unpack(int dtype, int64_t n, const int32_t* map, const void* packed, void* state, void* stream);
 
 #ifdef __cplusplus
 }

@@ -561,3 +561,39 @@ extern "C" int lhvi_mixture_map(int dtype, int K, int64_t n, const int32_t* q_of
         mixture_map_kernel<float><<<grid_for(n, 128), 128, 0, s>>>(K, n, q_off, q_dim, q_kind, (const float*)eta, (const float*)w, (float*)out);
     return check_launch("mixture_map_kernel");
 }
+
+// ---- compact host layout <-> padded device slots ------------------------------------------------
+
+namespace lhvi {
+template <typename real, bool PACK>
+__global__ void __launch_bounds__(256)
+state_move_kernel(long long n, const int* __restrict__ map, const real* __restrict__ src, real* __restrict__ dst) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (PACK) dst[i] = src[map[i]];
+        else dst[map[i]] = src[i];
+    }
+}
+}  // namespace lhvi
+
+template <bool PACK>
+static int state_move(int dtype, int64_t n, const int32_t* map, const void* src, void* dst, void* stream) {
+    if (n == 0) return LHVI_OK;
+    if (!map || !src || !dst) { lhvi::set_error("lhvi_state_pack/unpack: null buffer"); return LHVI_EINVAL; }
+    if (dtype != LHVI_F32 && dtype != LHVI_F64) { lhvi::set_error("dtype %d is neither LHVI_F32 nor LHVI_F64", dtype); return LHVI_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    long long blocks = (n + 1023) / 1024;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (dtype == LHVI_F64)
+        lhvi::state_move_kernel<double, PACK><<<(unsigned)blocks, 256, 0, s>>>(n, map, (const double*)src, (double*)dst);
+    else
+        lhvi::state_move_kernel<float, PACK><<<(unsigned)blocks, 256, 0, s>>>(n, map, (const float*)src, (float*)dst);
+    return lhvi::check_launch("state_move_kernel");
+}
+
+extern "C" int lhvi_state_pack(int dtype, int64_t n, const int32_t* map, const void* state, void* packed, void* stream) {
+    return state_move<true>(dtype, n, map, state, packed, stream);
+}
+
+extern "C" int lhvi_state_unpack(int dtype, int64_t n, const int32_t* map, const void* packed, void* state, void* stream) {
+    return state_move<false>(dtype, n, map, packed, state, stream);
+}

@@ -318,6 +318,33 @@ class DeviceEngine:
                 self.plan.merge(self.tau).double().cpu().numpy(),
                 ws[:K].copy(), ws[K:2 * K].copy())
 
+    # ---- compact host layout (what a reference caller holds: eta[rv] as K x 2 / K x D arrays) ------
+    def packed_map(self):
+        """Element offsets of the used slot elements, ascending (device int32) -- the compact
+        layout of ``pack_state`` / ``unpack_state``; host copy in ``self.packed_index``."""
+        if getattr(self, "_packed_map", None) is None:
+            m, K = self.full_model, self.K
+            sizes = K * m.var_dim.astype(np.int64)
+            off = m.var_off.astype(np.int64)
+            idx = np.repeat(off - (np.cumsum(sizes) - sizes), sizes) + np.arange(int(sizes.sum()))
+            self.packed_index = idx
+            self._packed_map = self._dev(idx.astype(np.int32))
+        return self._packed_map
+
+    def unpack_state(self, packed, which="eta"):
+        """Device tensor ``packed`` (compact layout) -> the padded slot vector ``eta`` / ``tau``."""
+        mp = self.packed_map()
+        dst = self.eta if which == "eta" else self.tau
+        _cabi.check(self.lib.lhvi_state_unpack(self.dcode, mp.numel(), mp.data_ptr(), packed.data_ptr(),
+                                               dst.data_ptr(), self._stream()), self.lib)
+
+    def pack_state(self, packed, which="eta"):
+        """The padded slot vector ``eta`` / ``tau`` -> device tensor ``packed`` (compact layout)."""
+        mp = self.packed_map()
+        src = self.eta if which == "eta" else self.tau
+        _cabi.check(self.lib.lhvi_state_pack(self.dcode, mp.numel(), mp.data_ptr(), src.data_ptr(),
+                                             packed.data_ptr(), self._stream()), self.lib)
+
     def check_exchange(self):
         if self.peer is not None and self.peer.timed_out():
             raise _cabi.LhviError("lhvi: a rank did not reach the gradient exchange within the "

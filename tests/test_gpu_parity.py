@@ -340,6 +340,29 @@ def test_large_scale_properties():
     np.testing.assert_allclose(grad, og, rtol=1e-4, atol=2e-5 * np.abs(og).max())
 
 
+def test_state_pack_unpack_round_trip(ns):
+    """lhvi_state_pack / lhvi_state_unpack: compact per-variable arrays <-> padded device slots."""
+    import torch
+    syn = lhvi_b200.synthetic
+    for model in (syn.relational_hybrid(200, 4, 3, 3, seed=0), syn.gaussian_grid(6, 2, 3)):
+        eta, tau, w_tau = syn.random_state(model, 3)
+        for dtype in ("float64", "float32"):
+            eng = _engine_for(model, dtype)
+            eng.set_state(eta, tau, w_tau)
+            mp = eng.packed_map()
+            idx = eng.packed_index
+            assert idx.size == int((model.K * model.var_dim).sum()) and (np.diff(idx) > 0).all()
+            packed = torch.empty(idx.size, dtype=eng.tdtype, device=eng.device)
+            eng.pack_state(packed, "eta")
+            np.testing.assert_array_equal(packed.cpu().numpy(), eta[idx].astype(packed.cpu().numpy().dtype))
+            eng.eta.zero_()
+            eng.unpack_state(packed, "eta")
+            got = eng.eta.double().cpu().numpy()
+            np.testing.assert_array_equal(got[idx], eta[idx].astype(packed.cpu().numpy().dtype).astype(np.float64))
+            mask = np.ones(got.size, bool); mask[idx] = False
+            assert (got[mask] == 0).all()
+
+
 def test_cabi_rejects_bad_arguments():
     import ctypes as C
     from lhvi_b200 import _cabi
