@@ -142,6 +142,9 @@ typedef struct lhvi_model {
     const void* w;                 /* [K]  mixture weights */
     void* grad;                    /* [n_param + K + 1]  parameter grads | G_w | energy */
     double* partials;              /* [rows][K+1] per-block partial sums of G_w | energy */
+    double quad_host[2 * LHVI_MAX_T]; /* host copy of quad (nodes, then weights / sqrt(pi)): the run-major
+                                      kernel takes the rule through its launch parameters (constant bank)
+                                      instead of registers; required when a group carries run_* columns */
 } lhvi_model;
 
 const char* lhvi_last_error(void);

@@ -47,7 +47,7 @@ class LhviModel(C.Structure):
         ("dtype", C.c_int32), ("K", C.c_int32), ("T", C.c_int32), ("rule_symmetric", C.c_int32),
         ("n_param", C.c_int64),
         ("quad", C.c_void_p), ("ptab", C.c_void_p), ("eta", C.c_void_p), ("w", C.c_void_p),
-        ("grad", C.c_void_p), ("partials", C.c_void_p),
+        ("grad", C.c_void_p), ("partials", C.c_void_p), ("quad_host", C.c_double * (2 * LHVI_MAX_T)),
     ]
 
 

@@ -20,13 +20,19 @@ namespace lhvi {
 
 constexpr int kRunMaxHubs = LHVI_RUN_MAX_HUBS;
 
+// The quadrature rule travels in the launch parameters (constant bank): the compiler then uses the
+// values as constant operands instead of holding ~25 registers of them.
+template <typename real, int T>
 struct RunLaunch {
     int n_hubs;
+    real xi[T], w0[T], w1[T], w2[T], eq[T];     // nodes, omega, omega xi, omega xi^2, exp(-xi^2)
+    real eq_min;
+    real cm0, cm2, cm22, cmd, xm;               // sum W, sum W xi^2, sum W xi^2 xi'^2, sum W xi^4 - cm22, max |xi|
 };
 
 template <typename real, int K, int T, int NE, bool WEIGHTED, int HUBPOS>
 __global__ void __launch_bounds__(kSpecThreads, 2)
-factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
+factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
     using F = Fast<real>;
     constexpr int NC = 2, NG = 0, NCT = 2 + NE, NV = 2 * K;
     using C = Ctx<real, K, T, NC, NG, NE>;
@@ -38,48 +44,32 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     real* s_acc = reinterpret_cast<real*>(s_dyn);   // [n_hubs][NV][kSpecThreads] thread-private sums
 
-    __shared__ real s_quad[2 * T];
-    __shared__ real s_eq[T];
     __shared__ real s_w[K];
-    __shared__ real s_mom[5];
+    __shared__ real s_quad[2 * T];      // for the literal (checked) path only
     __shared__ __align__(16) real s_hq[kRunMaxHubs][K][K][TP];   // q_{k2}(x_{k,t}) of every hub
     __shared__ __align__(16) real s_hnrm[kRunMaxHubs][4];        // 1 / (sqrt(2 pi) var_k2)
     __shared__ __align__(16) real s_hms[kRunMaxHubs][K][4];      // mu_k, sqrt(2 var_k), 2 var_k, 1 / var_k
     __shared__ int s_hkey[kRunMaxHubs];
     __shared__ double s_scratch[(kSpecThreads / 32) * (K + 1)];
+    __shared__ double s_gw[K][kSpecThreads];
 
     const int tid = threadIdx.x;
     const int H = L.n_hubs;
     for (int i = tid; i < 2 * T; i += blockDim.x) s_quad[i] = g.quad[i];
-    for (int i = tid; i < T; i += blockDim.x) s_eq[i] = (real)::exp(-(double)g.quad[i] * (double)g.quad[i]);
     for (int i = tid; i < K; i += blockDim.x) s_w[i] = g.w[i];
+    for (int k = 0; k < K; ++k) s_gw[k][tid] = 0.0;
     for (int i = tid; i < H; i += blockDim.x) s_hkey[i] = g.hub_keys[i];
     for (int i = tid; i < H * NV * kSpecThreads; i += blockDim.x) s_acc[i] = real(0);
-    if (tid == 0) {
-        real M0 = real(0), M2 = real(0), M4 = real(0), xm = real(0);
-        for (int t = 0; t < T; ++t) {
-            const real x = g.quad[t], om = g.quad[T + t];
-            M0 += om;
-            M2 += om * x * x;
-            M4 += om * x * x * x * x;
-            xm = fabs(x) > xm ? fabs(x) : xm;
-        }
-        s_mom[0] = M0 * M0;            // sum W            (two axes)
-        s_mom[1] = M0 * M2;            // sum W xi_a^2
-        s_mom[2] = M0 * M4;            // sum W xi_a^4
-        s_mom[3] = M2 * M2;            // sum W xi_a^2 xi_b^2
-        s_mom[4] = xm;
-    }
     __syncthreads();
     // axis tables of every hub
     for (int idx = tid; idx < H * K * K * T; idx += blockDim.x) {
         const int h = idx / (K * K * T), k = (idx / (K * T)) % K, k2 = (idx / T) % K, t = idx % T;
         const int key = s_hkey[h];
-        real q = s_eq[t];
+        real q = L.eq[t];
         if (k2 != k) {
             const real mu_k = g.eta[key + 2 * k], var_k = g.eta[key + 2 * k + 1];
             const real mu_2 = g.eta[key + 2 * k2], var_2 = g.eta[key + 2 * k2 + 1];
-            const real u = F::sqrt(real(2) * var_k) * s_quad[t] + (mu_k - mu_2);
+            const real u = F::sqrt(real(2) * var_k) * L.xi[t] + (mu_k - mu_2);
             q = F::exp_scaled(real(-0.5) * F::kExpScale * F::rcp(var_2) * (u * u));
         }
         s_hq[h][k][k2][t] = q;
@@ -98,60 +88,35 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
     __syncthreads();
 
     C c;
-    real eq[T], xi[T], wk[K];
-    real eq_min = real(1);
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-        xi[t] = s_quad[t];
-        c.w0[t] = s_quad[T + t];
-        c.w1[t] = c.w0[t] * xi[t];
-        c.w2[t] = c.w1[t] * xi[t];
-        eq[t] = s_eq[t];
-        eq_min = eq[t] < eq_min ? eq[t] : eq_min;
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) wk[k] = s_w[k];
     c.eta = g.eta;
     c.s_w = s_w;
-    const real cm0 = s_mom[0], cm2 = s_mom[1], cm22 = s_mom[3], cmd = s_mom[2] - s_mom[3], xm = s_mom[4];
     auto own_floor = [](real own) { return own < F::kBFloor; };
-
-    double acc[K + 1];
-#pragma unroll
-    for (int i = 0; i <= K; ++i) acc[i] = 0.0;
 
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long run = (long long)blockIdx.x * blockDim.x + tid; run < g.n_runs; run += stride) {
         const int keyE = __ldg(g.run_key + run);
         const int r0 = __ldg(g.run_start + run), r1 = __ldg(g.run_start + run + 1);
-        {   // warm L1 with the next run's first records and slot
-            const long long nxt = run + stride;
-            if (nxt < g.n_runs) {
-                const int rn = __ldg(g.run_start + nxt);
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(g.pot + rn));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(g.run_hid + rn));
-                if constexpr (WEIGHTED) {
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.wf + rn));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.gam + rn));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.gam + g.n + rn));
-                }
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(g.eta + __ldg(g.run_key + nxt)));
-            }
+        // the next run's first record and slot are fetched now and used to warm L1 once this
+        // run's records are done (by then the two loads have long arrived)
+        const long long nxt = run + stride;
+        int rn = -1, keyn = 0;
+        if (nxt < g.n_runs) {
+            rn = __ldg(g.run_start + nxt);
+            keyn = __ldg(g.run_key + nxt);
         }
 
         // ---- the run variable: parameters and axis tables, once per run
-        real muE[K], sdE[K], invE[K], nrmE[K], hvE[K], tvE[K];
+        real muE[K], sdE[K], wnE[K], hvE[K];     // mean, sqrt(2 var), w_k / (sqrt(2 pi) var), -log2(e) / (2 var)
         {
             real slot[NV];
             load_vec<NV>(g.eta + keyE, slot);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 muE[k] = slot[2 * k];
-                invE[k] = F::rcp(slot[2 * k + 1]);
-                hvE[k] = real(-0.5) * F::kExpScale * invE[k];
-                nrmE[k] = invE[k] * real(1.0 / kSqrt2Pi);
-                tvE[k] = real(2) * slot[2 * k + 1];
-                sdE[k] = F::sqrt(tvE[k]);
+                const real inv = F::rcp(slot[2 * k + 1]);
+                hvE[k] = real(-0.5) * F::kExpScale * inv;
+                wnE[k] = s_w[k] * (inv * real(1.0 / kSqrt2Pi));
+                sdE[k] = F::sqrt(real(2) * slot[2 * k + 1]);
             }
         }
         real qE[K][K][T];
@@ -159,22 +124,22 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
         for (int k = 0; k < K; ++k)
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-                const real dx = sdE[k] * xi[t];
+                const real dx = sdE[k] * L.xi[t];
 #pragma unroll
                 for (int k2 = 0; k2 < K; ++k2) {
                     if (k2 == k) {
-                        qE[k][k2][t] = eq[t];
+                        qE[k][k2][t] = L.eq[t];
                     } else {
                         const real u = dx + (muE[k] - muE[k2]);
                         qE[k][k2][t] = F::exp_scaled(hvE[k2] * (u * u));
                     }
                 }
             }
-        real G1[K], G2[K], af[K + 1];
+        real G1[K], G2[K], af[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) { G1[k] = real(0); G2[k] = real(0); }
 #pragma unroll
-        for (int i = 0; i <= K; ++i) af[i] = real(0);
+        for (int i = 0; i < K; ++i) af[i] = real(0);
         c.pt.poff[0] = keyE;
 
         // ---- its records (columns fetched one record ahead)
@@ -227,9 +192,8 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
 
             real pk0[K];
 #pragma unroll
-            for (int k2 = 0; k2 < K; ++k2) pk0[k2] = wk[k2] * nrmE[k2] * s_hnrm[h][k2];
+            for (int k2 = 0; k2 < K; ++k2) pk0[k2] = wnE[k2] * s_hnrm[h][k2];
 
-            real e_sum = real(0);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 real qH[K][T];
@@ -259,16 +223,16 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
                     if constexpr (T == 3) {              // one pair: its weights are applied at the end
                         hs = Lg[0] + Lg[2];
                         hd = Lg[2] - Lg[0];
-                        s0 = c.w0[0] * hs + c.w0[1] * Lg[1];
+                        s0 = L.w0[0] * hs + L.w0[1] * Lg[1];
                     } else {
 #pragma unroll
                         for (int t2 = 0; t2 < T / 2; ++t2) {
                             const real sm = Lg[t2] + Lg[T - 1 - t2];
-                            s0 += c.w0[t2] * sm;
-                            hs += c.w2[t2] * sm;
-                            hd += c.w1[T - 1 - t2] * (Lg[T - 1 - t2] - Lg[t2]);
+                            s0 += L.w0[t2] * sm;
+                            hs += L.w2[t2] * sm;
+                            hd += L.w1[T - 1 - t2] * (Lg[T - 1 - t2] - Lg[t2]);
                         }
-                        if constexpr ((T & 1) != 0) s0 += c.w0[T / 2] * Lg[T / 2];
+                        if constexpr ((T & 1) != 0) s0 += L.w0[T / 2] * Lg[T / 2];
                     }
                     S[t1] = s0; HS[t1] = hs; HD[t1] = hd;
                 }
@@ -276,32 +240,32 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
 #pragma unroll
                 for (int t1 = 0; t1 < T / 2; ++t1) {
                     const real sm = S[t1] + S[T - 1 - t1];
-                    Elb += c.w0[t1] * sm;
-                    e2 += c.w2[t1] * sm;
-                    e1 += c.w1[T - 1 - t1] * (S[T - 1 - t1] - S[t1]);
-                    g1 += c.w0[t1] * (HD[t1] + HD[T - 1 - t1]);
-                    g2 += c.w0[t1] * (HS[t1] + HS[T - 1 - t1]);
+                    Elb += L.w0[t1] * sm;
+                    e2 += L.w2[t1] * sm;
+                    e1 += L.w1[T - 1 - t1] * (S[T - 1 - t1] - S[t1]);
+                    g1 += L.w0[t1] * (HD[t1] + HD[T - 1 - t1]);
+                    g2 += L.w0[t1] * (HS[t1] + HS[T - 1 - t1]);
                 }
                 if constexpr ((T & 1) != 0) {
-                    Elb += c.w0[T / 2] * S[T / 2];
-                    g1 += c.w0[T / 2] * HD[T / 2];
-                    g2 += c.w0[T / 2] * HS[T / 2];
+                    Elb += L.w0[T / 2] * S[T / 2];
+                    g1 += L.w0[T / 2] * HD[T / 2];
+                    g2 += L.w0[T / 2] * HS[T / 2];
                 }
-                if constexpr (T == 3) { g1 *= c.w1[2]; g2 *= c.w2[0]; }
+                if constexpr (T == 3) { g1 *= L.w1[2]; g2 *= L.w2[0]; }
 
                 // ---- closed-form quadrature sums of log psi (see factor_spec_kernel)
                 const real h0 = a00 * e, h1 = a11 * muH, x01 = a01 * muH;
                 const real t0 = (l0 + h0) + x01, t1 = l1 + h1;
                 const real P = e * t0 + (muH * t1 + c0);
                 const real Q0 = sE * (t0 + h0), Q1 = sdH * (a01 * e + (t1 + h1));
-                const real R0 = a00 * tvE[k], R1 = a11 * tvH, Rs = R0 + R1;
+                const real R0 = a00 * (sE * sE), R1 = a11 * tvH, Rs = R0 + R1;
                 const real absR = fabs(a01) * (sE * sdH) + (fabs(R0) + fabs(R1));
-                const bool redo = own_floor(pk0[k] * eq_min * eq_min) ||
-                                  (P - xm * ((fabs(Q0) + fabs(Q1)) + xm * absR)) < F::kQFloor;
-                const real base2 = cm2 * P + cm22 * Rs;
-                real Ek = (cm0 * P + cm2 * Rs) - Elb;
-                real m1E = cm2 * Q0 - e1, m1H = cm2 * Q1 - g1;
-                real m2E = (cmd * R0 + base2) - e2, m2H = (cmd * R1 + base2) - g2;
+                const bool redo = own_floor(pk0[k] * (L.eq_min * L.eq_min)) ||
+                                  (P - L.xm * ((fabs(Q0) + fabs(Q1)) + L.xm * absR)) < F::kQFloor;
+                const real base2 = L.cm2 * P + L.cm22 * Rs;
+                real Ek = (L.cm0 * P + L.cm2 * Rs) - Elb;
+                real m1E = L.cm2 * Q0 - e1, m1H = L.cm2 * Q1 - g1;
+                real m2E = (L.cmd * R0 + base2) - e2, m2H = (L.cmd * R1 + base2) - g2;
                 if (redo) {
                     // a floor may be active on this grid: redo it with the literal formulas
                     real pk[K], lin0[NQ];
@@ -317,8 +281,9 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
                     c.A[0][0] = a00; c.A[1][1] = a11; c.A[0][1] = a01;
 #pragma unroll
                     for (int t = 0; t < T; ++t) {
-                        c.x[0][t] = sE * xi[t] + e;
-                        c.x[1][t] = sdH * xi[t] + muH;
+                        c.w0[t] = L.w0[t]; c.w1[t] = L.w1[t]; c.w2[t] = L.w2[t];
+                        c.x[0][t] = sE * L.xi[t] + e;
+                        c.x[1][t] = sdH * L.xi[t] + muH;
 #pragma unroll
                         for (int k2 = 0; k2 < K; ++k2) { c.q[0][k2][t] = real(0); c.q[1][k2][t] = real(0); }
                     }
@@ -335,22 +300,40 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch L) {
                 ap[0] += gamH * m1H;
                 ap[kSpecThreads] += gamH * (m2H * F::kUnit - real(0.5) * Ek);
                 af[k] += wf * Ek;
-                e_sum += wk[k] * Ek;
             }
-            af[K] += wf * e_sum;
         }
 #undef LHVI_RUN_FETCH
+        if (rn >= 0) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(g.pot + rn));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(g.run_hid + rn));
+            if constexpr (WEIGHTED) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(g.wf + rn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(g.gam + rn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(g.gam + g.n + rn));
+            }
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(g.eta + keyn));
+        }
 
         // ---- end of the run: the run variable's gradient, one vector RED
         real gvE[NV];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            gvE[2 * k] = -(sdE[k] * F::kUnit * G1[k]) * invE[k];
-            gvE[2 * k + 1] = -G2[k] * invE[k];
+            const real inv = real(2) * F::rcp(sdE[k] * sdE[k]);      // 1 / var
+            gvE[2 * k] = -(sdE[k] * F::kUnit * G1[k]) * inv;
+            gvE[2 * k + 1] = -G2[k] * inv;
         }
         if (r1 > r0) red_vec<NV>(g.grad + keyE, gvE);
+        // G_w sums of this thread, in double, kept in shared memory ([k][thread]: private slots)
 #pragma unroll
-        for (int i = 0; i <= K; ++i) acc[i] -= (double)af[i];
+        for (int k = 0; k < K; ++k) s_gw[k][tid] -= (double)af[k];
+    }
+    // the energy is the same sum weighted by w_k: E = sum_k w_k G_w[k]
+    double acc[K + 1];
+    acc[K] = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        acc[k] = s_gw[k][tid];
+        acc[K] += (double)s_w[k] * acc[k];
     }
 
     publish_partials(acc, K + 1, s_scratch, g.partials);      // ends with a barrier
@@ -406,8 +389,21 @@ static int launch_run(const lhvi_model* m, const lhvi_group* g, int64_t row0, cu
         if (blocks > resident) blocks = resident;
         if (blocks > LHVI_PARTIAL_ROWS - 1) blocks = LHVI_PARTIAL_ROWS - 1;
         if (blocks < 1) blocks = 1;
-        RunLaunch L;
+        RunLaunch<real, T> L;
         L.n_hubs = g->n_hubs;
+        double M0 = 0.0, M2 = 0.0, M4 = 0.0, xm = 0.0, eqm = 1.0;
+        for (int t = 0; t < T; ++t) {
+            const double x = m->quad_host[t], om = m->quad_host[T + t];
+            L.xi[t] = (real)x; L.w0[t] = (real)om; L.w1[t] = (real)(om * x); L.w2[t] = (real)(om * x * x);
+            L.eq[t] = (real)::exp(-x * x);
+            eqm = ::exp(-x * x) < eqm ? ::exp(-x * x) : eqm;
+            M0 += om; M2 += om * x * x; M4 += om * x * x * x * x;
+            xm = ::fabs(x) > xm ? ::fabs(x) : xm;
+        }
+        if (!(M0 > 0.5)) { set_error("factor_run_kernel: lhvi_model::quad_host is not filled in"); return (int)LHVI_EINVAL; }
+        L.eq_min = (real)eqm;
+        L.cm0 = (real)(M0 * M0); L.cm2 = (real)(M0 * M2); L.cm22 = (real)(M2 * M2);
+        L.cmd = (real)(M0 * M4 - M2 * M2); L.xm = (real)xm;
         kernel<<<(unsigned)blocks, kSpecThreads, dyn, s>>>(v, L);
         return check_launch("factor_run_kernel");
     };

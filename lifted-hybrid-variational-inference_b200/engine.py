@@ -282,6 +282,8 @@ class DeviceEngine:
         md = _cabi.LhviModel()
         md.dtype, md.K, md.T, md.n_param = self.dcode, K, self.T, n_param
         md.rule_symmetric = int(self.mirror_rule)
+        for i, v in enumerate(np.concatenate([qx, qw])):
+            md.quad_host[i] = float(v)
         md.quad, md.ptab = self.quad.data_ptr(), self.ptab.data_ptr()
         md.eta, md.w = self.eta.data_ptr(), self.wstate[K:2 * K].data_ptr()
         md.grad, md.partials = self.grad.data_ptr(), self.partials.data_ptr()
