@@ -19,6 +19,12 @@
 namespace lhvi {
 
 constexpr int kRunMaxHubs = LHVI_RUN_MAX_HUBS;
+#ifndef LHVI_RUN_THREADS
+#define LHVI_RUN_THREADS 256
+#define LHVI_RUN_BLOCKS 2
+#endif
+constexpr int kRunThreads = LHVI_RUN_THREADS;     // threads per block / resident blocks per SM: register budget
+constexpr int kRunBlocks = LHVI_RUN_BLOCKS;
 
 // The quadrature rule travels in the launch parameters (constant bank): the compiler then uses the
 // values as constant operands instead of holding ~25 registers of them.
@@ -31,7 +37,7 @@ struct RunLaunch {
 };
 
 template <typename real, int K, int T, int NE, bool WEIGHTED, int HUBPOS>
-__global__ void __launch_bounds__(kSpecThreads, 2)
+__global__ void __launch_bounds__(kRunThreads, kRunBlocks)
 factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
     using F = Fast<real>;
     constexpr int NC = 2, NG = 0, NCT = 2 + NE, NV = 2 * K;
@@ -42,7 +48,7 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
     static_assert(K <= 4, "hub normalisers are stored four to a row");
 
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    real* s_acc = reinterpret_cast<real*>(s_dyn);   // [n_hubs][NV][kSpecThreads] thread-private sums
+    real* s_acc = reinterpret_cast<real*>(s_dyn);   // [n_hubs][NV][kRunThreads] thread-private sums
 
     __shared__ real s_w[K];
     __shared__ real s_quad[2 * T];      // for the literal (checked) path only
@@ -50,8 +56,8 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
     __shared__ __align__(16) real s_hnrm[kRunMaxHubs][4];        // 1 / (sqrt(2 pi) var_k2)
     __shared__ __align__(16) real s_hms[kRunMaxHubs][K][4];      // mu_k, sqrt(2 var_k), 2 var_k, 1 / var_k
     __shared__ int s_hkey[kRunMaxHubs];
-    __shared__ double s_scratch[(kSpecThreads / 32) * (K + 1)];
-    __shared__ double s_gw[K][kSpecThreads];
+    __shared__ double s_scratch[(kRunThreads / 32) * (K + 1)];
+    __shared__ double s_gw[K][kRunThreads];
 
     const int tid = threadIdx.x;
     const int H = L.n_hubs;
@@ -59,7 +65,7 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
     for (int i = tid; i < K; i += blockDim.x) s_w[i] = g.w[i];
     for (int k = 0; k < K; ++k) s_gw[k][tid] = 0.0;
     for (int i = tid; i < H; i += blockDim.x) s_hkey[i] = g.hub_keys[i];
-    for (int i = tid; i < H * NV * kSpecThreads; i += blockDim.x) s_acc[i] = real(0);
+    for (int i = tid; i < H * NV * kRunThreads; i += blockDim.x) s_acc[i] = real(0);
     __syncthreads();
     // axis tables of every hub
     for (int idx = tid; idx < H * K * K * T; idx += blockDim.x) {
@@ -296,9 +302,9 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
                 // raw sums; the factors -sdev kUnit / var and -1 / var are applied once at the end
                 G1[k] += gamE * m1E;
                 G2[k] += gamE * (m2E * F::kUnit - real(0.5) * Ek);
-                real* ap = s_acc + ((h * NV + 2 * k) * kSpecThreads + tid);
+                real* ap = s_acc + ((h * NV + 2 * k) * kRunThreads + tid);
                 ap[0] += gamH * m1H;
-                ap[kSpecThreads] += gamH * (m2H * F::kUnit - real(0.5) * Ek);
+                ap[kRunThreads] += gamH * (m2H * F::kUnit - real(0.5) * Ek);
                 af[k] += wf * Ek;
             }
         }
@@ -346,9 +352,9 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 real s = real(0);
-                const real* src = s_acc + (h * NV + i) * kSpecThreads;
+                const real* src = s_acc + (h * NV + i) * kRunThreads;
 #pragma unroll
-                for (int j = 0; j < kSpecThreads / 32; ++j) s += src[lane + 32 * j];
+                for (int j = 0; j < kRunThreads / 32; ++j) s += src[lane + 32 * j];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 v[i] = s;
@@ -371,7 +377,7 @@ template <typename real, int K, int T, int NE>
 static int launch_run(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStream_t s) {
     const GroupView<real> v = make_view<real>(m, g, row0);
     if (g->n_hubs < 1 || g->n_hubs > kRunMaxHubs) return 1;
-    const size_t dyn = (size_t)g->n_hubs * 2 * K * kSpecThreads * sizeof(real);
+    const size_t dyn = (size_t)g->n_hubs * 2 * K * kRunThreads * sizeof(real);
     if (dyn > 96 * 1024) return 1;
     if (g->n >= (1ll << 31)) { set_error("factor_run_kernel: more than 2^31 records in one group"); return (int)LHVI_ELIMIT; }
     auto go = [&](auto kernel) {
@@ -383,9 +389,9 @@ static int launch_run(const lhvi_model* m, const lhvi_group* g, int64_t row0, cu
         int dev = 0, per_sm = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSpecThreads, dyn);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRunThreads, dyn);
         long long resident = (long long)(per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
-        long long blocks = (g->n_runs + kSpecThreads - 1) / kSpecThreads;
+        long long blocks = (g->n_runs + kRunThreads - 1) / kRunThreads;
         if (blocks > resident) blocks = resident;
         if (blocks > LHVI_PARTIAL_ROWS - 1) blocks = LHVI_PARTIAL_ROWS - 1;
         if (blocks < 1) blocks = 1;
@@ -404,7 +410,7 @@ static int launch_run(const lhvi_model* m, const lhvi_group* g, int64_t row0, cu
         L.eq_min = (real)eqm;
         L.cm0 = (real)(M0 * M0); L.cm2 = (real)(M0 * M2); L.cm22 = (real)(M2 * M2);
         L.cmd = (real)(M0 * M4 - M2 * M2); L.xm = (real)xm;
-        kernel<<<(unsigned)blocks, kSpecThreads, dyn, s>>>(v, L);
+        kernel<<<(unsigned)blocks, kRunThreads, dyn, s>>>(v, L);
         return check_launch("factor_run_kernel");
     };
     const bool weighted = g->weighted != 0;

@@ -1,0 +1,395 @@
+"""Array-native colour passing: the lifted engines at sizes where a
+Python object per ground variable and factor is not an option.
+
+The reference compresses a ground ``Graph`` with ``CompressedGraphWithObs.CompressedGraph.run``
+(``:264-271``): variables start coloured by (domain, hidden | exact evidence value)
+(``init_cluster`` ``:187-234``), factors by their potential (through the potentials' own
+``__hash__`` / ``__eq__``), and until the number of variable classes stops growing
+
+* factors are split by the tuple of their arguments' classes -- sorted if the potential is
+  ``symmetric`` (``split_factors`` ``:152-175,260-262``),
+* variables are split by the multiset of their neighbouring factor classes (positions are *not*
+  part of the key, ``split_rvs`` ``:47-76,249-258``).
+
+``colour_passing`` does exactly that on index arrays with sort / unique passes (numpy; the arrays
+are what ``synthetic.py``'s generators emit), ``quotient`` turns the fixed point into the few
+handle objects ``lowering.lower_compressed`` needs -- class size, representative degree ``N``
+(``:45``), neighbour counts ``count[f]`` (``:43``), mean evidence value / variance (``:9-13``) --
+so the compressed model is lowered by the same code as the object route, and
+``tests/test_lifting.py`` checks both routes give the same partition and the same lowered model
+on the object-graph twins of the generators.
+"""
+from __future__ import annotations
+
+from collections import Counter
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import lowering
+
+
+@dataclass
+class FactorBlock:
+    """``n`` ground factors sharing one potential object: ``args[i]`` are the variable indices of
+    factor i in argument order."""
+    potential: object
+    args: np.ndarray              # int64 [n, arity]
+
+    @property
+    def n(self):
+        return int(self.args.shape[0])
+
+    @property
+    def arity(self):
+        return int(self.args.shape[1])
+
+
+@dataclass
+class GroundArrays:
+    """A ground graph as arrays.  ``var_dom[v]`` indexes ``domains``; ``var_value[v]`` is the
+    evidence value (NaN: hidden; for a discrete domain the value itself, as the reference stores
+    it in ``RV.value``)."""
+    domains: list
+    var_dom: np.ndarray           # int32 [n_vars]
+    var_value: np.ndarray         # float64 [n_vars]
+    blocks: list = field(default_factory=list)
+
+    @property
+    def n_vars(self):
+        return int(self.var_dom.shape[0])
+
+    @property
+    def n_factors(self):
+        return sum(b.n for b in self.blocks)
+
+    def degrees(self):
+        """Ground degree of every variable (``Graph.init_nb``: one entry per argument position)."""
+        deg = np.zeros(self.n_vars, dtype=np.int64)
+        for b in self.blocks:
+            np.add.at(deg, b.args.reshape(-1), 1)
+        return deg
+
+
+def _rank_rows(cols):
+    """Dense ids (0..m-1, in lexicographic order of the rows) of the rows of ``cols`` (list of
+    equal-length integer arrays)."""
+    if len(cols) == 1:
+        _, inv = np.unique(cols[0], return_inverse=True)
+        return inv.astype(np.int64)
+    order = np.lexsort(cols[::-1])
+    stacked = np.stack([c[order] for c in cols])
+    new = np.ones(stacked.shape[1], dtype=bool)
+    new[1:] = (stacked[:, 1:] != stacked[:, :-1]).any(axis=0)
+    ids_sorted = np.cumsum(new) - 1
+    out = np.empty(stacked.shape[1], dtype=np.int64)
+    out[order] = ids_sorted
+    return out
+
+
+def _potential_ids(blocks):
+    """Colour of each block's potential: equal potentials (``==``, the reference's dict keys)
+    share an id."""
+    seen = {}
+    ids = []
+    for b in blocks:
+        ids.append(seen.setdefault(b.potential, len(seen)))
+    return ids
+
+
+_MASK = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix(x, seed):
+    """splitmix64 finaliser on uint64 arrays (wrap-around arithmetic)."""
+    with np.errstate(over="ignore"):
+        z = (x.astype(np.uint64) + np.uint64(seed)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def colour_passing(ga: GroundArrays, split_cont_evidence=True, max_sweeps=1000):
+    """Coarsest equitable partition the reference's ``CompressedGraph.run`` converges to.
+
+    Returns ``(var_colour [n_vars], [factor_colour of each block], sweeps)`` with dense class ids.
+    ``split_cont_evidence=False`` starts with all continuous observations of a domain in one
+    class (the coarse start of C2F, ``init_cluster(False)``).
+
+    The multiset of neighbouring factor classes of a variable is compared through two
+    independent 64-bit multiset hashes (sums of mixed class ids, order-free like the
+    reference's sorted tuple); a false merge needs a 128-bit collision."""
+    nv = ga.n_vars
+    hidden = np.isnan(ga.var_value)
+    val = np.where(hidden, 0.0, ga.var_value)
+    if not split_cont_evidence:
+        cont = np.array([bool(d.continuous) for d in ga.domains])[ga.var_dom]
+        val = np.where(cont, 0.0, val)
+    _, val_id = np.unique(val, return_inverse=True)
+    vcol = _rank_rows([ga.var_dom.astype(np.int64), hidden.astype(np.int64), val_id.astype(np.int64)])
+
+    # blocks whose potentials compare equal are one colour to start with: rank them together
+    pot_id = _potential_ids(ga.blocks)
+    merged = {}
+    for i, (b, pid) in enumerate(zip(ga.blocks, pot_id)):
+        merged.setdefault((pid, b.arity), []).append(i)
+    supers = []                                  # (member block indices, args, symmetric)
+    for (pid, arity), members in merged.items():
+        args = np.concatenate([ga.blocks[i].args for i in members]) if len(members) > 1 else ga.blocks[members[0]].args
+        supers.append((members, args.astype(np.int64), bool(getattr(ga.blocks[members[0]].potential, "symmetric", False))))
+    scols = [np.full(a.shape[0], j, dtype=np.int64) for j, (_, a, _) in enumerate(supers)]
+
+    # incidence entries (one per argument position), sorted by variable once
+    inc_var = np.concatenate([a.reshape(-1) for _, a, _ in supers]) if supers else np.zeros(0, np.int64)
+    sizes = [a.shape[0] for _, a, _ in supers]
+    foff = np.cumsum([0] + sizes)
+    inc_fac = np.concatenate([np.repeat(np.arange(a.shape[0]) + foff[j], a.shape[1])
+                              for j, (_, a, _) in enumerate(supers)]) if supers else np.zeros(0, np.int64)
+    by_var = np.argsort(inc_var, kind="stable")
+    inc_var_s, inc_fac_s = inc_var[by_var], inc_fac[by_var]
+    seg_first = np.ones(inc_var_s.size, dtype=bool)
+    seg_first[1:] = inc_var_s[1:] != inc_var_s[:-1]
+    seg_start = np.flatnonzero(seg_first)
+    seg_var = inc_var_s[seg_start]
+
+    n_classes = -1
+    sweeps = 0
+    while n_classes != int(vcol.max()) + 1 and sweeps < max_sweeps:
+        n_classes = int(vcol.max()) + 1
+        sweeps += 1
+        # ---- split factors by (own class, classes of the arguments)
+        offset = 0
+        for j, (_, args, sym) in enumerate(supers):
+            arg_cols = vcol[args]
+            if sym:
+                arg_cols = np.sort(arg_cols, axis=1)
+            ids = _rank_rows([scols[j]] + [arg_cols[:, a] for a in range(args.shape[1])])
+            scols[j] = ids + offset
+            offset += int(ids.max()) + 1 if args.shape[0] else 0
+        # ---- split variables by (own class, multiset of neighbouring factor classes)
+        if inc_var_s.size:
+            fc = np.concatenate(scols)[inc_fac_s]
+            with np.errstate(over="ignore"):
+                h1 = np.add.reduceat(_mix(fc, 0x243F6A8885A308D3), seg_start)
+                h2 = np.add.reduceat(_mix(fc, 0x13198A2E03707344), seg_start)
+            H1 = np.zeros(nv, dtype=np.uint64)
+            H2 = np.zeros(nv, dtype=np.uint64)
+            H1[seg_var], H2[seg_var] = h1, h2
+            vcol = _rank_rows([vcol, H1.view(np.int64), H2.view(np.int64)])
+    fcols = [None] * len(ga.blocks)
+    for j, (members, _, _) in enumerate(supers):
+        pos = 0
+        for i in members:
+            fcols[i] = scols[j][pos:pos + ga.blocks[i].n]
+            pos += ga.blocks[i].n
+    return vcol, fcols, sweeps
+
+
+class _ClassRV:
+    """Variable class handle for ``lowering.lower_graph`` (what it reads of a ``SuperRV``)."""
+
+    def __init__(self, uid, domain, value, variance, size, degree, rep):
+        self.uid, self.domain, self.value, self.variance = uid, domain, value, variance
+        self.rvs = range(size)
+        self.N = degree
+        self.rep = rep                 # ground index of the representative (smallest member)
+        self.count = Counter()
+        self.nb = ()
+
+    def __lt__(self, other):
+        return self.uid < other.uid
+
+
+class _ClassF:
+    def __init__(self, uid, potential, size, rep):
+        self.uid, self.potential = uid, potential
+        self.factors = range(size)
+        self.rep = rep
+        self.nb = ()
+
+    def __lt__(self, other):
+        return self.uid < other.uid
+
+
+class QuotientGraph:
+    """The compressed graph as ``lower_compressed`` wants it: ``rvs`` / ``factors`` are class
+    handles; ``var_class`` / ``factor_class`` map ground indices to them."""
+
+    def __init__(self, rvs, factors, var_colour, factor_colours):
+        self.rvs, self.factors = rvs, factors
+        self.var_colour, self.factor_colours = var_colour, factor_colours
+
+    @property
+    def compression(self):
+        ground = self.var_colour.size + sum(c.size for c in self.factor_colours)
+        return ground / max(1, len(self.rvs) + len(self.factors))
+
+
+def quotient(ga: GroundArrays, var_colour, factor_colours) -> QuotientGraph:
+    """Class handles of a partition (``SuperRV`` ``:8-45``, ``SuperF`` ``:133-150``): evidence
+    classes carry the mean value and population variance of their members, every class its
+    size, variable classes the representative's degree ``N`` and neighbour counts."""
+    nv = ga.n_vars
+    deg = ga.degrees()
+    ncls = int(var_colour.max()) + 1
+    order = np.argsort(var_colour, kind="stable")
+    starts = np.searchsorted(var_colour[order], np.arange(ncls))
+    sizes = np.diff(np.append(starts, nv))
+    reps = order[starts]                                               # smallest ground index
+    hidden = np.isnan(ga.var_value)
+    vsum = np.bincount(var_colour, weights=np.where(hidden, 0.0, ga.var_value), minlength=ncls)
+    mean = vsum / sizes
+    dev = np.where(hidden, 0.0, ga.var_value - mean[var_colour])
+    variance = np.bincount(var_colour, weights=dev * dev, minlength=ncls) / sizes
+    rvs = []
+    for c in range(ncls):
+        r = int(reps[c])
+        is_hidden = bool(hidden[r])
+        rvs.append(_ClassRV(c, ga.domains[int(ga.var_dom[r])], None if is_hidden else float(mean[c]),
+                            None if is_hidden else float(variance[c]), int(sizes[c]), int(deg[r]), r))
+    factors = []
+    rep_of_var = {int(r): rvs[c] for c, r in enumerate(reps)}
+    classes = {}                       # factor colour -> handle (a class may span several blocks)
+    sizes_f = Counter()
+    for fcol in factor_colours:
+        ids, counts = np.unique(fcol, return_counts=True)
+        for cid, cn in zip(ids, counts):
+            sizes_f[int(cid)] += int(cn)
+    for b, fcol in zip(ga.blocks, factor_colours):
+        if b.n == 0:
+            continue
+        ids, first = np.unique(fcol, return_index=True)
+        for cid, fi in zip(ids, first):
+            if int(cid) not in classes:
+                f = _ClassF(len(factors), b.potential, sizes_f[int(cid)], int(fi))
+                f.nb = tuple(rvs[int(var_colour[v])] for v in b.args[fi])
+                classes[int(cid)] = f
+                factors.append(f)
+        # neighbour counts of the representatives: factors of this block that touch one
+        for a in range(b.arity):
+            col = b.args[:, a]
+            hit = np.flatnonzero(np.isin(col, reps))
+            for fi in hit:
+                rep_of_var[int(col[fi])].count[classes[int(fcol[fi])]] += 1
+    for rv in rvs:
+        rv.nb = tuple(rv.count)
+    return QuotientGraph(rvs, factors, var_colour, list(factor_colours))
+
+
+def lift(ga: GroundArrays, split_cont_evidence=True) -> QuotientGraph:
+    vcol, fcols, _ = colour_passing(ga, split_cont_evidence)
+    return quotient(ga, vcol, fcols)
+
+
+def lower_lifted(ga: GroundArrays, K, T, **kw):
+    """``LiftedVarInference`` on arrays: colour passing, then the compressed lowering
+    (``lowering.lower_compressed``: W_f = class size, gamma = ``count[f]`` at the first
+    occurrence of the class in ``f.nb``, node terms weighted by the variable class size)."""
+    q = lift(ga)
+    return lowering.lower_compressed(q, K, T, **kw), q
+
+
+def lower_ground_arrays(ga: GroundArrays, K, T):
+    """``VarInference`` on arrays: every variable and factor its own class (all weights 1) --
+    the trivial partition pushed through the same route (small models; the benchmark-scale
+    ground models are emitted directly as record columns by ``synthetic.py``)."""
+    vcol = np.arange(ga.n_vars, dtype=np.int64)
+    fcols, off = [], 0
+    for b in ga.blocks:
+        fcols.append(np.arange(b.n, dtype=np.int64) + off)
+        off += b.n
+    q = quotient(ga, vcol, fcols)
+    return lowering.lower_compressed(q, K, T), q
+
+
+def arrays_from_graph(g) -> tuple:
+    """``GroundArrays`` of an object graph (any ``Graph`` of this repo or of the reference):
+    variables in id order, one block per potential object.  Returns ``(arrays, rvs)`` with
+    ``rvs[i]`` the object behind variable index i."""
+    rvs = sorted(g.rvs, key=lambda rv: rv.id) if all(hasattr(rv, "id") for rv in g.rvs) else list(g.rvs)
+    index = {id(rv): i for i, rv in enumerate(rvs)}
+    domains, dom_index = [], {}
+    var_dom = np.zeros(len(rvs), dtype=np.int32)
+    var_value = np.full(len(rvs), np.nan)
+    for i, rv in enumerate(rvs):
+        if id(rv.domain) not in dom_index:
+            dom_index[id(rv.domain)] = len(domains)
+            domains.append(rv.domain)
+        var_dom[i] = dom_index[id(rv.domain)]
+        if rv.value is not None:
+            var_value[i] = float(rv.value)
+    by_pot = {}
+    factors = sorted(g.factors, key=lambda f: f.id) if all(hasattr(f, "id") for f in g.factors) else list(g.factors)
+    for f in factors:
+        by_pot.setdefault(id(f.potential), (f.potential, []))[1].append([index[id(rv)] for rv in f.nb])
+    blocks = [FactorBlock(pot, np.asarray(rows, dtype=np.int64)) for pot, rows in by_pot.values()]
+    return GroundArrays(domains, var_dom, var_value, blocks), rvs
+
+
+class ArrayVI:
+    """``LiftedVarInference`` (``lifted=True``) or ``VarInference`` over a ``GroundArrays`` model:
+    colour passing on arrays, the compressed lowering, and the device engine
+    (``LiftedVarInference.py:14-26`` + ``VarInference.run`` ``:215-247``).  Per-variable results
+    are expanded from the classes back to the ground variables."""
+
+    def __init__(self, ga: GroundArrays, K, T, *, lifted=True, dtype="float64", device=None):
+        from .engine import DeviceEngine
+        self.ga, self.K, self.T = ga, K, T
+        if lifted:
+            self.quotient = lift(ga)
+            self.model = lowering.lower_compressed(self.quotient, K, T)
+        else:
+            self.model, self.quotient = lower_ground_arrays(ga, K, T)
+        self.engine = DeviceEngine(self.model, dtype=dtype, device=device)
+        self.init_param(0)
+
+    def init_param(self, seed=0):
+        """The reference's initial distributions (``VarInference.py:197-208``), drawn per class
+        from a generator seeded by the class representative's ground index -- so a lifted and a
+        ground run of the same model start from corresponding points."""
+        m, K = self.model, self.K
+        eta = np.zeros(m.n_param)
+        tau = np.zeros(m.n_param)
+        for h, off, kind, dim in zip(m.handles, m.var_off, m.var_kind, m.var_dim):
+            rep_class = self.quotient.rvs[int(self.quotient.var_colour[h.rep])]
+            rng = np.random.default_rng([seed, int(self._canonical_rep(rep_class))])
+            if kind == 0:
+                eta[off:off + 2 * K:2] = rng.random(K) * 3 - 1.5
+                eta[off + 1:off + 2 * K:2] = 1.0
+            else:
+                logits = rng.random((K, dim)) * 10
+                tau[off:off + K * dim] = logits.reshape(-1)
+                e = np.e ** logits
+                eta[off:off + K * dim] = (e / e.sum(axis=1, keepdims=True)).reshape(-1)
+        self.engine.set_state(eta, tau, np.zeros(K))
+        self.engine.reset_moments()
+
+    canonical = None        # optional ground-variable -> canonical representative map (see tie_to)
+
+    def _canonical_rep(self, cls):
+        return cls.rep if self.canonical is None else self.canonical[cls.rep]
+
+    def tie_to(self, other: "ArrayVI"):
+        """Start from the point that corresponds to ``other``'s (a coarser partition of the same
+        model): every class here draws with the representative of the class of ``other`` it lies in."""
+        reps = np.array([c.rep for c in other.quotient.rvs])
+        self.canonical = reps[other.quotient.var_colour]
+        self.init_param(0)
+
+    def run(self, iteration=100, lr=0.1):
+        self.engine.iterate(int(iteration), float(lr))
+
+    def free_energy(self):
+        return self.engine.free_energy()
+
+    def ground_params(self):
+        """``eta`` of every hidden ground variable: dict ground index -> ``[K, 2]`` (continuous) or
+        ``[K, D]`` array, expanded from the classes; and the mixture weights."""
+        eta, _, _, w = self.engine.get_state()
+        m, K = self.model, self.K
+        per_class = {}
+        for h, off, dim in zip(m.handles, m.var_off, m.var_dim):
+            per_class[h.uid] = eta[off:off + K * dim].reshape(K, dim)
+        col = self.quotient.var_colour
+        hidden = np.flatnonzero(np.isnan(self.ga.var_value))
+        return {int(v): per_class[self.quotient.rvs[int(col[v])].uid] for v in hidden}, w

@@ -14,6 +14,8 @@ Models
   unary priors ``exp(w0 * -(Pop(p) - 1)^2)``, session factors between groups, a fraction of the
   entity popularities observed with unique values.
 * ``gaussian_grid``: pairwise Gaussian MRF on an n x n grid with unary ``X2`` terms (config 4).
+* ``kalman_arrays``: the relational Kalman filter of ``KalmanFilter.grounded_graph`` with a sparse
+  transition matrix and quantised observations, as ``lifting.GroundArrays`` (config 2).
 """
 from __future__ import annotations
 
@@ -23,7 +25,7 @@ from . import lowering
 from .Graph import F, RV, Domain, Graph
 from .lowering import EC, ED, HC, LoweredModel, PotentialTable, RecordGroup, slot_size
 from .MLNPotential import MLNPotential, eq_op
-from .Potential import GaussianPotential, X2Potential
+from .Potential import GaussianPotential, LinearGaussianPotential, X2Potential, XYPotential
 
 _LINK_W, _PRIOR_W, _SESSION_W = 1.0, 0.3, 0.5
 
@@ -237,3 +239,107 @@ def random_state(model, seed=0):
         e = np.e ** logits
         eta[off:off + K * d] = (e / e.sum(axis=1, keepdims=True)).reshape(-1)
     return eta, tau, np.zeros(K)
+
+
+# ---- relational Kalman filter (config 2) -------------------------------------------------------
+
+def _kalman_setup(n, t_steps, a, c, levels, seed, period=None):
+    """Sparse transition ``A = a I + c shift`` (state x feeds x and x+1, cyclic), observations of
+    every state at every step quantised to ``levels`` values (SURVEY section 8 d, config 2).
+    With ``period`` (a divisor of n) the observation pattern repeats every ``period`` state
+    dimensions, so the model is invariant under that cyclic shift and colour passing lifts it to
+    ``period`` classes per time step; without, the observations are i.i.d. and nothing merges."""
+    rng = np.random.default_rng(seed)
+    A = np.zeros((n, n))
+    A[np.arange(n), np.arange(n)] = a
+    A[np.arange(n), (np.arange(n) + 1) % n] = c
+    if period is None:
+        data = rng.integers(0, levels, size=(n, t_steps)).astype(np.float64)
+    else:
+        if n % period:
+            raise ValueError("period must divide n")
+        data = np.tile(rng.integers(0, levels, size=(period, t_steps)), (n // period, 1)).astype(np.float64)
+    return A, data
+
+
+def kalman_arrays(n, t_steps, *, a=0.9, c=0.05, trans_var=1.0, obs_coeff=1.0, obs_var=0.5, levels=2, seed=0,
+                  period=None):
+    """``KalmanFilter.grounded_graph`` (reference ``KalmanFilter.py:15-104``) as arrays: state
+    variables ``(t, x)`` (t = 0 observed with ``data[x, 0]``, later steps hidden), one observation
+    leaf per hidden state, and the reference's decomposition of the transition into ``X2`` /
+    ``XY`` potentials.  Returns ``(GroundArrays, state_index [t_steps, n])``."""
+    from .lifting import FactorBlock, GroundArrays
+    A, data = _kalman_setup(n, t_steps, a, c, levels, seed, period)
+    dom = Domain((-30, 30), continuous=True)
+    state = np.arange(t_steps * n, dtype=np.int64).reshape(t_steps, n)
+    n_state = t_steps * n
+    obs = n_state + np.arange((t_steps - 1) * n, dtype=np.int64).reshape(t_steps - 1, n)
+    n_vars = n_state + (t_steps - 1) * n
+    var_value = np.full(n_vars, np.nan)
+    var_value[state[0]] = data[:, 0]
+    var_value[obs.reshape(-1)] = data[:, 1:].T.reshape(-1)
+    xy = A
+    xx = xy @ xy.T                                   # sum_y outer(xy[:, y], xy[:, y])
+    blocks = []
+    # observation factors F(LinearGaussian(obs_coeff, obs_var), [state(t, x), observe(t, x)]), t >= 1
+    blocks.append(FactorBlock(LinearGaussianPotential(obs_coeff, obs_var),
+                              np.stack([state[1:].reshape(-1), obs.reshape(-1)], axis=1)))
+    # node factors X2(xx[x, x]) for 0 < t < T - 1
+    for val in np.unique(np.diag(xx)):
+        if val != 0 and t_steps > 2:
+            xs = np.flatnonzero(np.diag(xx) == val)
+            blocks.append(FactorBlock(X2Potential(float(val), trans_var), state[1:t_steps - 1][:, xs].reshape(-1, 1)))
+    # xy factors XY(-2 xy[x, y]) on (state(t, x), state(t + 1, y)), one block per distinct coefficient
+    xs, ys = np.nonzero(xy)
+    for val in np.unique(xy[xs, ys]):
+        sel = xy[xs, ys] == val
+        left = state[:-1][:, xs[sel]].reshape(-1)
+        right = state[1:][:, ys[sel]].reshape(-1)
+        blocks.append(FactorBlock(XYPotential(float(-2 * val), trans_var), np.stack([left, right], axis=1)))
+    # xx factors XY(2 xx[x, y]) on (state(t, x), state(t, y)), x < y, 0 < t < T - 1
+    if t_steps > 2:
+        xs, ys = np.nonzero(np.triu(xx, 1))
+        for val in np.unique(xx[xs, ys]):
+            sel = xx[xs, ys] == val
+            left = state[1:t_steps - 1][:, xs[sel]].reshape(-1)
+            right = state[1:t_steps - 1][:, ys[sel]].reshape(-1)
+            blocks.append(FactorBlock(XYPotential(float(2 * val), trans_var), np.stack([left, right], axis=1)))
+    # X2(1) on every hidden state
+    blocks.append(FactorBlock(X2Potential(1.0, trans_var), state[1:].reshape(-1, 1)))
+    ga = GroundArrays([dom], np.zeros(n_vars, dtype=np.int32), var_value, blocks)
+    return ga, state
+
+
+def kalman_graph(n, t_steps, *, a=0.9, c=0.05, trans_var=1.0, obs_coeff=1.0, obs_var=0.5, levels=2, seed=0,
+                 period=None):
+    """Object-graph twin of ``kalman_arrays``: the loops of ``KalmanFilter.grounded_graph``
+    (reference ``KalmanFilter.py:15-104``) over this repo's ``Graph`` classes.  Variables are
+    created in the index order of the array model.  Returns ``(graph, rvs_in_index_order)``."""
+    A, data = _kalman_setup(n, t_steps, a, c, levels, seed, period)
+    dom = Domain((-30, 30), continuous=True)
+    table = [[RV(dom, float(data[x, 0]) if t == 0 else None) for x in range(n)] for t in range(t_steps)]
+    observe = [[RV(dom, float(data[x, t])) for x in range(n)] for t in range(1, t_steps)]
+    fs = []
+    for t in range(1, t_steps):
+        for x in range(n):
+            fs.append(F(LinearGaussianPotential(obs_coeff, obs_var), [table[t][x], observe[t - 1][x]]))
+    xy = A
+    xx = xy @ xy.T
+    for t in range(t_steps - 1):
+        for x in range(n):
+            if t > 0 and xx[x, x] != 0:
+                fs.append(F(X2Potential(float(xx[x, x]), trans_var), [table[t][x]]))
+            for y in range(n):
+                if xy[x, y] != 0:
+                    fs.append(F(XYPotential(float(-2 * xy[x, y]), trans_var), [table[t][x], table[t + 1][y]]))
+                if t > 0 and x < y and xx[x, y] != 0:
+                    fs.append(F(XYPotential(float(2 * xx[x, y]), trans_var), [table[t][x], table[t][y]]))
+    for t in range(1, t_steps):
+        for x in range(n):
+            fs.append(F(X2Potential(1.0, trans_var), [table[t][x]]))
+    rvs = [rv for row in table for rv in row] + [rv for row in observe for rv in row]
+    g = Graph()
+    g.rvs = set(rvs)
+    g.factors = set(fs)
+    g.init_nb()
+    return g, rvs
