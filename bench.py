@@ -226,8 +226,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     if world > 1:
         # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     syn = lhvi_b200.synthetic
@@ -293,7 +292,7 @@ def run_ours(a):
     n = model.n_param
     np_t = np.float32 if s == 4 else np.float64
     has_disc = bool((model.var_kind == 1).any())
-    eng.packed_map()
+    eng.packed_map(local=world > 1)        # N ranks: each holds the variables it steps (owned + shared)
     pidx = eng.packed_index
     n_packed = int(pidx.size)
     host_eta = torch.from_numpy(eta[pidx].astype(np_t)).pin_memory()
@@ -335,6 +334,10 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
+    if world > 1:                               # bytes of the whole job: sum over the ranks
+        b = torch.tensor([h2d, d2h], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        h2d, d2h = int(b[0]), int(b[1])
 
     if rank == 0:
         ms_per_step = ms / a.steps
@@ -366,7 +369,8 @@ def run_ours(a):
             "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "per step: variational parameters (compact eta[rv] arrays) host->device from pinned "
                             "memory, lhvi_state_unpack, one iteration, lhvi_state_pack, new parameters + G_w + "
-                            "free energy device->host; record table resident",
+                            "free energy device->host; record table resident; with N ranks every rank "
+                            "moves the variables it owns plus the shared ones (bytes are summed over the ranks)",
                     "free_energy_last": fe_last},
             "gpu_launches": launches,
             "roofline": roofline,

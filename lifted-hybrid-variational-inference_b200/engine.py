@@ -321,28 +321,35 @@ class DeviceEngine:
                 ws[:K].copy(), ws[K:2 * K].copy())
 
     # ---- compact host layout (what a reference caller holds: eta[rv] as K x 2 / K x D arrays) ------
-    def packed_map(self):
+    def packed_map(self, local=False):
         """Element offsets of the used slot elements, ascending (device int32) -- the compact
-        layout of ``pack_state`` / ``unpack_state``; host copy in ``self.packed_index``."""
-        if getattr(self, "_packed_map", None) is None:
-            m, K = self.full_model, self.K
+        layout of ``pack_state`` / ``unpack_state``; host copy in ``self.packed_index``.
+        ``local=True`` (sharded records): only the variables this rank steps -- the ones it owns
+        plus the shared ones -- so that N ranks move 1/N of the state each instead of all of it."""
+        if getattr(self, "_packed_map", None) is None or getattr(self, "_packed_local", None) != bool(local):
+            m, K = (self.model if local else self.full_model), self.K
             sizes = K * m.var_dim.astype(np.int64)
             off = m.var_off.astype(np.int64)
             idx = np.repeat(off - (np.cumsum(sizes) - sizes), sizes) + np.arange(int(sizes.sum()))
             self.packed_index = idx
             self._packed_map = self._dev(idx.astype(np.int32))
+            self._packed_local = bool(local)
         return self._packed_map
 
     def unpack_state(self, packed, which="eta"):
         """Device tensor ``packed`` (compact layout) -> the padded slot vector ``eta`` / ``tau``."""
-        mp = self.packed_map()
+        mp = self.packed_map(getattr(self, "_packed_local", False))
+        if packed.numel() != mp.numel():
+            raise ValueError(f"lhvi: packed state has {packed.numel()} elements, the compact layout {mp.numel()}")
         dst = self.eta if which == "eta" else self.tau
         _cabi.check(self.lib.lhvi_state_unpack(self.dcode, mp.numel(), mp.data_ptr(), packed.data_ptr(),
                                                dst.data_ptr(), self._stream()), self.lib)
 
     def pack_state(self, packed, which="eta"):
         """The padded slot vector ``eta`` / ``tau`` -> device tensor ``packed`` (compact layout)."""
-        mp = self.packed_map()
+        mp = self.packed_map(getattr(self, "_packed_local", False))
+        if packed.numel() != mp.numel():
+            raise ValueError(f"lhvi: packed state has {packed.numel()} elements, the compact layout {mp.numel()}")
         src = self.eta if which == "eta" else self.tau
         _cabi.check(self.lib.lhvi_state_pack(self.dcode, mp.numel(), mp.data_ptr(), src.data_ptr(),
                                              packed.data_ptr(), self._stream()), self.lib)
