@@ -109,24 +109,34 @@ def _mix(x, seed):
         return z ^ (z >> np.uint64(31))
 
 
-def colour_passing(ga: GroundArrays, split_cont_evidence=True, max_sweeps=1000):
-    """Coarsest equitable partition the reference's ``CompressedGraph.run`` converges to.
-
-    Returns ``(var_colour [n_vars], [factor_colour of each block], sweeps)`` with dense class ids.
-    ``split_cont_evidence=False`` starts with all continuous observations of a domain in one
-    class (the coarse start of C2F, ``init_cluster(False)``).
-
-    The multiset of neighbouring factor classes of a variable is compared through two
-    independent 64-bit multiset hashes (sums of mixed class ids, order-free like the
-    reference's sorted tuple); a false merge needs a 128-bit collision."""
-    nv = ga.n_vars
+def initial_colouring(ga: GroundArrays, split_cont_evidence=True):
+    """``init_cluster`` (``CompressedGraphWithObs.py:187-234``): one class per (domain, hidden |
+    evidence value); with ``split_cont_evidence=False`` all continuous observations of a domain
+    share one class."""
     hidden = np.isnan(ga.var_value)
     val = np.where(hidden, 0.0, ga.var_value)
     if not split_cont_evidence:
         cont = np.array([bool(d.continuous) for d in ga.domains])[ga.var_dom]
         val = np.where(cont, 0.0, val)
     _, val_id = np.unique(val, return_inverse=True)
-    vcol = _rank_rows([ga.var_dom.astype(np.int64), hidden.astype(np.int64), val_id.astype(np.int64)])
+    return _rank_rows([ga.var_dom.astype(np.int64), hidden.astype(np.int64), val_id.astype(np.int64)])
+
+
+def colour_passing(ga: GroundArrays, split_cont_evidence=True, max_sweeps=1000, start=None):
+    """Coarsest equitable partition the reference's ``CompressedGraph.run`` converges to.
+
+    Returns ``(var_colour [n_vars], [factor_colour of each block], sweeps)`` with dense class ids.
+    ``split_cont_evidence=False`` starts with all continuous observations of a domain in one
+    class (the coarse start of C2F, ``init_cluster(False)``).  ``start`` (a variable colouring)
+    replaces the initial classes: the result is the coarsest equitable refinement of it (C2F's
+    ``cp_run`` after an evidence split, ``C2FVarInference.py:33-61``).
+
+    The multiset of neighbouring factor classes of a variable is compared through two
+    independent 64-bit multiset hashes (sums of mixed class ids, order-free like the
+    reference's sorted tuple); a false merge needs a 128-bit collision."""
+    nv = ga.n_vars
+    vcol = initial_colouring(ga, split_cont_evidence) if start is None else \
+        _rank_rows([np.asarray(start, dtype=np.int64)])
 
     # blocks whose potentials compare equal are one colour to start with: rank them together
     pot_id = _potential_ids(ga.blocks)
@@ -225,7 +235,7 @@ class QuotientGraph:
         return ground / max(1, len(self.rvs) + len(self.factors))
 
 
-def quotient(ga: GroundArrays, var_colour, factor_colours) -> QuotientGraph:
+def quotient(ga: GroundArrays, var_colour, factor_colours, ev_value=None) -> QuotientGraph:
     """Class handles of a partition (``SuperRV`` ``:8-45``, ``SuperF`` ``:133-150``): evidence
     classes carry the mean value and population variance of their members, every class its
     size, variable classes the representative's degree ``N`` and neighbour counts."""
@@ -239,7 +249,11 @@ def quotient(ga: GroundArrays, var_colour, factor_colours) -> QuotientGraph:
     hidden = np.isnan(ga.var_value)
     vsum = np.bincount(var_colour, weights=np.where(hidden, 0.0, ga.var_value), minlength=ncls)
     mean = vsum / sizes
-    dev = np.where(hidden, 0.0, ga.var_value - mean[var_colour])
+    dev = np.where(hidden, 0.0, ga.var_value - mean[var_colour])       # spread around the members' mean
+    if ev_value:                                   # classes whose value was set by k-means (centroid)
+        mean = mean.copy()
+        for c, v in ev_value.items():
+            mean[int(c)] = v
     variance = np.bincount(var_colour, weights=dev * dev, minlength=ncls) / sizes
     rvs = []
     for c in range(ncls):
@@ -393,3 +407,256 @@ class ArrayVI:
         col = self.quotient.var_colour
         hidden = np.flatnonzero(np.isnan(self.ga.var_value))
         return {int(v): per_class[self.quotient.rvs[int(col[v])].uid] for v in hidden}, w
+
+
+def _kmeans_1d(values, k, iteration):
+    """The reference's evidence k-means (``CompressedGraphWithObs.py:78-130``) on the members'
+    values in member order: centroids start at the first ``k`` distinct values, ``iteration``
+    Lloyd sweeps over the value histogram, members go to their nearest centroid.  Returns
+    ``(owner [n], centroids [k])`` or ``None`` when there is nothing to split."""
+    uniq, first, counts = np.unique(values, return_index=True, return_counts=True)
+    k = min(k, uniq.size)
+    if values.size <= 1 or k <= 1:
+        return None
+    seen = np.argsort(first, kind="stable")              # histogram in first-seen (member) order
+    vals, cnts = uniq[seen].astype(float), counts[seen].astype(float)
+    centroids = vals[:k].copy()
+    for _ in range(iteration):
+        owner = np.abs(vals[:, None] - centroids[None, :]).argmin(axis=1)
+        mass = np.bincount(owner, weights=cnts, minlength=k)
+        tot = np.bincount(owner, weights=vals * cnts, minlength=k)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            centroids = tot / mass
+    owner = np.abs(values[:, None] - centroids[None, :]).argmin(axis=1)
+    return owner, centroids
+
+
+class C2FArrayVI:
+    """``C2FVarInference`` over a ``GroundArrays`` model (``C2FVarInference.py:301-352``).
+
+    Continuous evidence starts lumped into one class per domain and is integrated as a fixed
+    Gaussian (class mean, class variance); every ``update_obs_its`` iterations the evidence
+    classes whose spread exceeds a shrinking threshold are split by 1-D k-means, colour passing
+    refines the partition, the pieces of a hidden class inherit its parameters and Adam moments,
+    the compressed model is lowered and uploaded again, and the kernels continue.  The Adam step
+    counter runs across the rounds.  Class attributes are the reference's knobs."""
+
+    k_mean_k = 2
+    k_mean_its = 10
+    update_obs_its = 10
+    output_its = 0
+    min_obs_var = 0
+    gaussian_obs = True
+    var_threshold = 0.1
+
+    def __init__(self, ga: GroundArrays, K, T, *, dtype="float64", device=None, engine_factory=None,
+                 init_fn=None):
+        self.ga, self.K, self.T = ga, int(K), int(T)
+        self.dtype, self.device = dtype, device
+        self.engine_factory = engine_factory
+        self.init_fn = init_fn            # (representative ground index, is_continuous, dim) -> [K, dim] or None
+        self.hidden = np.isnan(ga.var_value)
+        self.cont_dom = np.array([bool(d.continuous) for d in ga.domains])[ga.var_dom]
+        self.t = 0.0
+        self.ev_value = {}                # evidence classes whose value is a k-means centroid
+        self.history = []                 # (number of variable classes, free energy) per round
+
+    # ---- engine ---------------------------------------------------------------------------
+    def _make_engine(self, model):
+        if self.engine_factory is not None:
+            return self.engine_factory(model)
+        from .engine import DeviceEngine
+        return DeviceEngine(model, dtype=self.dtype, device=self.device, var_threshold=self.var_threshold)
+
+    # ---- partition bookkeeping -------------------------------------------------------------
+    def _evidence_stats(self):
+        """(class ids, mean, variance, size) of the evidence classes of the current partition."""
+        ev = np.flatnonzero(~self.hidden)
+        col = self.vcol[ev]
+        ids, inv, cnt = np.unique(col, return_inverse=True, return_counts=True)
+        mean = np.bincount(inv, weights=self.ga.var_value[ev]) / cnt
+        dev = self.ga.var_value[ev] - mean[inv]
+        var = np.bincount(inv, weights=dev * dev) / cnt
+        return ids, mean, var, cnt
+
+    def _split_evidence(self, epsilon):
+        """``CompressedGraph.split_evidence`` (``:236-247``) until nothing changes."""
+        changed = True
+        while changed:
+            changed = False
+            next_id = int(self.vcol.max()) + 1
+            for cid in sorted(self.clustered):
+                members = np.flatnonzero(self.vcol == cid)
+                vals = self.ga.var_value[members]
+                if not np.sqrt(vals.var()) > epsilon:
+                    continue
+                res = _kmeans_1d(vals, self.k_mean_k, self.k_mean_its)
+                if res is None:
+                    if members.size == 1:
+                        self.clustered.discard(cid)
+                    continue
+                owner, centroids = res
+                pieces = [cid]
+                self.ev_value[cid] = float(centroids[0])
+                for j in range(1, centroids.size):
+                    sel = members[owner == j]
+                    if sel.size:
+                        self.vcol[sel] = next_id
+                        self.ev_value[next_id] = float(centroids[j])
+                        pieces.append(next_id)
+                        next_id += 1
+                if len(pieces) > 1:
+                    changed = True
+                    for pid in pieces:
+                        pv = self.ga.var_value[self.vcol == pid]
+                        if pv.size and pv.var() > epsilon:
+                            self.clustered.add(pid)
+                        elif pid != cid:
+                            self.clustered.discard(pid)
+
+    def _refine(self):
+        """Colour passing from the current classes; hidden pieces inherit (``:39-61``)."""
+        old = self.vcol
+        new, self.fcols, _ = colour_passing(self.ga, start=old)
+        # carry the evidence book-keeping over to the new ids
+        if self.clustered:
+            keep = set()
+            for cid in self.clustered:
+                keep.update(np.unique(new[old == cid]).tolist())
+            self.clustered = keep
+        # a class that colour passing left whole keeps its k-means centroid as value; pieces of a
+        # structure split take the mean of their members (SuperRV.split_by_structure, :57-62)
+        if self.ev_value:
+            size_old = np.bincount(old, minlength=int(old.max()) + 1)
+            size_new = np.bincount(new, minlength=int(new.max()) + 1)
+            carried = {}
+            for cid, v in self.ev_value.items():
+                kids = np.unique(new[old == cid])
+                if kids.size == 1 and size_new[kids[0]] == size_old[cid]:
+                    carried[int(kids[0])] = v
+            self.ev_value = carried
+        self._inherit(old, new)
+        self.vcol = new
+
+    def _inherit(self, old, new):
+        if not self.params:
+            return
+        reps_new = {}
+        order = np.argsort(new, kind="stable")
+        starts = np.searchsorted(new[order], np.arange(int(new.max()) + 1))
+        for c, r in enumerate(order[starts]):
+            reps_new[c] = int(r)
+        params, m1, m2 = {}, {}, {}
+        for c, r in reps_new.items():
+            if not self.hidden[r]:
+                continue
+            parent = int(old[r])
+            params[c] = self.params[parent].copy()
+            m1[c] = self.m1[parent].copy()
+            m2[c] = self.m2[parent].copy()
+        self.params, self.m1, self.m2 = params, m1, m2
+
+    # ---- parameters -----------------------------------------------------------------------
+    def _init_params(self):
+        self.params, self.m1, self.m2 = {}, {}, {}
+        K = self.K
+        order = np.argsort(self.vcol, kind="stable")
+        starts = np.searchsorted(self.vcol[order], np.arange(int(self.vcol.max()) + 1))
+        for c, r in enumerate(order[starts]):
+            r = int(r)
+            if not self.hidden[r]:
+                continue
+            dom = self.ga.domains[int(self.ga.var_dom[r])]
+            cont = bool(dom.continuous)
+            dim = 2 if cont else len(dom.values)
+            table = self.init_fn(r, cont, dim) if self.init_fn is not None else None
+            if table is None:
+                rng = np.random.default_rng([0, r])
+                if cont:
+                    table = np.ones((K, 2))
+                    table[:, 0] = rng.random(K) * 3 - 1.5
+                else:
+                    table = rng.random((K, dim)) * 10          # logits
+            self.params[c] = np.asarray(table, dtype=float)     # continuous: (mu, var); discrete: logits
+            self.m1[c] = np.zeros_like(self.params[c])
+            self.m2[c] = np.zeros_like(self.params[c])
+        self.w_tau = np.zeros(K)
+        self.m_w, self.u_w = np.zeros(K), np.zeros(K)
+        self.t = 0.0
+
+    def _push(self, model, engine, q):
+        K = self.K
+        eta, tau = np.zeros(model.n_param), np.zeros(model.n_param)
+        m1, m2 = np.zeros(model.n_param), np.zeros(model.n_param)
+        for h, off, kind, dim in zip(model.handles, model.var_off, model.var_kind, model.var_dim):
+            p = self.params[h.uid]
+            n = K * dim
+            if kind == 0:
+                eta[off:off + n] = p.reshape(-1)
+            else:
+                tau[off:off + n] = p.reshape(-1)
+                e = np.e ** p
+                eta[off:off + n] = (e / e.sum(axis=1, keepdims=True)).reshape(-1)
+            m1[off:off + n] = self.m1[h.uid].reshape(-1)
+            m2[off:off + n] = self.m2[h.uid].reshape(-1)
+        engine.set_state(eta, tau, self.w_tau)
+        engine.set_moments(m1, m2, self.m_w, self.u_w, self.t)
+
+    def _pull(self, model, engine):
+        K = self.K
+        eta, tau, w_tau, w = engine.get_state()
+        m1, m2, m_w, u_w, t = engine.get_moments()
+        for h, off, kind, dim in zip(model.handles, model.var_off, model.var_kind, model.var_dim):
+            n = K * dim
+            src = eta if kind == 0 else tau
+            self.params[h.uid] = src[off:off + n].reshape(K, dim).copy()
+            self.m1[h.uid] = m1[off:off + n].reshape(K, dim).copy()
+            self.m2[h.uid] = m2[off:off + n].reshape(K, dim).copy()
+        self.w_tau, self.w = w_tau, w
+        self.m_w, self.u_w, self.t = m_w, u_w, t
+
+    # ---- the run ---------------------------------------------------------------------------
+    def run(self, iteration=100, lr=0.1):
+        ga = self.ga
+        # initial classes, parameters per initial class (one hidden class per domain), then the
+        # first colour passing in which the pieces inherit (C2FVarInference.py:306-311)
+        self.vcol = initial_colouring(ga, split_cont_evidence=False)
+        ev_cont = np.flatnonzero(~self.hidden & self.cont_dom)
+        self.clustered = set(np.unique(self.vcol[ev_cont]).tolist())    # what k-means may split
+        self.ev_value = {}
+        self._init_params()
+        self._refine()
+        _, _, var, _ = self._evidence_stats()
+        epsilon = float(np.sqrt(var.max())) if var.size else 0.0
+        d = epsilon * self.update_obs_its / (iteration - self.output_its)
+        epsilon -= d
+        self.history = []
+        for _ in range(int(iteration / self.update_obs_its)):          # remainder dropped (H10)
+            self._split_evidence(epsilon)
+            self._refine()
+            epsilon = max(epsilon - d, self.min_obs_var)
+            self.quotient = quotient(ga, self.vcol, self.fcols, self.ev_value)
+            self.model = lowering.lower_compressed(self.quotient, self.K, self.T, gaussian_obs=self.gaussian_obs,
+                                                   min_obs_var=self.min_obs_var)
+            self.engine = self._make_engine(self.model)
+            self._push(self.model, self.engine, self.quotient)
+            self.engine.iterate(self.update_obs_its, lr)
+            self._pull(self.model, self.engine)
+            self.history.append((len(self.quotient.rvs), None))
+        return self
+
+    def free_energy(self):
+        return self.engine.free_energy()
+
+    def ground_params(self):
+        """Per hidden ground variable: its class's ``[K, dim]`` table (continuous: (mu, var);
+        discrete: probabilities) -- the reference's ``eta[rv.cluster]``."""
+        out = {}
+        for v in np.flatnonzero(self.hidden):
+            p = self.params[int(self.vcol[v])]
+            if self.cont_dom[v]:
+                out[int(v)] = p
+            else:
+                e = np.e ** p
+                out[int(v)] = e / e.sum(axis=1, keepdims=True)
+        return out, self.w

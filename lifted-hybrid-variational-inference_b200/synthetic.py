@@ -170,6 +170,39 @@ def relational_hybrid_graph(P, G, *, observed_frac=0.7, seed=0):
     return g, topics, entities
 
 
+def relational_hybrid_arrays(P, G, *, observed_frac=0.7, seed=0):
+    """``relational_hybrid`` / ``relational_hybrid_graph`` as ``lifting.GroundArrays`` -- the ground
+    graph itself (relation atoms included as observed discrete variables), the input of the
+    array-native colour passing and of ``lifting.C2FArrayVI`` (config 5 as the reference runs it).
+    Variable order: topics, entities, In(p, t) atoms (entity-major), session atoms."""
+    from .lifting import FactorBlock, GroundArrays
+    observed, value, member, sess = _relational_draws(P, G, observed_frac, seed)
+    prior, link, sesspot = _potentials()
+    d_bool = Domain((0, 1))
+    d_real = Domain((-15, 15), continuous=True)
+    topics = np.arange(G, dtype=np.int64)
+    ents = G + np.arange(P, dtype=np.int64)
+    rel = G + P + np.arange(P * G, dtype=np.int64).reshape(P, G)
+    pairs = [(a, b) for a in range(G) for b in range(G) if a != b]
+    srel = G + P + P * G + np.arange(len(pairs), dtype=np.int64)
+    n_vars = G + P + P * G + len(pairs)
+    var_dom = np.zeros(n_vars, dtype=np.int32)              # 0: real, 1: bool
+    var_dom[G + P:] = 1
+    var_value = np.full(n_vars, np.nan)
+    var_value[ents[observed]] = value[observed]
+    var_value[rel.reshape(-1)] = member.reshape(-1)
+    if pairs:
+        var_value[srel] = [sess[a, b] for a, b in pairs]
+    pp, tt = np.meshgrid(np.arange(P), np.arange(G), indexing="ij")
+    blocks = [
+        FactorBlock(prior, ents.reshape(-1, 1)),
+        FactorBlock(link, np.stack([rel.reshape(-1), ents[pp.reshape(-1)], topics[tt.reshape(-1)]], axis=1)),
+    ]
+    if pairs:
+        blocks.append(FactorBlock(sesspot, np.stack([srel, topics[[a for a, _ in pairs]], topics[[b for _, b in pairs]]], axis=1)))
+    return GroundArrays([d_real, d_bool], var_dom, var_value, blocks)
+
+
 # ---- pairwise Gaussian grid (config 4) -------------------------------------------------------
 
 _GRID_SIG = [[1.5, 0.6], [0.6, 1.5]]

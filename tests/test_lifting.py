@@ -111,3 +111,103 @@ def test_kalman_compression_at_scale():
     # 4 classes of states per time step; observation leaves merge by value as well
     assert len(np.unique(vcol[state.reshape(-1)])) == 4 * 50
     assert q.compression > 20
+
+
+# ---- coarse-to-fine on arrays against the object-level drop-in class --------------------------
+
+def _c2f_pair(builder_name, ns, K, T, iterations, lr):
+    """Run C2FVarInference (object route, oracle engine as device double) and C2FArrayVI (array
+    route, same double) from corresponding initial points; return both."""
+    import contextlib
+    import io
+    from oracle_engine import OracleEngine, use_oracle_engine
+    builder = specs.CASES[builder_name][0]
+    g, _ = builder(ns)
+    ga, rvs = lifting.arrays_from_graph(g)
+    index = {id(rv): i for i, rv in enumerate(rvs)}
+
+    def table_for(rep, cont, dim):
+        r = np.random.default_rng([7, rep])
+        if cont:
+            t = np.ones((K, 2))
+            t[:, 0] = r.random(K) * 3 - 1.5
+            return t
+        return r.random((K, dim)) * 10
+
+    arr = lifting.C2FArrayVI(ga, K, T, engine_factory=lambda m: OracleEngine(m, var_threshold=0.1), init_fn=table_for)
+    arr.run(iterations, lr)
+
+    vi = use_oracle_engine(lhvi_b200.C2FVarInference.VarInference(g, K, T))
+
+    def init_param():
+        vi.w_tau = np.zeros(K)
+        vi.eta, vi.eta_tau = {}, {}
+        for h in sorted(vi.g.rvs):
+            if h.value is not None:
+                continue
+            rep = min(index[id(rv)] for rv in h.rvs)
+            if h.domain.continuous:
+                vi.eta[h] = table_for(rep, True, 2)
+            else:
+                vi.eta_tau[h] = table_for(rep, False, len(h.domain.values))
+        e = np.e ** vi.w_tau
+        vi.w = e / e.sum()
+        for h, t in vi.eta_tau.items():
+            ex = np.e ** t
+            vi.eta[h] = ex / ex.sum(axis=1, keepdims=True)
+    vi.init_param = init_param
+    with contextlib.redirect_stdout(io.StringIO()):
+        vi.run(iterations, lr=lr, is_log=False)
+    return arr, vi, rvs, index
+
+
+@pytest.mark.parametrize("name", ["rgm_split", "hmln_evidence", "chain_table"])
+def test_c2f_arrays_follow_the_object_route(name, ns):
+    K, T = 2, 3
+    arr, vi, rvs, index = _c2f_pair(name, ns, K, T, 30, 0.05)
+    # same final partition
+    want = {frozenset(index[id(rv)] for rv in c.rvs) for c in vi.g.rvs}
+    assert _partition(arr.vcol) == want
+    # same parameters of every hidden ground variable, same mixture weights
+    got, w = arr.ground_params()
+    vi._pull()
+    for rv in rvs:
+        if rv.value is None:
+            np.testing.assert_allclose(got[index[id(rv)]], vi.eta[rv.cluster], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(arr.w_tau, vi.w_tau, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(arr.free_energy(), vi.free_energy(), rtol=1e-9)
+
+
+def test_relational_arrays_match_the_object_twin():
+    """``relational_hybrid_arrays`` describes the same ground graph as ``relational_hybrid_graph``:
+    same partition under colour passing, same lifted free energy as the ground array model
+    ``relational_hybrid`` under class-tied parameters."""
+    P, G, K, T = 40, 3, 2, 3
+    ga = syn.relational_hybrid_arrays(P, G, seed=4)
+    g, topics, entities = syn.relational_hybrid_graph(P, G, seed=4)
+    ga2, rvs = lifting.arrays_from_graph(g)
+    assert ga.n_vars == ga2.n_vars and ga.n_factors == ga2.n_factors
+    v1, _, _ = lifting.colour_passing(ga)
+    v2, _, _ = lifting.colour_passing(ga2)
+    assert len(np.unique(v1)) == len(np.unique(v2))
+    # lifted vs ground free energy (ground: the record-level generator)
+    m_l, q = lifting.lower_lifted(ga, K, T)
+    ground = syn.relational_hybrid(P, G, K, T, seed=4)
+    eta_g, _, _ = syn.random_state(ground, 0)
+    # tie the ground parameters by class: ground slots are topics then hidden entities
+    hidden_idx = np.flatnonzero(np.isnan(ga.var_value))
+    assert hidden_idx.size == ground.n_vars
+    rep = np.array([q.rvs[int(v1[v])].rep for v in hidden_idx])
+    pos = {int(v): i for i, v in enumerate(hidden_idx)}
+    for i, r in enumerate(rep):
+        o, orr = ground.var_off[i], ground.var_off[pos[int(r)]]
+        eta_g[o:o + 2 * K] = eta_g[orr:orr + 2 * K]
+    eta_l = np.zeros(m_l.n_param)
+    for h, off in zip(m_l.handles, m_l.var_off):
+        o = ground.var_off[pos[int(h.rep)]]
+        eta_l[off:off + 2 * K] = eta_g[o:o + 2 * K]
+    w = np.array([0.4, 0.6])
+    e_g = grad_pass(ground, eta_g, w)
+    e_l = grad_pass(m_l, eta_l, w)
+    np.testing.assert_allclose(e_l[2], e_g[2], rtol=1e-10)
+    np.testing.assert_allclose(e_l[1], e_g[1], rtol=1e-10)
