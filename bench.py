@@ -64,7 +64,9 @@ def workload_config(a, n_records, parallelism=None):
                     f"{a.groups} groups = {a.entities * a.groups} link factors (+priors, sessions), "
                     f"lifted record format, K={a.K}, T={a.T}",
         "factor_records": int(n_records),
-        "K": a.K, "T": a.T, "record_order": a.order,
+        "K": a.K, "T": a.T,
+        "record_order": f"generator: {a.order}-major; the engine re-sorts the two-hidden-argument group run-major "
+                        "and pads hub runs of the streamed group to whole tiles (results are order-independent)",
         "l2_policy": "inputs larger than L2 (record table ~1 GB >> 126 MB), no explicit flush",
         "parallelism": parallelism or f"{a.gpus} rank(s), owner-computes record partition",
     }
@@ -107,14 +109,17 @@ def variable_bytes(model, s):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of this
-# workload at N=1 (profiles/r1_ncu_summary.md); keyed by the group description without its size
+# workload at N=1 (profiles/r1_ncu_full_top_kernels_final.csv); keyed by the group description
+# without its size
 TRAFFIC = {
-    "full nd=0 nc=2 ng=0 ne=0": 91.5e6 + 4.1e6,
-    "pure streamed nd=0 nc=1 ng=0 ne=1": 168.0e6 + 2.6e6,
+    "full nd=0 nc=2 ng=0 ne=0": 81.8e6 + 7.1e6,
+    "pure streamed nd=0 nc=1 ng=0 ne=1": 171.3e6 + 7.1e6,
 }
-NOTE = ("the full (two hidden arguments) kernel is bound by FP32/MUFU issue, not by HBM: ncu shows issue "
-        "slots ~69% busy, FMA and XU pipes ~50% each, DRAM ~0.8 TB/s; its fraction of the HBM roofline is "
-        "reported as asked but its limiter is instruction issue (profiles/r1_ncu_summary.md)")
+NOTE = ("the full (two hidden arguments) group runs in the run-major kernel: 530 instructions per record, issue "
+        "slots 69% busy, FMA pipe 49%, XU 31%, 15 of 16 resident warps per SM (128 registers), DRAM at 15% -- its "
+        "limiter is instruction issue / latency at that occupancy, not HBM: the entity slots are hit ten times each "
+        "and stay in L1/L2, so physical traffic (89 MB) is a quarter of the algorithmic bytes SURVEY 8d counts "
+        "(361 MB) and the fraction of the HBM roofline is reported as asked (profiles/r1_ncu_summary.md)")
 
 
 # ---- clocks ------------------------------------------------------------------------------------
@@ -224,9 +229,12 @@ def run_ours(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    # rank 0 prints ONE JSON line on stdout: anything a library writes to file descriptor 1 meanwhile
+    # (NCCL's version banner is a C printf) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner out of it
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     syn = lhvi_b200.synthetic
@@ -251,7 +259,7 @@ def run_ours(a):
         d, _, g = eng.groups[i]
         kind = "node" if g.node else ("pure" if g.pure else "full")
         stream = " streamed" if (d.fold and (d.hub_mask >> g.nd) & 1) else ""
-        return f"{kind}{stream} nd={g.nd} nc={g.nc} ng={g.ng} ne={g.ne} n={g.n}"
+        return f"{kind}{stream} nd={g.nd} nc={g.nc} ng={g.ng} ne={g.ne} n={g.n}" + (" [run-major]" if d.run_start else "")
 
     for _ in range(a.warmup):
         eng.iterate(1, lr)
@@ -351,7 +359,7 @@ def run_ours(a):
         step_bytes = sum(gbytes(i) for i in range(len(eng.groups))) + variable_bytes(eng.model, s)
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak if achieved else None, "traffic": TRAFFIC.get(gname(dom).split(" n=")[0]) if (world == 1 and a.entities == 1_000_000) else None,
+            "frac": achieved / peak if achieved else None, "traffic": TRAFFIC.get(gname(dom).split(" n=")[0].strip()) if (world == 1 and a.entities == 1_000_000) else None,
             "kernel": f"longest launch of the step: {gname(dom)} (rank 0)",
             "kernel_ms": dom_ms, "kernel_bytes": dom_bytes, "peak_source": peak_src,
             "note": NOTE,
@@ -378,7 +386,8 @@ def run_ours(a):
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(a, model.n_records).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         # leave without tearing NCCL down: destroy_process_group() after CUDA-graph capture of a
         # collective was seen to hang at exit; every rank has passed its last collective here
