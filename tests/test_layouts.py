@@ -1,0 +1,113 @@
+"""Host-side record layouts the engine builds for the two large kernels (no GPU needed):
+``engine.run_layout`` (run-major columns of lhvi_group) and ``engine.align_runs`` (hub runs of a
+streamed group padded to whole tiles).  Both must leave every sum unchanged -- checked with the
+numpy oracle on the re-laid-out model -- and satisfy the invariants lhvi.h documents."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+import lhvi_b200
+from lhvi_b200 import engine as eng_mod
+from oracle.vi_numpy import grad_pass
+
+syn = lhvi_b200.synthetic
+
+
+def _full_group(model):
+    return next(i for i, g in enumerate(model.groups) if not g.node and not g.pure and g.nc == 2)
+
+
+def _streamed_group(model):
+    return next(i for i, g in enumerate(model.groups) if g.pure and g.nc == 1 and g.ne == 1)
+
+
+@pytest.mark.parametrize("P,G,K", [(300, 6, 3), (50, 3, 1), (2000, 10, 2)])
+def test_run_layout_invariants_and_sums(P, G, K):
+    model = syn.relational_hybrid(P, G, K, 3, seed=1, weighted=True)
+    gi = _full_group(model)
+    g = model.groups[gi]
+    out = eng_mod.run_layout(g, K, 4)
+    assert out is not None
+    sg, starts, run_key, hid, hubs, hub_arg = out
+    run_arg = 1 - hub_arg
+    assert sg.n == g.n and starts[0] == 0 and starts[-1] == g.n and (np.diff(starts) > 0).all()
+    assert hubs.size <= 16 and (np.diff(hubs) > 0).all()
+    np.testing.assert_array_equal(hubs[hid], sg.poff[hub_arg])
+    # every run is on one variable, and no run is longer than the split length
+    for a, b, key in zip(starts[:-1], starts[1:], run_key):
+        assert (sg.poff[run_arg, a:b] == key).all()
+    assert np.diff(starts).max() <= eng_mod.RUN_SPLIT
+    assert (np.diff(sg.poff[run_arg]) >= 0).all()
+    # the re-ordered group sums to the same gradients
+    eta, tau, w_tau = syn.random_state(model, 0)
+    w = np.full(K, 1.0 / K)
+    groups = list(model.groups)
+    groups[gi] = sg
+    a = grad_pass(model, eta, w)
+    b = grad_pass(dataclasses.replace(model, groups=groups), eta, w)
+    np.testing.assert_allclose(b[0], a[0], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(b[1], a[1], rtol=1e-12)
+    np.testing.assert_allclose(b[2], a[2], rtol=1e-12)
+
+
+def test_run_layout_declines_groups_it_cannot_serve():
+    grid = syn.gaussian_grid(8, 2, 3)
+    for g in grid.groups:
+        assert eng_mod.run_layout(g, 2, 4) is None            # both arguments take many values
+    model = syn.relational_hybrid(100, 4, 3, 3, seed=0)
+    for g in model.groups:
+        if g.node or g.pure:
+            assert eng_mod.run_layout(g, 3, 4) is None
+    # too many hubs for the thread-private accumulators in fp64
+    big = syn.relational_hybrid(400, 12, 3, 3, seed=0)
+    g = big.groups[_full_group(big)]
+    assert eng_mod.run_layout(g, 3, 4) is not None
+    assert eng_mod.run_layout(g, 3, 8) is None
+
+
+def test_small_shards_get_shorter_runs():
+    model = syn.relational_hybrid(3000, 10, 3, 3, seed=0)
+    g = model.groups[_full_group(model)]
+    starts = eng_mod.run_layout(g, 3, 4)[1]
+    assert np.diff(starts).max() == 2          # far fewer records than resident threads: runs are cut
+
+
+@pytest.mark.parametrize("P,G", [(30_000, 3), (9_000, 2)])
+def test_align_runs_pads_long_runs_to_whole_tiles(P, G):
+    K, tile = 3, 1024
+    model = syn.relational_hybrid(P, G, K, 3, seed=0, weighted=True)
+    gi = _streamed_group(model)
+    g = model.groups[gi]
+    null_pot = model.ptab.size
+    ptab = np.concatenate([model.ptab, np.zeros(6)])
+    pg = eng_mod.align_runs(g, null_pot, tile)
+    assert pg.n % tile == 0 and pg.n >= g.n
+    key = pg.poff[0]
+    starts = np.concatenate([[0], np.flatnonzero(key[1:] != key[:-1]) + 1])
+    lens = np.diff(np.append(starts, pg.n))
+    long_runs = lens >= eng_mod.FOLD_ALIGN_MIN_TILES * tile
+    assert (starts[long_runs] % tile == 0).all() and long_runs.any()
+    assert pg.n - g.n < tile * (long_runs.sum() + 1)
+    # null records: zero coefficients and zero weights
+    null = pg.pot == null_pot
+    assert null.sum() == pg.n - g.n and (pg.wf[null] == 0).all() and (pg.gam[:, null] == 0).all()
+    eta, tau, w_tau = syn.random_state(model, 0)
+    w = np.full(K, 1.0 / K)
+    groups = list(model.groups)
+    groups[gi] = pg
+    a = grad_pass(model, eta, w)
+    b = grad_pass(dataclasses.replace(model, groups=groups, ptab=ptab), eta, w)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
+    # also when the group ships no weight columns: the null potential alone must silence the records
+    unweighted = syn.relational_hybrid(P, G, K, 3, seed=0, weighted=False)
+    g2 = unweighted.groups[_streamed_group(unweighted)]
+    pg2 = eng_mod.align_runs(g2, null_pot, tile)
+    pg2 = dataclasses.replace(pg2, wf=np.ones(pg2.n), gam=np.ones((1, pg2.n)))     # what the kernels assume
+    groups = list(unweighted.groups)
+    groups[gi] = pg2
+    a = grad_pass(unweighted, eta, w)
+    b = grad_pass(dataclasses.replace(unweighted, groups=groups, ptab=ptab), eta, w)
+    np.testing.assert_allclose(b[0], a[0], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(b[2], a[2], rtol=1e-12)
