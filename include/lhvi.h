@@ -37,6 +37,7 @@
  *                             memory inside the same kernel.  The reference is single-process:
  *                             these are still its `energy -= ...` / `g_w[k] -= ...` /
  *                             `g_mu -= ...` sums (VarInference.py:72,88,120-129), split by rank.
+ *   lhvi_finish_step          lhvi_finish + lhvi_param_step fused into one launch.
  *   lhvi_peer_*               life cycle of the peer-visible exchange buffers (CUDA IPC).
  *   lhvi_state_pack/unpack    the compact per-variable parameter arrays of the reference
  *                             (eta[rv], VarInference.py:197-213) <-> the padded device slots.
@@ -248,6 +249,21 @@ int lhvi_mixture_belief(int dtype, int K, int64_t n, const int32_t* q_off, const
  */
 int lhvi_mixture_map(int dtype, int K, int64_t n, const int32_t* q_off, const int32_t* q_dim,
                      const uint8_t* q_kind, const void* eta, const void* w, void* out, void* stream);
+
+/*
+ * lhvi_finish and lhvi_param_step in ONE launch (the iteration's critical path loses a launch
+ * level).  Block 0 reduces the partial rows, exchanges (x->blocks must be 1) and then steps the
+ * mixture weights and the variables n_owned .. n_vars-1 of the table -- the ones whose gradients
+ * are completed by the exchange; all other blocks step the variables 0 .. n_owned-1 right away.
+ * With one GPU n_owned = n_vars.  The step counter is NOT advanced here: call lhvi_step_tick
+ * earlier in the iteration (it can run beside the factor kernels).  eta and grad are taken from
+ * the model; gradient slots are always reset (zero_grad = 1).
+ */
+int lhvi_finish_step(const lhvi_model* m, int64_t rows, const lhvi_exchange* x, int64_t n_vars,
+                     int64_t n_owned, const uint8_t* var_kind, const int32_t* var_dim,
+                     const int32_t* var_off, void* tau, void* mom1, void* mom2, void* wstate,
+                     const double* step, double lr, double b1, double b2, double eps,
+                     double var_threshold, int sgd, void* stream);
 
 /*
  * The state a reference caller holds between ADAM_update calls is eta[rv] as K x 2 / K x D arrays

@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblhvi.so"
 
 SYMBOLS = ("lhvi_last_error", "lhvi_abi_version", "lhvi_has_specialisation",
            "lhvi_factor_expect_grad", "lhvi_elbo_reduce", "lhvi_step_tick",
-           "lhvi_param_step", "lhvi_mixture_belief", "lhvi_mixture_map", "lhvi_finish", "lhvi_state_pack", "lhvi_state_unpack",
+           "lhvi_param_step", "lhvi_mixture_belief", "lhvi_mixture_map", "lhvi_finish", "lhvi_state_pack", "lhvi_state_unpack", "lhvi_finish_step",
            "lhvi_peer_alloc", "lhvi_peer_open", "lhvi_peer_close", "lhvi_peer_free")
 
 
@@ -122,6 +122,11 @@ def load(build_if_missing: bool = False):
     lib.lhvi_mixture_belief.restype = C.c_int
     lib.lhvi_mixture_belief.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lhvi_finish_step.restype = C.c_int
+    lib.lhvi_finish_step.argtypes = [C.POINTER(LhviModel), C.c_int64, C.POINTER(LhviExchange), C.c_int64, C.c_int64,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                     C.c_double, C.c_int, C.c_void_p]
     for fn in (lib.lhvi_state_pack, lib.lhvi_state_unpack):
         fn.restype = C.c_int
         fn.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

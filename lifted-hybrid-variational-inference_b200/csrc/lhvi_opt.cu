@@ -85,54 +85,56 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+// Block-wide: sum the valid partial rows into grad[n_param ..] (G_w, energy) and, if a.step is
+// given, advance the step counter.  Call with every thread of ONE block.
 template <typename real>
-__global__ void __launch_bounds__(kFinishThreads)
-finish_kernel(const FinishArgs<real> a) {
-    __shared__ double s[(kFinishThreads / 32) * (LHVI_MAX_K + 1)];
-    __shared__ double res[LHVI_MAX_K + 1];
+__device__ void finish_reduce(const FinishArgs<real>& a, double* s, double* res) {
     const int W = a.K + 1;
-    if (blockIdx.x == 0) {
-        // all region headers first (one round trip), then one flat pass over the valid rows
-        __shared__ int s_start[kFinishRegions + 1];
-        const int regions = (int)(a.regions < kFinishRegions ? a.regions : kFinishRegions);
-        if (threadIdx.x < regions)
-            s_start[threadIdx.x + 1] = (int)a.partials[(long long)threadIdx.x * LHVI_PARTIAL_ROWS * W];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            s_start[0] = 0;
-            for (int i = 0; i < regions; ++i) s_start[i + 1] += s_start[i];
-        }
-        __syncthreads();
-        double acc[LHVI_MAX_K + 1];
-        for (int i = 0; i < W; ++i) acc[i] = 0.0;
-        const int total = s_start[regions];
-        for (int f = threadIdx.x; f < total; f += blockDim.x) {
-            int reg = 0;
-            while (f >= s_start[reg + 1]) ++reg;
-            const double* row = a.partials + ((long long)reg * LHVI_PARTIAL_ROWS + 1 + (f - s_start[reg])) * W;
-            for (int i = 0; i < W; ++i) acc[i] += row[i];
-        }
-        // more regions than the header table holds: the rest one by one
-        for (long long reg = regions; reg < a.regions; ++reg) {
-            const double* base = a.partials + reg * LHVI_PARTIAL_ROWS * W;
-            const int valid = (int)base[0];
-            for (int r = threadIdx.x; r < valid; r += blockDim.x)
-                for (int i = 0; i < W; ++i) acc[i] += base[(long long)(1 + r) * W + i];
-        }
-        block_sum_to(acc, W, s, res);
-        if (threadIdx.x < W) a.grad[a.n_param + threadIdx.x] = (real)res[threadIdx.x];
-        if (threadIdx.x == 0 && a.step != nullptr) {
-            // b^t as a running product (b^(t-1) = 1 - step[.]): no pow() on the critical path
-            a.step[0] = a.step[0] + 1.0;
-            a.step[1] = 1.0 - (1.0 - a.step[1]) * a.b1;
-            a.step[2] = 1.0 - (1.0 - a.step[2]) * a.b2;
-        }
-        __syncthreads();
+    // all region headers first (one round trip), then one flat pass over the valid rows
+    __shared__ int s_start[kFinishRegions + 1];
+    const int regions = (int)(a.regions < kFinishRegions ? a.regions : kFinishRegions);
+    if (threadIdx.x < regions)
+        s_start[threadIdx.x + 1] = (int)a.partials[(long long)threadIdx.x * LHVI_PARTIAL_ROWS * W];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_start[0] = 0;
+        for (int i = 0; i < regions; ++i) s_start[i + 1] += s_start[i];
     }
-    if (a.world <= 1) return;
+    __syncthreads();
+    double acc[LHVI_MAX_K + 1];
+    for (int i = 0; i < W; ++i) acc[i] = 0.0;
+    const int total = s_start[regions];
+    for (int f = threadIdx.x; f < total; f += blockDim.x) {
+        int reg = 0;
+        while (f >= s_start[reg + 1]) ++reg;
+        const double* row = a.partials + ((long long)reg * LHVI_PARTIAL_ROWS + 1 + (f - s_start[reg])) * W;
+        for (int i = 0; i < W; ++i) acc[i] += row[i];
+    }
+    // more regions than the header table holds: the rest one by one
+    for (long long reg = regions; reg < a.regions; ++reg) {
+        const double* base = a.partials + reg * LHVI_PARTIAL_ROWS * W;
+        const int valid = (int)base[0];
+        for (int r = threadIdx.x; r < valid; r += blockDim.x)
+            for (int i = 0; i < W; ++i) acc[i] += base[(long long)(1 + r) * W + i];
+    }
+    block_sum_to(acc, W, s, res);
+    if (threadIdx.x < W) a.grad[a.n_param + threadIdx.x] = (real)res[threadIdx.x];
+    if (threadIdx.x == 0 && a.step != nullptr) {
+        // b^t as a running product (b^(t-1) = 1 - step[.]): no pow() on the critical path
+        a.step[0] = a.step[0] + 1.0;
+        a.step[1] = 1.0 - (1.0 - a.step[1]) * a.b1;
+        a.step[2] = 1.0 - (1.0 - a.step[2]) * a.b2;
+    }
+    __syncthreads();
+}
 
+// The cross-GPU sum of x = [G_w | energy | grad[idx[*]]] over peer memory; `nblocks` blocks
+// (blockIdx.x < nblocks) take part, each with its slice.
+template <typename real>
+__device__ void finish_exchange(const FinishArgs<real>& a, int nblocks) {
+    const int W = a.K + 1;
     const long long n_x = a.n_idx + W;
-    const long long chunk = (n_x + gridDim.x - 1) / gridDim.x;
+    const long long chunk = (n_x + nblocks - 1) / nblocks;
     const long long lo = blockIdx.x * chunk;
     const long long hi = lo + chunk < n_x ? lo + chunk : n_x;
     const unsigned long long seq = a.seq[blockIdx.x] + 1ull;
@@ -150,10 +152,10 @@ finish_kernel(const FinishArgs<real> a) {
     // round trips overlap instead of queueing behind one thread's release stores
     if (threadIdx.x < a.world) {
         __threadfence_system();
-        st_relaxed_sys(a.flags[threadIdx.x] + (size_t)a.rank * gridDim.x + blockIdx.x, seq);
+        st_relaxed_sys(a.flags[threadIdx.x] + (size_t)a.rank * nblocks + blockIdx.x, seq);
     }
     if (threadIdx.x < a.world) {
-        const unsigned long long* f = a.flags[a.rank] + (size_t)threadIdx.x * gridDim.x + blockIdx.x;
+        const unsigned long long* f = a.flags[a.rank] + (size_t)threadIdx.x * nblocks + blockIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < seq) {
             if (clock64() - t0 > kSpinLimit) { *a.status = 1; break; }
@@ -169,6 +171,16 @@ finish_kernel(const FinishArgs<real> a) {
     }
     __syncthreads();
     if (threadIdx.x == 0) a.seq[blockIdx.x] = seq;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(kFinishThreads)
+finish_kernel(const FinishArgs<real> a) {
+    __shared__ double s[(kFinishThreads / 32) * (LHVI_MAX_K + 1)];
+    __shared__ double res[LHVI_MAX_K + 1];
+    if (blockIdx.x == 0) finish_reduce<real>(a, s, res);
+    if (a.world <= 1) return;
+    finish_exchange<real>(a, (int)gridDim.x);
 }
 
 // ---- optimiser step ------------------------------------------------------------------------
@@ -205,100 +217,136 @@ __device__ __forceinline__ real moved(real theta, real g, real& m1, real& m2, co
     return theta - (a.lr * (m1 / c1)) / (Math<real>::sqrt(m2 / c2) + a.eps);
 }
 
+// mixture weights: one thread (K <= 8)
+template <typename real>
+__device__ void step_mixture_weights(const StepArgs<real>& a, real c1, real c2) {
+    using M = Math<real>;
+    const int K = a.K;
+    real* w_tau = a.wstate;
+    real* w = a.wstate + K;
+    real* m1 = a.wstate + 2 * K;
+    real* m2 = a.wstate + 3 * K;
+    const real* G = a.grad + a.n_param;
+    real dot = real(0);
+    for (int k = 0; k < K; ++k) dot += G[k] * w[k];
+    real mx = real(-1e30);
+    for (int k = 0; k < K; ++k) {
+        const real gk = w[k] * (G[k] - dot);                     // VarInference.py:90
+        w_tau[k] = moved<real>(w_tau[k], gk, m1[k], m2[k], a, c1, c2);
+        mx = w_tau[k] > mx ? w_tau[k] : mx;
+    }
+    real z = real(0);
+    for (int k = 0; k < K; ++k) z += M::exp(w_tau[k] - mx);
+    for (int k = 0; k < K; ++k) w[k] = M::exp(w_tau[k] - mx) / z;
+}
+
+// one variable: softmax Jacobian (discrete), Adam / SGD, variance clip, re-normalisation, and the
+// reset of the gradient slots it consumed
+template <typename real>
+__device__ __forceinline__ void step_variable(const StepArgs<real>& a, long long v, real c1, real c2) {
+    using M = Math<real>;
+    const int K = a.K;
+    const int off = a.off[v];
+    if (a.kind[v] == 0) {
+        // slots are 16-byte aligned (8 for K == 1): move them with vector loads / stores
+        using V = typename PairVec<real>::type;
+        constexpr int PER = PairVec<real>::pairs;                 // (mu, var) pairs per vector
+        const int nvec = (K + PER - 1) / PER;
+        for (int c = 0; c < nvec; ++c) {
+            const int i = off + 2 * PER * c;
+            if (PER == 2 && K == 1) {                              // lone pair: scalar fallback
+                a.eta[i] = moved<real>(a.eta[i], a.grad[i], a.m1[i], a.m2[i], a, c1, c2);
+                real var = moved<real>(a.eta[i + 1], a.grad[i + 1], a.m1[i + 1], a.m2[i + 1], a, c1, c2);
+                a.eta[i + 1] = var < a.var_floor ? a.var_floor : var;
+                if (a.zero_grad) { a.grad[i] = real(0); a.grad[i + 1] = real(0); }
+                continue;
+            }
+            V ve = *reinterpret_cast<V*>(a.eta + i);
+            const V vg = *reinterpret_cast<const V*>(a.grad + i);
+            V vm = *reinterpret_cast<V*>(a.m1 + i);
+            V vu = *reinterpret_cast<V*>(a.m2 + i);
+            real* e = reinterpret_cast<real*>(&ve);
+            const real* gq = reinterpret_cast<const real*>(&vg);
+            real* m = reinterpret_cast<real*>(&vm);
+            real* u = reinterpret_cast<real*>(&vu);
+#pragma unroll
+            for (int p = 0; p < PER; ++p) {
+                if (PER * c + p < K) {
+                    e[2 * p] = moved<real>(e[2 * p], gq[2 * p], m[2 * p], u[2 * p], a, c1, c2);
+                    const real var = moved<real>(e[2 * p + 1], gq[2 * p + 1], m[2 * p + 1], u[2 * p + 1], a, c1, c2);
+                    e[2 * p + 1] = var < a.var_floor ? a.var_floor : var;   // VarInference.py:281
+                }
+            }
+            *reinterpret_cast<V*>(a.eta + i) = ve;
+            *reinterpret_cast<V*>(a.m1 + i) = vm;
+            *reinterpret_cast<V*>(a.m2 + i) = vu;
+            if (a.zero_grad) {
+                V zero;
+                real* zq = reinterpret_cast<real*>(&zero);
+#pragma unroll
+                for (int p = 0; p < 2 * PER; ++p) zq[p] = real(0);
+                *reinterpret_cast<V*>(a.grad + i) = zero;
+            }
+        }
+    } else {
+        const int D = a.dim[v];
+        for (int k = 0; k < K; ++k) {
+            const int row = off + k * D;
+            real dot = real(0);
+            for (int d = 0; d < D; ++d) dot += a.grad[row + d] * a.eta[row + d];
+            real mx = real(-1e30);
+            for (int d = 0; d < D; ++d) {
+                const real p = a.eta[row + d];
+                const real gt = p * (a.grad[row + d] - dot);          // VarInference.py:160
+                const real t = moved<real>(a.tau[row + d], gt, a.m1[row + d], a.m2[row + d], a, c1, c2);
+                a.tau[row + d] = t;
+                mx = t > mx ? t : mx;
+            }
+            real z = real(0);
+            for (int d = 0; d < D; ++d) z += M::exp(a.tau[row + d] - mx);
+            const real iz = real(1) / z;
+            for (int d = 0; d < D; ++d) a.eta[row + d] = M::exp(a.tau[row + d] - mx) * iz;
+            if (a.zero_grad)
+                for (int d = 0; d < D; ++d) a.grad[row + d] = real(0);
+        }
+    }
+}
+
 template <typename real>
 __global__ void __launch_bounds__(256)
 param_step_kernel(const StepArgs<real> a) {
-    using M = Math<real>;
-    const int K = a.K;
     const real c1 = (real)a.step[1], c2 = (real)a.step[2];
-
-    // mixture weights: one thread (K <= 8)
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        real* w_tau = a.wstate;
-        real* w = a.wstate + K;
-        real* m1 = a.wstate + 2 * K;
-        real* m2 = a.wstate + 3 * K;
-        const real* G = a.grad + a.n_param;
-        real dot = real(0);
-        for (int k = 0; k < K; ++k) dot += G[k] * w[k];
-        real mx = real(-1e30);
-        for (int k = 0; k < K; ++k) {
-            const real gk = w[k] * (G[k] - dot);                     // VarInference.py:90
-            w_tau[k] = moved<real>(w_tau[k], gk, m1[k], m2[k], a, c1, c2);
-            mx = w_tau[k] > mx ? w_tau[k] : mx;
-        }
-        real z = real(0);
-        for (int k = 0; k < K; ++k) z += M::exp(w_tau[k] - mx);
-        for (int k = 0; k < K; ++k) w[k] = M::exp(w_tau[k] - mx) / z;
-    }
-
+    if (blockIdx.x == 0 && threadIdx.x == 0) step_mixture_weights<real>(a, c1, c2);
     for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < a.n_vars;
-         v += (long long)gridDim.x * blockDim.x) {
-        const int off = a.off[v];
-        if (a.kind[v] == 0) {
-            // slots are 16-byte aligned (8 for K == 1): move them with vector loads / stores
-            using V = typename PairVec<real>::type;
-            constexpr int PER = PairVec<real>::pairs;                 // (mu, var) pairs per vector
-            const int nvec = (K + PER - 1) / PER;
-            for (int c = 0; c < nvec; ++c) {
-                const int i = off + 2 * PER * c;
-                if (PER == 2 && K == 1) {                              // lone pair: scalar fallback
-                    a.eta[i] = moved<real>(a.eta[i], a.grad[i], a.m1[i], a.m2[i], a, c1, c2);
-                    real var = moved<real>(a.eta[i + 1], a.grad[i + 1], a.m1[i + 1], a.m2[i + 1], a, c1, c2);
-                    a.eta[i + 1] = var < a.var_floor ? a.var_floor : var;
-                    if (a.zero_grad) { a.grad[i] = real(0); a.grad[i + 1] = real(0); }
-                    continue;
-                }
-                V ve = *reinterpret_cast<V*>(a.eta + i);
-                const V vg = *reinterpret_cast<const V*>(a.grad + i);
-                V vm = *reinterpret_cast<V*>(a.m1 + i);
-                V vu = *reinterpret_cast<V*>(a.m2 + i);
-                real* e = reinterpret_cast<real*>(&ve);
-                const real* gq = reinterpret_cast<const real*>(&vg);
-                real* m = reinterpret_cast<real*>(&vm);
-                real* u = reinterpret_cast<real*>(&vu);
-#pragma unroll
-                for (int p = 0; p < PER; ++p) {
-                    if (PER * c + p < K) {
-                        e[2 * p] = moved<real>(e[2 * p], gq[2 * p], m[2 * p], u[2 * p], a, c1, c2);
-                        const real var = moved<real>(e[2 * p + 1], gq[2 * p + 1], m[2 * p + 1], u[2 * p + 1], a, c1, c2);
-                        e[2 * p + 1] = var < a.var_floor ? a.var_floor : var;   // VarInference.py:281
-                    }
-                }
-                *reinterpret_cast<V*>(a.eta + i) = ve;
-                *reinterpret_cast<V*>(a.m1 + i) = vm;
-                *reinterpret_cast<V*>(a.m2 + i) = vu;
-                if (a.zero_grad) {
-                    V zero;
-                    real* zq = reinterpret_cast<real*>(&zero);
-#pragma unroll
-                    for (int p = 0; p < 2 * PER; ++p) zq[p] = real(0);
-                    *reinterpret_cast<V*>(a.grad + i) = zero;
-                }
-            }
-        } else {
-            const int D = a.dim[v];
-            for (int k = 0; k < K; ++k) {
-                const int row = off + k * D;
-                real dot = real(0);
-                for (int d = 0; d < D; ++d) dot += a.grad[row + d] * a.eta[row + d];
-                real mx = real(-1e30);
-                for (int d = 0; d < D; ++d) {
-                    const real p = a.eta[row + d];
-                    const real gt = p * (a.grad[row + d] - dot);          // VarInference.py:160
-                    const real t = moved<real>(a.tau[row + d], gt, a.m1[row + d], a.m2[row + d], a, c1, c2);
-                    a.tau[row + d] = t;
-                    mx = t > mx ? t : mx;
-                }
-                real z = real(0);
-                for (int d = 0; d < D; ++d) z += M::exp(a.tau[row + d] - mx);
-                const real iz = real(1) / z;
-                for (int d = 0; d < D; ++d) a.eta[row + d] = M::exp(a.tau[row + d] - mx) * iz;
-                if (a.zero_grad)
-                    for (int d = 0; d < D; ++d) a.grad[row + d] = real(0);
-            }
-        }
+         v += (long long)gridDim.x * blockDim.x)
+        step_variable<real>(a, v, c1, c2);
+}
+
+// ---- finish + step in one launch ---------------------------------------------------------------
+//
+// Block 0 does lhvi_finish's work (partial rows -> G_w, energy; with several GPUs the exchange)
+// and then steps the mixture weights and the *shared* variables (a.n_vars - n_owned of them, listed
+// last), whose gradients only exist after the exchange.  Every other block steps owned variables
+// right away: they depend on nothing block 0 does, so the reduction and the NVLink round trip are
+// off the critical path and one launch level of the iteration is gone.  The step counter must
+// already be advanced for this iteration (lhvi_step_tick, launched beside the factor kernels).
+template <typename real>
+__global__ void __launch_bounds__(256)
+finish_step_kernel(const FinishArgs<real> f, const StepArgs<real> a, long long n_owned) {
+    __shared__ double s[(256 / 32) * (LHVI_MAX_K + 1)];
+    __shared__ double res[LHVI_MAX_K + 1];
+    const real c1 = (real)a.step[1], c2 = (real)a.step[2];
+    if (blockIdx.x == 0) {
+        finish_reduce<real>(f, s, res);
+        if (f.world > 1) finish_exchange<real>(f, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) step_mixture_weights<real>(a, c1, c2);
+        for (long long v = n_owned + threadIdx.x; v < a.n_vars; v += blockDim.x) step_variable<real>(a, v, c1, c2);
+        return;
     }
+    for (long long v = (blockIdx.x - 1) * (long long)blockDim.x + threadIdx.x; v < n_owned;
+         v += (long long)(gridDim.x - 1) * blockDim.x)
+        step_variable<real>(a, v, c1, c2);
 }
 
 // ---- batched belief queries ------------------------------------------------------------------
@@ -533,6 +581,63 @@ extern "C" int lhvi_param_step(int dtype, int K, int64_t n_vars, const uint8_t* 
     return dtype == LHVI_F64
         ? param_step_t<double>(K, n_vars, var_kind, var_dim, var_off, eta, tau, grad, n_param, mom1, mom2, wstate, step, lr, b1, b2, eps, var_threshold, sgd, zero_grad, s)
         : param_step_t<float>(K, n_vars, var_kind, var_dim, var_off, eta, tau, grad, n_param, mom1, mom2, wstate, step, lr, b1, b2, eps, var_threshold, sgd, zero_grad, s);
+}
+
+template <typename real>
+static int finish_step_t(const lhvi_model* m, long long regions, const lhvi_exchange* x, int K, int64_t n_vars,
+                         int64_t n_owned, const uint8_t* kind, const int32_t* dim, const int32_t* off, void* eta,
+                         void* tau, void* m1, void* m2, void* wstate, const double* step, double lr, double b1,
+                         double b2, double eps, double var_floor, int sgd, cudaStream_t s) {
+    FinishArgs<real> f;
+    f.partials = m->partials; f.regions = regions; f.K = m->K;
+    f.grad = (real*)m->grad; f.n_param = m->n_param;
+    f.step = nullptr; f.b1 = b1; f.b2 = b2;
+    f.world = 1; f.rank = 0; f.n_idx = 0; f.idx = nullptr; f.seq = nullptr; f.status = nullptr;
+    for (int p = 0; p < LHVI_MAX_PEERS; ++p) { f.recv[p] = nullptr; f.flags[p] = nullptr; }
+    if (x != nullptr && x->world > 1) {
+        f.world = x->world; f.rank = x->rank; f.n_idx = x->n_idx; f.idx = x->idx;
+        f.seq = (unsigned long long*)x->seq; f.status = x->status;
+        for (int p = 0; p < x->world; ++p) {
+            f.recv[p] = (real*)x->recv[p];
+            f.flags[p] = (unsigned long long*)x->flags[p];
+        }
+    }
+    StepArgs<real> a;
+    a.K = K; a.n_vars = n_vars; a.n_param = m->n_param;
+    a.kind = kind; a.dim = dim; a.off = off;
+    a.eta = (real*)eta; a.tau = (real*)tau; a.grad = (real*)m->grad;
+    a.m1 = (real*)m1; a.m2 = (real*)m2; a.wstate = (real*)wstate; a.step = step;
+    a.lr = (real)lr; a.b1 = (real)b1; a.b2 = (real)b2; a.eps = (real)eps; a.var_floor = (real)var_floor;
+    a.sgd = sgd; a.zero_grad = 1;
+    finish_step_kernel<real><<<1 + grid_for(n_owned > 0 ? n_owned : 1, 256), 256, 0, s>>>(f, a, (long long)n_owned);
+    return check_launch("finish_step_kernel");
+}
+
+extern "C" int lhvi_finish_step(const lhvi_model* m, int64_t rows, const lhvi_exchange* x, int64_t n_vars,
+                                int64_t n_owned, const uint8_t* var_kind, const int32_t* var_dim,
+                                const int32_t* var_off, void* tau, void* mom1, void* mom2, void* wstate,
+                                const double* step, double lr, double b1, double b2, double eps,
+                                double var_threshold, int sgd, void* stream) {
+    if (!m || !m->partials || !m->grad || !m->eta || rows < 0) { set_error("lhvi_finish_step: null buffer or negative rows"); return LHVI_EINVAL; }
+    if (!tau || !mom1 || !mom2 || !wstate || !step) { set_error("lhvi_finish_step: null buffer"); return LHVI_EINVAL; }
+    if (n_vars > 0 && (!var_kind || !var_dim || !var_off)) { set_error("lhvi_finish_step: null variable table"); return LHVI_EINVAL; }
+    if (n_owned < 0 || n_owned > n_vars) { set_error("lhvi_finish_step: n_owned=%lld outside 0..n_vars=%lld", (long long)n_owned, (long long)n_vars); return LHVI_EINVAL; }
+    if (m->K < 1 || m->K > LHVI_MAX_K) { set_error("K=%d out of range 1..%d", m->K, LHVI_MAX_K); return LHVI_ELIMIT; }
+    if (rows % LHVI_PARTIAL_ROWS != 0) { set_error("lhvi_finish_step: rows must be a multiple of LHVI_PARTIAL_ROWS"); return LHVI_EINVAL; }
+    if (x != nullptr && x->world > 1) {
+        if (x->world > LHVI_MAX_PEERS) { set_error("lhvi_finish_step: world=%d exceeds LHVI_MAX_PEERS=%d", x->world, LHVI_MAX_PEERS); return LHVI_ELIMIT; }
+        if (x->rank < 0 || x->rank >= x->world) { set_error("lhvi_finish_step: rank %d outside world %d", x->rank, x->world); return LHVI_EINVAL; }
+        if (x->blocks != 1) { set_error("lhvi_finish_step: the fused launch exchanges with one block (blocks=%d): use lhvi_finish + lhvi_param_step", x->blocks); return LHVI_EINVAL; }
+        if (x->n_idx < 0 || (x->n_idx > 0 && !x->idx) || !x->seq || !x->status) { set_error("lhvi_finish_step: incomplete exchange descriptor"); return LHVI_EINVAL; }
+        for (int p = 0; p < x->world; ++p)
+            if (!x->recv[p] || !x->flags[p]) { set_error("lhvi_finish_step: peer %d has no mapped buffer", p); return LHVI_EINVAL; }
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long regions = rows / LHVI_PARTIAL_ROWS;
+    void* eta = const_cast<void*>(m->eta);
+    return m->dtype == LHVI_F64
+        ? finish_step_t<double>(m, regions, x, m->K, n_vars, n_owned, var_kind, var_dim, var_off, eta, tau, mom1, mom2, wstate, step, lr, b1, b2, eps, var_threshold, sgd, s)
+        : finish_step_t<float>(m, regions, x, m->K, n_vars, n_owned, var_kind, var_dim, var_off, eta, tau, mom1, mom2, wstate, step, lr, b1, b2, eps, var_threshold, sgd, s);
 }
 
 extern "C" int lhvi_mixture_belief(int dtype, int K, int64_t n, const int32_t* q_off, const int32_t* q_dim,

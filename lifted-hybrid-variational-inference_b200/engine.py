@@ -141,6 +141,10 @@ class DeviceEngine:
         self.dom_events = []
         self.use_graph = True          # replay one captured iteration instead of ~8 launches
         self.parallel_groups = True    # independent group launches on parallel graph branches
+        # lhvi_finish_step instead of lhvi_finish + lhvi_param_step: on for one GPU (measured 143.1 ->
+        # 141.7 us per iteration), off for several unless LHVI_FUSED_STEP=1 (measured 89.5 -> 91.6 us
+        # at two GPUs: block 0 then carries reduction + exchange + shared variables alone)
+        self.fused_step = os.environ.get("LHVI_FUSED_STEP", "auto")
         self._graphs = {}
         self._side_streams = []
         self._grad_clean = False       # True: every gradient slot is zero (param_step cleared them)
@@ -192,9 +196,18 @@ class DeviceEngine:
         qx, qw = hermgauss_scaled(self.T)
         self.quad = self._dev(np.concatenate([qx, qw]), self.tdtype)
         ptab_host = np.asarray(m.ptab, dtype=np.float64)
-        self.var_kind = self._dev(m.var_kind.astype(np.uint8))
-        self.var_dim = self._dev(m.var_dim.astype(np.int32))
-        self.var_off = self._dev(m.var_off.astype(np.int32))
+        # variable table of the optimiser step: the variables only this rank touches first, the
+        # shared ones (whose gradients are completed by the exchange) last -- lhvi_finish_step
+        order = np.arange(int(m.n_vars))
+        self.n_owned = int(m.n_vars)
+        if self.plan.active:
+            shared_off = self.full_model.var_off[self.plan.part.shared]
+            is_shared = np.isin(m.var_off, shared_off)
+            order = np.concatenate([np.flatnonzero(~is_shared), np.flatnonzero(is_shared)])
+            self.n_owned = int((~is_shared).sum())
+        self.var_kind = self._dev(m.var_kind[order].astype(np.uint8))
+        self.var_dim = self._dev(m.var_dim[order].astype(np.int32))
+        self.var_off = self._dev(m.var_off[order].astype(np.int32))
         self.n_vars = int(m.n_vars)
 
         def z(n, dt=None):
@@ -392,14 +405,20 @@ class DeviceEngine:
             C.byref(self.desc), C.byref(d), i * _cabi.LHVI_PARTIAL_ROWS, int(self.force_generic),
             C.c_void_p(stream.cuda_stream)), self.lib)
 
-    def _launch_groups(self):
-        """One launch per record group.  The launches only share atomics into ``grad``, so
+    def _tick(self, stream):
+        _cabi.check(self.lib.lhvi_step_tick(self.step.data_ptr(), self.b1, self.b2,
+                                            C.c_void_p(stream.cuda_stream)), self.lib)
+
+    def _launch_groups(self, tick=False):
+        """One launch per record group (and, with ``tick``, the step-counter kernel beside them).  The launches only share atomics into ``grad``, so
         they are forked onto side streams (parallel branches once captured in a CUDA graph),
         largest group first; with ``profile_group`` set they run in order on the current
         stream with CUDA events around that group's launch (bench.py roofline)."""
         main = torch.cuda.current_stream(self.device)
         n = len(self.groups)
         if self.profile_group is not None or not self.parallel_groups or n < 2:
+            if tick:
+                self._tick(main)
             for i in range(n):
                 timed = self.profile_group == i or self.profile_group == "all"
                 if timed:
@@ -410,7 +429,7 @@ class DeviceEngine:
                     ev[1].record(main)
                     self.dom_events.append((i, ev[0], ev[1]))
             return n
-        while len(self._side_streams) < n - 1:
+        while len(self._side_streams) < n:
             self._side_streams.append(torch.cuda.Stream(device=self.device))
         order = sorted(range(n), key=lambda i: -self.groups[i][2].n)
         fork = torch.cuda.Event()
@@ -420,6 +439,13 @@ class DeviceEngine:
             side = self._side_streams[j]
             side.wait_event(fork)
             self._launch_group(i, side)
+            join = torch.cuda.Event()
+            join.record(side)
+            main.wait_event(join)
+        if tick:
+            side = self._side_streams[n - 1]
+            side.wait_event(fork)
+            self._tick(side)
             join = torch.cuda.Event()
             join.record(side)
             main.wait_event(join)
@@ -456,8 +482,27 @@ class DeviceEngine:
             self.step.data_ptr(), float(lr), self.b1, self.b2, self.eps, self.var_threshold,
             int(bool(sgd)), int(bool(zero_grad)), st), lib)
 
+    def _can_fuse(self):
+        if self.fused_step == "0":
+            return False
+        if not self.plan.active:
+            return True
+        return self.fused_step == "1" and self.exchange == "p2p" and int(self.peer.desc.blocks) == 1
+
     def _iteration(self, lr, sgd):
         """One Jacobi iteration; expects clean gradient slots and leaves them clean."""
+        if self._can_fuse():
+            # the step counter is advanced beside the factor kernels; finish + step are one launch
+            launches = self._launch_groups(tick=not sgd)
+            x = C.byref(self.peer.desc) if self.plan.active else None
+            _cabi.check(self.lib.lhvi_finish_step(
+                C.byref(self.desc), self.partial_rows, x, self.n_vars, self.n_owned,
+                self.var_kind.data_ptr(), self.var_dim.data_ptr(), self.var_off.data_ptr(),
+                self.tau.data_ptr(), self.mom1.data_ptr(), self.mom2.data_ptr(), self.wstate.data_ptr(),
+                self.step.data_ptr(), float(lr), self.b1, self.b2, self.eps, self.var_threshold,
+                int(bool(sgd)), self._stream()), self.lib)
+            self.launches_per_pass = launches + (0 if sgd else 1)
+            return
         launches = self._launch_groups()
         self._finish(tick=not sgd, exchange=self.plan.active)
         self.param_step(lr, sgd=sgd, zero_grad=True)
