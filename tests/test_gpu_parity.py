@@ -340,6 +340,29 @@ def test_large_scale_properties():
     np.testing.assert_allclose(grad, og, rtol=1e-4, atol=2e-5 * np.abs(og).max())
 
 
+@pytest.mark.parametrize("weighted", [True, False])
+def test_tile_aligned_hub_runs_through_every_kernel(weighted, monkeypatch):
+    """Hub runs of the streamed group padded to whole tiles with null records (engine.align_runs):
+    the streaming kernel, the per-record kernels and the generic kernel all sum the same values."""
+    from lhvi_b200 import engine as eng_mod
+    monkeypatch.setattr(eng_mod, "FOLD_ALIGN_MIN_TILES", 0)          # pad every run, however short
+    syn = lhvi_b200.synthetic
+    model = syn.relational_hybrid(500, 4, 3, 3, seed=6, weighted=weighted)
+    eta, tau, w_tau = syn.random_state(model, 2)
+    w = np.full(3, 1.0 / 3)
+    og, ogw, oe = grad_pass(model, eta, w)
+    for dtype, tol in (("float64", 1e-9), ("float32", 5e-5)):
+        for force_generic in (False, True):
+            eng = _engine_for(model, dtype, force_generic=force_generic)
+            padded = [d for d, _, g in eng.groups if d.fold and (d.hub_mask >> g.nd) & 1]
+            assert padded and all(int(d.n) % 1024 == 0 and int(d.n) >= 4 * 1024 for d in padded)
+            eng.set_state(eta, tau, w_tau)
+            grad, g_w, energy = eng.gradients()
+            np.testing.assert_allclose(energy, oe, rtol=tol)
+            np.testing.assert_allclose(g_w, ogw, rtol=tol, atol=tol * np.abs(ogw).max())
+            np.testing.assert_allclose(grad, og, rtol=tol, atol=tol * np.abs(og).max())
+
+
 def test_state_pack_unpack_round_trip(ns):
     """lhvi_state_pack / lhvi_state_unpack: compact per-variable arrays <-> padded device slots."""
     import torch
