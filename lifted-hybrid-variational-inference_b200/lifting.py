@@ -77,6 +77,18 @@ def _rank_rows(cols):
     if len(cols) == 1:
         _, inv = np.unique(cols[0], return_inverse=True)
         return inv.astype(np.int64)
+    # non-negative columns whose ranges multiply to less than 2^62 pack into one sortable key
+    if all(c.dtype.kind in "iu" for c in cols) and all(c.size and int(c.min()) >= 0 for c in cols):
+        spans = [int(c.max()) + 1 for c in cols]
+        total = 1
+        for sp in spans:
+            total *= sp
+        if total < (1 << 62):
+            key = np.zeros(cols[0].shape[0], dtype=np.int64)
+            for c, sp in zip(cols, spans):
+                key = key * sp + c.astype(np.int64)
+            _, inv = np.unique(key, return_inverse=True)
+            return inv.astype(np.int64)
     order = np.lexsort(cols[::-1])
     stacked = np.stack([c[order] for c in cols])
     new = np.ones(stacked.shape[1], dtype=bool)
@@ -262,7 +274,8 @@ def quotient(ga: GroundArrays, var_colour, factor_colours, ev_value=None) -> Quo
         rvs.append(_ClassRV(c, ga.domains[int(ga.var_dom[r])], None if is_hidden else float(mean[c]),
                             None if is_hidden else float(variance[c]), int(sizes[c]), int(deg[r]), r))
     factors = []
-    rep_of_var = {int(r): rvs[c] for c, r in enumerate(reps)}
+    is_rep = np.zeros(nv, dtype=bool)
+    is_rep[reps] = True
     classes = {}                       # factor colour -> handle (a class may span several blocks)
     sizes_f = Counter()
     for fcol in factor_colours:
@@ -279,12 +292,17 @@ def quotient(ga: GroundArrays, var_colour, factor_colours, ev_value=None) -> Quo
                 f.nb = tuple(rvs[int(var_colour[v])] for v in b.args[fi])
                 classes[int(cid)] = f
                 factors.append(f)
-        # neighbour counts of the representatives: factors of this block that touch one
+        # neighbour counts of the representatives: factors of this block that touch one, counted
+        # per (variable class, factor class) pair with one unique pass per argument position
+        n_fc = int(fcol.max()) + 1
         for a in range(b.arity):
             col = b.args[:, a]
-            hit = np.flatnonzero(np.isin(col, reps))
-            for fi in hit:
-                rep_of_var[int(col[fi])].count[classes[int(fcol[fi])]] += 1
+            hit = np.flatnonzero(is_rep[col])
+            if hit.size == 0:
+                continue
+            pairs, cnt = np.unique(var_colour[col[hit]].astype(np.int64) * n_fc + fcol[hit], return_counts=True)
+            for pk, cn in zip(pairs.tolist(), cnt.tolist()):
+                rvs[pk // n_fc].count[classes[pk % n_fc]] += cn
     for rv in rvs:
         rv.nb = tuple(rv.count)
     return QuotientGraph(rvs, factors, var_colour, list(factor_colours))
@@ -479,14 +497,21 @@ class C2FArrayVI:
         var = np.bincount(inv, weights=dev * dev) / cnt
         return ids, mean, var, cnt
 
+    def _members_by_class(self):
+        """(order, starts): members of class c are ``order[starts[c]:starts[c + 1]]``, ascending."""
+        order = np.argsort(self.vcol, kind="stable")
+        starts = np.searchsorted(self.vcol[order], np.arange(int(self.vcol.max()) + 2))
+        return order, starts
+
     def _split_evidence(self, epsilon):
         """``CompressedGraph.split_evidence`` (``:236-247``) until nothing changes."""
         changed = True
         while changed:
             changed = False
             next_id = int(self.vcol.max()) + 1
+            order, starts = self._members_by_class()         # classes are disjoint: one grouping per pass
             for cid in sorted(self.clustered):
-                members = np.flatnonzero(self.vcol == cid)
+                members = order[starts[cid]:starts[cid + 1]]
                 vals = self.ga.var_value[members]
                 if not np.sqrt(vals.var()) > epsilon:
                     continue
@@ -496,19 +521,18 @@ class C2FArrayVI:
                         self.clustered.discard(cid)
                     continue
                 owner, centroids = res
-                pieces = [cid]
+                pieces = [(cid, vals[owner == 0])]
                 self.ev_value[cid] = float(centroids[0])
                 for j in range(1, centroids.size):
-                    sel = members[owner == j]
-                    if sel.size:
-                        self.vcol[sel] = next_id
+                    pick = owner == j
+                    if pick.any():
+                        self.vcol[members[pick]] = next_id
                         self.ev_value[next_id] = float(centroids[j])
-                        pieces.append(next_id)
+                        pieces.append((next_id, vals[pick]))
                         next_id += 1
                 if len(pieces) > 1:
                     changed = True
-                    for pid in pieces:
-                        pv = self.ga.var_value[self.vcol == pid]
+                    for pid, pv in pieces:
                         if pv.size and pv.var() > epsilon:
                             self.clustered.add(pid)
                         elif pid != cid:
@@ -518,23 +542,22 @@ class C2FArrayVI:
         """Colour passing from the current classes; hidden pieces inherit (``:39-61``)."""
         old = self.vcol
         new, self.fcols, _ = colour_passing(self.ga, start=old)
+        # distinct (old class, new class) pairs: the new partition refines the old one
+        n_new = int(new.max()) + 1
+        key = np.unique(old.astype(np.int64) * n_new + new)
+        pair = np.stack([key // n_new, key % n_new])
+        kids_of = np.bincount(pair[0], minlength=int(old.max()) + 1)
         # carry the evidence book-keeping over to the new ids
         if self.clustered:
-            keep = set()
-            for cid in self.clustered:
-                keep.update(np.unique(new[old == cid]).tolist())
-            self.clustered = keep
+            was = np.zeros(int(old.max()) + 1, dtype=bool)
+            was[np.fromiter(self.clustered, dtype=np.int64, count=len(self.clustered))] = True
+            self.clustered = set(pair[1][was[pair[0]]].tolist())
         # a class that colour passing left whole keeps its k-means centroid as value; pieces of a
         # structure split take the mean of their members (SuperRV.split_by_structure, :57-62)
         if self.ev_value:
-            size_old = np.bincount(old, minlength=int(old.max()) + 1)
-            size_new = np.bincount(new, minlength=int(new.max()) + 1)
-            carried = {}
-            for cid, v in self.ev_value.items():
-                kids = np.unique(new[old == cid])
-                if kids.size == 1 and size_new[kids[0]] == size_old[cid]:
-                    carried[int(kids[0])] = v
-            self.ev_value = carried
+            first_kid = np.full(int(old.max()) + 1, -1, dtype=np.int64)
+            first_kid[pair[0][::-1]] = pair[1][::-1]
+            self.ev_value = {int(first_kid[c]): v for c, v in self.ev_value.items() if kids_of[c] == 1}
         self._inherit(old, new)
         self.vcol = new
 
