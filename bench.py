@@ -136,8 +136,46 @@ class ClockSampler:
         self.max_mhz = None
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+
+    def _init_nvml(self):
+        """NVML polling (about a microsecond per query, so that even a timed region of a few
+        milliseconds is sampled many times).  Set up before the thread starts: loading the
+        library takes longer than the timed region.  False if NVML is not usable here."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            int(reasons_fn(h))
+        except Exception:
+            return False
+        self._nvml = (pynvml, h, reasons_fn)
+        return True
+
+    def _run_nvml(self):
+        if self._nvml is None:
+            return False
+        pynvml, h, reasons_fn = self._nvml
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                mask = int(reasons_fn(h))
+                for bit, name in bits.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.0005)
+        return True
 
     def _run(self):
+        if self._run_nvml():
+            return
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop.is_set():
             try:
@@ -154,6 +192,7 @@ class ClockSampler:
             self._stop.wait(0.1)
 
     def __enter__(self):
+        self._init_nvml()
         self._thread.start()
         return self
 
