@@ -1712,6 +1712,13 @@ static int launch_unary_fold(const lhvi_model* m, const lhvi_group* g, int64_t r
         // LHVI_FOLD_WAVES > 1 oversubscribes the SMs so that the hardware block scheduler evens out
         // slow SMs; measured neutral (44-46 us either way on the bench workload), so one wave
         long long blocks = tiles < LHVI_FOLD_WAVES * resident ? tiles : LHVI_FOLD_WAVES * resident;
+        // a small group (a rank's shard of a strong-scaled model): whole chunks of ceil(tiles /
+        // resident) tiles per block -- the host pads hub runs to that chunk (engine.align_runs), so
+        // that no block crosses a hub boundary at all
+        if (tiles <= 4 * (long long)resident) {
+            const long long c = (tiles + resident - 1) / resident;
+            blocks = (tiles + c - 1) / c;
+        }
         if (blocks > LHVI_PARTIAL_ROWS - 1) blocks = LHVI_PARTIAL_ROWS - 1;
         SpecLaunch L;
         L.chunk = tiles;

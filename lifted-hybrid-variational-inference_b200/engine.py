@@ -53,6 +53,7 @@ def hub_mask(g):
 
 
 FOLD_ALIGN_MIN_TILES = 4   # runs of a streamed group at least this long are padded to whole tiles
+FOLD_BLOCK_SLOTS = 148 * 4  # resident blocks of the streaming kernel on one B200 (a hint: launch_unary_fold)
 
 
 def align_runs(g, null_pot, tile):
@@ -64,9 +65,22 @@ def align_runs(g, null_pot, tile):
     key = g.poff[0]
     starts = np.concatenate([[0], np.flatnonzero(key[1:] != key[:-1]) + 1, [g.n]])
     lens = np.diff(starts)
-    plen = np.where(lens >= FOLD_ALIGN_MIN_TILES * tile, (lens + tile - 1) // tile * tile, lens)
+    # a small group is launched with whole chunks of ceil(tiles / resident blocks) tiles per block
+    # (launch_unary_fold): pad the long runs to that chunk, so that no block crosses a hub boundary
+    unit = tile
+    tiles0 = -(-g.n // tile)
+    if tiles0 <= 4 * FOLD_BLOCK_SLOTS:
+        for _ in range(4):
+            chunk = max(1, -(-tiles0 // FOLD_BLOCK_SLOTS))
+            unit = chunk * tile
+            padded = np.where(lens >= FOLD_ALIGN_MIN_TILES * tile, (lens + unit - 1) // unit * unit, lens)
+            tiles1 = -(-int(padded.sum()) // unit) * chunk
+            if -(-tiles1 // FOLD_BLOCK_SLOTS) == chunk:
+                break
+            tiles0 = tiles1
+    plen = np.where(lens >= FOLD_ALIGN_MIN_TILES * tile, (lens + unit - 1) // unit * unit, lens)
     total = int(plen.sum())
-    plen[-1] += (total + tile - 1) // tile * tile - total          # the tail, as before
+    plen[-1] += (total + unit - 1) // unit * unit - total           # the tail
     if int(plen.sum()) == g.n:
         return g
     dst0 = np.cumsum(plen) - plen
