@@ -109,9 +109,6 @@ def _potential_ids(blocks):
     return ids
 
 
-_MASK = np.uint64(0xFFFFFFFFFFFFFFFF)
-
-
 def _mix(x, seed):
     """splitmix64 finaliser on uint64 arrays (wrap-around arithmetic)."""
     with np.errstate(over="ignore"):
