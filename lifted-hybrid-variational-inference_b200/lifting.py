@@ -67,7 +67,7 @@ class GroundArrays:
         """Ground degree of every variable (``Graph.init_nb``: one entry per argument position)."""
         deg = np.zeros(self.n_vars, dtype=np.int64)
         for b in self.blocks:
-            np.add.at(deg, b.args.reshape(-1), 1)
+            deg += np.bincount(b.args.reshape(-1), minlength=self.n_vars)
         return deg
 
 
@@ -204,6 +204,16 @@ def colour_passing(ga: GroundArrays, split_cont_evidence=True, max_sweeps=1000, 
     return vcol, fcols, sweeps
 
 
+def _domain_value(domain, x):
+    """The element of a discrete domain's ``values`` that equals ``x`` (evidence travels as
+    float64 in ``GroundArrays.var_value``; table potentials index with the original value)."""
+    if not domain.continuous:
+        for v in domain.values:
+            if v == x:
+                return v
+    return float(x)
+
+
 class _ClassRV:
     """Variable class handle for ``lowering.lower_graph`` (what it reads of a ``SuperRV``)."""
 
@@ -268,7 +278,8 @@ def quotient(ga: GroundArrays, var_colour, factor_colours, ev_value=None) -> Quo
     for c in range(ncls):
         r = int(reps[c])
         is_hidden = bool(hidden[r])
-        rvs.append(_ClassRV(c, ga.domains[int(ga.var_dom[r])], None if is_hidden else float(mean[c]),
+        dom = ga.domains[int(ga.var_dom[r])]
+        rvs.append(_ClassRV(c, dom, None if is_hidden else _domain_value(dom, mean[c]),
                             None if is_hidden else float(variance[c]), int(sizes[c]), int(deg[r]), r))
     factors = []
     is_rep = np.zeros(nv, dtype=bool)
@@ -331,6 +342,200 @@ def lower_ground_arrays(ga: GroundArrays, K, T):
     return lowering.lower_compressed(q, K, T), q
 
 
+def class_stats(ga: GroundArrays, var_colour, ev_value=None, degrees=None):
+    """Per variable class, as arrays: size, representative (smallest member), hidden flag, mean
+    evidence value (k-means centroid where ``ev_value`` names one), population variance around
+    the members' mean, representative degree, domain (``SuperRV`` ``:8-45``)."""
+    nv = ga.n_vars
+    ncls = int(var_colour.max()) + 1 if nv else 0
+    order = np.argsort(var_colour, kind="stable")
+    starts = np.searchsorted(var_colour[order], np.arange(ncls))
+    sizes = np.diff(np.append(starts, nv))
+    reps = order[starts]
+    hidden = np.isnan(ga.var_value)
+    mean = np.bincount(var_colour, weights=np.where(hidden, 0.0, ga.var_value), minlength=ncls) / sizes
+    dev = np.where(hidden, 0.0, ga.var_value - mean[var_colour])
+    variance = np.bincount(var_colour, weights=dev * dev, minlength=ncls) / sizes
+    if ev_value:
+        mean = mean.copy()
+        ids = np.fromiter(ev_value.keys(), dtype=np.int64, count=len(ev_value))
+        mean[ids] = np.fromiter(ev_value.values(), dtype=float, count=len(ev_value))
+    return dict(n=ncls, size=sizes, rep=reps, hidden=hidden[reps], mean=mean, variance=variance,
+                degree=(ga.degrees() if degrees is None else degrees)[reps], dom=ga.var_dom[reps].astype(np.int64))
+
+
+def slot_layout(K, dom, domains):
+    """Parameter slots of hidden variable classes with domains ``dom`` (indices into ``domains``),
+    in the given order: ``(kind, dim, off, n_param)`` as ``lowering.lower_graph`` lays them out."""
+    cont = np.array([bool(d.continuous) for d in domains], dtype=bool)
+    ddim = np.array([2 if d.continuous else len(d.values) for d in domains], dtype=np.int64)
+    if np.any(~cont & (ddim > lowering.MAX_DSTATES)):
+        raise ValueError(f"discrete variable with more than {lowering.MAX_DSTATES} states")
+    dim = ddim[dom]
+    n = K * dim
+    slot = np.where(n <= 2, 2, (n + 3) // 4 * 4)
+    off = np.cumsum(slot) - slot
+    return (~cont[dom]).astype(np.uint8), dim.astype(np.int32), off.astype(np.int32), int(slot.sum())
+
+
+def lower_partition(ga: GroundArrays, var_colour, factor_colours, K, T, *, ev_value=None,
+                    gaussian_obs=False, min_obs_var=0.0, degrees=None) -> lowering.LoweredModel:
+    """``lowering.lower_compressed(quotient(...))`` without an object per class: the record
+    columns of the compressed model straight from the partition arrays (same groups, same
+    records in the same order, same coefficient table -- ``tests/test_lifting.py`` compares the
+    two column by column).  Weights as in ``LiftedVarInference.py:74,90,111-112,131-132``:
+    W_f = factor class size, gamma = incidences of the class's factors on the variable class's
+    representative, at the first position of that class in the representative factor's
+    argument list; node terms scaled by the variable class size (energy, G_w) and 1 (gradients).
+    ``model.slot_class[i]`` is the variable class behind parameter slot i (``handles`` is empty)."""
+    if not 1 <= K <= lowering.MAX_K:
+        raise ValueError(f"num_mixtures must be in 1..{lowering.MAX_K}, got {K}")
+    if not 1 <= T <= lowering.MAX_T:
+        raise ValueError(f"num_quadrature_points must be in 1..{lowering.MAX_T}, got {T}")
+    HD, HC, EG, EC, ED = lowering.HD, lowering.HC, lowering.EG, lowering.EC, lowering.ED
+    var_colour = np.asarray(var_colour, dtype=np.int64)
+    st = class_stats(ga, var_colour, ev_value, degrees)
+    ncls, mean, variance = st["n"], st["mean"], st["variance"]
+    cont_dom = np.array([bool(d.continuous) for d in ga.domains], dtype=bool)
+    cls_cont = cont_dom[st["dom"]]
+    cls_hidden = st["hidden"]
+    cls_gauss = ~cls_hidden & (variance > min_obs_var) if gaussian_obs else np.zeros(ncls, dtype=bool)
+    role_of = np.where(cls_hidden, np.where(cls_cont, HC, HD),
+                       np.where(cls_gauss, EG, np.where(cls_cont, EC, ED))).astype(np.int64)
+
+    slot_class = np.flatnonzero(cls_hidden)
+    kind, dim, off, n_param = slot_layout(K, st["dom"][slot_class], ga.domains)
+    class_off = np.full(ncls, -1, dtype=np.int64)
+    class_off[slot_class] = off
+
+    # ---- factor classes in the order the object route numbers them: block by block, ascending
+    # colour inside a block, a class that spans blocks at its first one
+    n_fc = max((int(c.max()) + 1 for c in factor_colours if c.size), default=0)
+    size_f = np.zeros(n_fc, dtype=np.int64)
+    for c in factor_colours:
+        size_f += np.bincount(c, minlength=n_fc)
+    # incidences of each factor class on the class representatives (rv.count[f])
+    is_rep = np.zeros(ga.n_vars, dtype=bool)
+    is_rep[st["rep"]] = True
+    keys = []
+    for b, fcol in zip(ga.blocks, factor_colours):
+        for a in range(b.arity):
+            col = b.args[:, a]
+            hit = np.flatnonzero(is_rep[col])
+            if hit.size:
+                keys.append(var_colour[col[hit]] * n_fc + fcol[hit])
+    if keys:
+        cnt_key, cnt_val = np.unique(np.concatenate(keys), return_counts=True)
+    else:
+        cnt_key, cnt_val = np.zeros(0, np.int64), np.zeros(0, np.int64)
+
+    def count_of(vcls, fcls):
+        if cnt_key.size == 0:
+            return np.zeros(vcls.shape, dtype=float)
+        k = vcls * n_fc + fcls
+        at = np.minimum(np.searchsorted(cnt_key, k), cnt_key.size - 1)
+        return np.where(cnt_key[at] == k, cnt_val[at], 0).astype(float)
+
+    table = lowering.PotentialTable()
+    chunks = {}                    # group key -> list of column dicts
+    unary_w = np.zeros(ncls)
+    unary_g = np.zeros(ncls)
+    seen = np.zeros(n_fc, dtype=bool)
+    uid_next = 0
+    for b, fcol in zip(ga.blocks, factor_colours):
+        if b.n == 0:
+            continue
+        ids, first = np.unique(fcol, return_index=True)
+        fresh = ~seen[ids]
+        seen[ids] = True
+        ids, first = ids[fresh], first[fresh]
+        if ids.size == 0:
+            continue
+        uid = uid_next + np.arange(ids.size)
+        uid_next += ids.size
+        nbcls = var_colour[b.args[first]]                       # [m, arity] classes of the representative's arguments
+        roles = role_of[nbcls]
+        arity = b.arity
+        # records that share (roles, domains of the hidden discrete arguments, discrete evidence
+        # values) share a coefficient block; distinct combinations in order of first appearance
+        doms = np.where((roles == HD) | (roles == ED), st["dom"][nbcls], 0).astype(float)
+        vals = np.where(roles == ED, mean[nbcls], 0.0)
+        combo, where, inv = np.unique(np.concatenate([roles.astype(float), doms, vals], axis=1), axis=0,
+                                      return_index=True, return_inverse=True)
+        inv = inv.reshape(-1)
+        for ci in np.argsort(where, kind="stable"):
+            sel = np.flatnonzero(inv == ci)
+            r = [int(x) for x in combo[ci, :arity]]
+            pos = {q: [i for i in range(arity) if r[i] == q] for q in (HD, HC, EG, EC)}
+            nd, nc, ng, ne = (len(pos[q]) for q in (HD, HC, EG, EC))
+            if nd + nc + ng > lowering.MAX_ARITY:
+                raise ValueError(f"factor with {nd + nc + ng} integrated arguments (max {lowering.MAX_ARITY})")
+            args = []
+            for i in range(arity):
+                if r[i] == HD:
+                    args.append(tuple(ga.domains[int(combo[ci, arity + i])].values))
+                elif r[i] == ED:
+                    args.append(_domain_value(ga.domains[int(combo[ci, arity + i])], combo[ci, 2 * arity + i]))
+                else:
+                    args.append(None)
+            dims = tuple(len(args[i]) for i in pos[HD])
+            hid = pos[HD] + pos[HC]
+            nb = nbcls[sel]
+            w_f = size_f[ids[sel]].astype(float)
+            gam = np.zeros((len(hid), sel.size))
+            for j, i in enumerate(hid):
+                is_first = np.ones(sel.size, dtype=bool)
+                for e in range(i):
+                    is_first &= nb[:, e] != nb[:, i]
+                gam[j] = np.where(is_first, count_of(nb[:, i], ids[sel]), 0.0)
+            pure = (nd + nc + ng == 0) or (nd + nc == 1 and ng == 0)
+            if pure and hid:
+                np.add.at(unary_w, nb[:, hid[0]], w_f)
+                np.add.at(unary_g, nb[:, hid[0]], gam[0])
+            pot = table.block(b.potential, r, args)
+            chunks.setdefault((nd, nc, ng, ne, dims, False, pure), []).append(dict(
+                uid=uid[sel], pot=np.full(sel.size, pot, dtype=np.int32),
+                poff=class_off[nb[:, hid]].T.reshape(len(hid), sel.size),
+                egval=mean[nb[:, pos[EG]]].T.reshape(ng, sel.size),
+                egvar=variance[nb[:, pos[EG]]].T.reshape(ng, sel.size),
+                ecval=mean[nb[:, pos[EC]]].T.reshape(ne, sel.size),
+                wf=w_f, gam=gam, nscale=np.zeros(sel.size)))
+
+    # ---- node-entropy records, one per hidden class and per Gaussian-evidence class
+    scale = (st["degree"] - 1).astype(float)
+    c_v = st["size"].astype(float)
+    for is_disc, d in sorted({(int(k_), int(d_)) for k_, d_ in zip(kind, dim)}):
+        pick = slot_class[(kind == is_disc) & (dim == d)]
+        key = (1, 0, 0, 0, (d,), True, False) if is_disc else (0, 1, 0, 0, (), True, False)
+        chunks.setdefault(key, []).append(dict(
+            uid=pick, pot=np.zeros(pick.size, dtype=np.int32), poff=class_off[pick][None, :],
+            egval=np.zeros((0, pick.size)), egvar=np.zeros((0, pick.size)), ecval=np.zeros((0, pick.size)),
+            wf=c_v[pick] * scale[pick] - unary_w[pick], gam=np.ones((1, pick.size)),
+            nscale=scale[pick] - unary_g[pick]))
+    pick = np.flatnonzero(cls_gauss)
+    if pick.size:
+        chunks.setdefault((0, 0, 1, 0, (), True, False), []).append(dict(
+            uid=pick, pot=np.zeros(pick.size, dtype=np.int32), poff=np.zeros((0, pick.size), dtype=np.int64),
+            egval=mean[pick][None, :], egvar=variance[pick][None, :], ecval=np.zeros((0, pick.size)),
+            wf=c_v[pick] * scale[pick], gam=np.zeros((0, pick.size)), nscale=scale[pick]))
+
+    groups = []
+    for (nd, nc, ng, ne, dims, node, pure), parts in chunks.items():
+        cat = {k: np.concatenate([p[k] for p in parts], axis=-1) for k in parts[0]}
+        order = np.argsort(cat["uid"], kind="stable")
+        wf, gam = cat["wf"][order], cat["gam"][:, order]
+        weighted = bool(node or np.any(wf != 1.0) or np.any(gam != 1.0))
+        groups.append(lowering.RecordGroup(
+            nd, nc, ng, ne, dims, node, cat["pot"][order].astype(np.int32),
+            np.ascontiguousarray(cat["poff"][:, order].astype(np.int32)),
+            np.ascontiguousarray(cat["egval"][:, order]), np.ascontiguousarray(cat["egvar"][:, order]),
+            np.ascontiguousarray(cat["ecval"][:, order]), wf, np.ascontiguousarray(gam),
+            cat["nscale"][order], weighted, pure))
+    groups.sort(key=lambda g: (not g.node, not g.pure, g.nd + g.nc + g.ng, g.nd, g.nc, g.ng, g.ne, g.dims))
+    return lowering.LoweredModel(K, T, max(n_param, 2), kind, dim, off, table.array(), groups, [], {},
+                                 slot_class.astype(np.int64))
+
+
 def arrays_from_graph(g) -> tuple:
     """``GroundArrays`` of an object graph (any ``Graph`` of this repo or of the reference):
     variables in id order, one block per potential object.  Returns ``(arrays, rvs)`` with
@@ -355,21 +560,65 @@ def arrays_from_graph(g) -> tuple:
     return GroundArrays(domains, var_dom, var_value, blocks), rvs
 
 
+class PartitionInfo:
+    """What callers ask of a partition: the colourings and the compression ratio."""
+
+    def __init__(self, var_colour, factor_colours):
+        self.var_colour, self.factor_colours = var_colour, list(factor_colours)
+
+    @property
+    def n_var_classes(self):
+        return int(self.var_colour.max()) + 1 if self.var_colour.size else 0
+
+    @property
+    def n_factor_classes(self):
+        return max((int(c.max()) + 1 for c in self.factor_colours if c.size), default=0)
+
+    @property
+    def compression(self):
+        ground = self.var_colour.size + sum(c.size for c in self.factor_colours)
+        return ground / max(1, self.n_var_classes + self.n_factor_classes)
+
+
+def slot_elements(off, n):
+    """Flat element indices of blocks of ``n[i]`` elements starting at ``off[i]``, concatenated."""
+    off = np.asarray(off, dtype=np.int64)
+    n = np.asarray(n, dtype=np.int64)
+    start = np.cumsum(n) - n
+    return np.repeat(off - start, n) + np.arange(int(n.sum()), dtype=np.int64)
+
+
+def softmax_slots(tau, eta, K, kind, dim, off):
+    """``eta = softmax(tau)`` row by row in every discrete slot (``VarInference.py:210-213``)."""
+    for d in np.unique(dim[kind == 1]):
+        o = off[(kind == 1) & (dim == d)].astype(np.int64)
+        idx = o[:, None, None] + (np.arange(K) * int(d))[None, :, None] + np.arange(int(d))[None, None, :]
+        e = np.e ** tau[idx]
+        eta[idx] = e / e.sum(axis=2, keepdims=True)
+
+
 class ArrayVI:
     """``LiftedVarInference`` (``lifted=True``) or ``VarInference`` over a ``GroundArrays`` model:
-    colour passing on arrays, the compressed lowering, and the device engine
-    (``LiftedVarInference.py:14-26`` + ``VarInference.run`` ``:215-247``).  Per-variable results
-    are expanded from the classes back to the ground variables."""
+    colour passing on arrays, the array-native compressed lowering (``lower_partition``), and
+    the device engine (``LiftedVarInference.py:14-26`` + ``VarInference.run`` ``:215-247``).
+    Per-variable results are expanded from the classes back to the ground variables."""
 
-    def __init__(self, ga: GroundArrays, K, T, *, lifted=True, dtype="float64", device=None):
-        from .engine import DeviceEngine
+    def __init__(self, ga: GroundArrays, K, T, *, lifted=True, dtype="float64", device=None, engine_factory=None):
         self.ga, self.K, self.T = ga, K, T
         if lifted:
-            self.quotient = lift(ga)
-            self.model = lowering.lower_compressed(self.quotient, K, T)
+            vcol, fcols, _ = colour_passing(ga)
+        else:                                   # every variable and factor its own class
+            vcol = np.arange(ga.n_vars, dtype=np.int64)
+            sizes = np.cumsum([0] + [b.n for b in ga.blocks])
+            fcols = [np.arange(b.n, dtype=np.int64) + o for b, o in zip(ga.blocks, sizes)]
+        self.quotient = PartitionInfo(vcol, fcols)
+        self.class_rep = class_stats(ga, vcol)["rep"]
+        self.model = lower_partition(ga, vcol, fcols, K, T)
+        if engine_factory is not None:
+            self.engine = engine_factory(self.model)
         else:
-            self.model, self.quotient = lower_ground_arrays(ga, K, T)
-        self.engine = DeviceEngine(self.model, dtype=dtype, device=device)
+            from .engine import DeviceEngine
+            self.engine = DeviceEngine(self.model, dtype=dtype, device=device)
         self.init_param(0)
 
     def init_param(self, seed=0):
@@ -379,30 +628,26 @@ class ArrayVI:
         m, K = self.model, self.K
         eta = np.zeros(m.n_param)
         tau = np.zeros(m.n_param)
-        for h, off, kind, dim in zip(m.handles, m.var_off, m.var_kind, m.var_dim):
-            rep_class = self.quotient.rvs[int(self.quotient.var_colour[h.rep])]
-            rng = np.random.default_rng([seed, int(self._canonical_rep(rep_class))])
+        reps = self.class_rep[m.slot_class]
+        if self.canonical is not None:
+            reps = self.canonical[reps]
+        for rep, off, kind, dim in zip(reps, m.var_off, m.var_kind, m.var_dim):
+            rng = np.random.default_rng([seed, int(rep)])
             if kind == 0:
                 eta[off:off + 2 * K:2] = rng.random(K) * 3 - 1.5
                 eta[off + 1:off + 2 * K:2] = 1.0
             else:
-                logits = rng.random((K, dim)) * 10
-                tau[off:off + K * dim] = logits.reshape(-1)
-                e = np.e ** logits
-                eta[off:off + K * dim] = (e / e.sum(axis=1, keepdims=True)).reshape(-1)
+                tau[off:off + K * dim] = (rng.random((K, dim)) * 10).reshape(-1)
+        softmax_slots(tau, eta, K, m.var_kind, m.var_dim, m.var_off)
         self.engine.set_state(eta, tau, np.zeros(K))
         self.engine.reset_moments()
 
     canonical = None        # optional ground-variable -> canonical representative map (see tie_to)
 
-    def _canonical_rep(self, cls):
-        return cls.rep if self.canonical is None else self.canonical[cls.rep]
-
     def tie_to(self, other: "ArrayVI"):
         """Start from the point that corresponds to ``other``'s (a coarser partition of the same
         model): every class here draws with the representative of the class of ``other`` it lies in."""
-        reps = np.array([c.rep for c in other.quotient.rvs])
-        self.canonical = reps[other.quotient.var_colour]
+        self.canonical = other.class_rep[other.quotient.var_colour]
         self.init_param(0)
 
     def run(self, iteration=100, lr=0.1):
@@ -416,12 +661,12 @@ class ArrayVI:
         ``[K, D]`` array, expanded from the classes; and the mixture weights."""
         eta, _, _, w = self.engine.get_state()
         m, K = self.model, self.K
-        per_class = {}
-        for h, off, dim in zip(m.handles, m.var_off, m.var_dim):
-            per_class[h.uid] = eta[off:off + K * dim].reshape(K, dim)
+        slot_of = np.full(self.quotient.n_var_classes, -1, dtype=np.int64)
+        slot_of[m.slot_class] = np.arange(m.slot_class.size)
+        tables = [eta[off:off + K * dim].reshape(K, dim) for off, dim in zip(m.var_off, m.var_dim)]
         col = self.quotient.var_colour
         hidden = np.flatnonzero(np.isnan(self.ga.var_value))
-        return {int(v): per_class[self.quotient.rvs[int(col[v])].uid] for v in hidden}, w
+        return {int(v): tables[slot_of[col[v]]] for v in hidden}, w
 
 
 def _kmeans_1d(values, k, iteration):
@@ -470,6 +715,7 @@ class C2FArrayVI:
         self.dtype, self.device = dtype, device
         self.engine_factory = engine_factory
         self.init_fn = init_fn            # (representative ground index, is_continuous, dim) -> [K, dim] or None
+        self.layout = None
         self.hidden = np.isnan(ga.var_value)
         self.cont_dom = np.array([bool(d.continuous) for d in ga.domains])[ga.var_dom]
         self.t = 0.0
@@ -558,37 +804,41 @@ class C2FArrayVI:
         self._inherit(old, new)
         self.vcol = new
 
+    def _layout(self, vcol):
+        """Parameter slots of the hidden classes of a partition, in class order."""
+        st = class_stats(self.ga, vcol, degrees=self.degrees)
+        cls = np.flatnonzero(st["hidden"])
+        kind, dim, off, n_param = slot_layout(self.K, st["dom"][cls], self.ga.domains)
+        slot_of = np.full(st["n"], -1, dtype=np.int64)
+        slot_of[cls] = np.arange(cls.size)
+        return dict(cls=cls, rep=st["rep"][cls], kind=kind, dim=dim, off=off, n_param=max(n_param, 2), slot_of=slot_of)
+
     def _inherit(self, old, new):
-        if not self.params:
+        """The pieces of a hidden class start from its parameters and Adam moments
+        (``C2FVarInference.py:39-61``): one gather from the old slot layout into the new one."""
+        if self.layout is None:
             return
-        reps_new = {}
-        order = np.argsort(new, kind="stable")
-        starts = np.searchsorted(new[order], np.arange(int(new.max()) + 1))
-        for c, r in enumerate(order[starts]):
-            reps_new[c] = int(r)
-        params, m1, m2 = {}, {}, {}
-        for c, r in reps_new.items():
-            if not self.hidden[r]:
-                continue
-            parent = int(old[r])
-            params[c] = self.params[parent].copy()
-            m1[c] = self.m1[parent].copy()
-            m2[c] = self.m2[parent].copy()
-        self.params, self.m1, self.m2 = params, m1, m2
+        lay_old, lay = self.layout, self._layout(new)
+        parent = lay_old["slot_of"][old[lay["rep"]]]
+        n = self.K * lay["dim"].astype(np.int64)
+        dst = slot_elements(lay["off"], n)
+        src = slot_elements(lay_old["off"][parent], n)
+        for name in ("P", "m1", "m2"):
+            fresh = np.zeros(lay["n_param"])
+            fresh[dst] = getattr(self, name)[src]
+            setattr(self, name, fresh)
+        self.layout = lay
 
     # ---- parameters -----------------------------------------------------------------------
     def _init_params(self):
-        self.params, self.m1, self.m2 = {}, {}, {}
+        """One table per initial hidden class (one class per domain), ``VarInference.py:197-208``:
+        ``P`` holds (mu, var) pairs of continuous classes and the logits of discrete ones, in the
+        slot layout of the current partition; ``m1`` / ``m2`` are the Adam moments beside it."""
         K = self.K
-        order = np.argsort(self.vcol, kind="stable")
-        starts = np.searchsorted(self.vcol[order], np.arange(int(self.vcol.max()) + 1))
-        for c, r in enumerate(order[starts]):
-            r = int(r)
-            if not self.hidden[r]:
-                continue
-            dom = self.ga.domains[int(self.ga.var_dom[r])]
-            cont = bool(dom.continuous)
-            dim = 2 if cont else len(dom.values)
+        lay = self.layout = self._layout(self.vcol)
+        self.P = np.zeros(lay["n_param"])
+        for r, kind, dim, off in zip(lay["rep"], lay["kind"], lay["dim"], lay["off"]):
+            r, dim, cont = int(r), int(dim), kind == 0
             table = self.init_fn(r, cont, dim) if self.init_fn is not None else None
             if table is None:
                 rng = np.random.default_rng([0, r])
@@ -597,47 +847,41 @@ class C2FArrayVI:
                     table[:, 0] = rng.random(K) * 3 - 1.5
                 else:
                     table = rng.random((K, dim)) * 10          # logits
-            self.params[c] = np.asarray(table, dtype=float)     # continuous: (mu, var); discrete: logits
-            self.m1[c] = np.zeros_like(self.params[c])
-            self.m2[c] = np.zeros_like(self.params[c])
+            self.P[off:off + K * dim] = np.asarray(table, dtype=float).reshape(-1)
+        self.m1, self.m2 = np.zeros_like(self.P), np.zeros_like(self.P)
         self.w_tau = np.zeros(K)
+        self.w = np.full(K, 1.0 / K)
         self.m_w, self.u_w = np.zeros(K), np.zeros(K)
         self.t = 0.0
 
-    def _push(self, model, engine, q):
-        K = self.K
-        eta, tau = np.zeros(model.n_param), np.zeros(model.n_param)
-        m1, m2 = np.zeros(model.n_param), np.zeros(model.n_param)
-        for h, off, kind, dim in zip(model.handles, model.var_off, model.var_kind, model.var_dim):
-            p = self.params[h.uid]
-            n = K * dim
-            if kind == 0:
-                eta[off:off + n] = p.reshape(-1)
-            else:
-                tau[off:off + n] = p.reshape(-1)
-                e = np.e ** p
-                eta[off:off + n] = (e / e.sum(axis=1, keepdims=True)).reshape(-1)
-            m1[off:off + n] = self.m1[h.uid].reshape(-1)
-            m2[off:off + n] = self.m2[h.uid].reshape(-1)
+    def _discrete_elements(self, lay):
+        disc = lay["kind"] == 1
+        return slot_elements(lay["off"][disc], self.K * lay["dim"][disc].astype(np.int64))
+
+    def _push(self, model, engine):
+        lay = self.layout
+        assert np.array_equal(lay["cls"], model.slot_class) and np.array_equal(lay["off"], model.var_off)
+        eta, tau = self.P.copy(), np.zeros_like(self.P)
+        d = self._discrete_elements(lay)
+        tau[d] = self.P[d]
+        softmax_slots(tau, eta, self.K, lay["kind"], lay["dim"], lay["off"])
         engine.set_state(eta, tau, self.w_tau)
-        engine.set_moments(m1, m2, self.m_w, self.u_w, self.t)
+        engine.set_moments(self.m1, self.m2, self.m_w, self.u_w, self.t)
 
     def _pull(self, model, engine):
-        K = self.K
         eta, tau, w_tau, w = engine.get_state()
         m1, m2, m_w, u_w, t = engine.get_moments()
-        for h, off, kind, dim in zip(model.handles, model.var_off, model.var_kind, model.var_dim):
-            n = K * dim
-            src = eta if kind == 0 else tau
-            self.params[h.uid] = src[off:off + n].reshape(K, dim).copy()
-            self.m1[h.uid] = m1[off:off + n].reshape(K, dim).copy()
-            self.m2[h.uid] = m2[off:off + n].reshape(K, dim).copy()
+        d = self._discrete_elements(self.layout)
+        self.P = np.array(eta, dtype=float)
+        self.P[d] = np.asarray(tau)[d]
+        self.m1, self.m2 = np.array(m1, dtype=float), np.array(m2, dtype=float)
         self.w_tau, self.w = w_tau, w
         self.m_w, self.u_w, self.t = m_w, u_w, t
 
     # ---- the run ---------------------------------------------------------------------------
     def run(self, iteration=100, lr=0.1):
         ga = self.ga
+        self.degrees = ga.degrees()
         # initial classes, parameters per initial class (one hidden class per domain), then the
         # first colour passing in which the pieces inherit (C2FVarInference.py:306-311)
         self.vcol = initial_colouring(ga, split_cont_evidence=False)
@@ -655,28 +899,33 @@ class C2FArrayVI:
             self._split_evidence(epsilon)
             self._refine()
             epsilon = max(epsilon - d, self.min_obs_var)
-            self.quotient = quotient(ga, self.vcol, self.fcols, self.ev_value)
-            self.model = lowering.lower_compressed(self.quotient, self.K, self.T, gaussian_obs=self.gaussian_obs,
-                                                   min_obs_var=self.min_obs_var)
+            self.quotient = PartitionInfo(self.vcol, self.fcols)
+            self.model = lower_partition(ga, self.vcol, self.fcols, self.K, self.T, ev_value=self.ev_value,
+                                         gaussian_obs=self.gaussian_obs, min_obs_var=self.min_obs_var,
+                                         degrees=self.degrees)
             self.engine = self._make_engine(self.model)
-            self._push(self.model, self.engine, self.quotient)
+            self._push(self.model, self.engine)
             self.engine.iterate(self.update_obs_its, lr)
             self._pull(self.model, self.engine)
-            self.history.append((len(self.quotient.rvs), None))
+            self.history.append((self.quotient.n_var_classes, None))
         return self
 
     def free_energy(self):
         return self.engine.free_energy()
 
+    def class_tables(self):
+        """``(slot_of_class, tables)``: ``tables[slot_of_class[c]]`` is the ``[K, dim]`` table of hidden
+        class c (continuous: (mu, var); discrete: probabilities)."""
+        lay, K = self.layout, self.K
+        eta = self.P.copy()
+        tau = np.zeros_like(eta)
+        d = self._discrete_elements(lay)
+        tau[d] = self.P[d]
+        softmax_slots(tau, eta, K, lay["kind"], lay["dim"], lay["off"])
+        return lay["slot_of"], [eta[o:o + K * n].reshape(K, n) for o, n in zip(lay["off"], lay["dim"])]
+
     def ground_params(self):
         """Per hidden ground variable: its class's ``[K, dim]`` table (continuous: (mu, var);
         discrete: probabilities) -- the reference's ``eta[rv.cluster]``."""
-        out = {}
-        for v in np.flatnonzero(self.hidden):
-            p = self.params[int(self.vcol[v])]
-            if self.cont_dom[v]:
-                out[int(v)] = p
-            else:
-                e = np.e ** p
-                out[int(v)] = e / e.sum(axis=1, keepdims=True)
-        return out, self.w
+        slot_of, tables = self.class_tables()
+        return {int(v): tables[slot_of[self.vcol[v]]] for v in np.flatnonzero(self.hidden)}, self.w

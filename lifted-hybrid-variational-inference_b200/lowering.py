@@ -117,6 +117,7 @@ class LoweredModel:
     groups: list
     handles: list = field(default_factory=list)      # hidden variable objects, slot order
     index: dict = field(default_factory=dict)        # handle -> position in `handles`
+    slot_class: np.ndarray = None     # int64 [V]  variable class behind each slot (array-native lowering)
 
     @property
     def n_vars(self) -> int:
@@ -142,7 +143,7 @@ class LoweredModel:
             if hi > lo:
                 parts.append(g.take(slice(lo, hi)))
         return LoweredModel(self.K, self.T, self.n_param, self.var_kind, self.var_dim,
-                            self.var_off, self.ptab, parts, self.handles, self.index)
+                            self.var_off, self.ptab, parts, self.handles, self.index, self.slot_class)
 
 
 # ----------------------------------------------------------------------------------------

@@ -41,6 +41,13 @@ class OracleEngine:
         self.vi.u_w = np.array(u_w, dtype=float)
         self.vi.t = int(round(t))
 
+    def reset_moments(self):
+        self.vi.m[:] = 0
+        self.vi.u[:] = 0
+        self.vi.m_w = np.zeros(self.K)
+        self.vi.u_w = np.zeros(self.K)
+        self.vi.t = 0
+
     def iterate(self, n, lr, sgd=False):
         self.vi.var_threshold = self.var_threshold
         for _ in range(int(n)):

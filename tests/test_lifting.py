@@ -211,3 +211,81 @@ def test_relational_arrays_match_the_object_twin():
     e_l = grad_pass(m_l, eta_l, w)
     np.testing.assert_allclose(e_l[2], e_g[2], rtol=1e-10)
     np.testing.assert_allclose(e_l[1], e_g[1], rtol=1e-10)
+
+
+# ---- array-native lowering (lower_partition) against the object-level lowering -----------------
+
+def _assert_same_model(got, want, tag):
+    assert got.n_param == want.n_param, tag
+    for f in ("var_kind", "var_dim", "var_off", "ptab"):
+        x, y = getattr(got, f), getattr(want, f)
+        assert x.dtype == y.dtype, (tag, f)
+        np.testing.assert_array_equal(x, y, err_msg=f"{tag} {f}")
+    assert [g.signature for g in got.groups] == [g.signature for g in want.groups], tag
+    for a, b in zip(got.groups, want.groups):
+        for f in ("pot", "poff", "egval", "egvar", "ecval", "wf", "gam", "nscale"):
+            x, y = getattr(a, f), getattr(b, f)
+            assert x.shape == y.shape and x.dtype == y.dtype, (tag, a.signature, f)
+            np.testing.assert_array_equal(x, y, err_msg=f"{tag} {a.signature} {f}")
+    np.testing.assert_array_equal(got.slot_class, [h.uid for h in want.handles])
+
+
+def _check_array_lowering(ga, tag):
+    for split in (True, False):
+        vcol, fcols, _ = lifting.colour_passing(ga, split_cont_evidence=split)
+        ev = np.flatnonzero(~np.isnan(ga.var_value))
+        centroids = {int(c): 0.25 + 0.5 * i for i, c in enumerate(np.unique(vcol[ev])[:2])}
+        for gobs, ev_value, K in ((False, None, 1), (True, None, 3), (True, centroids, 2)):
+            q = lifting.quotient(ga, vcol, fcols, ev_value)
+            want = lhvi_b200.lowering.lower_compressed(q, K, 3, gaussian_obs=gobs, min_obs_var=0.0)
+            got = lifting.lower_partition(ga, vcol, fcols, K, 3, ev_value=ev_value, gaussian_obs=gobs)
+            _assert_same_model(got, want, f"{tag} split={split} gaussian_obs={gobs} K={K}")
+    want, _ = lifting.lower_ground_arrays(ga, 2, 3)
+    off = np.cumsum([0] + [b.n for b in ga.blocks])
+    trivial = [np.arange(b.n, dtype=np.int64) + o for b, o in zip(ga.blocks, off)]
+    _assert_same_model(lifting.lower_partition(ga, np.arange(ga.n_vars), trivial, 2, 3), want, f"{tag} ground")
+
+
+@pytest.mark.parametrize("name", sorted(specs.CASES))
+def test_array_lowering_equals_object_lowering(name, ns):
+    """Every column of every record group, the coefficient table and the slot layout: the
+    partition lowered on arrays is the model ``lower_compressed`` builds from class objects --
+    exact and lumped evidence, Gaussian-evidence mode, k-means centroids as values, and the
+    trivial (ground) partition."""
+    g, _ = specs.CASES[name][0](ns)
+    ga, _ = lifting.arrays_from_graph(g)
+    if name in ("hmln_hidden", "robot_like", "smokers", "tri_table3", "chain_table"):
+        # discrete evidence: centroids only make sense for continuous observations
+        vcol, fcols, _ = lifting.colour_passing(ga)
+        for gobs, K in ((False, 2), (True, 3)):
+            want = lhvi_b200.lowering.lower_compressed(lifting.quotient(ga, vcol, fcols), K, 3, gaussian_obs=gobs)
+            _assert_same_model(lifting.lower_partition(ga, vcol, fcols, K, 3, gaussian_obs=gobs), want, name)
+    else:
+        _check_array_lowering(ga, name)
+
+
+def test_array_lowering_on_generated_models():
+    _check_array_lowering(syn.kalman_arrays(6, 5, levels=2, seed=1, period=2)[0], "kalman")
+    _check_array_lowering(syn.relational_hybrid_arrays(40, 3, seed=1), "relational")
+
+
+def test_array_vi_lifted_follows_ground_on_the_oracle_engine():
+    """``ArrayVI`` host logic without a GPU (the numpy oracle as the device double): a lifted and
+    a ground run of the relational Kalman filter from corresponding starts stay together."""
+    from oracle_engine import OracleEngine
+    factory = lambda m: OracleEngine(m, var_threshold=0.1)
+    ga, _ = syn.kalman_arrays(8, 4, levels=2, seed=3, period=2)
+    lifted = lifting.ArrayVI(ga, 2, 3, lifted=True, engine_factory=factory)
+    ground = lifting.ArrayVI(ga, 2, 3, lifted=False, engine_factory=factory)
+    assert lifted.quotient.compression > 1.5 and ground.quotient.compression == 1.0
+    ground.tie_to(lifted)
+    lifted.init_param(0)
+    np.testing.assert_allclose(lifted.free_energy(), ground.free_energy(), rtol=1e-10)
+    lifted.run(25, 0.05)
+    ground.run(25, 0.05)
+    pl, wl = lifted.ground_params()
+    pg, wg = ground.ground_params()
+    assert set(pl) == set(pg) == set(np.flatnonzero(np.isnan(ga.var_value)).tolist())
+    for v in pg:
+        np.testing.assert_allclose(pl[v], pg[v], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(wl, wg, rtol=1e-9)
