@@ -99,6 +99,20 @@ def _rank_rows(cols):
     return out
 
 
+def _rank_hashed(vcol, H1, H2):
+    """Dense ids of the rows (vcol, H1, H2): one sort of a 64-bit key that mixes the own class
+    into the first hash, then an exact check that every resulting group is constant in all three
+    columns (so a key collision cannot merge classes); falls back to the general ranking if not."""
+    with np.errstate(over="ignore"):
+        key = _mix(vcol, 0xA4093822299F31D0) + H1
+    uniq, first, ids = np.unique(key, return_index=True, return_inverse=True)
+    ids = ids.astype(np.int64).reshape(-1)
+    if (np.array_equal(vcol[first][ids], vcol) and np.array_equal(H1[first][ids], H1)
+            and np.array_equal(H2[first][ids], H2)):
+        return ids
+    return _rank_rows([vcol, H1.view(np.int64), H2.view(np.int64)])
+
+
 def _potential_ids(blocks):
     """Colour of each block's potential: equal potentials (``==``, the reference's dict keys)
     share an id."""
@@ -194,7 +208,7 @@ def colour_passing(ga: GroundArrays, split_cont_evidence=True, max_sweeps=1000, 
             H1 = np.zeros(nv, dtype=np.uint64)
             H2 = np.zeros(nv, dtype=np.uint64)
             H1[seg_var], H2[seg_var] = h1, h2
-            vcol = _rank_rows([vcol, H1.view(np.int64), H2.view(np.int64)])
+            vcol = _rank_hashed(vcol, H1, H2)
     fcols = [None] * len(ga.blocks)
     for j, (members, _, _) in enumerate(supers):
         pos = 0
@@ -752,10 +766,26 @@ class C2FArrayVI:
         while changed:
             changed = False
             next_id = int(self.vcol.max()) + 1
-            order, starts = self._members_by_class()         # classes are disjoint: one grouping per pass
-            for cid in sorted(self.clustered):
-                members = order[starts[cid]:starts[cid + 1]]
-                vals = self.ga.var_value[members]
+            if not self.clustered:
+                break
+            # members of the classes k-means may still split, grouped by class (classes are
+            # disjoint: one grouping per pass); classes whose spread is within epsilon are skipped
+            # after one vectorised variance pass
+            may = np.zeros(next_id, dtype=bool)
+            may[np.fromiter(self.clustered, dtype=np.int64, count=len(self.clustered))] = True
+            cand = np.flatnonzero(may[self.vcol])
+            cand = cand[np.argsort(self.vcol[cand], kind="stable")]
+            ccol = self.vcol[cand]
+            cids, cstart, ccnt = np.unique(ccol, return_index=True, return_counts=True)
+            cval = self.ga.var_value[cand]
+            cmean = np.add.reduceat(cval, cstart) / ccnt
+            cdev = cval - np.repeat(cmean, ccnt)
+            wide = np.sqrt(np.add.reduceat(cdev * cdev, cstart) / ccnt) > epsilon * (1 - 1e-9)
+            wide &= np.maximum.reduceat(cval, cstart) > np.minimum.reduceat(cval, cstart)   # nothing to split otherwise
+            for j in np.flatnonzero(wide):
+                cid = int(cids[j])
+                members = cand[cstart[j]:cstart[j] + ccnt[j]]
+                vals = cval[cstart[j]:cstart[j] + ccnt[j]]
                 if not np.sqrt(vals.var()) > epsilon:
                     continue
                 res = _kmeans_1d(vals, self.k_mean_k, self.k_mean_its)
@@ -766,11 +796,11 @@ class C2FArrayVI:
                 owner, centroids = res
                 pieces = [(cid, vals[owner == 0])]
                 self.ev_value[cid] = float(centroids[0])
-                for j in range(1, centroids.size):
-                    pick = owner == j
+                for c in range(1, centroids.size):
+                    pick = owner == c
                     if pick.any():
                         self.vcol[members[pick]] = next_id
-                        self.ev_value[next_id] = float(centroids[j])
+                        self.ev_value[next_id] = float(centroids[c])
                         pieces.append((next_id, vals[pick]))
                         next_id += 1
                 if len(pieces) > 1:

@@ -188,6 +188,27 @@ def ring_xy(ns):
     return _graph(ns, X, fs)
 
 
+def edge_mix(ns):
+    """Degenerate pieces in one graph: hidden variables with no factor at all (N = 0: the node
+    term has scale -1), a variable with a single unary factor (N = 1: the node term vanishes), a
+    factor that takes the same variable twice (the reference's ``f.nb.index(rv)`` first-occurrence
+    rule), and a factor whose arguments are all observed (a constant of the energy)."""
+    dc = ns.Domain((-10, 10), continuous=True)
+    db = ns.Domain((0, 1))
+    lonely_c, lonely_b = ns.RV(dc), ns.RV(db)
+    single = ns.RV(dc)
+    twice, other = ns.RV(dc), ns.RV(dc)
+    seen_a, seen_b = ns.RV(dc, 0.7), ns.RV(dc, -1.1)
+    flag = ns.RV(db)
+    pg = ns.GaussianPotential([0.5, -0.5], [[2.0, 0.6], [0.6, 1.5]])
+    xy = ns.XYPotential(-0.4, 1.5)
+    x2 = ns.X2Potential(1.0, 2.0)
+    mix = ns.MLNPotential(lambda x: x[0] * ns.eq_op(x[1], x[2]), w=0.4)
+    fs = [ns.F(x2, [single]), ns.F(pg, [twice, twice]), ns.F(xy, [twice, other]), ns.F(x2, [other]),
+          ns.F(pg, [seen_a, seen_b]), ns.F(mix, [flag, other, seen_a]), ns.F(mix, [flag, twice, twice])]
+    return _graph(ns, [lonely_c, lonely_b, single, twice, other, seen_a, seen_b, flag], fs)
+
+
 CASES = {
     # name: (builder, K, T, engines)
     "chain_table": (chain_table, 3, 3, ("ground", "lifted", "c2f")),
@@ -201,6 +222,7 @@ CASES = {
     "rgm_exact": (rgm_exact, 1, 3, ("lifted", "c2f")),
     "smokers": (smokers, 2, 4, ("ground", "lifted")),
     "ring_xy": (ring_xy, 2, 3, ("ground", "lifted")),
+    "edge_mix": (edge_mix, 2, 3, ("ground", "lifted")),
 }
 
 

@@ -13,8 +13,17 @@ import specs
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*__*.npz")))
+# Goldens added after the round's GPU budget was spent: pinned on the CPU side (three oracles, host
+# logic, lifting) and held back from the ``-m gpu`` parametrisations until they have run on a B200
+# once.  Empty this set to include them.
+GPU_PENDING = {"edge_mix"}
+
+
+def golden_files(gpu=False):
+    paths = sorted(glob.glob(os.path.join(GOLDEN_DIR, "*__*.npz")))
+    if gpu:
+        paths = [p for p in paths if os.path.basename(p).split("__")[0] not in GPU_PENDING]
+    return paths
 
 
 def golden_id(path):

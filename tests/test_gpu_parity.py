@@ -40,7 +40,7 @@ def _golden_setup(path, ns):
     return name, engine, gold, model, rvs, ref
 
 
-@pytest.mark.parametrize("path", helpers.golden_files(), ids=helpers.golden_id)
+@pytest.mark.parametrize("path", helpers.golden_files(gpu=True), ids=helpers.golden_id)
 @pytest.mark.parametrize("force_generic", [True, False], ids=["generic", "dispatch"])
 def test_snapshot_fp64(path, force_generic, ns):
     name, engine, gold, model, rvs, ref = _golden_setup(path, ns)
@@ -61,7 +61,7 @@ def test_snapshot_fp64(path, force_generic, ns):
     np.testing.assert_allclose(g_w, ogw, rtol=FP64_RTOL, atol=1e-10)
 
 
-@pytest.mark.parametrize("path", helpers.golden_files(), ids=helpers.golden_id)
+@pytest.mark.parametrize("path", helpers.golden_files(gpu=True), ids=helpers.golden_id)
 def test_snapshot_fp32(path, ns):
     name, engine, gold, model, rvs, ref = _golden_setup(path, ns)
     eng = _engine_for(model, "float32")
@@ -75,7 +75,7 @@ def test_snapshot_fp32(path, ns):
     np.testing.assert_allclose(grad, og, rtol=2e-5, atol=2e-5 * scale)
 
 
-@pytest.mark.parametrize("path", helpers.golden_files(), ids=helpers.golden_id)
+@pytest.mark.parametrize("path", helpers.golden_files(gpu=True), ids=helpers.golden_id)
 def test_trajectory_fp64(path, ns):
     """Drop-in classes on the real engine: same Adam trajectory as the reference, including
     the C2F split rounds."""
