@@ -1,0 +1,60 @@
+/* lhvi_lift.h -- host-side (CPU) C ABI of the lifting passes that sit in front of the device loop.
+ *
+ * The reference compresses a ground graph by colour passing before (LiftedVarInference.py:14-26)
+ * and, in the coarse-to-fine engine, between the blocks of ten iterations
+ * (C2FVarInference.py:33-61,301-352) with Python sets of objects
+ * (CompressedGraphWithObs.py:47-76 split_rvs, :152-175 split_factors, :249-271 run).  Here the same
+ * fixed point is computed on index arrays with hash tables: linear passes, no sort, no object per
+ * ground variable.  `liblhvi_lift.so` is plain C++ (no CUDA); `lifting.colour_passing` binds it
+ * through ctypes and keeps a numpy implementation of the same passes as its cross-check
+ * (tests/test_lifting.py compares the partitions of the two on every model of the suite).
+ *
+ * Conventions: plain pointers and sizes, the caller owns every buffer, return value >= 0 on success
+ * (a count) and a negative code on bad arguments or allocation failure; not thread-safe per call
+ * site only in the sense that the caller's buffers are written.
+ */
+#ifndef LHVI_LIFT_H
+#define LHVI_LIFT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LHVI_LIFT_ABI_VERSION 1
+#define LHVI_LIFT_MAX_ARITY 16
+
+/* One block of ground factors that share a potential object (lifting.FactorBlock). */
+typedef struct lhvi_lift_block {
+    const int64_t *args;  /* [n * arity] variable indices, row-major (factor i: args[i*arity .. ]) */
+    int64_t n;            /* factors in the block */
+    int32_t arity;        /* arguments per factor, 1..LHVI_LIFT_MAX_ARITY */
+    int32_t symmetric;    /* != 0: argument order is not part of a factor's key (Potential.symmetric,
+                             CompressedGraphWithObs.py:161-164) */
+    int64_t *colour;      /* [n] in: initial colour (blocks whose potentials compare equal share it);
+                             out: dense factor class ids, one id space over all blocks */
+} lhvi_lift_block;
+
+int32_t lhvi_lift_abi_version(void);
+
+/* Coarsest equitable refinement of `var_colour` (CompressedGraph.run, :264-271): until the number of
+ * variable classes stops growing, split the factors by (own class, classes of the arguments) and the
+ * variables by (own class, multiset of the classes of the incident factors, positions not part of
+ * the key).  The multiset is compared through two independent 64-bit sums of mixed class ids and
+ * the own class exactly; factor keys are compared exactly.
+ *   var_colour  [n_vars] in: start colouring (any int64 labels >= 0); out: dense class ids in order
+ *               of first appearance.
+ *   sweeps_out  optional: number of sweeps done.
+ * Returns the number of variable classes, or < 0: -1 null pointer / bad size, -2 bad arity,
+ * -3 a variable index out of range, -4 out of memory. */
+int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour, lhvi_lift_block *blocks,
+                                 int32_t n_blocks, int32_t max_sweeps, int32_t *sweeps_out);
+
+/* Dense ids (order of first appearance) of 64-bit keys; returns the number of distinct keys or < 0. */
+int64_t lhvi_lift_rank64(const uint64_t *key, int64_t n, int64_t *ids);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

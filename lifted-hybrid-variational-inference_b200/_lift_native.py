@@ -1,0 +1,77 @@
+"""ctypes binding of ``liblhvi_lift.so`` (include/lhvi_lift.h): the host-side C++ colour passing.
+
+``load()`` returns the library or ``None`` when it has not been built (``build.build_lift()``);
+``lifting.colour_passing`` then uses its numpy implementation of the same passes.  Set
+``LHVI_LIFT_NATIVE=0`` to force the numpy passes (the tests compare the two)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "liblhvi_lift.so")
+ABI_VERSION = 1
+SYMBOLS = ("lhvi_lift_abi_version", "lhvi_lift_colour_passing", "lhvi_lift_rank64")
+ERRORS = {-1: "null pointer or negative size", -2: "factor arity outside 1..16",
+          -3: "variable index out of range", -4: "out of memory"}
+
+
+class LiftBlock(C.Structure):
+    _fields_ = [("args", C.c_void_p), ("n", C.c_int64), ("arity", C.c_int32), ("symmetric", C.c_int32),
+                ("colour", C.c_void_p)]
+
+
+_lib = None
+
+
+def load(build_if_missing=False):
+    global _lib
+    if _lib is not None:
+        return _lib
+    if os.environ.get("LHVI_LIFT_NATIVE", "1") == "0":
+        return None
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            return None
+        from . import build
+        build.build_lift()
+    lib = C.CDLL(LIB_PATH)
+    lib.lhvi_lift_abi_version.restype = C.c_int32
+    if lib.lhvi_lift_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"liblhvi_lift.so has ABI {lib.lhvi_lift_abi_version()}, the binding expects {ABI_VERSION}; "
+                           "rebuild with lifted-hybrid-variational-inference_b200/build.py")
+    lib.lhvi_lift_colour_passing.restype = C.c_int64
+    lib.lhvi_lift_colour_passing.argtypes = [C.c_int64, C.c_void_p, C.POINTER(LiftBlock), C.c_int32, C.c_int32,
+                                             C.POINTER(C.c_int32)]
+    lib.lhvi_lift_rank64.restype = C.c_int64
+    lib.lhvi_lift_rank64.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def colour_passing(lib, start, blocks, max_sweeps):
+    """``blocks``: list of ``(args int64 [n, arity], symmetric, initial colour)``.  Returns
+    ``(var_colour, [factor colour per block], sweeps)``."""
+    vcol = np.ascontiguousarray(start, dtype=np.int64).copy()
+    keep, descs = [], (LiftBlock * max(1, len(blocks)))()
+    for d, (args, symmetric, colour) in zip(descs, blocks):
+        a = np.ascontiguousarray(args, dtype=np.int64)
+        c = np.full(a.shape[0], int(colour), dtype=np.int64)
+        keep.append((a, c))
+        d.args, d.n, d.arity, d.symmetric, d.colour = a.ctypes.data, a.shape[0], a.shape[1], int(bool(symmetric)), c.ctypes.data
+    sweeps = C.c_int32(0)
+    rc = lib.lhvi_lift_colour_passing(vcol.size, vcol.ctypes.data, descs, len(blocks), int(max_sweeps), C.byref(sweeps))
+    if rc < 0:
+        raise ValueError(f"lhvi_lift_colour_passing: {ERRORS.get(int(rc), rc)}")
+    return vcol, [c for _, c in keep], int(sweeps.value)
+
+
+def rank64(lib, key):
+    key = np.ascontiguousarray(key).view(np.uint64)
+    ids = np.empty(key.size, dtype=np.int64)
+    n = lib.lhvi_lift_rank64(key.ctypes.data, key.size, ids.ctypes.data)
+    if n < 0:
+        raise ValueError(f"lhvi_lift_rank64: {ERRORS.get(int(n), n)}")
+    return ids, int(n)

@@ -3,7 +3,8 @@
     python lifted-hybrid-variational-inference_b200/build.py [--force] [--verbose]
 
 Every ``csrc/*.cu`` is compiled to an object file in parallel, then linked into
-``liblhvi.so`` next to this file.  nvcc cross-compiles without a GPU; the resulting ``.so``
+``liblhvi.so`` next to this file; ``csrc/host/lhvi_lift.cpp`` (host-side lifting passes, no CUDA)
+is compiled with g++ into ``liblhvi_lift.so``.  nvcc cross-compiles without a GPU; the resulting ``.so``
 is git-ignored but travels to the GPU box with the repo snapshot.
 """
 from __future__ import annotations
@@ -20,6 +21,8 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(PKG_DIR, "csrc", "_obj")
 LIB_PATH = os.path.join(PKG_DIR, "liblhvi.so")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
+LIFT_SRC = os.path.join(CSRC, "host", "lhvi_lift.cpp")
+LIFT_LIB = os.path.join(PKG_DIR, "liblhvi_lift.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -46,7 +49,7 @@ def dependencies():
 
 def headers():
     return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) \
-        + glob.glob(os.path.join(INCLUDE, "*.h"))
+        + [h for h in glob.glob(os.path.join(INCLUDE, "*.h")) if os.path.basename(h) != "lhvi_lift.h"]
 
 
 def up_to_date() -> bool:
@@ -71,7 +74,23 @@ def _compile(src: str, verbose: bool) -> str:
     return obj
 
 
+def build_lift(force: bool = False) -> str:
+    """``liblhvi_lift.so``: the host-side C++ lifting passes (include/lhvi_lift.h), plain g++."""
+    deps = [LIFT_SRC, os.path.join(INCLUDE, "lhvi_lift.h")]
+    if not force and os.path.exists(LIFT_LIB) and all(os.path.getmtime(p) <= os.path.getmtime(LIFT_LIB) for p in deps):
+        return LIFT_LIB
+    cxx = shutil.which("g++") or shutil.which("c++")
+    if cxx is None:
+        raise RuntimeError("g++ not found; liblhvi_lift.so cannot be built")
+    cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-I", INCLUDE, LIFT_SRC, "-o", LIFT_LIB]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"g++ failed on {LIFT_SRC}:\n{res.stdout}\n{res.stderr}")
+    return LIFT_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    build_lift(force)
     if not force and up_to_date():
         return LIB_PATH
     os.makedirs(OBJ_DIR, exist_ok=True)

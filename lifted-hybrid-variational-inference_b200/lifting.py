@@ -26,7 +26,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import lowering
+from . import _lift_native, lowering
 
 
 @dataclass
@@ -145,7 +145,7 @@ def initial_colouring(ga: GroundArrays, split_cont_evidence=True):
     return _rank_rows([ga.var_dom.astype(np.int64), hidden.astype(np.int64), val_id.astype(np.int64)])
 
 
-def colour_passing(ga: GroundArrays, split_cont_evidence=True, max_sweeps=1000, start=None):
+def colour_passing(ga: GroundArrays, split_cont_evidence=True, max_sweeps=1000, start=None, use_native=None):
     """Coarsest equitable partition the reference's ``CompressedGraph.run`` converges to.
 
     Returns ``(var_colour [n_vars], [factor_colour of each block], sweeps)`` with dense class ids.
@@ -163,6 +163,13 @@ def colour_passing(ga: GroundArrays, split_cont_evidence=True, max_sweeps=1000, 
 
     # blocks whose potentials compare equal are one colour to start with: rank them together
     pot_id = _potential_ids(ga.blocks)
+    native = _lift_native.load() if use_native is None else (_lift_native.load() if use_native else None)
+    if native is not None and all(1 <= b.arity <= 16 for b in ga.blocks):
+        # the same passes in C++ with hash tables (include/lhvi_lift.h); ids in order of first appearance
+        first_colour = {}
+        blocks = [(b.args, getattr(b.potential, "symmetric", False),
+                   first_colour.setdefault((pid, b.arity), len(first_colour))) for b, pid in zip(ga.blocks, pot_id)]
+        return _lift_native.colour_passing(native, vcol, blocks, max_sweeps)
     merged = {}
     for i, (b, pid) in enumerate(zip(ga.blocks, pot_id)):
         merged.setdefault((pid, b.arity), []).append(i)

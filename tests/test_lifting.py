@@ -36,11 +36,12 @@ def _object_partition(g, rvs, split=True):
 
 @pytest.mark.parametrize("name", sorted(specs.CASES))
 @pytest.mark.parametrize("split", [True, False], ids=["exact-evidence", "lumped-evidence"])
-def test_partition_matches_object_colour_passing(name, split, ns):
+@pytest.mark.parametrize("native", [True, False], ids=["c++", "numpy"])
+def test_partition_matches_object_colour_passing(name, split, native, ns):
     builder = specs.CASES[name][0]
     g, _ = builder(ns)
     ga, rvs = lifting.arrays_from_graph(g)
-    vcol, fcols, sweeps = lifting.colour_passing(ga, split_cont_evidence=split)
+    vcol, fcols, sweeps = lifting.colour_passing(ga, split_cont_evidence=split, use_native=native)
     want, cg = _object_partition(g, rvs, split)
     assert _partition(vcol) == want
     assert sum(len(np.unique(c)) for c in fcols) >= 1
@@ -289,3 +290,84 @@ def test_array_vi_lifted_follows_ground_on_the_oracle_engine():
     for v in pg:
         np.testing.assert_allclose(pl[v], pg[v], rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(wl, wg, rtol=1e-9)
+
+
+# ---- host-side C++ passes (liblhvi_lift.so) against the numpy statement of the same passes -------
+
+def _same_partition(a, b):
+    """Two labelings describe the same partition: the label pairs are a bijection."""
+    pairs = np.unique(np.stack([np.asarray(a), np.asarray(b)]), axis=1)
+    return len(np.unique(pairs[0])) == pairs.shape[1] == len(np.unique(pairs[1]))
+
+
+def test_native_lifting_library_is_built_and_exports_its_header():
+    import ctypes
+    import os
+    import re
+    from lhvi_b200 import _lift_native, build
+    build.build_lift()
+    lib = _lift_native.load()
+    assert lib is not None and lib.lhvi_lift_abi_version() == _lift_native.ABI_VERSION
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "lhvi_lift.h")).read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(lhvi_lift_[a-z0-9_]+)\s*\(", text)))
+    assert declared == sorted(_lift_native.SYMBOLS)
+    raw = ctypes.CDLL(_lift_native.LIB_PATH)
+    assert all(hasattr(raw, name) for name in declared)
+    # argument validation
+    blk = (_lift_native.LiftBlock * 1)()
+    col = np.zeros(3, dtype=np.int64)
+    assert lib.lhvi_lift_colour_passing(3, None, blk, 0, 10, None) == -1
+    args = np.array([[0, 5]], dtype=np.int64)
+    fc = np.zeros(1, dtype=np.int64)
+    blk[0].args, blk[0].n, blk[0].arity, blk[0].colour = args.ctypes.data, 1, 2, fc.ctypes.data
+    assert lib.lhvi_lift_colour_passing(3, col.ctypes.data, blk, 1, 10, None) == -3
+    blk[0].arity = 0
+    assert lib.lhvi_lift_colour_passing(3, col.ctypes.data, blk, 1, 10, None) == -2
+    ids, n = _lift_native.rank64(lib, np.array([7, 3, 7, 2 ** 63, 3], dtype=np.uint64))
+    assert n == 3 and ids.tolist() == [0, 1, 0, 2, 1]
+    assert lib.lhvi_lift_colour_passing(0, None, None, 0, 10, None) == 0
+
+
+@pytest.mark.parametrize("model", ["kalman", "relational", "relational-lumped", "grid"])
+def test_native_colour_passing_equals_numpy(model):
+    if model == "kalman":
+        ga, split = syn.kalman_arrays(40, 12, levels=2, seed=1, period=4)[0], True
+    elif model == "grid":
+        g, _ = syn.gaussian_grid_graph(7)
+        ga, split = lifting.arrays_from_graph(g)[0], True
+    else:
+        ga, split = syn.relational_hybrid_arrays(300, 4, seed=3), model == "relational"
+    v_np, f_np, s_np = lifting.colour_passing(ga, split_cont_evidence=split, use_native=False)
+    v_cc, f_cc, s_cc = lifting.colour_passing(ga, split_cont_evidence=split, use_native=True)
+    assert s_np == s_cc
+    assert _same_partition(v_np, v_cc)
+    assert _same_partition(np.concatenate(f_np), np.concatenate(f_cc))
+    assert v_cc.min() == 0 and v_cc.max() + 1 == len(np.unique(v_cc))
+    # refinement of a coarser start (C2F's cp_run): same result from both
+    start = lifting.initial_colouring(ga, split_cont_evidence=False)
+    r_np = lifting.colour_passing(ga, start=start, use_native=False)[0]
+    r_cc = lifting.colour_passing(ga, start=start, use_native=True)[0]
+    assert _same_partition(r_np, r_cc)
+    # and the lowered models agree in every sum (labels, hence record order, differ)
+    m_np = lifting.lower_partition(ga, v_np, f_np, 2, 3)
+    m_cc = lifting.lower_partition(ga, v_cc, f_cc, 2, 3)
+    assert m_np.n_records == m_cc.n_records and m_np.n_param == m_cc.n_param
+    w = np.array([0.4, 0.6])
+
+    def tied(m, vcol):
+        reps = lifting.class_stats(ga, vcol)["rep"][m.slot_class]
+        eta = np.zeros(m.n_param)
+        for r, off, kind, dim in zip(reps, m.var_off, m.var_kind, m.var_dim):
+            rg = np.random.default_rng(int(r))
+            if kind == 0:
+                eta[off:off + 4:2] = rg.uniform(-1.5, 1.5, 2)
+                eta[off + 1:off + 4:2] = rg.uniform(0.5, 2.0, 2)
+            else:
+                p = rg.uniform(0.1, 1.0, (2, dim))
+                eta[off:off + 2 * dim] = (p / p.sum(axis=1, keepdims=True)).reshape(-1)
+        return eta
+    e_np = grad_pass(m_np, tied(m_np, v_np), w)
+    e_cc = grad_pass(m_cc, tied(m_cc, v_cc), w)
+    np.testing.assert_allclose(e_np[2], e_cc[2], rtol=1e-12)
+    np.testing.assert_allclose(e_np[1], e_cc[1], rtol=1e-12)
