@@ -51,6 +51,25 @@ int32_t lhvi_lift_abi_version(void);
 int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour, lhvi_lift_block *blocks,
                                  int32_t n_blocks, int32_t max_sweeps, int32_t *sweeps_out);
 
+/* Evidence split of the coarse-to-fine engine (CompressedGraph.split_evidence, :236-247, with
+ * SuperRV.split_by_evidence, :78-130), repeated until nothing changes: every class flagged in
+ * `may_split` whose members' values spread more than `epsilon` (standard deviation) is cut by a
+ * one-dimensional k-means over the histogram of its values -- centroids start at the first k
+ * distinct values in member order, `iterations` Lloyd sweeps, members go to the nearest centroid --
+ * piece 0 keeps the class id, the other non-empty pieces get new ids from n_classes upwards; every
+ * piece records its centroid as the class value; pieces whose variance still exceeds `epsilon` stay
+ * (or become) flagged.  Arithmetic follows numpy's (pairwise sums in the variances, first-minimum
+ * arg-min in which a NaN distance wins) so that the result equals lifting.py's statement bit for bit.
+ *   var_colour   [n_vars] in/out class of every variable
+ *   value        [n_vars] evidence values (read for members of flagged classes only)
+ *   capacity     length of may_split / has_centroid / centroid; must be >= n_classes + number of
+ *                members of flagged classes (every new class has at least one member)
+ * Returns the new number of classes, or < 0 (-1 bad argument, -4 out of memory, -5 capacity). */
+int64_t lhvi_lift_split_evidence(int64_t n_vars, int64_t *var_colour, const double *value,
+                                 int64_t n_classes, int64_t capacity, uint8_t *may_split,
+                                 uint8_t *has_centroid, double *centroid, double epsilon, int32_t k,
+                                 int32_t iterations);
+
 /* Dense ids (order of first appearance) of 64-bit keys; returns the number of distinct keys or < 0. */
 int64_t lhvi_lift_rank64(const uint64_t *key, int64_t n, int64_t *ids);
 

@@ -13,9 +13,9 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "liblhvi_lift.so")
 ABI_VERSION = 1
-SYMBOLS = ("lhvi_lift_abi_version", "lhvi_lift_colour_passing", "lhvi_lift_rank64")
-ERRORS = {-1: "null pointer or negative size", -2: "factor arity outside 1..16",
-          -3: "variable index out of range", -4: "out of memory"}
+SYMBOLS = ("lhvi_lift_abi_version", "lhvi_lift_colour_passing", "lhvi_lift_rank64", "lhvi_lift_split_evidence")
+ERRORS = {-1: "null pointer, negative size or class id out of range", -2: "factor arity outside 1..16",
+          -3: "variable index out of range", -4: "out of memory", -5: "class arrays too short for the new classes"}
 
 
 class LiftBlock(C.Structure):
@@ -47,6 +47,9 @@ def load(build_if_missing=False):
                                              C.POINTER(C.c_int32)]
     lib.lhvi_lift_rank64.restype = C.c_int64
     lib.lhvi_lift_rank64.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    lib.lhvi_lift_split_evidence.restype = C.c_int64
+    lib.lhvi_lift_split_evidence.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_int32]
     _lib = lib
     return lib
 
@@ -75,3 +78,18 @@ def rank64(lib, key):
     if n < 0:
         raise ValueError(f"lhvi_lift_rank64: {ERRORS.get(int(n), n)}")
     return ids, int(n)
+
+
+def split_evidence(lib, var_colour, value, n_classes, may_split, has_centroid, centroid, epsilon, k, iterations):
+    """In place on ``var_colour`` (int64) and the three class arrays (uint8, uint8, float64, all of
+    the same capacity); returns the new number of classes."""
+    for a, dt in ((var_colour, np.int64), (value, np.float64), (may_split, np.uint8), (has_centroid, np.uint8),
+                  (centroid, np.float64)):
+        if a.dtype != dt or not a.flags.c_contiguous:
+            raise TypeError("split_evidence: arrays must be contiguous int64 / float64 / uint8")
+    n = lib.lhvi_lift_split_evidence(var_colour.size, var_colour.ctypes.data, value.ctypes.data, int(n_classes),
+                                     may_split.size, may_split.ctypes.data, has_centroid.ctypes.data,
+                                     centroid.ctypes.data, float(epsilon), int(k), int(iterations))
+    if n < 0:
+        raise ValueError(f"lhvi_lift_split_evidence: {ERRORS.get(int(n), n)}")
+    return int(n)

@@ -5,6 +5,7 @@
 #include "lhvi_lift.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -196,5 +197,186 @@ extern "C" int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour,
     }
     std::copy(vcol.begin(), vcol.end(), var_colour);
     if (sweeps_out) *sweeps_out = sweeps;
+    return n_classes;
+}
+
+// ---- evidence split ------------------------------------------------------------------------------
+namespace {
+
+// numpy's pairwise summation of a contiguous float64 vector (the rounding np.var / np.mean see)
+double pairwise_sum(const double *a, int64_t n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int64_t i = 0; i < n; ++i) r += a[i];
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int64_t i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return pairwise_sum(a, n2) + pairwise_sum(a + n2, n - n2);
+}
+
+double np_var(const double *a, int64_t n, std::vector<double> &scratch) {     // ndarray.var(), ddof = 0
+    double mean = pairwise_sum(a, n) / static_cast<double>(n);
+    scratch.resize(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) {
+        double d = a[i] - mean;
+        scratch[i] = d * d;
+    }
+    return pairwise_sum(scratch.data(), n) / static_cast<double>(n);
+}
+
+// np.abs(x - centroids).argmin(): the first NaN wins, else the first minimum
+inline int nearest(double x, const double *cen, int k) {
+    int best = 0;
+    double bd = std::fabs(x - cen[0]);
+    if (std::isnan(bd)) return 0;
+    for (int c = 1; c < k; ++c) {
+        double d = std::fabs(x - cen[c]);
+        if (std::isnan(d)) return c;
+        if (d < bd) {
+            bd = d;
+            best = c;
+        }
+    }
+    return best;
+}
+
+}  // namespace
+
+extern "C" int64_t lhvi_lift_split_evidence(int64_t n_vars, int64_t *var_colour, const double *value,
+                                            int64_t n_classes, int64_t capacity, uint8_t *may_split,
+                                            uint8_t *has_centroid, double *centroid, double epsilon, int32_t k,
+                                            int32_t iterations) {
+    if (n_vars < 0 || n_classes < 0 || capacity < n_classes || k < 1 || iterations < 0) return -1;
+    if (n_vars > 0 && (!var_colour || !value)) return -1;
+    if (capacity > 0 && (!may_split || !has_centroid || !centroid)) return -1;
+    for (int64_t v = 0; v < n_vars; ++v)
+        if (var_colour[v] < 0 || var_colour[v] >= n_classes) return -1;
+    try {
+        std::vector<int64_t> cand, start, fill, order;
+        std::vector<double> vals, scratch, piece, hist_val, hist_cnt, hist_w, cen, mass, tot;
+        std::vector<std::pair<double, int64_t>> sorted;
+        std::vector<int> owner;
+        std::vector<int64_t> piece_id;
+        bool changed = true;
+        while (changed) {
+            changed = false;
+            int64_t next_id = n_classes;
+            // members of the flagged classes grouped by class (ascending id), ascending inside a class
+            start.assign(static_cast<size_t>(n_classes) + 1, 0);
+            int64_t n_cand = 0;
+            for (int64_t v = 0; v < n_vars; ++v)
+                if (may_split[var_colour[v]]) {
+                    ++start[var_colour[v] + 1];
+                    ++n_cand;
+                }
+            if (n_cand == 0) break;
+            for (int64_t c = 0; c < n_classes; ++c) start[c + 1] += start[c];
+            cand.resize(static_cast<size_t>(n_cand));
+            fill.assign(start.begin(), start.end() - 1);
+            for (int64_t v = 0; v < n_vars; ++v)
+                if (may_split[var_colour[v]]) cand[fill[var_colour[v]]++] = v;
+            for (int64_t cid = 0; cid < n_classes; ++cid) {
+                int64_t m = start[cid + 1] - start[cid];
+                if (m == 0) continue;
+                const int64_t *members = cand.data() + start[cid];
+                vals.resize(static_cast<size_t>(m));
+                for (int64_t i = 0; i < m; ++i) vals[i] = value[members[i]];
+                if (!(std::sqrt(np_var(vals.data(), m, scratch)) > epsilon)) continue;
+                // histogram of the values in first-seen order
+                sorted.resize(static_cast<size_t>(m));
+                for (int64_t i = 0; i < m; ++i) sorted[i] = {vals[i], i};
+                std::sort(sorted.begin(), sorted.end());
+                order.clear();            // first index of every distinct value
+                hist_cnt.clear();
+                for (int64_t i = 0; i < m;) {
+                    int64_t j = i;
+                    while (j < m && sorted[j].first == sorted[i].first) ++j;
+                    order.push_back(sorted[i].second);
+                    hist_cnt.push_back(static_cast<double>(j - i));
+                    i = j;
+                }
+                int64_t n_uniq = static_cast<int64_t>(order.size());
+                int kk = static_cast<int>(std::min<int64_t>(k, n_uniq));
+                if (m <= 1 || kk <= 1) {
+                    if (m == 1) may_split[cid] = 0;
+                    continue;
+                }
+                // sort the histogram by first appearance
+                std::vector<int64_t> perm(static_cast<size_t>(n_uniq));
+                for (int64_t i = 0; i < n_uniq; ++i) perm[i] = i;
+                std::sort(perm.begin(), perm.end(), [&](int64_t a, int64_t b) { return order[a] < order[b]; });
+                hist_val.resize(static_cast<size_t>(n_uniq));
+                hist_w.resize(static_cast<size_t>(n_uniq));
+                for (int64_t i = 0; i < n_uniq; ++i) {
+                    hist_val[i] = vals[order[perm[i]]];
+                    hist_w[i] = hist_cnt[perm[i]];
+                }
+                cen.assign(hist_val.begin(), hist_val.begin() + kk);
+                mass.resize(kk);
+                tot.resize(kk);
+                for (int32_t it = 0; it < iterations; ++it) {
+                    std::fill(mass.begin(), mass.end(), 0.0);
+                    std::fill(tot.begin(), tot.end(), 0.0);
+                    for (int64_t i = 0; i < n_uniq; ++i) {
+                        int o = nearest(hist_val[i], cen.data(), kk);
+                        mass[o] += hist_w[i];
+                        tot[o] += hist_val[i] * hist_w[i];
+                    }
+                    for (int c = 0; c < kk; ++c) cen[c] = tot[c] / mass[c];
+                }
+                owner.resize(static_cast<size_t>(m));
+                for (int64_t i = 0; i < m; ++i) owner[i] = nearest(vals[i], cen.data(), kk);
+                // pieces: 0 keeps the id, the other non-empty ones get new ids
+                piece_id.assign(static_cast<size_t>(kk), -1);
+                piece_id[0] = cid;
+                has_centroid[cid] = 1;
+                centroid[cid] = cen[0];
+                int n_pieces = 1;
+                for (int c = 1; c < kk; ++c) {
+                    bool any = false;
+                    for (int64_t i = 0; i < m && !any; ++i) any = owner[i] == c;
+                    if (!any) continue;
+                    if (next_id >= capacity) return -5;
+                    piece_id[c] = next_id;
+                    for (int64_t i = 0; i < m; ++i)
+                        if (owner[i] == c) var_colour[members[i]] = next_id;
+                    has_centroid[next_id] = 1;
+                    centroid[next_id] = cen[c];
+                    may_split[next_id] = 0;
+                    ++next_id;
+                    ++n_pieces;
+                }
+                if (n_pieces > 1) {
+                    changed = true;
+                    for (int c = 0; c < kk; ++c) {
+                        if (piece_id[c] < 0) continue;
+                        piece.clear();
+                        for (int64_t i = 0; i < m; ++i)
+                            if (owner[i] == c) piece.push_back(vals[i]);
+                        bool wide = !piece.empty() &&
+                                    np_var(piece.data(), static_cast<int64_t>(piece.size()), scratch) > epsilon;
+                        if (wide)
+                            may_split[piece_id[c]] = 1;
+                        else if (piece_id[c] != cid)
+                            may_split[piece_id[c]] = 0;
+                    }
+                }
+            }
+            n_classes = next_id;
+        }
+    } catch (const std::bad_alloc &) {
+        return -4;
+    }
     return n_classes;
 }

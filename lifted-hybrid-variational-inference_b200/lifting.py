@@ -377,7 +377,9 @@ def class_stats(ga: GroundArrays, var_colour, ev_value=None, degrees=None):
     mean = np.bincount(var_colour, weights=np.where(hidden, 0.0, ga.var_value), minlength=ncls) / sizes
     dev = np.where(hidden, 0.0, ga.var_value - mean[var_colour])
     variance = np.bincount(var_colour, weights=dev * dev, minlength=ncls) / sizes
-    if ev_value:
+    if isinstance(ev_value, tuple):                       # (has_centroid [ncls], centroid [ncls])
+        mean = np.where(ev_value[0][:ncls], ev_value[1][:ncls], mean)
+    elif ev_value:
         mean = mean.copy()
         ids = np.fromiter(ev_value.keys(), dtype=np.int64, count=len(ev_value))
         mean[ids] = np.fromiter(ev_value.values(), dtype=float, count=len(ev_value))
@@ -731,7 +733,7 @@ class C2FArrayVI:
     var_threshold = 0.1
 
     def __init__(self, ga: GroundArrays, K, T, *, dtype="float64", device=None, engine_factory=None,
-                 init_fn=None):
+                 init_fn=None, use_native=None):
         self.ga, self.K, self.T = ga, int(K), int(T)
         self.dtype, self.device = dtype, device
         self.engine_factory = engine_factory
@@ -740,7 +742,7 @@ class C2FArrayVI:
         self.hidden = np.isnan(ga.var_value)
         self.cont_dom = np.array([bool(d.continuous) for d in ga.domains])[ga.var_dom]
         self.t = 0.0
-        self.ev_value = {}                # evidence classes whose value is a k-means centroid
+        self.use_native = use_native      # None: C++ passes when built; False: numpy passes
         self.history = []                 # (number of variable classes, free energy) per round
 
     # ---- engine ---------------------------------------------------------------------------
@@ -761,26 +763,40 @@ class C2FArrayVI:
         var = np.bincount(inv, weights=dev * dev) / cnt
         return ids, mean, var, cnt
 
-    def _members_by_class(self):
-        """(order, starts): members of class c are ``order[starts[c]:starts[c + 1]]``, ascending."""
-        order = np.argsort(self.vcol, kind="stable")
-        starts = np.searchsorted(self.vcol[order], np.arange(int(self.vcol.max()) + 2))
-        return order, starts
-
     def _split_evidence(self, epsilon):
-        """``CompressedGraph.split_evidence`` (``:236-247``) until nothing changes."""
+        """``CompressedGraph.split_evidence`` (``:236-247``) until nothing changes.  Book-keeping per
+        class id: ``may_split`` (the reference's ``clustered_evidence``), ``ev_has`` / ``ev_val`` (classes
+        whose value is a k-means centroid rather than the members' mean).  Runs in the host-side C++
+        library when it is built (``lhvi_lift_split_evidence``), else in ``_split_evidence_numpy``;
+        the two give the same arrays bit for bit (``tests/test_lifting.py``)."""
+        n = int(self.vcol.max()) + 1
+        room = n + int(np.count_nonzero(self.may_split[self.vcol]))     # every new class has a member
+        may = np.zeros(room, dtype=np.uint8)
+        has = np.zeros(room, dtype=np.uint8)
+        val = np.zeros(room)
+        may[:n], has[:n], val[:n] = self.may_split, self.ev_has, self.ev_val
+        lib = _lift_native.load() if self.use_native is not False else None
+        if lib is not None:
+            vcol = np.ascontiguousarray(self.vcol, dtype=np.int64)
+            n_new = _lift_native.split_evidence(lib, vcol, np.ascontiguousarray(self.ga.var_value, dtype=np.float64),
+                                                n, may, has, val, epsilon, self.k_mean_k, self.k_mean_its)
+            self.vcol = vcol
+        else:
+            n_new = self._split_evidence_numpy(epsilon, may, has, val)
+        self.may_split, self.ev_has, self.ev_val = may[:n_new].astype(bool), has[:n_new].astype(bool), val[:n_new].copy()
+
+    def _split_evidence_numpy(self, epsilon, may, has, val):
         changed = True
+        next_id = int(self.vcol.max()) + 1
         while changed:
             changed = False
-            next_id = int(self.vcol.max()) + 1
-            if not self.clustered:
+            n_now = next_id
+            if not may[:n_now].any():
                 break
             # members of the classes k-means may still split, grouped by class (classes are
             # disjoint: one grouping per pass); classes whose spread is within epsilon are skipped
             # after one vectorised variance pass
-            may = np.zeros(next_id, dtype=bool)
-            may[np.fromiter(self.clustered, dtype=np.int64, count=len(self.clustered))] = True
-            cand = np.flatnonzero(may[self.vcol])
+            cand = np.flatnonzero(may[self.vcol] != 0)
             cand = cand[np.argsort(self.vcol[cand], kind="stable")]
             ccol = self.vcol[cand]
             cids, cstart, ccnt = np.unique(ccol, return_index=True, return_counts=True)
@@ -798,46 +814,49 @@ class C2FArrayVI:
                 res = _kmeans_1d(vals, self.k_mean_k, self.k_mean_its)
                 if res is None:
                     if members.size == 1:
-                        self.clustered.discard(cid)
+                        may[cid] = 0
                     continue
                 owner, centroids = res
                 pieces = [(cid, vals[owner == 0])]
-                self.ev_value[cid] = float(centroids[0])
+                has[cid], val[cid] = 1, centroids[0]
                 for c in range(1, centroids.size):
                     pick = owner == c
                     if pick.any():
                         self.vcol[members[pick]] = next_id
-                        self.ev_value[next_id] = float(centroids[c])
+                        has[next_id], val[next_id], may[next_id] = 1, centroids[c], 0
                         pieces.append((next_id, vals[pick]))
                         next_id += 1
                 if len(pieces) > 1:
                     changed = True
                     for pid, pv in pieces:
                         if pv.size and pv.var() > epsilon:
-                            self.clustered.add(pid)
+                            may[pid] = 1
                         elif pid != cid:
-                            self.clustered.discard(pid)
+                            may[pid] = 0
+        return next_id
 
     def _refine(self):
         """Colour passing from the current classes; hidden pieces inherit (``:39-61``)."""
         old = self.vcol
-        new, self.fcols, _ = colour_passing(self.ga, start=old)
+        new, self.fcols, _ = colour_passing(self.ga, start=old, use_native=self.use_native)
         # distinct (old class, new class) pairs: the new partition refines the old one
-        n_new = int(new.max()) + 1
+        n_old, n_new = int(old.max()) + 1, int(new.max()) + 1
         key = np.unique(old.astype(np.int64) * n_new + new)
         pair = np.stack([key // n_new, key % n_new])
-        kids_of = np.bincount(pair[0], minlength=int(old.max()) + 1)
-        # carry the evidence book-keeping over to the new ids
-        if self.clustered:
-            was = np.zeros(int(old.max()) + 1, dtype=bool)
-            was[np.fromiter(self.clustered, dtype=np.int64, count=len(self.clustered))] = True
-            self.clustered = set(pair[1][was[pair[0]]].tolist())
-        # a class that colour passing left whole keeps its k-means centroid as value; pieces of a
-        # structure split take the mean of their members (SuperRV.split_by_structure, :57-62)
-        if self.ev_value:
-            first_kid = np.full(int(old.max()) + 1, -1, dtype=np.int64)
-            first_kid[pair[0][::-1]] = pair[1][::-1]
-            self.ev_value = {int(first_kid[c]): v for c, v in self.ev_value.items() if kids_of[c] == 1}
+        kids_of = np.bincount(pair[0], minlength=n_old)
+        # carry the evidence book-keeping over to the new ids: every piece of a class k-means may
+        # split may be split; a class that colour passing left whole keeps its k-means centroid as
+        # value, pieces of a structure split take the mean of their members
+        # (SuperRV.split_by_structure, :57-62)
+        may = np.zeros(n_new, dtype=bool)
+        may[pair[1][self.may_split[pair[0]]]] = True
+        first_kid = np.full(n_old, -1, dtype=np.int64)
+        first_kid[pair[0][::-1]] = pair[1][::-1]
+        keep = np.flatnonzero(self.ev_has[:n_old] & (kids_of == 1))
+        has, val = np.zeros(n_new, dtype=bool), np.zeros(n_new)
+        has[first_kid[keep]] = True
+        val[first_kid[keep]] = self.ev_val[keep]
+        self.may_split, self.ev_has, self.ev_val = may, has, val
         self._inherit(old, new)
         self.vcol = new
 
@@ -922,9 +941,10 @@ class C2FArrayVI:
         # initial classes, parameters per initial class (one hidden class per domain), then the
         # first colour passing in which the pieces inherit (C2FVarInference.py:306-311)
         self.vcol = initial_colouring(ga, split_cont_evidence=False)
-        ev_cont = np.flatnonzero(~self.hidden & self.cont_dom)
-        self.clustered = set(np.unique(self.vcol[ev_cont]).tolist())    # what k-means may split
-        self.ev_value = {}
+        n0 = int(self.vcol.max()) + 1
+        self.may_split = np.zeros(n0, dtype=bool)                       # what k-means may split
+        self.may_split[self.vcol[~self.hidden & self.cont_dom]] = True
+        self.ev_has, self.ev_val = np.zeros(n0, dtype=bool), np.zeros(n0)
         self._init_params()
         self._refine()
         _, _, var, _ = self._evidence_stats()
@@ -937,7 +957,7 @@ class C2FArrayVI:
             self._refine()
             epsilon = max(epsilon - d, self.min_obs_var)
             self.quotient = PartitionInfo(self.vcol, self.fcols)
-            self.model = lower_partition(ga, self.vcol, self.fcols, self.K, self.T, ev_value=self.ev_value,
+            self.model = lower_partition(ga, self.vcol, self.fcols, self.K, self.T, ev_value=(self.ev_has, self.ev_val),
                                          gaussian_obs=self.gaussian_obs, min_obs_var=self.min_obs_var,
                                          degrees=self.degrees)
             self.engine = self._make_engine(self.model)

@@ -371,3 +371,54 @@ def test_native_colour_passing_equals_numpy(model):
     e_cc = grad_pass(m_cc, tied(m_cc, v_cc), w)
     np.testing.assert_allclose(e_np[2], e_cc[2], rtol=1e-12)
     np.testing.assert_allclose(e_np[1], e_cc[1], rtol=1e-12)
+
+
+@pytest.mark.parametrize("k,its,seed", [(2, 10, 0), (3, 4, 1), (2, 1, 2), (5, 10, 3)])
+def test_native_evidence_split_equals_numpy_bit_for_bit(k, its, seed):
+    """``lhvi_lift_split_evidence`` against ``_split_evidence_numpy``: same classes with the same
+    ids, same flags, same centroids to the last bit -- classes of 1 to ~3000 members (numpy's
+    pairwise sums recurse above 128), repeated values, several thresholds."""
+    from oracle_engine import OracleEngine
+    rng = np.random.default_rng(seed)
+    ga = syn.relational_hybrid_arrays(1500, 4, observed_frac=0.8, seed=seed)
+    # make the observed values lumpy: many repeats, a few wide clusters
+    ev = np.flatnonzero(~np.isnan(ga.var_value))
+    ga.var_value[ev] = np.round(rng.normal(0, 3, ev.size) + rng.choice([-8.0, 0.0, 5.0], ev.size), rng.integers(0, 3))
+    runs = []
+    for native in (True, False):
+        vi = lifting.C2FArrayVI(ga, 2, 3, engine_factory=lambda m: OracleEngine(m), use_native=native)
+        vi.k_mean_k, vi.k_mean_its = k, its
+        vi.degrees = ga.degrees()
+        vi.vcol = lifting.initial_colouring(ga, split_cont_evidence=False)
+        n0 = int(vi.vcol.max()) + 1
+        vi.may_split = np.zeros(n0, dtype=bool)
+        vi.may_split[vi.vcol[~vi.hidden & vi.cont_dom]] = True
+        vi.ev_has, vi.ev_val = np.zeros(n0, dtype=bool), np.zeros(n0)
+        trace = []
+        for epsilon in (4.0, 2.5, 1.0, 0.3, 0.0):
+            vi._split_evidence(epsilon)
+            trace.append((vi.vcol.copy(), vi.may_split.copy(), vi.ev_has.copy(), vi.ev_val.copy()))
+        runs.append(trace)
+    assert len(np.unique(runs[0][-1][0])) >= 20
+    for a, b in zip(*runs):
+        for x, y in zip(a, b):
+            assert x.dtype == y.dtype and x.shape == y.shape
+            np.testing.assert_array_equal(x, y)
+
+
+def test_c2f_native_and_numpy_passes_give_the_same_run():
+    from oracle_engine import OracleEngine
+    ga = syn.relational_hybrid_arrays(120, 3, seed=5)
+    out = []
+    for native in (True, False):
+        vi = lifting.C2FArrayVI(ga, 2, 3, engine_factory=lambda m: OracleEngine(m, var_threshold=0.1), use_native=native)
+        vi.run(40, 0.05)
+        out.append(vi)
+    a, b = out
+    assert [n for n, _ in a.history] == [n for n, _ in b.history]
+    assert _same_partition(a.vcol, b.vcol)
+    np.testing.assert_allclose(a.free_energy(), b.free_energy(), rtol=1e-10)
+    pa, wa = a.ground_params()
+    pb, wb = b.ground_params()
+    for v in pa:
+        np.testing.assert_allclose(pa[v], pb[v], rtol=1e-8, atol=1e-10)
