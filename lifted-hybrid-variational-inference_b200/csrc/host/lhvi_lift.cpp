@@ -19,46 +19,51 @@ inline uint64_t mix(uint64_t x, uint64_t seed) {        // splitmix64 finaliser
     return z ^ (z >> 31);
 }
 
-// Open-addressing table from a hash to the index of the first item seen with that key.  The caller
-// resolves hash matches with an exact comparison of the two items.
+// Open-addressing table from a hash to a dense class id.  The caller resolves hash matches with an
+// exact comparison against the class's stored key and creates the class on a miss.
 struct Table {
-    std::vector<int64_t> slot;      // item index or -1
-    std::vector<uint64_t> tag;      // full hash of the stored item
+    struct Slot {
+        uint64_t tag;               // full hash of the class's key
+        int64_t id;                 // class id or -1
+    };
+    std::vector<Slot> slot;         // one cache line per probe
     uint64_t mask = 0;
 
     bool reserve(int64_t items) {
         uint64_t cap = 16;
         while (cap < static_cast<uint64_t>(items) * 2 + 2) cap <<= 1;
         try {
-            slot.assign(cap, -1);
-            tag.assign(cap, 0);
+            slot.assign(cap, Slot{0, -1});
         } catch (const std::bad_alloc &) {
             return false;
         }
         mask = cap - 1;
         return true;
     }
-    void clear() { std::fill(slot.begin(), slot.end(), int64_t(-1)); }
+    void clear() { std::fill(slot.begin(), slot.end(), Slot{0, -1}); }
+    void prefetch(uint64_t h) const { __builtin_prefetch(&slot[h & mask], 1, 1); }
 
-    template <class Same>
-    int64_t find_or_insert(uint64_t h, int64_t item, Same same) {     // returns the first item with this key
+    template <class Same, class Create>
+    int64_t find_or_insert(uint64_t h, Same same, Create create) {
         uint64_t p = h & mask;
         for (;;) {
-            int64_t s = slot[p];
-            if (s < 0) {
-                slot[p] = item;
-                tag[p] = h;
-                return item;
+            Slot &s = slot[p];
+            if (s.id < 0) {
+                s.id = create();
+                s.tag = h;
+                return s.id;
             }
-            if (tag[p] == h && same(s, item)) return s;
+            if (s.tag == h && same(s.id)) return s.id;
             p = (p + 1) & mask;
         }
     }
 };
 
-struct FactorRef {
-    int32_t block;
-    int64_t row;
+constexpr int64_t AHEAD = 16;       // items whose table slot / gathered operands are prefetched ahead
+
+struct VarKey {
+    int64_t colour;
+    uint64_t h1, h2;
 };
 
 }  // namespace
@@ -69,26 +74,28 @@ extern "C" int64_t lhvi_lift_rank64(const uint64_t *key, int64_t n, int64_t *ids
     if (n < 0 || (n > 0 && (!key || !ids))) return -1;
     Table t;
     if (!t.reserve(n)) return -4;
-    std::vector<int64_t> id_of;      // dense id of the item that owns a key, indexed by that item
+    std::vector<uint64_t> key_of_class;
     try {
-        id_of.assign(static_cast<size_t>(n), -1);
+        key_of_class.reserve(static_cast<size_t>(n));
+        for (int64_t i = 0; i < n; ++i) {
+            uint64_t k = key[i];
+            ids[i] = t.find_or_insert(mix(k, 0x243F6A8885A308D3ull),
+                                      [&](int64_t c) { return key_of_class[c] == k; },
+                                      [&]() {
+                                          key_of_class.push_back(k);
+                                          return static_cast<int64_t>(key_of_class.size()) - 1;
+                                      });
+        }
     } catch (const std::bad_alloc &) {
         return -4;
     }
-    int64_t next = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        int64_t first = t.find_or_insert(mix(key[i], 0x243F6A8885A308D3ull), i,
-                                         [&](int64_t a, int64_t b) { return key[a] == key[b]; });
-        if (first == i) id_of[i] = next++;
-        ids[i] = id_of[first];
-    }
-    return next;
+    return static_cast<int64_t>(key_of_class.size());
 }
 
 extern "C" int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour, lhvi_lift_block *blocks,
                                             int32_t n_blocks, int32_t max_sweeps, int32_t *sweeps_out) {
     if (n_vars < 0 || n_blocks < 0 || (n_vars > 0 && !var_colour) || (n_blocks > 0 && !blocks)) return -1;
-    int64_t n_fac = 0, n_inc = 0;
+    int64_t n_fac = 0;
     for (int32_t b = 0; b < n_blocks; ++b) {
         const lhvi_lift_block &B = blocks[b];
         if (B.n < 0 || (B.n > 0 && (!B.args || !B.colour))) return -1;
@@ -96,108 +103,127 @@ extern "C" int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour,
         for (int64_t i = 0; i < B.n * B.arity; ++i)
             if (B.args[i] < 0 || B.args[i] >= n_vars) return -3;
         n_fac += B.n;
-        n_inc += B.n * B.arity;
     }
-    (void)n_inc;
-    std::vector<int64_t> vcol, vnew, fold, h_first;
-    std::vector<uint64_t> H1, H2;
-    std::vector<int64_t> foff(static_cast<size_t>(n_blocks) + 1, 0);
-    Table vt, ft;
     try {
-        vcol.assign(var_colour, var_colour + n_vars);
-        vnew.assign(static_cast<size_t>(n_vars), 0);
-        H1.assign(static_cast<size_t>(n_vars), 0);
-        H2.assign(static_cast<size_t>(n_vars), 0);
-        fold.assign(static_cast<size_t>(n_fac), 0);
-        h_first.assign(static_cast<size_t>(std::max(n_fac, n_vars)), -1);
+        std::vector<int64_t> vcol(var_colour, var_colour + n_vars), vnew(static_cast<size_t>(n_vars), 0);
+        std::vector<uint64_t> H1(static_cast<size_t>(n_vars), 0), H2(static_cast<size_t>(n_vars), 0);
+        std::vector<VarKey> vkey;               // key of every variable class of the pass, by class id
+        std::vector<int64_t> fkey;              // keys of the factor classes of the pass, back to back:
+        std::vector<int64_t> fkey_at;           //   class c: fkey[fkey_at[c]] = arity | symmetric << 8, then own colour, then argument colours
+        Table vt, ft;
+        if (!vt.reserve(n_vars) || !ft.reserve(n_fac)) return -4;
+
+        // dense start colouring, order of first appearance
+        int64_t n_classes = 0;
+        {
+            std::vector<int64_t> label;
+            for (int64_t v = 0; v < n_vars; ++v) {
+                int64_t c0 = vcol[v];
+                vnew[v] = vt.find_or_insert(mix(static_cast<uint64_t>(c0), 1), [&](int64_t c) { return label[c] == c0; },
+                                            [&]() {
+                                                label.push_back(c0);
+                                                return static_cast<int64_t>(label.size()) - 1;
+                                            });
+            }
+            n_classes = static_cast<int64_t>(label.size());
+            vcol.swap(vnew);
+        }
+
+        int64_t before = -1;
+        int32_t sweeps = 0;
+        while (before != n_classes && sweeps < max_sweeps) {
+            before = n_classes;
+            ++sweeps;
+            // ---- factors: (own class, classes of the arguments; sorted for a symmetric potential)
+            ft.clear();
+            fkey.clear();
+            fkey_at.clear();
+            for (int32_t b = 0; b < n_blocks; ++b) {
+                lhvi_lift_block &B = blocks[b];
+                const int32_t arity = B.arity;
+                int64_t mine[LHVI_LIFT_MAX_ARITY + 2];
+                mine[0] = arity | (B.symmetric ? 256 : 0);
+                // chunks of AHEAD factors: gather the keys and hashes (prefetching the argument
+                // colours of the next chunk), prefetch the table slots, then look them up
+                int64_t keys[AHEAD][LHVI_LIFT_MAX_ARITY + 2];
+                uint64_t hs[AHEAD];
+                for (int64_t i0 = 0; i0 < B.n; i0 += AHEAD) {
+                    const int64_t m = std::min<int64_t>(AHEAD, B.n - i0);
+                    if (i0 + AHEAD < B.n) {
+                        const int64_t *nx = B.args + (i0 + AHEAD) * arity;
+                        const int64_t cnt = std::min<int64_t>(AHEAD, B.n - i0 - AHEAD) * arity;
+                        for (int64_t q = 0; q < cnt; ++q) __builtin_prefetch(&vcol[nx[q]], 0, 1);
+                    }
+                    for (int64_t r = 0; r < m; ++r) {
+                        const int64_t *a = B.args + (i0 + r) * arity;
+                        int64_t *k = keys[r];
+                        k[0] = mine[0];
+                        k[1] = B.colour[i0 + r];
+                        for (int32_t j = 0; j < arity; ++j) k[2 + j] = vcol[a[j]];
+                        if (B.symmetric) std::sort(k + 2, k + 2 + arity);
+                        uint64_t h = mix(static_cast<uint64_t>(k[1]), 0x452821E638D01377ull + static_cast<uint64_t>(k[0]));
+                        for (int32_t j = 0; j < arity; ++j) h = mix(h ^ static_cast<uint64_t>(k[2 + j]), 0xBE5466CF34E90C6Cull);
+                        hs[r] = h;
+                        ft.prefetch(h);
+                    }
+                    for (int64_t r = 0; r < m; ++r) {
+                        const int64_t *k = keys[r];
+                        B.colour[i0 + r] = ft.find_or_insert(
+                            hs[r], [&](int64_t c) { return std::equal(k, k + 2 + arity, fkey.data() + fkey_at[c]); },
+                            [&]() {
+                                fkey_at.push_back(static_cast<int64_t>(fkey.size()));
+                                fkey.insert(fkey.end(), k, k + 2 + arity);
+                                return static_cast<int64_t>(fkey_at.size()) - 1;
+                            });
+                    }
+                }
+            }
+            // ---- variables: (own class, multiset of incident factor classes) through two 64-bit sums
+            std::fill(H1.begin(), H1.end(), 0);
+            std::fill(H2.begin(), H2.end(), 0);
+            for (int32_t b = 0; b < n_blocks; ++b) {
+                const lhvi_lift_block &B = blocks[b];
+                const int64_t total = B.n * B.arity;
+                for (int64_t i = 0; i < B.n; ++i) {
+                    uint64_t c = static_cast<uint64_t>(B.colour[i]);
+                    uint64_t m1 = mix(c, 0x243F6A8885A308D3ull), m2 = mix(c, 0x13198A2E03707344ull);
+                    const int64_t *a = B.args + i * B.arity;
+                    for (int32_t j = 0; j < B.arity; ++j) {
+                        const int64_t q = i * B.arity + j + 2 * AHEAD;
+                        if (q < total) {
+                            __builtin_prefetch(&H1[B.args[q]], 1, 1);
+                            __builtin_prefetch(&H2[B.args[q]], 1, 1);
+                        }
+                        H1[a[j]] += m1;
+                        H2[a[j]] += m2;
+                    }
+                }
+            }
+            vt.clear();
+            vkey.clear();
+            auto var_hash = [&](int64_t v) {
+                return mix(static_cast<uint64_t>(vcol[v]), 0xA4093822299F31D0ull) + H1[v] + mix(H2[v], 0x082EFA98EC4E6C89ull);
+            };
+            for (int64_t v = 0; v < std::min<int64_t>(AHEAD, n_vars); ++v) vt.prefetch(var_hash(v));
+            for (int64_t v = 0; v < n_vars; ++v) {
+                if (v + AHEAD < n_vars) vt.prefetch(var_hash(v + AHEAD));
+                VarKey k{vcol[v], H1[v], H2[v]};
+                vnew[v] = vt.find_or_insert(
+                    var_hash(v), [&](int64_t c) { return vkey[c].colour == k.colour && vkey[c].h1 == k.h1 && vkey[c].h2 == k.h2; },
+                    [&]() {
+                        vkey.push_back(k);
+                        return static_cast<int64_t>(vkey.size()) - 1;
+                    });
+            }
+            n_classes = static_cast<int64_t>(vkey.size());
+            vcol.swap(vnew);
+        }
+        std::copy(vcol.begin(), vcol.end(), var_colour);
+        if (sweeps_out) *sweeps_out = sweeps;
+        return n_classes;
     } catch (const std::bad_alloc &) {
         return -4;
     }
-    if (!vt.reserve(n_vars) || !ft.reserve(n_fac)) return -4;
-    for (int32_t b = 0; b < n_blocks; ++b) foff[b + 1] = foff[b] + blocks[b].n;
-
-    // dense start colouring, order of first appearance
-    int64_t n_classes = 0;
-    {
-        for (int64_t v = 0; v < n_vars; ++v) {
-            int64_t first = vt.find_or_insert(mix(static_cast<uint64_t>(vcol[v]), 1), v,
-                                              [&](int64_t a, int64_t c) { return vcol[a] == vcol[c]; });
-            if (first == v) h_first[v] = n_classes++;
-            vnew[v] = h_first[first];
-        }
-        vcol.swap(vnew);
-    }
-
-    auto block_of = [&](int64_t f) {          // global factor index -> (block, row)
-        int32_t b = static_cast<int32_t>(std::upper_bound(foff.begin(), foff.end(), f) - foff.begin()) - 1;
-        return FactorRef{b, f - foff[b]};
-    };
-    auto key_of = [&](const lhvi_lift_block &B, int64_t row, int64_t *out) {   // classes of the arguments
-        const int64_t *a = B.args + row * B.arity;
-        for (int32_t j = 0; j < B.arity; ++j) out[j] = vcol[a[j]];
-        if (B.symmetric) std::sort(out, out + B.arity);
-    };
-
-    int64_t before = -1;
-    int32_t sweeps = 0;
-    while (before != n_classes && sweeps < max_sweeps) {
-        before = n_classes;
-        ++sweeps;
-        // ---- factors: (own class, classes of the arguments)
-        for (int32_t b = 0; b < n_blocks; ++b)
-            std::memcpy(fold.data() + foff[b], blocks[b].colour, sizeof(int64_t) * static_cast<size_t>(blocks[b].n));
-        ft.clear();
-        int64_t n_fclasses = 0;
-        for (int32_t b = 0; b < n_blocks; ++b) {
-            lhvi_lift_block &B = blocks[b];
-            int64_t mine[LHVI_LIFT_MAX_ARITY], theirs[LHVI_LIFT_MAX_ARITY];
-            for (int64_t i = 0; i < B.n; ++i) {
-                key_of(B, i, mine);
-                uint64_t h = mix(static_cast<uint64_t>(fold[foff[b] + i]), 0x452821E638D01377ull + B.arity);
-                for (int32_t j = 0; j < B.arity; ++j) h = mix(h ^ static_cast<uint64_t>(mine[j]), 0xBE5466CF34E90C6Cull);
-                int64_t self = foff[b] + i;
-                int64_t first = ft.find_or_insert(h, self, [&](int64_t s, int64_t) {
-                    if (fold[s] != fold[self]) return false;
-                    FactorRef r = block_of(s);
-                    const lhvi_lift_block &R = blocks[r.block];
-                    if (R.arity != B.arity || (R.symmetric != 0) != (B.symmetric != 0)) return false;
-                    key_of(R, r.row, theirs);
-                    return std::equal(mine, mine + B.arity, theirs);
-                });
-                if (first == self) h_first[self] = n_fclasses++;
-                B.colour[i] = h_first[first];
-            }
-        }
-        // ---- variables: (own class, multiset of incident factor classes) through two 64-bit sums
-        std::fill(H1.begin(), H1.end(), 0);
-        std::fill(H2.begin(), H2.end(), 0);
-        for (int32_t b = 0; b < n_blocks; ++b) {
-            const lhvi_lift_block &B = blocks[b];
-            for (int64_t i = 0; i < B.n; ++i) {
-                uint64_t c = static_cast<uint64_t>(B.colour[i]);
-                uint64_t m1 = mix(c, 0x243F6A8885A308D3ull), m2 = mix(c, 0x13198A2E03707344ull);
-                const int64_t *a = B.args + i * B.arity;
-                for (int32_t j = 0; j < B.arity; ++j) {
-                    H1[a[j]] += m1;
-                    H2[a[j]] += m2;
-                }
-            }
-        }
-        vt.clear();
-        n_classes = 0;
-        for (int64_t v = 0; v < n_vars; ++v) {
-            uint64_t h = mix(static_cast<uint64_t>(vcol[v]), 0xA4093822299F31D0ull) + H1[v] + mix(H2[v], 0x082EFA98EC4E6C89ull);
-            int64_t first = vt.find_or_insert(h, v, [&](int64_t a, int64_t c) {
-                return vcol[a] == vcol[c] && H1[a] == H1[c] && H2[a] == H2[c];
-            });
-            if (first == v) h_first[v] = n_classes++;
-            vnew[v] = h_first[first];
-        }
-        vcol.swap(vnew);
-    }
-    std::copy(vcol.begin(), vcol.end(), var_colour);
-    if (sweeps_out) *sweeps_out = sweeps;
-    return n_classes;
 }
 
 // ---- evidence split ------------------------------------------------------------------------------
