@@ -363,16 +363,21 @@ def lower_ground_arrays(ga: GroundArrays, K, T):
     return lowering.lower_compressed(q, K, T), q
 
 
+def _first_index(labels, n):
+    """``first[c]`` = smallest position i with ``labels[i] == c`` (-1: label unused); no sort."""
+    first = np.full(n, -1, dtype=np.int64)
+    first[labels[::-1]] = np.arange(labels.size - 1, -1, -1, dtype=np.int64)      # the last write is the smallest index
+    return first
+
+
 def class_stats(ga: GroundArrays, var_colour, ev_value=None, degrees=None):
     """Per variable class, as arrays: size, representative (smallest member), hidden flag, mean
     evidence value (k-means centroid where ``ev_value`` names one), population variance around
     the members' mean, representative degree, domain (``SuperRV`` ``:8-45``)."""
     nv = ga.n_vars
     ncls = int(var_colour.max()) + 1 if nv else 0
-    order = np.argsort(var_colour, kind="stable")
-    starts = np.searchsorted(var_colour[order], np.arange(ncls))
-    sizes = np.diff(np.append(starts, nv))
-    reps = order[starts]
+    sizes = np.bincount(var_colour, minlength=ncls)
+    reps = _first_index(var_colour, ncls)                  # smallest member
     hidden = np.isnan(ga.var_value)
     mean = np.bincount(var_colour, weights=np.where(hidden, 0.0, ga.var_value), minlength=ncls) / sizes
     dev = np.where(hidden, 0.0, ga.var_value - mean[var_colour])
@@ -468,10 +473,10 @@ def lower_partition(ga: GroundArrays, var_colour, factor_colours, K, T, *, ev_va
     for b, fcol in zip(ga.blocks, factor_colours):
         if b.n == 0:
             continue
-        ids, first = np.unique(fcol, return_index=True)
-        fresh = ~seen[ids]
+        first_of = _first_index(fcol, n_fc)
+        ids = np.flatnonzero((first_of >= 0) & ~seen)            # classes first met in this block, ascending id
+        first = first_of[ids]
         seen[ids] = True
-        ids, first = ids[fresh], first[fresh]
         if ids.size == 0:
             continue
         uid = uid_next + np.arange(ids.size)
@@ -481,11 +486,19 @@ def lower_partition(ga: GroundArrays, var_colour, factor_colours, K, T, *, ev_va
         arity = b.arity
         # records that share (roles, domains of the hidden discrete arguments, discrete evidence
         # values) share a coefficient block; distinct combinations in order of first appearance
-        doms = np.where((roles == HD) | (roles == ED), st["dom"][nbcls], 0).astype(float)
+        doms = np.where((roles == HD) | (roles == ED), st["dom"][nbcls], 0)
         vals = np.where(roles == ED, mean[nbcls], 0.0)
-        combo, where, inv = np.unique(np.concatenate([roles.astype(float), doms, vals], axis=1), axis=0,
-                                      return_index=True, return_inverse=True)
-        inv = inv.reshape(-1)
+        # one integer code per row: roles and domains packed positionally, evidence values by rank
+        code = np.zeros(ids.size, dtype=np.int64)
+        n_dom = len(ga.domains) + 1
+        for j in range(arity):
+            code = (code * 8 + roles[:, j]) * n_dom + doms[:, j]
+        cols = [code]
+        if np.any(roles == ED):
+            cols += [np.unique(vals[:, j], return_inverse=True)[1].reshape(-1).astype(np.int64) for j in range(arity)]
+        inv = _rank_rows(cols)
+        where = _first_index(inv, int(inv.max()) + 1)
+        combo = np.concatenate([roles.astype(float), doms.astype(float), vals], axis=1)[where]
         for ci in np.argsort(where, kind="stable"):
             sel = np.flatnonzero(inv == ci)
             r = [int(x) for x in combo[ci, :arity]]
