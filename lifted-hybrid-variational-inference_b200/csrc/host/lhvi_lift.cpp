@@ -29,18 +29,38 @@ struct Table {
     std::vector<Slot> slot;         // one cache line per probe
     uint64_t mask = 0;
 
-    bool reserve(int64_t items) {
-        uint64_t cap = 16;
-        while (cap < static_cast<uint64_t>(items) * 2 + 2) cap <<= 1;
+    int64_t count = 0;              // classes stored
+
+    // Sized for the classes, not the items: a table of a few thousand classes stays in cache however
+    // many items are looked up.  Grows (rehash by the stored tags) when half full.
+    bool reserve(int64_t classes) {
+        uint64_t cap = 1024;
+        while (cap < static_cast<uint64_t>(classes) * 2 + 2) cap <<= 1;
         try {
             slot.assign(cap, Slot{0, -1});
         } catch (const std::bad_alloc &) {
             return false;
         }
         mask = cap - 1;
+        count = 0;
         return true;
     }
-    void clear() { std::fill(slot.begin(), slot.end(), Slot{0, -1}); }
+    void clear() {
+        std::fill(slot.begin(), slot.end(), Slot{0, -1});
+        count = 0;
+    }
+    void grow() {                   // may throw std::bad_alloc; callers run inside try blocks
+        std::vector<Slot> old;
+        old.swap(slot);
+        slot.assign(old.size() * 2, Slot{0, -1});
+        mask = slot.size() - 1;
+        for (const Slot &s : old) {
+            if (s.id < 0) continue;
+            uint64_t p = s.tag & mask;
+            while (slot[p].id >= 0) p = (p + 1) & mask;
+            slot[p] = s;
+        }
+    }
     void prefetch(uint64_t h) const { __builtin_prefetch(&slot[h & mask], 1, 1); }
 
     template <class Same, class Create>
@@ -49,8 +69,13 @@ struct Table {
         for (;;) {
             Slot &s = slot[p];
             if (s.id < 0) {
+                if (static_cast<uint64_t>(count + 1) * 2 > slot.size()) {
+                    grow();
+                    return find_or_insert(h, same, create);
+                }
                 s.id = create();
                 s.tag = h;
+                ++count;
                 return s.id;
             }
             if (s.tag == h && same(s.id)) return s.id;
@@ -73,7 +98,7 @@ extern "C" int32_t lhvi_lift_abi_version(void) { return LHVI_LIFT_ABI_VERSION; }
 extern "C" int64_t lhvi_lift_rank64(const uint64_t *key, int64_t n, int64_t *ids) {
     if (n < 0 || (n > 0 && (!key || !ids))) return -1;
     Table t;
-    if (!t.reserve(n)) return -4;
+    if (!t.reserve(1024)) return -4;
     std::vector<uint64_t> key_of_class;
     try {
         key_of_class.reserve(static_cast<size_t>(n));
@@ -111,7 +136,7 @@ extern "C" int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour,
         std::vector<int64_t> fkey;              // keys of the factor classes of the pass, back to back:
         std::vector<int64_t> fkey_at;           //   class c: fkey[fkey_at[c]] = arity | symmetric << 8, then own colour, then argument colours
         Table vt, ft;
-        if (!vt.reserve(n_vars) || !ft.reserve(n_fac)) return -4;
+        if (!vt.reserve(1024) || !ft.reserve(1024)) return -4;
 
         // dense start colouring, order of first appearance
         int64_t n_classes = 0;
@@ -127,6 +152,8 @@ extern "C" int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour,
             }
             n_classes = static_cast<int64_t>(label.size());
             vcol.swap(vnew);
+            // the refinement has at least as many classes as the start: size the tables for that
+            if (!vt.reserve(2 * n_classes) || !ft.reserve(2 * n_classes)) return -4;
         }
 
         int64_t before = -1;
