@@ -540,6 +540,10 @@ class DeviceEngine:
             self._graphs[key] = graph
         return graph
 
+    def synchronize(self):
+        """Wait for everything this engine has launched (timing probes)."""
+        torch.cuda.synchronize(self.device)
+
     def iterate(self, n, lr, sgd=False):
         """``n`` Jacobi iterations: all gradients at the old parameters, then the step."""
         n = int(n)

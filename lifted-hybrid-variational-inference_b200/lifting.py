@@ -21,6 +21,7 @@ on the object-graph twins of the generators.
 """
 from __future__ import annotations
 
+import time
 from collections import Counter
 from dataclasses import dataclass, field
 
@@ -965,18 +966,37 @@ class C2FArrayVI:
         d = epsilon * self.update_obs_its / (iteration - self.output_its)
         epsilon -= d
         self.history = []
+        self.timing = {"split": 0.0, "refine": 0.0, "lower": 0.0, "upload": 0.0, "iterate": 0.0, "pull": 0.0}
+
+        self.timing_rounds = []           # the same per refinement round
+
+        def clock(phase, t0):
+            now = time.perf_counter()
+            self.timing[phase] += now - t0
+            self.timing_rounds[-1][phase] = now - t0
+            return now
         for _ in range(int(iteration / self.update_obs_its)):          # remainder dropped (H10)
+            self.timing_rounds.append({})
+            t = time.perf_counter()
             self._split_evidence(epsilon)
+            t = clock("split", t)
             self._refine()
+            t = clock("refine", t)
             epsilon = max(epsilon - d, self.min_obs_var)
             self.quotient = PartitionInfo(self.vcol, self.fcols)
             self.model = lower_partition(ga, self.vcol, self.fcols, self.K, self.T, ev_value=(self.ev_has, self.ev_val),
                                          gaussian_obs=self.gaussian_obs, min_obs_var=self.min_obs_var,
                                          degrees=self.degrees)
+            t = clock("lower", t)
             self.engine = self._make_engine(self.model)
             self._push(self.model, self.engine)
+            t = clock("upload", t)
             self.engine.iterate(self.update_obs_its, lr)
+            if hasattr(self.engine, "synchronize"):
+                self.engine.synchronize()
+            t = clock("iterate", t)
             self._pull(self.model, self.engine)
+            clock("pull", t)
             self.history.append((self.quotient.n_var_classes, None))
         return self
 

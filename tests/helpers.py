@@ -13,10 +13,12 @@ import specs
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-# Goldens added after the round's GPU budget was spent: pinned on the CPU side (three oracles, host
-# logic, lifting) and held back from the ``-m gpu`` parametrisations until they have run on a B200
-# once.  Empty this set to include them.
-GPU_PENDING = {"edge_mix"}
+# Goldens that have not run on a B200 yet are pinned on the CPU side only (three oracles, host logic,
+# lifting) and held back from the ``-m gpu`` parametrisations: name them here.  (``edge_mix`` was
+# held back for part of round 1 and passed its 8 GPU cases on the first run: profiles/r1_gpu_tests_s4.txt.)
+GPU_PENDING = set()
+if "LHVI_GPU_PENDING" in os.environ:             # e.g. LHVI_GPU_PENDING= to run them on a GPU box
+    GPU_PENDING = set(filter(None, os.environ["LHVI_GPU_PENDING"].split(",")))
 
 
 def golden_files(gpu=False):
