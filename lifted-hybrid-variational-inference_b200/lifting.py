@@ -159,13 +159,18 @@ def colour_passing(ga: GroundArrays, split_cont_evidence=True, max_sweeps=1000, 
     independent 64-bit multiset hashes (sums of mixed class ids, order-free like the
     reference's sorted tuple); a false merge needs a 128-bit collision."""
     nv = ga.n_vars
-    vcol = initial_colouring(ga, split_cont_evidence) if start is None else \
-        _rank_rows([np.asarray(start, dtype=np.int64)])
-
-    # blocks whose potentials compare equal are one colour to start with: rank them together
     pot_id = _potential_ids(ga.blocks)
     native = _lift_native.load() if use_native is None else (_lift_native.load() if use_native else None)
-    if native is not None and all(1 <= b.arity <= 16 for b in ga.blocks):
+    native_ok = native is not None and all(1 <= b.arity <= 16 for b in ga.blocks)
+    if start is None:
+        vcol = initial_colouring(ga, split_cont_evidence)
+    elif native_ok:
+        vcol = np.asarray(start, dtype=np.int64)         # any labels >= 0: the library makes them dense
+    else:
+        vcol = _rank_rows([np.asarray(start, dtype=np.int64)])
+
+    # blocks whose potentials compare equal are one colour to start with: rank them together
+    if native_ok:
         # the same passes in C++ with hash tables (include/lhvi_lift.h); ids in order of first appearance
         first_colour = {}
         blocks = [(b.args, getattr(b.potential, "symmetric", False),
@@ -371,10 +376,20 @@ def _first_index(labels, n):
     return first
 
 
-def class_stats(ga: GroundArrays, var_colour, ev_value=None, degrees=None):
+def class_stats(ga: GroundArrays, var_colour, ev_value=None, degrees=None, base=None):
     """Per variable class, as arrays: size, representative (smallest member), hidden flag, mean
     evidence value (k-means centroid where ``ev_value`` names one), population variance around
     the members' mean, representative degree, domain (``SuperRV`` ``:8-45``)."""
+    if base is not None:          # statistics of this very colouring without centroids: only the means change
+        st = dict(base)
+        ncls, mean = st["n"], st["mean"]
+        if isinstance(ev_value, tuple):
+            st["mean"] = np.where(ev_value[0][:ncls], ev_value[1][:ncls], mean)
+        elif ev_value:
+            st["mean"] = mean.copy()
+            ids = np.fromiter(ev_value.keys(), dtype=np.int64, count=len(ev_value))
+            st["mean"][ids] = np.fromiter(ev_value.values(), dtype=float, count=len(ev_value))
+        return st
     nv = ga.n_vars
     ncls = int(var_colour.max()) + 1 if nv else 0
     sizes = np.bincount(var_colour, minlength=ncls)
@@ -408,7 +423,7 @@ def slot_layout(K, dom, domains):
 
 
 def lower_partition(ga: GroundArrays, var_colour, factor_colours, K, T, *, ev_value=None,
-                    gaussian_obs=False, min_obs_var=0.0, degrees=None) -> lowering.LoweredModel:
+                    gaussian_obs=False, min_obs_var=0.0, degrees=None, stats=None) -> lowering.LoweredModel:
     """``lowering.lower_compressed(quotient(...))`` without an object per class: the record
     columns of the compressed model straight from the partition arrays (same groups, same
     records in the same order, same coefficient table -- ``tests/test_lifting.py`` compares the
@@ -423,7 +438,7 @@ def lower_partition(ga: GroundArrays, var_colour, factor_colours, K, T, *, ev_va
         raise ValueError(f"num_quadrature_points must be in 1..{lowering.MAX_T}, got {T}")
     HD, HC, EG, EC, ED = lowering.HD, lowering.HC, lowering.EG, lowering.EC, lowering.ED
     var_colour = np.asarray(var_colour, dtype=np.int64)
-    st = class_stats(ga, var_colour, ev_value, degrees)
+    st = class_stats(ga, var_colour, ev_value, degrees, base=stats)
     ncls, mean, variance = st["n"], st["mean"], st["variance"]
     cont_dom = np.array([bool(d.continuous) for d in ga.domains], dtype=bool)
     cls_cont = cont_dom[st["dom"]]
@@ -853,10 +868,12 @@ class C2FArrayVI:
         """Colour passing from the current classes; hidden pieces inherit (``:39-61``)."""
         old = self.vcol
         new, self.fcols, _ = colour_passing(self.ga, start=old, use_native=self.use_native)
-        # distinct (old class, new class) pairs: the new partition refines the old one
+        # (old class, new class) pairs: the new partition refines the old one, so every new class
+        # has one parent -- the old class of any of its members
         n_old, n_new = int(old.max()) + 1, int(new.max()) + 1
-        key = np.unique(old.astype(np.int64) * n_new + new)
-        pair = np.stack([key // n_new, key % n_new])
+        parent = old[_first_index(new, n_new)]
+        by_parent = np.argsort(parent, kind="stable")          # pairs ordered by (old, new)
+        pair = np.stack([parent[by_parent], by_parent])
         kids_of = np.bincount(pair[0], minlength=n_old)
         # carry the evidence book-keeping over to the new ids: every piece of a class k-means may
         # split may be split; a class that colour passing left whole keeps its k-means centroid as
@@ -876,7 +893,7 @@ class C2FArrayVI:
 
     def _layout(self, vcol):
         """Parameter slots of the hidden classes of a partition, in class order."""
-        st = class_stats(self.ga, vcol, degrees=self.degrees)
+        st = self.stats = class_stats(self.ga, vcol, degrees=self.degrees)     # of the colouring laid out last
         cls = np.flatnonzero(st["hidden"])
         kind, dim, off, n_param = slot_layout(self.K, st["dom"][cls], self.ga.domains)
         slot_of = np.full(st["n"], -1, dtype=np.int64)
@@ -986,7 +1003,7 @@ class C2FArrayVI:
             self.quotient = PartitionInfo(self.vcol, self.fcols)
             self.model = lower_partition(ga, self.vcol, self.fcols, self.K, self.T, ev_value=(self.ev_has, self.ev_val),
                                          gaussian_obs=self.gaussian_obs, min_obs_var=self.min_obs_var,
-                                         degrees=self.degrees)
+                                         degrees=self.degrees, stats=self.stats)
             t = clock("lower", t)
             self.engine = self._make_engine(self.model)
             self._push(self.model, self.engine)
