@@ -47,9 +47,26 @@ int32_t lhvi_lift_abi_version(void);
  *               of first appearance.
  *   sweeps_out  optional: number of sweeps done.
  * Returns the number of variable classes, or < 0: -1 null pointer / bad size, -2 bad arity,
- * -3 a variable index out of range, -4 out of memory. */
+ * -3 a variable index out of range, -4 out of memory, -6 more than 2^31 - 1 variables or factors.
+ * The gather / hash and scatter loops run on all OpenMP threads (OMP_NUM_THREADS); class ids are
+ * assigned by one thread in stream order, so the result does not depend on the thread count. */
 int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour, lhvi_lift_block *blocks,
                                  int32_t n_blocks, int32_t max_sweeps, int32_t *sweeps_out);
+
+/* The same on a prepared graph, for callers that refine the same ground graph again and again (the
+ * coarse-to-fine engine: once per block of ten iterations): `lhvi_lift_graph_create` validates the
+ * blocks, builds the incidence lists by variable and allocates the scratch buffers of the sweeps once;
+ * the argument arrays stay the caller's and must outlive the graph (`colour` of the blocks is ignored
+ * here).  `status` (optional) receives 0 or the negative code when NULL is returned.
+ * `lhvi_lift_graph_colour_passing` takes the factor colours per block in `factor_colour[b]`
+ * (in: initial colour, out: class ids) and otherwise behaves as `lhvi_lift_colour_passing`. */
+typedef struct lhvi_lift_graph lhvi_lift_graph;
+lhvi_lift_graph *lhvi_lift_graph_create(int64_t n_vars, const lhvi_lift_block *blocks, int32_t n_blocks,
+                                        int32_t *status);
+void lhvi_lift_graph_destroy(lhvi_lift_graph *graph);
+int64_t lhvi_lift_graph_colour_passing(lhvi_lift_graph *graph, int64_t *var_colour,
+                                       int64_t *const *factor_colour, int32_t max_sweeps,
+                                       int32_t *sweeps_out);
 
 /* Evidence split of the coarse-to-fine engine (CompressedGraph.split_evidence, :236-247, with
  * SuperRV.split_by_evidence, :78-130), repeated until nothing changes: every class flagged in

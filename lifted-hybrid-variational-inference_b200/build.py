@@ -82,7 +82,7 @@ def build_lift(force: bool = False) -> str:
     cxx = shutil.which("g++") or shutil.which("c++")
     if cxx is None:
         raise RuntimeError("g++ not found; liblhvi_lift.so cannot be built")
-    cmd = [cxx, "-O3", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wextra", "-I", INCLUDE,
+    cmd = [cxx, "-O3", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wextra", "-I", INCLUDE,
            LIFT_SRC, "-o", LIFT_LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

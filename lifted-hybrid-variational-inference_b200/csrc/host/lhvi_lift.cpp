@@ -6,6 +6,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -86,6 +90,10 @@ struct Table {
 
 constexpr int64_t AHEAD = 16;       // items whose table slot / gathered operands are prefetched ahead
 
+struct Mixed {
+    uint64_t m1, m2;
+};
+
 struct VarKey {
     int64_t colour;
     uint64_t h1, h2;
@@ -117,31 +125,117 @@ extern "C" int64_t lhvi_lift_rank64(const uint64_t *key, int64_t n, int64_t *ids
     return static_cast<int64_t>(key_of_class.size());
 }
 
-extern "C" int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour, lhvi_lift_block *blocks,
-                                            int32_t n_blocks, int32_t max_sweeps, int32_t *sweeps_out) {
-    if (n_vars < 0 || n_blocks < 0 || (n_vars > 0 && !var_colour) || (n_blocks > 0 && !blocks)) return -1;
+// A ground graph prepared for repeated colour passing: validated blocks, incidences by variable and
+// the scratch buffers of the sweeps.  The argument arrays stay the caller's and must outlive it.
+struct lhvi_lift_graph {
+    int64_t n_vars = 0, n_fac = 0;
+    std::vector<lhvi_lift_block> blocks;            // colour pointers are set per call
+    std::vector<int64_t> foff, koff, inc_ptr;
+    std::vector<int32_t> inc_fac, key32, fkey;
+    std::vector<int64_t> fkey_at, vcol, vnew;
+    std::vector<uint64_t> hash64, H1, H2;
+    std::vector<Mixed> mixed;
+    std::vector<VarKey> vkey;
+    Table vt, ft;
+};
+
+extern "C" lhvi_lift_graph *lhvi_lift_graph_create(int64_t n_vars, const lhvi_lift_block *blocks_in, int32_t n_blocks,
+                                                   int32_t *status) {
+    auto fail = [&](int32_t code) {
+        if (status) *status = code;
+        return static_cast<lhvi_lift_graph *>(nullptr);
+    };
+    if (n_vars < 0 || n_blocks < 0 || (n_blocks > 0 && !blocks_in)) return fail(-1);
     int64_t n_fac = 0;
     for (int32_t b = 0; b < n_blocks; ++b) {
-        const lhvi_lift_block &B = blocks[b];
-        if (B.n < 0 || (B.n > 0 && (!B.args || !B.colour))) return -1;
-        if (B.arity < 1 || B.arity > LHVI_LIFT_MAX_ARITY) return -2;
-        for (int64_t i = 0; i < B.n * B.arity; ++i)
-            if (B.args[i] < 0 || B.args[i] >= n_vars) return -3;
+        const lhvi_lift_block &B = blocks_in[b];
+        if (B.n < 0 || (B.n > 0 && !B.args)) return fail(-1);
+        if (B.arity < 1 || B.arity > LHVI_LIFT_MAX_ARITY) return fail(-2);
+        int bad = 0;
+        const int64_t total = B.n * B.arity;
+#pragma omp parallel for schedule(static) reduction(| : bad) if (total > 65536)
+        for (int64_t i = 0; i < total; ++i) bad |= (B.args[i] < 0 || B.args[i] >= n_vars);
+        if (bad) return fail(-3);
         n_fac += B.n;
     }
+    if (n_vars > INT32_MAX || n_fac > INT32_MAX) return fail(-6);       // class ids are keyed in 32 bits
+    lhvi_lift_graph *g = nullptr;
     try {
-        std::vector<int64_t> vcol(var_colour, var_colour + n_vars), vnew(static_cast<size_t>(n_vars), 0);
-        std::vector<uint64_t> H1(static_cast<size_t>(n_vars), 0), H2(static_cast<size_t>(n_vars), 0);
-        std::vector<VarKey> vkey;               // key of every variable class of the pass, by class id
-        std::vector<int64_t> fkey;              // keys of the factor classes of the pass, back to back:
-        std::vector<int64_t> fkey_at;           //   class c: fkey[fkey_at[c]] = arity | symmetric << 8, then own colour, then argument colours
-        Table vt, ft;
-        if (!vt.reserve(1024) || !ft.reserve(1024)) return -4;
+        g = new lhvi_lift_graph();
+        g->n_vars = n_vars;
+        g->n_fac = n_fac;
+        g->blocks.assign(blocks_in, blocks_in + n_blocks);
+        g->foff.assign(static_cast<size_t>(n_blocks) + 1, 0);
+        g->koff.assign(static_cast<size_t>(n_blocks) + 1, 0);
+        for (int32_t b = 0; b < n_blocks; ++b) {
+            g->foff[b + 1] = g->foff[b] + blocks_in[b].n;
+            g->koff[b + 1] = g->koff[b] + blocks_in[b].n * (blocks_in[b].arity + 1);
+        }
+        // incidences by variable (one entry per argument position)
+        g->inc_ptr.assign(static_cast<size_t>(n_vars) + 1, 0);
+        for (int32_t b = 0; b < n_blocks; ++b) {
+            const int64_t total = blocks_in[b].n * blocks_in[b].arity;
+            for (int64_t i = 0; i < total; ++i) ++g->inc_ptr[blocks_in[b].args[i] + 1];
+        }
+        for (int64_t v = 0; v < n_vars; ++v) g->inc_ptr[v + 1] += g->inc_ptr[v];
+        g->inc_fac.resize(static_cast<size_t>(g->inc_ptr[n_vars]));
+        {
+            std::vector<int64_t> fill(g->inc_ptr.begin(), g->inc_ptr.end() - 1);
+            for (int32_t b = 0; b < n_blocks; ++b) {
+                const lhvi_lift_block &B = blocks_in[b];
+                for (int64_t i = 0; i < B.n; ++i)
+                    for (int32_t j = 0; j < B.arity; ++j)
+                        g->inc_fac[fill[B.args[i * B.arity + j]]++] = static_cast<int32_t>(g->foff[b] + i);
+            }
+        }
+        g->mixed.resize(static_cast<size_t>(n_fac));
+        g->key32.resize(static_cast<size_t>(g->koff[n_blocks]));
+        g->hash64.resize(static_cast<size_t>(n_fac));
+        g->vcol.resize(static_cast<size_t>(n_vars));
+        g->vnew.resize(static_cast<size_t>(n_vars));
+        g->H1.resize(static_cast<size_t>(n_vars));
+        g->H2.resize(static_cast<size_t>(n_vars));
+        if (!g->vt.reserve(1024) || !g->ft.reserve(1024)) throw std::bad_alloc();
+    } catch (const std::bad_alloc &) {
+        delete g;
+        return fail(-4);
+    }
+    if (status) *status = 0;
+    return g;
+}
 
+extern "C" void lhvi_lift_graph_destroy(lhvi_lift_graph *g) { delete g; }
+
+extern "C" int64_t lhvi_lift_graph_colour_passing(lhvi_lift_graph *g, int64_t *var_colour, int64_t *const *factor_colour,
+                                                  int32_t max_sweeps, int32_t *sweeps_out) {
+    if (!g || (g->n_vars > 0 && !var_colour) || (!g->blocks.empty() && !factor_colour)) return -1;
+    const int64_t n_vars = g->n_vars;
+    const int32_t n_blocks = static_cast<int32_t>(g->blocks.size());
+    for (int32_t b = 0; b < n_blocks; ++b) {
+        lhvi_lift_block &B = g->blocks[b];
+        B.colour = factor_colour[b];
+        if (B.n > 0 && !B.colour) return -1;
+        int bad = 0;
+        for (int64_t i = 0; i < B.n; ++i) bad |= (B.colour[i] < 0 || B.colour[i] > INT32_MAX);
+        if (bad) return -1;
+    }
+    for (int64_t v = 0; v < n_vars; ++v)
+        if (var_colour[v] < 0) return -1;
+    lhvi_lift_block *blocks = g->blocks.data();
+    std::vector<int64_t> &foff = g->foff, &koff = g->koff, &inc_ptr = g->inc_ptr, &fkey_at = g->fkey_at;
+    std::vector<int64_t> &vcol = g->vcol, &vnew = g->vnew;
+    std::vector<int32_t> &inc_fac = g->inc_fac, &key32 = g->key32, &fkey = g->fkey;
+    std::vector<uint64_t> &hash64 = g->hash64, &H1 = g->H1, &H2 = g->H2;
+    std::vector<Mixed> &mixed = g->mixed;
+    std::vector<VarKey> &vkey = g->vkey;
+    Table &vt = g->vt, &ft = g->ft;
+    try {
+        std::copy(var_colour, var_colour + n_vars, vcol.begin());
         // dense start colouring, order of first appearance
         int64_t n_classes = 0;
         {
             std::vector<int64_t> label;
+            if (!vt.reserve(1024)) return -4;       // small again after a fine partition: coarse ones stay in cache
             for (int64_t v = 0; v < n_vars; ++v) {
                 int64_t c0 = vcol[v];
                 vnew[v] = vt.find_or_insert(mix(static_cast<uint64_t>(c0), 1), [&](int64_t c) { return label[c] == c0; },
@@ -158,74 +252,90 @@ extern "C" int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour,
 
         int64_t before = -1;
         int32_t sweeps = 0;
+        const bool timing = std::getenv("LHVI_LIFT_TIMING") != nullptr;
+        double t_gather = 0, t_lookup = 0, t_scatter = 0, t_vars = 0;
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         while (before != n_classes && sweeps < max_sweeps) {
             before = n_classes;
             ++sweeps;
             // ---- factors: (own class, classes of the arguments; sorted for a symmetric potential)
+            // (1) all threads: gather every factor's key (32-bit ids) and hash it -- the random reads;
+            // (2) one thread: look the keys up in stream order, so class ids stay in order of first
+            //     appearance whatever the thread count.
             ft.clear();
             fkey.clear();
             fkey_at.clear();
             for (int32_t b = 0; b < n_blocks; ++b) {
                 lhvi_lift_block &B = blocks[b];
-                const int32_t arity = B.arity;
-                int64_t mine[LHVI_LIFT_MAX_ARITY + 2];
-                mine[0] = arity | (B.symmetric ? 256 : 0);
-                // chunks of AHEAD factors: gather the keys and hashes (prefetching the argument
-                // colours of the next chunk), prefetch the table slots, then look them up
-                int64_t keys[AHEAD][LHVI_LIFT_MAX_ARITY + 2];
-                uint64_t hs[AHEAD];
-                for (int64_t i0 = 0; i0 < B.n; i0 += AHEAD) {
-                    const int64_t m = std::min<int64_t>(AHEAD, B.n - i0);
-                    if (i0 + AHEAD < B.n) {
-                        const int64_t *nx = B.args + (i0 + AHEAD) * arity;
-                        const int64_t cnt = std::min<int64_t>(AHEAD, B.n - i0 - AHEAD) * arity;
-                        for (int64_t q = 0; q < cnt; ++q) __builtin_prefetch(&vcol[nx[q]], 0, 1);
-                    }
-                    for (int64_t r = 0; r < m; ++r) {
-                        const int64_t *a = B.args + (i0 + r) * arity;
-                        int64_t *k = keys[r];
-                        k[0] = mine[0];
-                        k[1] = B.colour[i0 + r];
-                        for (int32_t j = 0; j < arity; ++j) k[2 + j] = vcol[a[j]];
-                        if (B.symmetric) std::sort(k + 2, k + 2 + arity);
-                        uint64_t h = mix(static_cast<uint64_t>(k[1]), 0x452821E638D01377ull + static_cast<uint64_t>(k[0]));
-                        for (int32_t j = 0; j < arity; ++j) h = mix(h ^ static_cast<uint64_t>(k[2 + j]), 0xBE5466CF34E90C6Cull);
-                        hs[r] = h;
-                        ft.prefetch(h);
-                    }
-                    for (int64_t r = 0; r < m; ++r) {
-                        const int64_t *k = keys[r];
-                        B.colour[i0 + r] = ft.find_or_insert(
-                            hs[r], [&](int64_t c) { return std::equal(k, k + 2 + arity, fkey.data() + fkey_at[c]); },
-                            [&]() {
-                                fkey_at.push_back(static_cast<int64_t>(fkey.size()));
-                                fkey.insert(fkey.end(), k, k + 2 + arity);
-                                return static_cast<int64_t>(fkey_at.size()) - 1;
-                            });
-                    }
+                const int32_t arity = B.arity, width = arity + 1;
+                const int32_t header = arity | (B.symmetric ? 256 : 0);
+                int32_t *keys = key32.data() + koff[b];
+                uint64_t *hs = hash64.data() + foff[b];
+                double t0 = now();
+#pragma omp parallel for schedule(static) if (B.n > 32768)
+                for (int64_t i = 0; i < B.n; ++i) {
+                    const int64_t *a = B.args + i * arity;
+                    int32_t *k = keys + i * width;
+                    k[0] = static_cast<int32_t>(B.colour[i]);
+                    for (int32_t j = 0; j < arity; ++j) k[1 + j] = static_cast<int32_t>(vcol[a[j]]);
+                    if (B.symmetric) std::sort(k + 1, k + 1 + arity);
+                    uint64_t h = mix(static_cast<uint64_t>(k[0]), 0x452821E638D01377ull + static_cast<uint64_t>(header));
+                    for (int32_t j = 0; j < arity; ++j) h = mix(h ^ static_cast<uint64_t>(k[1 + j]), 0xBE5466CF34E90C6Cull);
+                    hs[i] = h;
                 }
+                double t1 = now();
+                t_gather += t1 - t0;
+                for (int64_t i = 0; i < std::min<int64_t>(AHEAD, B.n); ++i) ft.prefetch(hs[i]);
+                for (int64_t i = 0; i < B.n; ++i) {
+                    if (i + AHEAD < B.n) ft.prefetch(hs[i + AHEAD]);
+                    const int32_t *k = keys + i * width;
+                    B.colour[i] = ft.find_or_insert(
+                        hs[i],
+                        [&](int64_t c) {
+                            const int32_t *q = fkey.data() + fkey_at[c];
+                            return q[0] == header && std::equal(k, k + width, q + 1);
+                        },
+                        [&]() {
+                            fkey_at.push_back(static_cast<int64_t>(fkey.size()));
+                            fkey.push_back(header);
+                            fkey.insert(fkey.end(), k, k + width);
+                            return static_cast<int64_t>(fkey_at.size()) - 1;
+                        });
+                }
+                t_lookup += now() - t1;
             }
-            // ---- variables: (own class, multiset of incident factor classes) through two 64-bit sums
-            std::fill(H1.begin(), H1.end(), 0);
-            std::fill(H2.begin(), H2.end(), 0);
+            double t2 = now();
+            // ---- variables: (own class, multiset of incident factor classes) through two 64-bit sums:
+            // every factor's two mixed class ids once, then every variable sums over its incidences
+            // (no atomics: a group-level variable with 10^5 incidences would serialise them)
             for (int32_t b = 0; b < n_blocks; ++b) {
                 const lhvi_lift_block &B = blocks[b];
-                const int64_t total = B.n * B.arity;
+                Mixed *out = mixed.data() + foff[b];
+#pragma omp parallel for schedule(static) if (B.n > 32768)
                 for (int64_t i = 0; i < B.n; ++i) {
                     uint64_t c = static_cast<uint64_t>(B.colour[i]);
-                    uint64_t m1 = mix(c, 0x243F6A8885A308D3ull), m2 = mix(c, 0x13198A2E03707344ull);
-                    const int64_t *a = B.args + i * B.arity;
-                    for (int32_t j = 0; j < B.arity; ++j) {
-                        const int64_t q = i * B.arity + j + 2 * AHEAD;
-                        if (q < total) {
-                            __builtin_prefetch(&H1[B.args[q]], 1, 1);
-                            __builtin_prefetch(&H2[B.args[q]], 1, 1);
-                        }
-                        H1[a[j]] += m1;
-                        H2[a[j]] += m2;
-                    }
+                    out[i] = Mixed{mix(c, 0x243F6A8885A308D3ull), mix(c, 0x13198A2E03707344ull)};
                 }
             }
+            {
+                const int64_t *ptr = inc_ptr.data();
+                const int32_t *inc = inc_fac.data();
+                const Mixed *mx = mixed.data();
+                uint64_t *h1 = H1.data(), *h2 = H2.data();
+#pragma omp parallel for schedule(dynamic, 2048) if (n_vars > 32768)
+                for (int64_t v = 0; v < n_vars; ++v) {
+                    uint64_t a1 = 0, a2 = 0;
+                    for (int64_t e = ptr[v]; e < ptr[v + 1]; ++e) {
+                        const Mixed &m = mx[inc[e]];
+                        a1 += m.m1;
+                        a2 += m.m2;
+                    }
+                    h1[v] = a1;
+                    h2[v] = a2;
+                }
+            }
+            double t3 = now();
+            t_scatter += t3 - t2;
             vt.clear();
             vkey.clear();
             auto var_hash = [&](int64_t v) {
@@ -244,13 +354,30 @@ extern "C" int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour,
             }
             n_classes = static_cast<int64_t>(vkey.size());
             vcol.swap(vnew);
+            t_vars += now() - t3;
         }
+        if (timing)
+            std::fprintf(stderr, "[lhvi_lift] %d sweeps: gather %.3f s, factor lookup %.3f s, scatter %.3f s, variable lookup %.3f s\n",
+                         sweeps, t_gather, t_lookup, t_scatter, t_vars);
         std::copy(vcol.begin(), vcol.end(), var_colour);
         if (sweeps_out) *sweeps_out = sweeps;
         return n_classes;
     } catch (const std::bad_alloc &) {
         return -4;
     }
+}
+
+extern "C" int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour, lhvi_lift_block *blocks,
+                                            int32_t n_blocks, int32_t max_sweeps, int32_t *sweeps_out) {
+    if (n_vars > 0 && !var_colour) return -1;
+    int32_t status = 0;
+    lhvi_lift_graph *g = lhvi_lift_graph_create(n_vars, blocks, n_blocks, &status);
+    if (!g) return status;
+    std::vector<int64_t *> colours(static_cast<size_t>(n_blocks));
+    for (int32_t b = 0; b < n_blocks; ++b) colours[b] = blocks[b].colour;
+    int64_t rc = lhvi_lift_graph_colour_passing(g, var_colour, colours.data(), max_sweeps, sweeps_out);
+    lhvi_lift_graph_destroy(g);
+    return rc;
 }
 
 // ---- evidence split ------------------------------------------------------------------------------

@@ -175,7 +175,7 @@ def colour_passing(ga: GroundArrays, split_cont_evidence=True, max_sweeps=1000, 
         first_colour = {}
         blocks = [(b.args, getattr(b.potential, "symmetric", False),
                    first_colour.setdefault((pid, b.arity), len(first_colour))) for b, pid in zip(ga.blocks, pot_id)]
-        return _lift_native.colour_passing(native, vcol, blocks, max_sweeps)
+        return _lift_native.colour_passing(native, vcol, blocks, max_sweeps, holder=ga)
     merged = {}
     for i, (b, pid) in enumerate(zip(ga.blocks, pot_id)):
         merged.setdefault((pid, b.arity), []).append(i)

@@ -422,3 +422,23 @@ def test_c2f_native_and_numpy_passes_give_the_same_run():
     pb, wb = b.ground_params()
     for v in pa:
         np.testing.assert_allclose(pa[v], pb[v], rtol=1e-8, atol=1e-10)
+
+
+def test_prepared_graph_is_reused_and_survives_copies():
+    """The native incidence lists are built once per ``GroundArrays`` and reused by later calls;
+    a deep copy of the arrays drops them and rebuilds on first use; replacing a block's
+    argument array invalidates them."""
+    import copy
+    ga = syn.relational_hybrid_arrays(200, 3, seed=4)
+    v1 = lifting.colour_passing(ga)[0]
+    g1 = ga._lift_graph
+    v2 = lifting.colour_passing(ga, start=lifting.initial_colouring(ga, split_cont_evidence=False))[0]
+    assert ga._lift_graph is g1
+    clone = copy.deepcopy(ga)
+    assert clone._lift_graph is None
+    np.testing.assert_array_equal(lifting.colour_passing(clone)[0], v1)
+    assert clone._lift_graph is not None and clone._lift_graph is not g1
+    ga.blocks[0].args = ga.blocks[0].args.copy()
+    np.testing.assert_array_equal(lifting.colour_passing(ga)[0], v1)
+    assert ga._lift_graph is not g1
+    assert _same_partition(v2, lifting.colour_passing(ga, split_cont_evidence=False)[0])
