@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--order", default="hub", choices=["hub", "entity"])
     ap.add_argument("--generic", action="store_true", help="force the generic kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c2f", action="store_true", help="skip the auxiliary coarse-to-fine figure")
     ap.add_argument("--cpu-sample-entities", type=int, default=200_000)
     return ap.parse_args()
 
@@ -255,6 +256,27 @@ def run_reference(a):
 
 # ---- our arm ------------------------------------------------------------------------------------
 
+def c2f_probe(a, iterations=50):
+    """Auxiliary figure beside the headline (not part of `value`): the coarse-to-fine engine
+    (C2FVarInference.py:301-352: evidence split, colour passing, re-lowering and upload between
+    blocks of ten iterations) over a tenth of the workload's entities through `lifting.C2FArrayVI`,
+    with the time of the host passes and of the device iterations."""
+    import lhvi_b200
+    lifting, syn = lhvi_b200.lifting, lhvi_b200.synthetic
+    entities = max(1000, min(100_000, a.entities // 10))
+    ga = syn.relational_hybrid_arrays(entities, a.groups, observed_frac=0.7, seed=0)
+    vi = lifting.C2FArrayVI(ga, a.K, a.T, dtype=a.dtype)
+    t0 = time.perf_counter()
+    vi.run(iterations, 0.05)
+    total = time.perf_counter() - t0
+    host = sum(vi.timing[k] for k in ("split", "refine", "lower"))
+    return {"engine": "C2FArrayVI", "ground_factors": ga.n_factors, "iterations": iterations, "rounds": len(vi.history),
+            "classes_per_round": [n for n, _ in vi.history], "records_last_round": vi.model.n_records,
+            "run_s": round(total, 4), "host_passes_s": round(host, 4), "upload_s": round(vi.timing["upload"], 4),
+            "device_iterations_s": round(vi.timing["iterate"], 4), "readback_s": round(vi.timing["pull"], 4),
+            "free_energy_finite": bool(np.isfinite(vi.free_energy()))}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -425,6 +447,11 @@ def run_ours(a):
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(a, model.n_records).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
+        if world == 1 and not a.no_c2f:
+            try:
+                line["c2f"] = c2f_probe(a)
+            except Exception as exc:            # an auxiliary figure must not cost the bench line
+                line["c2f"] = {"error": repr(exc)[:300]}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

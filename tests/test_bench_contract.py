@@ -40,3 +40,25 @@ def test_product_arm_fails_loudly_without_a_gpu():
     assert res.returncode != 0
     assert "no CPU fallback" in (res.stdout + res.stderr)
     assert not [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_c2f_figure_of_the_bench_line(monkeypatch):
+    """`bench.c2f_probe` (the auxiliary coarse-to-fine figure) with the numpy oracle standing in for
+    the device: keys, consistency of the phase times."""
+    import importlib.util
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import lhvi_b200
+    from oracle_engine import OracleEngine
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(lhvi_b200.lifting.C2FArrayVI, "_make_engine",
+                        lambda self, model: OracleEngine(model, var_threshold=0.1))
+    a = types.SimpleNamespace(entities=3000, groups=3, K=2, T=3, dtype="float64")
+    out = bench.c2f_probe(a, iterations=20)
+    assert out["rounds"] == 2 and out["iterations"] == 20 and out["free_energy_finite"]
+    assert out["ground_factors"] == 1000 * 3 + 1000 + 3 * 2 or out["ground_factors"] > 3000
+    assert out["classes_per_round"] == sorted(out["classes_per_round"])
+    parts = out["host_passes_s"] + out["upload_s"] + out["device_iterations_s"] + out["readback_s"]
+    assert 0 < parts <= out["run_s"] * 1.001
