@@ -48,8 +48,10 @@ int32_t lhvi_lift_abi_version(void);
  *   sweeps_out  optional: number of sweeps done.
  * Returns the number of variable classes, or < 0: -1 null pointer / bad size, -2 bad arity,
  * -3 a variable index out of range, -4 out of memory, -6 more than 2^31 - 1 variables or factors.
- * The gather / hash and scatter loops run on all OpenMP threads (OMP_NUM_THREADS); class ids are
- * assigned by one thread in stream order, so the result does not depend on the thread count. */
+ * The passes run on all OpenMP threads (OMP_NUM_THREADS): the hash space of the keys is split over
+ * the threads, every thread keeps the first item of each key of its share, and class ids are handed
+ * out in one streaming pass in order of first appearance -- the result does not depend on the thread
+ * count. */
 int64_t lhvi_lift_colour_passing(int64_t n_vars, int64_t *var_colour, lhvi_lift_block *blocks,
                                  int32_t n_blocks, int32_t max_sweeps, int32_t *sweeps_out);
 

@@ -12,6 +12,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <vector>
 
 namespace {
@@ -94,10 +97,54 @@ struct Mixed {
     uint64_t m1, m2;
 };
 
-struct VarKey {
-    int64_t colour;
-    uint64_t h1, h2;
-};
+// Dense ids, in order of first appearance, of n items given their hashes and an exact equality
+// `same(i, j)` on item indices.  The hash space is split over the OpenMP threads: every thread scans
+// all hashes and keeps, in a private table, the first item of every key of its share; ids are then
+// handed out in one streaming pass, so they do not depend on the number of threads.
+// `first` is scratch (n entries); returns the number of distinct keys or -4.
+template <class Same>
+int64_t rank_first(int64_t n, const uint64_t *hs, Same same, std::vector<int32_t> &first, int64_t *ids,
+                   std::vector<Table> &tables, int64_t expect_classes) {
+    int threads = 1;
+#ifdef _OPENMP
+    if (n > 65536) threads = std::max(1, omp_get_max_threads());
+#endif
+    if (static_cast<int>(tables.size()) < threads) tables.resize(static_cast<size_t>(threads));
+    first.resize(static_cast<size_t>(n));
+    int oom = 0;
+    int32_t *fst = first.data();
+#pragma omp parallel num_threads(threads)
+    {
+        int t = 0, nt = 1;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+        nt = omp_get_num_threads();
+#endif
+        Table &tb = tables[static_cast<size_t>(t)];
+        try {
+            if (!tb.reserve(2 * expect_classes / nt + 1024)) throw std::bad_alloc();
+            const uint64_t unt = static_cast<uint64_t>(nt), ut = static_cast<uint64_t>(t);
+            for (int64_t i = 0; i < n; ++i) {
+                if (i + AHEAD < n) {
+                    const uint64_t hn = hs[i + AHEAD];
+                    if (nt == 1 || (((hn >> 40) * unt) >> 24) == ut) tb.prefetch(hn);
+                }
+                const uint64_t h = hs[i];
+                if (nt > 1 && (((h >> 40) * unt) >> 24) != ut) continue;
+                fst[i] = static_cast<int32_t>(tb.find_or_insert(
+                    h, [&](int64_t c) { return same(c, i); }, [&]() { return i; }));
+            }
+        } catch (const std::bad_alloc &) {
+#pragma omp atomic write
+            oom = 1;
+        }
+    }
+    if (oom) return -4;
+    int64_t next = 0;
+    for (int64_t i = 0; i < n; ++i) ids[i] = fst[i] == i ? next++ : ids[fst[i]];
+    return next;
+}
+
 
 }  // namespace
 
@@ -105,38 +152,30 @@ extern "C" int32_t lhvi_lift_abi_version(void) { return LHVI_LIFT_ABI_VERSION; }
 
 extern "C" int64_t lhvi_lift_rank64(const uint64_t *key, int64_t n, int64_t *ids) {
     if (n < 0 || (n > 0 && (!key || !ids))) return -1;
-    Table t;
-    if (!t.reserve(1024)) return -4;
-    std::vector<uint64_t> key_of_class;
+    if (n > INT32_MAX) return -6;
     try {
-        key_of_class.reserve(static_cast<size_t>(n));
-        for (int64_t i = 0; i < n; ++i) {
-            uint64_t k = key[i];
-            ids[i] = t.find_or_insert(mix(k, 0x243F6A8885A308D3ull),
-                                      [&](int64_t c) { return key_of_class[c] == k; },
-                                      [&]() {
-                                          key_of_class.push_back(k);
-                                          return static_cast<int64_t>(key_of_class.size()) - 1;
-                                      });
-        }
+        std::vector<uint64_t> hs(static_cast<size_t>(n));
+#pragma omp parallel for schedule(static) if (n > 65536)
+        for (int64_t i = 0; i < n; ++i) hs[i] = mix(key[i], 0x243F6A8885A308D3ull);
+        std::vector<int32_t> first;
+        std::vector<Table> tables;
+        return rank_first(n, hs.data(), [&](int64_t a, int64_t b) { return key[a] == key[b]; }, first, ids, tables, 1024);
     } catch (const std::bad_alloc &) {
         return -4;
     }
-    return static_cast<int64_t>(key_of_class.size());
 }
 
 // A ground graph prepared for repeated colour passing: validated blocks, incidences by variable and
 // the scratch buffers of the sweeps.  The argument arrays stay the caller's and must outlive it.
 struct lhvi_lift_graph {
-    int64_t n_vars = 0, n_fac = 0;
+    int64_t n_vars = 0, n_fac = 0, width = 2;
     std::vector<lhvi_lift_block> blocks;            // colour pointers are set per call
     std::vector<int64_t> foff, koff, inc_ptr;
-    std::vector<int32_t> inc_fac, key32, fkey;
-    std::vector<int64_t> fkey_at, vcol, vnew;
-    std::vector<uint64_t> hash64, H1, H2;
+    std::vector<int32_t> inc_fac, key32, first, header;
+    std::vector<int64_t> vcol, vnew, fid;
+    std::vector<uint64_t> hash64, vhash, H1, H2;
     std::vector<Mixed> mixed;
-    std::vector<VarKey> vkey;
-    Table vt, ft;
+    std::vector<Table> tables;                      // one per thread
 };
 
 extern "C" lhvi_lift_graph *lhvi_lift_graph_create(int64_t n_vars, const lhvi_lift_block *blocks_in, int32_t n_blocks,
@@ -189,13 +228,18 @@ extern "C" lhvi_lift_graph *lhvi_lift_graph_create(int64_t n_vars, const lhvi_li
             }
         }
         g->mixed.resize(static_cast<size_t>(n_fac));
-        g->key32.resize(static_cast<size_t>(g->koff[n_blocks]));
+        g->width = 2;
+        for (int32_t b = 0; b < n_blocks; ++b) g->width = std::max<int64_t>(g->width, blocks_in[b].arity + 2);
+        g->key32.assign(static_cast<size_t>(n_fac * g->width), 0);          // padding stays zero
         g->hash64.resize(static_cast<size_t>(n_fac));
         g->vcol.resize(static_cast<size_t>(n_vars));
         g->vnew.resize(static_cast<size_t>(n_vars));
         g->H1.resize(static_cast<size_t>(n_vars));
         g->H2.resize(static_cast<size_t>(n_vars));
-        if (!g->vt.reserve(1024) || !g->ft.reserve(1024)) throw std::bad_alloc();
+        g->vhash.resize(static_cast<size_t>(n_vars));
+        g->fid.resize(static_cast<size_t>(n_fac));
+        g->header.resize(static_cast<size_t>(n_blocks));
+        for (int32_t b = 0; b < n_blocks; ++b) g->header[b] = blocks_in[b].arity | (blocks_in[b].symmetric ? 256 : 0);
     } catch (const std::bad_alloc &) {
         delete g;
         return fail(-4);
@@ -222,35 +266,31 @@ extern "C" int64_t lhvi_lift_graph_colour_passing(lhvi_lift_graph *g, int64_t *v
     for (int64_t v = 0; v < n_vars; ++v)
         if (var_colour[v] < 0) return -1;
     lhvi_lift_block *blocks = g->blocks.data();
-    std::vector<int64_t> &foff = g->foff, &koff = g->koff, &inc_ptr = g->inc_ptr, &fkey_at = g->fkey_at;
-    std::vector<int64_t> &vcol = g->vcol, &vnew = g->vnew;
-    std::vector<int32_t> &inc_fac = g->inc_fac, &key32 = g->key32, &fkey = g->fkey;
-    std::vector<uint64_t> &hash64 = g->hash64, &H1 = g->H1, &H2 = g->H2;
+    std::vector<int64_t> &foff = g->foff, &inc_ptr = g->inc_ptr;
+    std::vector<int64_t> &vcol = g->vcol, &vnew = g->vnew, &fid = g->fid;
+    std::vector<int32_t> &inc_fac = g->inc_fac, &key32 = g->key32, &header = g->header;
+    std::vector<uint64_t> &hash64 = g->hash64, &vhash = g->vhash, &H1 = g->H1, &H2 = g->H2;
     std::vector<Mixed> &mixed = g->mixed;
-    std::vector<VarKey> &vkey = g->vkey;
-    Table &vt = g->vt, &ft = g->ft;
+    const int64_t n_fac = g->n_fac;
     try {
-        std::copy(var_colour, var_colour + n_vars, vcol.begin());
         // dense start colouring, order of first appearance
         int64_t n_classes = 0;
         {
-            std::vector<int64_t> label;
-            if (!vt.reserve(1024)) return -4;       // small again after a fine partition: coarse ones stay in cache
-            for (int64_t v = 0; v < n_vars; ++v) {
-                int64_t c0 = vcol[v];
-                vnew[v] = vt.find_or_insert(mix(static_cast<uint64_t>(c0), 1), [&](int64_t c) { return label[c] == c0; },
-                                            [&]() {
-                                                label.push_back(c0);
-                                                return static_cast<int64_t>(label.size()) - 1;
-                                            });
-            }
-            n_classes = static_cast<int64_t>(label.size());
-            vcol.swap(vnew);
-            // the refinement has at least as many classes as the start: size the tables for that
-            if (!vt.reserve(2 * n_classes) || !ft.reserve(2 * n_classes)) return -4;
+            uint64_t *vh = vhash.data();
+#pragma omp parallel for schedule(static) if (n_vars > 65536)
+            for (int64_t v = 0; v < n_vars; ++v) vh[v] = mix(static_cast<uint64_t>(var_colour[v]), 1);
+            n_classes = rank_first(n_vars, vh, [&](int64_t a, int64_t b) { return var_colour[a] == var_colour[b]; },
+                                   g->first, vcol.data(), g->tables, 1024);
+            if (n_classes < 0) return n_classes;
         }
+        const int64_t W = g->width;          // key row: arity | symmetric << 8, own class, argument classes, zero padding
+        auto same_factor = [&](int64_t fa, int64_t fb) {
+            const int32_t *ka = key32.data() + fa * W, *kb = key32.data() + fb * W;
+            return std::equal(ka, ka + W, kb);
+        };
+        auto same_variable = [&](int64_t a, int64_t b) { return vcol[a] == vcol[b] && H1[a] == H1[b] && H2[a] == H2[b]; };
 
-        int64_t before = -1;
+        int64_t before = -1, n_fclasses = 1024;
         int32_t sweeps = 0;
         const bool timing = std::getenv("LHVI_LIFT_TIMING") != nullptr;
         double t_gather = 0, t_lookup = 0, t_scatter = 0, t_vars = 0;
@@ -258,101 +298,67 @@ extern "C" int64_t lhvi_lift_graph_colour_passing(lhvi_lift_graph *g, int64_t *v
         while (before != n_classes && sweeps < max_sweeps) {
             before = n_classes;
             ++sweeps;
-            // ---- factors: (own class, classes of the arguments; sorted for a symmetric potential)
-            // (1) all threads: gather every factor's key (32-bit ids) and hash it -- the random reads;
-            // (2) one thread: look the keys up in stream order, so class ids stay in order of first
-            //     appearance whatever the thread count.
-            ft.clear();
-            fkey.clear();
-            fkey_at.clear();
+            // ---- factors: (own class, classes of the arguments; sorted for a symmetric potential):
+            // gather every factor's key (32-bit ids) and hash it, then rank the keys
+            double t0 = now();
             for (int32_t b = 0; b < n_blocks; ++b) {
                 lhvi_lift_block &B = blocks[b];
-                const int32_t arity = B.arity, width = arity + 1;
-                const int32_t header = arity | (B.symmetric ? 256 : 0);
-                int32_t *keys = key32.data() + koff[b];
+                const int32_t arity = B.arity, hdr = header[b];
+                int32_t *keys = key32.data() + foff[b] * W;
                 uint64_t *hs = hash64.data() + foff[b];
-                double t0 = now();
 #pragma omp parallel for schedule(static) if (B.n > 32768)
                 for (int64_t i = 0; i < B.n; ++i) {
                     const int64_t *a = B.args + i * arity;
-                    int32_t *k = keys + i * width;
-                    k[0] = static_cast<int32_t>(B.colour[i]);
-                    for (int32_t j = 0; j < arity; ++j) k[1 + j] = static_cast<int32_t>(vcol[a[j]]);
-                    if (B.symmetric) std::sort(k + 1, k + 1 + arity);
-                    uint64_t h = mix(static_cast<uint64_t>(k[0]), 0x452821E638D01377ull + static_cast<uint64_t>(header));
-                    for (int32_t j = 0; j < arity; ++j) h = mix(h ^ static_cast<uint64_t>(k[1 + j]), 0xBE5466CF34E90C6Cull);
+                    int32_t *k = keys + i * W;
+                    k[0] = hdr;
+                    k[1] = static_cast<int32_t>(B.colour[i]);
+                    for (int32_t j = 0; j < arity; ++j) k[2 + j] = static_cast<int32_t>(vcol[a[j]]);
+                    if (B.symmetric) std::sort(k + 2, k + 2 + arity);
+                    uint64_t h = mix(static_cast<uint64_t>(k[1]), 0x452821E638D01377ull + static_cast<uint64_t>(hdr));
+                    for (int32_t j = 0; j < arity; ++j) h = mix(h ^ static_cast<uint64_t>(k[2 + j]), 0xBE5466CF34E90C6Cull);
                     hs[i] = h;
                 }
-                double t1 = now();
-                t_gather += t1 - t0;
-                for (int64_t i = 0; i < std::min<int64_t>(AHEAD, B.n); ++i) ft.prefetch(hs[i]);
-                for (int64_t i = 0; i < B.n; ++i) {
-                    if (i + AHEAD < B.n) ft.prefetch(hs[i + AHEAD]);
-                    const int32_t *k = keys + i * width;
-                    B.colour[i] = ft.find_or_insert(
-                        hs[i],
-                        [&](int64_t c) {
-                            const int32_t *q = fkey.data() + fkey_at[c];
-                            return q[0] == header && std::equal(k, k + width, q + 1);
-                        },
-                        [&]() {
-                            fkey_at.push_back(static_cast<int64_t>(fkey.size()));
-                            fkey.push_back(header);
-                            fkey.insert(fkey.end(), k, k + width);
-                            return static_cast<int64_t>(fkey_at.size()) - 1;
-                        });
-                }
-                t_lookup += now() - t1;
             }
+            double t1 = now();
+            t_gather += t1 - t0;
+            n_fclasses = rank_first(n_fac, hash64.data(), same_factor, g->first, fid.data(), g->tables, n_fclasses);
+            if (n_fclasses < 0) return n_fclasses;
+            for (int32_t b = 0; b < n_blocks; ++b)
+                std::copy(fid.begin() + foff[b], fid.begin() + foff[b + 1], blocks[b].colour);
             double t2 = now();
+            t_lookup += t2 - t1;
             // ---- variables: (own class, multiset of incident factor classes) through two 64-bit sums:
             // every factor's two mixed class ids once, then every variable sums over its incidences
             // (no atomics: a group-level variable with 10^5 incidences would serialise them)
-            for (int32_t b = 0; b < n_blocks; ++b) {
-                const lhvi_lift_block &B = blocks[b];
-                Mixed *out = mixed.data() + foff[b];
-#pragma omp parallel for schedule(static) if (B.n > 32768)
-                for (int64_t i = 0; i < B.n; ++i) {
-                    uint64_t c = static_cast<uint64_t>(B.colour[i]);
-                    out[i] = Mixed{mix(c, 0x243F6A8885A308D3ull), mix(c, 0x13198A2E03707344ull)};
-                }
-            }
             {
+                Mixed *out = mixed.data();
+                const int64_t *id = fid.data();
+#pragma omp parallel for schedule(static) if (n_fac > 32768)
+                for (int64_t f = 0; f < n_fac; ++f) {
+                    uint64_t c = static_cast<uint64_t>(id[f]);
+                    out[f] = Mixed{mix(c, 0x243F6A8885A308D3ull), mix(c, 0x13198A2E03707344ull)};
+                }
                 const int64_t *ptr = inc_ptr.data();
                 const int32_t *inc = inc_fac.data();
-                const Mixed *mx = mixed.data();
-                uint64_t *h1 = H1.data(), *h2 = H2.data();
+                const int64_t *vc = vcol.data();
+                uint64_t *h1 = H1.data(), *h2 = H2.data(), *vh = vhash.data();
 #pragma omp parallel for schedule(dynamic, 2048) if (n_vars > 32768)
                 for (int64_t v = 0; v < n_vars; ++v) {
                     uint64_t a1 = 0, a2 = 0;
                     for (int64_t e = ptr[v]; e < ptr[v + 1]; ++e) {
-                        const Mixed &m = mx[inc[e]];
+                        const Mixed &m = out[inc[e]];
                         a1 += m.m1;
                         a2 += m.m2;
                     }
                     h1[v] = a1;
                     h2[v] = a2;
+                    vh[v] = mix(static_cast<uint64_t>(vc[v]), 0xA4093822299F31D0ull) + a1 + mix(a2, 0x082EFA98EC4E6C89ull);
                 }
             }
             double t3 = now();
             t_scatter += t3 - t2;
-            vt.clear();
-            vkey.clear();
-            auto var_hash = [&](int64_t v) {
-                return mix(static_cast<uint64_t>(vcol[v]), 0xA4093822299F31D0ull) + H1[v] + mix(H2[v], 0x082EFA98EC4E6C89ull);
-            };
-            for (int64_t v = 0; v < std::min<int64_t>(AHEAD, n_vars); ++v) vt.prefetch(var_hash(v));
-            for (int64_t v = 0; v < n_vars; ++v) {
-                if (v + AHEAD < n_vars) vt.prefetch(var_hash(v + AHEAD));
-                VarKey k{vcol[v], H1[v], H2[v]};
-                vnew[v] = vt.find_or_insert(
-                    var_hash(v), [&](int64_t c) { return vkey[c].colour == k.colour && vkey[c].h1 == k.h1 && vkey[c].h2 == k.h2; },
-                    [&]() {
-                        vkey.push_back(k);
-                        return static_cast<int64_t>(vkey.size()) - 1;
-                    });
-            }
-            n_classes = static_cast<int64_t>(vkey.size());
+            n_classes = rank_first(n_vars, vhash.data(), same_variable, g->first, vnew.data(), g->tables, n_classes);
+            if (n_classes < 0) return n_classes;
             vcol.swap(vnew);
             t_vars += now() - t3;
         }
