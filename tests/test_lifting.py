@@ -442,3 +442,33 @@ def test_prepared_graph_is_reused_and_survives_copies():
     np.testing.assert_array_equal(lifting.colour_passing(ga)[0], v1)
     assert ga._lift_graph is not g1
     assert _same_partition(v2, lifting.colour_passing(ga, split_cont_evidence=False)[0])
+
+
+def test_native_passes_do_not_depend_on_the_thread_count(tmp_path):
+    """Same class ids (not just the same partition) with 1, 3 and all OpenMP threads, on a model
+    large enough for the parallel paths (> 65 536 items)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "import lhvi_b200\n"
+        "ga = lhvi_b200.synthetic.relational_hybrid_arrays(30000, 4, seed=2)\n"
+        "v, f, s = lhvi_b200.lifting.colour_passing(ga, use_native=True)\n"
+        "r = lhvi_b200.lifting.colour_passing(ga, start=lhvi_b200.lifting.initial_colouring(ga, False), use_native=True)[0]\n"
+        "np.savez(sys.argv[1], v=v, f=np.concatenate(f), r=r, s=s)\n")
+    outs = []
+    for threads in ("1", "3", None):
+        env = dict(os.environ)
+        env.pop("OMP_NUM_THREADS", None)
+        if threads:
+            env["OMP_NUM_THREADS"] = threads
+        path = str(tmp_path / f"cp_{threads}.npz")
+        subprocess.run([sys.executable, "-c", script, path], check=True, env=env, timeout=300)
+        outs.append(dict(np.load(path)))
+    assert outs[0]["v"].max() > 1000
+    for other in outs[1:]:
+        for k in ("v", "f", "r", "s"):
+            np.testing.assert_array_equal(outs[0][k], other[k])
