@@ -188,6 +188,40 @@ def ring_xy(ns):
     return _graph(ns, X, fs)
 
 
+def hmln_demo(ns):
+    """The reference's paper-popularity demo at its own size (Demo/HMLN/DemoPaperPopularity.py with
+    Demo/Data/HMLN/GeneratorPaperPopularity.py: 300 papers x 10 topics, 3410 ground atoms, 3390
+    factors) and its own evidence file (Demo/Data/HMLN/0, copied to hmln_demo_evidence.json):
+    70 % of the popularities and about a third of the PaperIn atoms observed, the rest -- hidden
+    booleans next to hidden reals -- inferred.  BASELINE config 1's model."""
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    data = {tuple(k): v for k, v in json.load(open(os.path.join(here, "hmln_demo_evidence.json")))["evidence"]}
+    n_paper, n_topic = 300, 10
+    d_bool = ns.Domain((0, 1))
+    d_real = ns.Domain((-15, 15), continuous=True)
+    prior = ns.MLNPotential(lambda x: ns.eq_op(x[0], 1), w=0.3)
+    sess = ns.MLNPotential(lambda x: x[0] * ns.eq_op(x[1], x[2]), w=0.5)
+    link = ns.MLNPotential(lambda x: x[0] * ns.eq_op(x[1], x[2]), w=1)
+    topics = [ns.RV(d_real, data.get(("TopicPopularity", f"t{t}"))) for t in range(n_topic)]
+    papers = [ns.RV(d_real, data.get(("PaperPopularity", f"p{p}"))) for p in range(n_paper)]
+    rvs = topics + papers
+    fs = [ns.F(prior, [p]) for p in papers]
+    for a in range(n_topic):
+        for b in range(n_topic):
+            if a != b:
+                same = ns.RV(d_bool, data.get(("SameSession", f"t{a}", f"t{b}")))
+                rvs.append(same)
+                fs.append(ns.F(sess, [same, topics[a], topics[b]]))
+    for i, p in enumerate(papers):
+        for j, t in enumerate(topics):
+            pin = ns.RV(d_bool, data.get(("PaperIn", f"p{i}", f"t{j}")))
+            rvs.append(pin)
+            fs.append(ns.F(link, [pin, p, t]))
+    return _graph(ns, rvs, fs)
+
+
 def edge_mix(ns):
     """Degenerate pieces in one graph: hidden variables with no factor at all (N = 0: the node
     term has scale -1), a variable with a single unary factor (N = 1: the node term vanishes), a
@@ -223,6 +257,7 @@ CASES = {
     "smokers": (smokers, 2, 4, ("ground", "lifted")),
     "ring_xy": (ring_xy, 2, 3, ("ground", "lifted")),
     "edge_mix": (edge_mix, 2, 3, ("ground", "lifted")),
+    "hmln_demo": (hmln_demo, 2, 3, ("ground", "lifted")),
 }
 
 
