@@ -190,7 +190,7 @@ def ring_xy(ns):
 
 def hmln_demo(ns):
     """The reference's paper-popularity demo at its own size (Demo/HMLN/DemoPaperPopularity.py with
-    Demo/Data/HMLN/GeneratorPaperPopularity.py: 300 papers x 10 topics, 3410 ground atoms, 3390
+    Demo/Data/HMLN/GeneratorPaperPopularity.py: 300 papers x 10 topics, 3400 ground atoms, 3390
     factors) and its own evidence file (Demo/Data/HMLN/0, copied to hmln_demo_evidence.json):
     70 % of the popularities and about a third of the PaperIn atoms observed, the rest -- hidden
     booleans next to hidden reals -- inferred.  BASELINE config 1's model."""
