@@ -222,6 +222,58 @@ def hmln_demo(ns):
     return _graph(ns, rvs, fs)
 
 
+def robot_demo(ns):
+    """The reference's robot-mapping demo (Demo/HMLN/DemoRobotMapping.py with
+    Demo/Data/HMLN/GeneratorRobotMapping.py and the laser-scan facts Demo/Data/HMLN/robot-map, copied
+    to robot_demo_evidence.json): 37 segments, 2 lines, 3 segment types -- 1628 ground atoms, 3182
+    factors, among them 2664 five-argument clauses over four hidden booleans -- with the demo's
+    closed-world assumption on the Aligned atoms."""
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    data = {tuple(k): v for k, v in json.load(open(os.path.join(here, "robot_demo_evidence.json")))["evidence"]}
+    seg = [f"A1_{i}" for i in range(1, 38)]
+    typ, line = ["W", "D", "O"], ["LA1", "LA2"]
+    d_bool = ns.Domain((0, 1))
+    d_len = ns.Domain((0, 1), continuous=True)
+    d_dep = ns.Domain((0, 0.5), continuous=True)
+    rvs = []
+
+    def atom(domain, key, closed_world=False):
+        value = data.get(key, 0 if closed_world else None)
+        rv = ns.RV(domain, value)
+        rvs.append(rv)
+        return rv
+    part = {(s_, l): atom(d_bool, ("PartOf", s_, l)) for s_ in seg for l in line}
+    stype = {(s_, t): atom(d_bool, ("SegType", s_, t)) for s_ in seg for t in typ}
+    aligned = {(a, b): atom(d_bool, ("Aligned", a, b), closed_world=True) for a in seg for b in seg}
+    length = {s_: atom(d_len, ("Length", s_)) for s_ in seg}
+    depth = {s_: atom(d_dep, ("Depth", s_)) for s_ in seg}
+    p0 = ns.MLNPotential(lambda x: ns.or_op(ns.neg_op(x[0]), ns.neg_op(x[1])), w=3)
+    p1 = ns.MLNPotential(lambda x: 1 - (x[0] == 0) * (x[1] == 0) * (x[2] == 0), w=3)
+    p2 = ns.MLNPotential(lambda x: 1 - (x[0] == 1) * (x[1] == 1) * (x[2] == 0) * (x[3] == 1) * (1 - x[4]), w=1.591)
+    p3 = ns.MLNPotential(lambda x: x[0], w=0.3)
+    p4 = ns.MLNPotential(lambda x: x[0], w=-0.737)
+    p5 = ns.MLNPotential(lambda x: x[0], w=-0.077)
+    p6 = ns.MLNPotential(lambda x: x[0] * ns.eq_op(x[1], 0.1), w=3.228)
+    p7 = ns.MLNPotential(lambda x: x[0] * ns.eq_op(x[1], 0.02), w=2.668)
+    p8 = ns.MLNPotential(lambda x: x[0] * ns.eq_op(x[1], 0.341), w=3.754)
+    p9 = ns.MLNPotential(lambda x: x[0] * ns.eq_op(x[1], 0.001), w=2.532)
+    fs = []
+    for s_ in seg:
+        fs += [ns.F(p0, [stype[s_, a], stype[s_, b]]) for a in typ for b in typ if a != b]
+        fs.append(ns.F(p1, [stype[s_, "W"], stype[s_, "D"], stype[s_, "O"]]))
+        fs += [ns.F(p3, [stype[s_, "W"]]), ns.F(p4, [stype[s_, "D"]]), ns.F(p5, [stype[s_, "O"]])]
+        fs += [ns.F(p6, [stype[s_, "D"], length[s_]]), ns.F(p7, [stype[s_, "D"], depth[s_]]),
+               ns.F(p8, [stype[s_, "W"], length[s_]]), ns.F(p9, [stype[s_, "W"], depth[s_]])]
+    for s1 in seg:
+        for s2 in seg:
+            if s1 != s2:
+                fs += [ns.F(p2, [stype[s1, "W"], stype[s2, "W"], part[s1, l], part[s2, l], aligned[s2, s1]])
+                       for l in line]
+    return _graph(ns, rvs, fs)
+
+
 def edge_mix(ns):
     """Degenerate pieces in one graph: hidden variables with no factor at all (N = 0: the node
     term has scale -1), a variable with a single unary factor (N = 1: the node term vanishes), a
@@ -258,6 +310,7 @@ CASES = {
     "ring_xy": (ring_xy, 2, 3, ("ground", "lifted")),
     "edge_mix": (edge_mix, 2, 3, ("ground", "lifted")),
     "hmln_demo": (hmln_demo, 2, 3, ("ground", "lifted")),
+    "robot_demo": (robot_demo, 2, 3, ("ground",)),
 }
 
 

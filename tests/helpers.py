@@ -16,9 +16,12 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # Goldens that have not run on a B200 yet are pinned on the CPU side only (three oracles, host logic,
 # lifting) and held back from the ``-m gpu`` parametrisations: name them here.  (``edge_mix`` was
 # held back for part of round 1 and passed its 8 GPU cases on the first run: profiles/r1_gpu_tests_s4.txt.)
-GPU_PENDING = {"hmln_demo"}        # added after the round-1 GPU budget was spent
+GPU_PENDING = {"hmln_demo", "robot_demo"}        # added after the round-1 GPU budget was spent
 if "LHVI_GPU_PENDING" in os.environ:             # e.g. LHVI_GPU_PENDING= to run them on a GPU box
     GPU_PENDING = set(filter(None, os.environ["LHVI_GPU_PENDING"].split(",")))
+
+
+DEMO_SIZED = {"hmln_demo", "robot_demo"}      # the reference's demos at their own size (thousands of factors)
 
 
 def golden_files(gpu=False):

@@ -60,6 +60,11 @@ def test_snapshot(path, variant, ns):
 @pytest.mark.parametrize("variant", ["", "_fixed"])
 def test_adam_trajectory(path, variant, ns):
     name, engine, gold = helpers.load_golden(path)
+    if name in helpers.DEMO_SIZED and variant == "_fixed":
+        # the pure-Python loops take ~20-40 s per trajectory at the demos' sizes: this oracle walks the
+        # unmodified reference's trajectory there; the patched one is walked by the vectorised and the
+        # C oracles (test_numpy_oracle.py, test_c_port.py) and by this oracle's snapshot test
+        pytest.skip("demo-sized golden: patched trajectory covered by the fast oracles")
     orc, rvs, _ = _oracle(name, engine, ns, h2_compat=(variant == ""), gold=gold)
     orc.init_adam()
     for _ in range(int(gold["steps"])):
