@@ -6,10 +6,10 @@ Import through the repo-root alias: ``import lhvi_b200``.
 import importlib
 import sys
 
-__all__ = ["Graph", "Potential", "MLNPotential", "CompressedGraphWithObs", "RelationalGraph", "lowering",
-           "lifting", "install_flat_aliases"]
+__all__ = ["Graph", "Potential", "MLNPotential", "CompressedGraphWithObs", "RelationalGraph", "KalmanFilter",
+           "lowering", "lifting", "install_flat_aliases"]
 
-_FLAT = ("Graph", "Potential", "MLNPotential", "CompressedGraphWithObs", "RelationalGraph", "utils",
+_FLAT = ("Graph", "Potential", "MLNPotential", "CompressedGraphWithObs", "RelationalGraph", "KalmanFilter", "utils",
          "VarInference", "LiftedVarInference", "C2FVarInference")
 
 

@@ -1,0 +1,95 @@
+"""The reference's relational Kalman filter demo (Demo/RKF/LRKFDemoCycle.py: 6 wells x 20 steps, dense
+transition matrix, five parameter settings, the demo's own observation data) through the drop-in
+``KalmanFilter`` builder and the lifted engines, against the unmodified reference
+(tests/golden/rkf_cycle.json, written by make_rkf_fixture.py): the grounding (sizes and the exact
+posterior means of the ground model), the lifted run's free energy and means, and the LRKF means the
+demo itself compares with.  The numpy oracle stands in for the device."""
+import contextlib
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+import lhvi_b200
+from oracle_engine import OracleEngine, use_oracle_engine
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIX = json.load(open(os.path.join(HERE, "golden", "rkf_cycle.json")))
+DATA, PARAM, RES = np.array(FIX["data"]), np.array(FIX["param"]), np.array(FIX["lrkf_res"])
+T = 20
+lifting = lhvi_b200.lifting
+
+
+def builder(i):
+    n = DATA.shape[0]
+    domain = lhvi_b200.Graph.Domain((-4, 4), continuous=True)
+    return lhvi_b200.KalmanFilter.KalmanFilter(domain, np.eye(n) * PARAM[2, i] + 0.01, PARAM[0, i], np.eye(n), PARAM[1, i])
+
+
+def exact_last_step_means(ga, state):
+    """Solve J mu = h of the all-Gaussian ground model (from the potentials' quadratic parameters)."""
+    hidden = np.flatnonzero(np.isnan(ga.var_value))
+    pos = -np.ones(ga.n_vars, dtype=np.int64)
+    pos[hidden] = np.arange(hidden.size)
+    J, h = np.zeros((hidden.size, hidden.size)), np.zeros(hidden.size)
+    for b in ga.blocks:
+        A, lin, _ = b.potential.get_quadratic_params()
+        S = np.asarray(A, float) + np.asarray(A, float).T
+        lin = np.asarray(lin, float).reshape(-1)
+        for row in b.args:
+            for a, v in enumerate(row):
+                if pos[v] < 0:
+                    continue
+                h[pos[v]] += lin[a]
+                for c, u in enumerate(row):
+                    if pos[u] >= 0:
+                        J[pos[v], pos[u]] -= S[a, c]
+                    else:
+                        h[pos[v]] += S[a, c] * ga.var_value[u]
+    mu = np.linalg.solve(J, h)
+    return mu[pos[state[T - 1]]]
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_grounding_is_the_reference_model(i):
+    """Same ground model as the reference's KalmanFilter.grounded_graph: sizes, and exact posterior
+    means of the last step equal to those of the reference's graph (1e-9); object and array
+    groundings agree; the LRKF means the demo compares with are within its own error band."""
+    kf = builder(i)
+    g, table = kf.grounded_graph(T, DATA)
+    assert len(g.rvs) == FIX["exact"][i]["rvs"] and len(g.factors) == FIX["exact"][i]["factors"]
+    assert isinstance(g.rvs, list) and all(rv.value is not None for rv in table[0])
+    ga, state = kf.grounded_arrays(T, DATA)
+    assert ga.n_vars == len(g.rvs) and ga.n_factors == len(g.factors)
+    ga2, _ = lifting.arrays_from_graph(g)
+    assert np.array_equal(np.sort(ga.degrees()), np.sort(ga2.degrees()))
+    mu = exact_last_step_means(ga, state)
+    np.testing.assert_allclose(mu, FIX["exact"][i]["means"], rtol=1e-9, atol=1e-12)
+    assert np.abs(mu - RES[:, i]).max() < 0.2
+
+
+@pytest.mark.parametrize("i", sorted(int(k) for k in FIX["lvi"]))
+def test_lifted_run_reaches_the_reference_result(i):
+    want = FIX["lvi"][str(i)]
+    kf = builder(i)
+    # object route: the drop-in LiftedVarInference on the drop-in graph
+    g, table = kf.grounded_graph(T, DATA)
+    vi = use_oracle_engine(lhvi_b200.LiftedVarInference.VarInference(g, 1, 3))
+    with contextlib.redirect_stdout(io.StringIO()):
+        vi.run(400, lr=0.1)
+    assert len(vi.g.rvs) == want["classes"]
+    np.testing.assert_allclose(vi.free_energy(), want["free_energy"], rtol=1e-7)
+    got = [vi.eta[rv.cluster][0, 0] for rv in table[T - 1]]
+    np.testing.assert_allclose(got, want["means"], atol=2e-3)
+    # array route
+    ga, state = kf.grounded_arrays(T, DATA)
+    arr = lifting.ArrayVI(ga, 1, 3, lifted=True, engine_factory=lambda m: OracleEngine(m, var_threshold=0.1))
+    assert arr.quotient.n_var_classes == want["classes"]
+    arr.run(400, 0.1)
+    np.testing.assert_allclose(arr.free_energy(), want["free_energy"], rtol=1e-7)
+    params, _ = arr.ground_params()
+    np.testing.assert_allclose([params[int(v)][0, 0] for v in state[T - 1]], want["means"], atol=2e-3)
+    # and the variational means are the exact posterior means (K=1, Gaussian model)
+    np.testing.assert_allclose(want["means"], FIX["exact"][i]["means"], atol=5e-3)
