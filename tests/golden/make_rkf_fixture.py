@@ -12,6 +12,8 @@ Written to rkf_cycle.json:
   exact        per setting: exact posterior means of the last step's variables on the reference's own
                ground graph (solve of J mu = h assembled from its potentials' quadratic parameters),
                and the graph's size
+  tree         the same four entries (data 76 x 20, param, lrkf_res 76 x 5, exact) for
+               Demo/RKF/LRKFDemoTree.py: the 76 wells of cluster 1 with a diagonal transition matrix
   lvi          for the settings in RUN: free energy and last-step means of the reference's
                LiftedVarInference(g, 1, 3) after 400 Adam iterations at lr 0.1, numpy seed 0 (K=1 over
                Gaussian factors is convex: the end point does not depend on the draw)
@@ -102,7 +104,44 @@ def lifted_run(i):
                "classes": len(vi.g.rvs)}
 
 
+def setup_tree():
+    """Demo/RKF/LRKFDemoTree.py: the 76 wells of cluster 1, diagonal transition matrix."""
+    import numpy as np
+    import scipy.io
+    d = os.path.join(REF, "Demo", "Data", "RKF")
+    cluster_mat = scipy.io.loadmat(os.path.join(d, "cluster_NcutDiscrete.mat"))["NcutDiscrete"]
+    well_t = scipy.io.loadmat(os.path.join(d, "well_t.mat"))["well_t"]
+    mat = scipy.io.loadmat(os.path.join(d, "LRKF_tree.mat"))
+    well_t = well_t[:, 199:]
+    well_t[well_t[:, 0] == 5000, 0] = 0
+    well_t[well_t == 5000] = 1
+    rvs_id = np.where(cluster_mat[:, 1] == 1)[0]
+    return well_t[rvs_id, :T].astype(float), mat["param"].astype(float), mat["res"].astype(float)
+
+
+def tree_part():
+    import numpy as np
+    from Graph import Domain
+    from KalmanFilter import KalmanFilter
+    from numpy import linspace
+    data, param, res = setup_tree()
+    n = data.shape[0]
+    out = {"data": data.tolist(), "param": param.tolist(), "lrkf_res": res.tolist(), "exact": []}
+    for i in range(param.shape[1]):
+        domain = Domain((-4, 4), continuous=True, integral_points=linspace(-4, 4, 30))
+        kmf = KalmanFilter(domain, np.eye(n) * param[2, i], param[0, i], np.eye(n), param[1, i])
+        g, table = kmf.grounded_graph(T, data)
+        out["exact"].append({"means": exact_means(g, table), "rvs": len(g.rvs), "factors": len(g.factors)})
+    return out
+
+
 def main():
+    if "--tree-only" in sys.argv:          # add the tree demo to an existing fixture without the long runs
+        setup()
+        out = json.load(open(os.path.join(HERE, "rkf_cycle.json")))
+        out["tree"] = tree_part()
+        json.dump(out, open(os.path.join(HERE, "rkf_cycle.json"), "w"))
+        return
     data, param, res = setup()
     out = {"data": data.tolist(), "param": param.tolist(), "lrkf_res": res.tolist(), "exact": [], "lvi": {}}
     for i in range(param.shape[1]):
@@ -112,6 +151,7 @@ def main():
         for i, r in pool.map(lifted_run, RUN):
             out["lvi"][str(i)] = r
             print(i, r["free_energy"], r["classes"], flush=True)
+    out["tree"] = tree_part()
     json.dump(out, open(os.path.join(HERE, "rkf_cycle.json"), "w"))
 
 

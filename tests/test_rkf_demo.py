@@ -93,3 +93,24 @@ def test_lifted_run_reaches_the_reference_result(i):
     np.testing.assert_allclose([params[int(v)][0, 0] for v in state[T - 1]], want["means"], atol=2e-3)
     # and the variational means are the exact posterior means (K=1, Gaussian model)
     np.testing.assert_allclose(want["means"], FIX["exact"][i]["means"], atol=5e-3)
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_tree_demo_grounding_and_lrkf_means(i):
+    """Demo/RKF/LRKFDemoTree.py: 76 wells, diagonal transition matrix (2964 variables, 5700 factors).
+    Same ground model as the reference's (exact last-step means to 1e-9); the LRKF means the demo
+    compares with are within 0.05 of them; colour passing lifts the 76 chains to the few distinct
+    observation histories."""
+    tree = FIX["tree"]
+    data, param, res = np.array(tree["data"]), np.array(tree["param"]), np.array(tree["lrkf_res"])
+    n = data.shape[0]
+    domain = lhvi_b200.Graph.Domain((-4, 4), continuous=True)
+    kf = lhvi_b200.KalmanFilter.KalmanFilter(domain, np.eye(n) * param[2, i], param[0, i], np.eye(n), param[1, i])
+    ga, state = kf.grounded_arrays(T, data)
+    assert ga.n_vars == tree["exact"][i]["rvs"] == 2964 and ga.n_factors == tree["exact"][i]["factors"] == 5700
+    mu = exact_last_step_means(ga, state)
+    np.testing.assert_allclose(mu, tree["exact"][i]["means"], rtol=1e-9, atol=1e-12)
+    assert np.abs(mu - res[:, i]).max() < 0.05
+    vcol, fcols, _ = lifting.colour_passing(ga)
+    histories = len({tuple(row) for row in data})
+    assert len(np.unique(vcol[state[T - 1]])) == histories < n
