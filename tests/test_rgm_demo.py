@@ -14,6 +14,7 @@ import numpy as np
 import pytest
 
 import lhvi_b200
+import helpers
 import relational_specs
 from oracle_engine import OracleEngine, use_oracle_engine
 
@@ -122,3 +123,26 @@ def test_c2f_follows_the_reference_round_by_round(tag, rns):
     got, _ = arr.ground_params()
     for key, mu in FIX[tag]["c2f_mu"]:
         assert abs(got[index.index_of(tuple(key))][0, 0] - mu) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not helpers.RUN_PENDING_GPU, reason="written without a B200 at hand: run with LHVI_GPU_PENDING=")
+@pytest.mark.parametrize("tag", ["5", "20"])
+def test_gpu_lifted_and_c2f_runs_on_the_device(tag, rns):
+    """The same demo on the CUDA path (fp64): the lifted run ends at the reference's free energy; the
+    C2F run on arrays gives what the same host logic gives over the numpy oracle, within 0.5 % of the
+    reference's own (set-order dependent) end value."""
+    rel, data = demo_model(rns, tag)
+    g, _ = rel.ground_graph()
+    rel.add_evidence(data)
+    vi = quiet_run(lhvi_b200.LiftedVarInference.VarInference(g, 1, 3, dtype="float64"), 200, lr=0.2)
+    np.testing.assert_allclose(vi.free_energy(), FIX[tag]["lvi_final"], rtol=1e-8)
+    rel, data = demo_model(rns, tag)
+    ga, index = rel.ground_arrays(data)
+    start = lambda rep, cont, dim: np.array([[0.5, 1.0]])
+    dev = lifting.C2FArrayVI(ga, 1, 3, dtype="float64", init_fn=start).run(200, 0.2)
+    ref = lifting.C2FArrayVI(ga, 1, 3, init_fn=start,
+                             engine_factory=lambda m: OracleEngine(m, var_threshold=0.1)).run(200, 0.2)
+    np.testing.assert_array_equal(dev.vcol, ref.vcol)
+    np.testing.assert_allclose(dev.free_energy(), ref.free_energy(), rtol=1e-7)
+    np.testing.assert_allclose(dev.free_energy(), FIX[tag]["c2f_final"], rtol=5e-3)

@@ -12,6 +12,7 @@ import os
 import numpy as np
 import pytest
 
+import helpers
 import lhvi_b200
 from oracle_engine import OracleEngine, use_oracle_engine
 
@@ -114,3 +115,23 @@ def test_tree_demo_grounding_and_lrkf_means(i):
     vcol, fcols, _ = lifting.colour_passing(ga)
     histories = len({tuple(row) for row in data})
     assert len(np.unique(vcol[state[T - 1]])) == histories < n
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not helpers.RUN_PENDING_GPU, reason="written without a B200 at hand: run with LHVI_GPU_PENDING=")
+@pytest.mark.parametrize("i", sorted(int(k) for k in FIX["lvi"]))
+def test_gpu_lifted_run_on_the_device(i):
+    """The cycle demo on the CUDA path (fp64): reference free energy, classes and exact means."""
+    want = FIX["lvi"][str(i)]
+    kf = builder(i)
+    g, table = kf.grounded_graph(T, DATA)
+    vi = lhvi_b200.LiftedVarInference.VarInference(g, 1, 3, dtype="float64")
+    with contextlib.redirect_stdout(io.StringIO()):
+        vi.run(400, lr=0.1)
+    assert len(vi.g.rvs) == want["classes"]
+    np.testing.assert_allclose(vi.free_energy(), want["free_energy"], rtol=1e-7)
+    np.testing.assert_allclose([vi.eta[rv.cluster][0, 0] for rv in table[T - 1]], want["means"], atol=2e-3)
+    ga, state = kf.grounded_arrays(T, DATA)
+    arr = lifting.ArrayVI(ga, 1, 3, lifted=True, dtype="float64")
+    arr.run(400, 0.1)
+    np.testing.assert_allclose(arr.free_energy(), want["free_energy"], rtol=1e-7)
