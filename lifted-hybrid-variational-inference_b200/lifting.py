@@ -11,13 +11,16 @@ The reference compresses a ground ``Graph`` with ``CompressedGraphWithObs.Compre
 * variables are split by the multiset of their neighbouring factor classes (positions are *not*
   part of the key, ``split_rvs`` ``:47-76,249-258``).
 
-``colour_passing`` does exactly that on index arrays with sort / unique passes (numpy; the arrays
-are what ``synthetic.py``'s generators emit), ``quotient`` turns the fixed point into the few
-handle objects ``lowering.lower_compressed`` needs -- class size, representative degree ``N``
-(``:45``), neighbour counts ``count[f]`` (``:43``), mean evidence value / variance (``:9-13``) --
-so the compressed model is lowered by the same code as the object route, and
-``tests/test_lifting.py`` checks both routes give the same partition and the same lowered model
-on the object-graph twins of the generators.
+``colour_passing`` does exactly that on index arrays: in the host-side C++ library when it is built
+(``csrc/host/lhvi_lift.cpp`` through ``_lift_native``: hash-table passes on all OpenMP threads, class
+ids in order of first appearance), else with numpy sort / unique passes -- the same partition either
+way.  ``lower_partition`` writes the compressed model's record columns straight from the colour
+arrays -- class size, representative degree ``N`` (``:45``), neighbour counts ``count[f]`` (``:43``),
+mean evidence value / variance (``:9-13``) by ``bincount`` / ``unique`` passes -- and is checked column
+for column against ``lowering.lower_compressed`` over the class handles of ``quotient`` (the object
+route, kept as that cross-check).  ``ArrayVI`` / ``C2FArrayVI`` are ``LiftedVarInference`` /
+``C2FVarInference`` over such models; ``tests/test_lifting.py`` checks every piece against the
+object-level implementation on the object-graph twins of the generators and on the golden graphs.
 """
 from __future__ import annotations
 
