@@ -652,6 +652,30 @@ def softmax_slots(tau, eta, K, kind, dim, off):
         eta[idx] = e / e.sum(axis=2, keepdims=True)
 
 
+def expand_map(engine, model, var_colour, ga: GroundArrays):
+    """MAP value of every ground variable (reference ``VarInference.map``, ``:355-376``): one batched
+    device call over the hidden classes (``lhvi_mixture_map``: safeguarded Newton from the best
+    component mean; arg-max state for discrete classes), expanded to the members; observed variables
+    carry their evidence value.  Discrete entries are the domain values themselves."""
+    res = engine.mixture_map()
+    res = np.asarray(res.double().cpu().numpy() if hasattr(res, "cpu") else res, dtype=float)
+    n_cls = int(var_colour.max()) + 1 if var_colour.size else 0
+    slot_of = np.full(n_cls, -1, dtype=np.int64)
+    slot_of[model.slot_class] = np.arange(model.slot_class.size)
+    out = np.array(ga.var_value, dtype=float)
+    hidden = np.flatnonzero(np.isnan(ga.var_value))
+    slots = slot_of[var_colour[hidden]]
+    val = res[slots]
+    disc = model.var_kind[slots] == 1
+    if disc.any():                                   # state index -> domain value
+        for d in np.unique(ga.var_dom[hidden[disc]]):
+            values = np.asarray(ga.domains[int(d)].values, dtype=float)
+            pick = disc & (ga.var_dom[hidden] == d)
+            val[pick] = values[val[pick].astype(np.int64)]
+    out[hidden] = val
+    return out
+
+
 class ArrayVI:
     """``LiftedVarInference`` (``lifted=True``) or ``VarInference`` over a ``GroundArrays`` model:
     colour passing on arrays, the array-native compressed lowering (``lower_partition``), and
@@ -710,6 +734,10 @@ class ArrayVI:
 
     def free_energy(self):
         return self.engine.free_energy()
+
+    def map_values(self):
+        """MAP value of every ground variable as one array (see ``expand_map``)."""
+        return expand_map(self.engine, self.model, self.quotient.var_colour, self.ga)
 
     def ground_params(self):
         """``eta`` of every hidden ground variable: dict ground index -> ``[K, 2]`` (continuous) or
@@ -1022,6 +1050,11 @@ class C2FArrayVI:
 
     def free_energy(self):
         return self.engine.free_energy()
+
+    def map_values(self):
+        """MAP value of every ground variable as one array (see ``expand_map``), from the engine of
+        the last refinement round."""
+        return expand_map(self.engine, self.model, self.vcol, self.ga)
 
     def class_tables(self):
         """``(slot_of_class, tables)``: ``tables[slot_of_class[c]]`` is the ``[K, dim]`` table of hidden

@@ -472,3 +472,48 @@ def test_native_passes_do_not_depend_on_the_thread_count(tmp_path):
     for other in outs[1:]:
         for k in ("v", "f", "r", "s"):
             np.testing.assert_array_equal(outs[0][k], other[k])
+
+
+def test_map_values_of_the_array_engines_match_the_object_route(ns):
+    """``ArrayVI.map_values`` / ``C2FArrayVI.map_values`` against ``LiftedVarInference.map`` on the
+    hybrid paper-popularity golden graph (hidden reals and hidden booleans)."""
+    import contextlib
+    import io
+    from oracle_engine import OracleEngine, use_oracle_engine
+    factory = lambda m: OracleEngine(m, var_threshold=0.1)
+    g, rvs = specs.CASES["hmln_hidden"][0](ns)
+    ga, order = lifting.arrays_from_graph(g)
+    arr = lifting.ArrayVI(ga, 2, 3, lifted=True, engine_factory=factory)
+    arr.run(30, 0.1)
+    got = arr.map_values()
+    assert got.shape == (ga.n_vars,) and not np.isnan(got).any()
+    ev = ~np.isnan(ga.var_value)
+    np.testing.assert_array_equal(got[ev], ga.var_value[ev])
+    # the same state pushed through the object-level class: same MAP values
+    vi = use_oracle_engine(lhvi_b200.LiftedVarInference.VarInference(g, 2, 3))
+    params, w = arr.ground_params()
+    index = {id(rv): i for i, rv in enumerate(order)}
+
+    def init_param():
+        vi.w_tau = np.log(w)
+        vi.w = w.copy()
+        vi.eta, vi.eta_tau = {}, {}
+        for h in vi.g.rvs:
+            if h.value is not None:
+                continue
+            table = params[min(index[id(rv)] for rv in h.rvs)]
+            vi.eta[h] = table.copy()
+            if not h.domain.continuous:
+                vi.eta_tau[h] = np.log(table)
+    vi.init_param = init_param
+    with contextlib.redirect_stdout(io.StringIO()):
+        vi.run(0, lr=0.1)
+    for rv in order:
+        if rv.value is None:
+            want = vi.map(rv)
+            assert abs(got[index[id(rv)]] - want) < 1e-6, (rv, got[index[id(rv)]], want)
+    hidden_disc = [index[id(rv)] for rv in order if rv.value is None and not rv.domain.continuous]
+    assert hidden_disc and set(got[hidden_disc]) <= {0.0, 1.0}
+    c2f = lifting.C2FArrayVI(ga, 2, 3, engine_factory=factory).run(20, 0.1)
+    m = c2f.map_values()
+    assert m.shape == (ga.n_vars,) and not np.isnan(m).any() and set(m[hidden_disc]) <= {0.0, 1.0}
