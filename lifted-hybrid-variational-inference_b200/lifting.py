@@ -997,7 +997,10 @@ class C2FArrayVI:
         self.m_w, self.u_w, self.t = m_w, u_w, t
 
     # ---- the run ---------------------------------------------------------------------------
-    def run(self, iteration=100, lr=0.1):
+    def run(self, iteration=100, lr=0.1, log_fe=False):
+        """``log_fe=True`` evaluates the free energy at the end of every refinement round (one more
+        pass over the records) into ``history`` -- the reference logs it after every iteration
+        (``C2FVarInference.py:354-377``)."""
         ga = self.ga
         self.degrees = ga.degrees()
         # initial classes, parameters per initial class (one hidden class per domain), then the
@@ -1045,7 +1048,7 @@ class C2FArrayVI:
             t = clock("iterate", t)
             self._pull(self.model, self.engine)
             clock("pull", t)
-            self.history.append((self.quotient.n_var_classes, None))
+            self.history.append((self.quotient.n_var_classes, float(self.engine.free_energy()) if log_fe else None))
         return self
 
     def free_energy(self):

