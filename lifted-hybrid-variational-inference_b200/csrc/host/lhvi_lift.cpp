@@ -1,7 +1,8 @@
 // Host-side lifting passes (include/lhvi_lift.h): colour passing on index arrays with open-addressing
-// hash tables.  Follows CompressedGraphWithObs.py:47-76 (split_rvs), :152-175 (split_factors),
-// :249-271 (run) of the reference; see lifting.colour_passing for the numpy statement of the same
-// passes.
+// hash tables, and the evidence k-means of the coarse-to-fine engine.  Follows
+// CompressedGraphWithObs.py:47-76 (split_rvs), :152-175 (split_factors), :249-271 (run), :78-130
+// (split_by_evidence) and :236-247 (split_evidence) of the reference; lifting.py holds the numpy
+// statement of the same passes.  LHVI_LIFT_TIMING=1 prints the phase times of a colour passing call.
 #include "lhvi_lift.h"
 
 #include <algorithm>
@@ -170,7 +171,7 @@ extern "C" int64_t lhvi_lift_rank64(const uint64_t *key, int64_t n, int64_t *ids
 struct lhvi_lift_graph {
     int64_t n_vars = 0, n_fac = 0, width = 2;
     std::vector<lhvi_lift_block> blocks;            // colour pointers are set per call
-    std::vector<int64_t> foff, koff, inc_ptr;
+    std::vector<int64_t> foff, inc_ptr;
     std::vector<int32_t> inc_fac, key32, first, header;
     std::vector<int64_t> vcol, vnew, fid;
     std::vector<uint64_t> hash64, vhash, H1, H2;
@@ -205,11 +206,7 @@ extern "C" lhvi_lift_graph *lhvi_lift_graph_create(int64_t n_vars, const lhvi_li
         g->n_fac = n_fac;
         g->blocks.assign(blocks_in, blocks_in + n_blocks);
         g->foff.assign(static_cast<size_t>(n_blocks) + 1, 0);
-        g->koff.assign(static_cast<size_t>(n_blocks) + 1, 0);
-        for (int32_t b = 0; b < n_blocks; ++b) {
-            g->foff[b + 1] = g->foff[b] + blocks_in[b].n;
-            g->koff[b + 1] = g->koff[b] + blocks_in[b].n * (blocks_in[b].arity + 1);
-        }
+        for (int32_t b = 0; b < n_blocks; ++b) g->foff[b + 1] = g->foff[b] + blocks_in[b].n;
         // incidences by variable (one entry per argument position)
         g->inc_ptr.assign(static_cast<size_t>(n_vars) + 1, 0);
         for (int32_t b = 0; b < n_blocks; ++b) {
