@@ -4,8 +4,7 @@ the device, and the read-back.
 
     python tools/c2f_probe.py [entities=100000] [iterations=50] [groups=10] [dtype=float32]
 
-Prints one JSON line.  `--oracle` runs the numpy oracle instead of the device (tiny sizes, CPU check
-of the script itself)."""
+Prints one JSON line.  Needs a CUDA device (the engine has no CPU fallback)."""
 import json
 import os
 import sys
@@ -29,19 +28,12 @@ def main():
     t0 = time.perf_counter()
     ga = syn.relational_hybrid_arrays(P, G, observed_frac=0.7, seed=0)
     t_gen = time.perf_counter() - t0
-    factory = None
-    if "--oracle" in sys.argv:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from oracle_engine import OracleEngine
-        factory = lambda m: OracleEngine(m, var_threshold=0.1)
-    t_warm = 0.0
-    if factory is None:
-        # CUDA context, library load and first launches on a toy model, outside the timed run
-        t0 = time.perf_counter()
-        toy = lifting.C2FArrayVI(syn.relational_hybrid_arrays(50, 3, seed=1), 3, 3, dtype=dtype)
-        toy.run(10, 0.05)
-        t_warm = time.perf_counter() - t0
-    vi = lifting.C2FArrayVI(ga, 3, 3, dtype=dtype, engine_factory=factory)
+    # CUDA context, library load and first launches on a toy model, outside the timed run
+    t0 = time.perf_counter()
+    toy = lifting.C2FArrayVI(syn.relational_hybrid_arrays(50, 3, seed=1), 3, 3, dtype=dtype)
+    toy.run(10, 0.05)
+    t_warm = time.perf_counter() - t0
+    vi = lifting.C2FArrayVI(ga, 3, 3, dtype=dtype)
     t0 = time.perf_counter()
     vi.run(its, 0.05)
     total = time.perf_counter() - t0
