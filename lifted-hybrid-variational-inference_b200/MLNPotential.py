@@ -16,47 +16,70 @@ except ImportError:
     from Graph import Potential
 
 
+# ---- soft-logic connectives ----------------------------------------------------------------------
+# Truth values are 0 / 1 (or soft values in [0, 1]); every connective is a polynomial in its
+# arguments, which is what lets ``lowering.py`` tabulate a formula per discrete configuration and fit
+# the remaining continuous part exactly.
+
 def and_op(x, y):
+    """Conjunction as a product."""
     return x * y
 
 
-def or_op(x, y):
-    return x + y - x * y
-
-
 def neg_op(x):
+    """Negation: the complement to one."""
     return 1 - x
 
 
+def or_op(x, y):
+    """Disjunction by inclusion-exclusion."""
+    both = x * y
+    return x + y - both
+
+
 def imp_op(x, y):
+    """Implication ``x -> y`` = ``not x or y``, expanded: false only for x = 1, y = 0."""
     return 1 - x + x * y
 
 
 def bic_op(x, y):
-    return imp_op(x, y) * imp_op(y, x)
+    """Biconditional: both implications hold."""
+    forward, backward = imp_op(x, y), imp_op(y, x)
+    return forward * backward
 
 
 def eq_op(x, y):
+    """Soft equality of two reals: minus the squared difference (0 at equality, the log of a
+    Gaussian bump once scaled by the formula weight)."""
     d = x - y
     return -(d * d)
 
 
-class MLNPotential(Potential):
-    def __init__(self, formula, w=1):
+# ---- potentials ------------------------------------------------------------------------------------
+
+class _FormulaPotential(Potential):
+    """A potential defined by a Python callable over the argument tuple; never symmetric, compared
+    by identity (two factors share a colour only if they share the object)."""
+
+    def __init__(self, formula):
         super().__init__(symmetric=False)
         self.formula = formula
+
+
+class MLNPotential(_FormulaPotential):
+    """``psi(x) = exp(w * formula(x))`` (reference ``MLNPotential.py:30-40``)."""
+
+    def __init__(self, formula, w=1):
+        super().__init__(formula)
         self.w = w
 
     def get(self, parameters):
         return math.e ** (self.formula(parameters) * self.w)
 
 
-class MLNHardPotential(Potential):
-    """Indicator of ``formula(x) > 0``; only lowerable when every argument is discrete."""
-
-    def __init__(self, formula):
-        super().__init__(symmetric=False)
-        self.formula = formula
+class MLNHardPotential(_FormulaPotential):
+    """Indicator of ``formula(x) > 0`` (reference ``MLNPotential.py:43-49``); only lowerable when
+    every argument is discrete."""
 
     def get(self, parameters):
         return 1 if self.formula(parameters) > 0 else 0
