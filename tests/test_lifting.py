@@ -517,3 +517,34 @@ def test_map_values_of_the_array_engines_match_the_object_route(ns):
     c2f = lifting.C2FArrayVI(ga, 2, 3, engine_factory=factory).run(20, 0.1)
     m = c2f.map_values()
     assert m.shape == (ga.n_vars,) and not np.isnan(m).any() and set(m[hidden_disc]) <= {0.0, 1.0}
+
+
+def test_native_and_numpy_colour_passing_agree_on_random_graphs():
+    """Random small factor graphs: several blocks of arity 1-4, symmetric and ordered potentials,
+    repeated rows, blocks sharing a potential object, mixed evidence -- same partitions of variables
+    and factors and the same number of sweeps from both implementations."""
+    class Stub:                     # only .symmetric and identity matter to colour passing
+        def __init__(self, symmetric):
+            self.symmetric = symmetric
+    doms = [lhvi_b200.Graph.Domain((-5, 5), continuous=True), lhvi_b200.Graph.Domain((0, 1))]
+    for seed in range(80):
+        rng = np.random.default_rng(seed)
+        nv = int(rng.integers(3, 60))
+        var_dom = rng.integers(0, 2, nv).astype(np.int32)
+        val = np.full(nv, np.nan)
+        ev = rng.random(nv) < 0.4
+        val[ev] = np.where(var_dom[ev] == 0, rng.integers(0, 3, ev.sum()) * 0.5, rng.integers(0, 2, ev.sum()))
+        blocks = []
+        for _ in range(int(rng.integers(1, 5))):
+            arity, n = int(rng.integers(1, 5)), int(rng.integers(1, 40))
+            base = rng.integers(0, nv, (max(1, n // 3), arity))
+            blocks.append(lifting.FactorBlock(Stub(bool(rng.integers(0, 2))), base[rng.integers(0, base.shape[0], n)].astype(np.int64)))
+        if rng.random() < 0.3 and len(blocks) > 1:
+            blocks[1] = lifting.FactorBlock(blocks[0].potential, rng.integers(0, nv, (5, blocks[0].arity)).astype(np.int64))
+        ga = lifting.GroundArrays(doms, var_dom, val, blocks)
+        for split in (True, False):
+            a = lifting.colour_passing(ga, split_cont_evidence=split, use_native=False)
+            b = lifting.colour_passing(ga, split_cont_evidence=split, use_native=True)
+            assert a[2] == b[2], (seed, split)
+            assert _same_partition(a[0], b[0]), (seed, split)
+            assert _same_partition(np.concatenate(a[1]), np.concatenate(b[1])), (seed, split)
