@@ -81,12 +81,12 @@ class VarInference(VIBase):
             n = len(self.g.rvs)
             self.g.split_factors()
             self.split_rvs()
-        self._engine = None      # graph changed: lower + upload again before the next pass
+        self._drop_engine()      # graph changed: lower + upload again before the next pass
 
     def run(self, iteration=100, lr=0.1, is_log=True, log_fe=True):
         self._start_run(lr, is_log, log_fe)
         self.g.init_cluster(is_split_cont_evidence=False)
-        self._engine = None
+        self._drop_engine()
         self.init_param()
         self._zero_moments()
         self.cp_run()

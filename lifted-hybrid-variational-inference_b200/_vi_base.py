@@ -154,9 +154,16 @@ class VIBase:
     def _rebuild(self):
         """(Re)lower the current graph and create the device engine."""
         self._model = self._lower()
+        self._drop_engine()
         self._engine = self._make_engine(self._model)
         self._pushed = None
         self._grad_cache = None
+
+    def _drop_engine(self):
+        """Release the current engine's graphs / peer buffers before it is replaced."""
+        eng, self._engine = self._engine, None
+        if eng is not None and hasattr(eng, "close"):
+            eng.close()
 
     def _flat(self, cont_dict, disc_dict, fill=0.0):
         m, K = self._model, self.K
@@ -268,10 +275,13 @@ class VIBase:
         torch.cuda.synchronize()
 
     def _update_loop(self, iteration, lr, sgd):
-        self._push(moments=not sgd)
+        if self._engine is None:
+            self._rebuild()
         eng = self._engine
+        # before the moments go up: set_moments seeds the bias corrections 1 - b^t from these
         eng.b1, eng.b2, eng.eps = self.b1, self.b2, self.eps
         eng.var_threshold = float(self.var_threshold)
+        self._push(moments=not sgd)
         if not (self.is_log or sgd):
             eng.iterate(iteration, lr, sgd=False)
             self._pull(moments=True)

@@ -22,8 +22,8 @@ constructing the engine without CUDA or without the built library raises.
 from __future__ import annotations
 
 import ctypes as C
+import gc
 import os
-import warnings
 
 import numpy as np
 import torch
@@ -171,6 +171,7 @@ class DeviceEngine:
         self._upload()
         self.exchange = None           # "p2p" | "collective" when the records are sharded
         self.peer = None
+        self._closed = False
         if self.plan.active:
             self._setup_exchange()
 
@@ -195,6 +196,32 @@ class DeviceEngine:
                 self.exchange = "p2p"
             elif mode == "p2p":
                 raise RuntimeError("lhvi: LHVI_EXCHANGE=p2p but the peers' buffers could not be mapped")
+
+    def close(self):
+        """Release what the engine holds outside PyTorch's allocator: the captured CUDA graphs and
+        the peer-visible exchange buffer with its IPC mappings.  Collective when the records are
+        sharded (every rank must call it: the peers' mappings are closed behind a barrier).  Called
+        by the drop-in classes and the array engines before they replace an engine."""
+        if getattr(self, "_closed", True):
+            return
+        self._closed = True
+        torch.cuda.synchronize(self.device)
+        self._graphs.clear()
+        if self.peer is not None:
+            import torch.distributed as dist
+            dist.barrier(group=self.plan.group)       # nobody is still writing into a peer's buffer
+            self.peer.close()
+            self.peer = None
+
+    def __del__(self):
+        # graphs are released by their own destructors; the peer buffer needs the explicit call
+        # (close() is collective), so only the local, non-collective part is done here
+        try:
+            if not getattr(self, "_closed", True) and self.peer is not None:
+                torch.cuda.synchronize(self.device)
+                self.peer.close()
+        except Exception:
+            pass
 
     # ---- buffers --------------------------------------------------------------------------
     def _dev(self, arr, dtype=None):
@@ -534,8 +561,21 @@ class DeviceEngine:
             self.grad.zero_()
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._iteration(lr, sgd)
+            # Python's cyclic collector must not run inside the capture: a dead cycle that holds
+            # another engine (its CUDA graphs, peer buffers) would be finalised there, and
+            # cudaGraphExecDestroy / cudaFree under capture invalidate it ("operation not permitted
+            # when stream is capturing"; seen intermittently when the previous model's drop-in
+            # object -- compressed graphs are full of cycles -- died mid-capture).  torch's context
+            # manager only collects when torch.compiler.config.force_cudagraph_gc is set.
+            gc.collect()
+            gc_was_enabled = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    self._iteration(lr, sgd)
+            finally:
+                if gc_was_enabled:
+                    gc.enable()
             # capture records the launches without running them: nothing has changed yet
             self._graphs[key] = graph
         return graph
@@ -551,11 +591,9 @@ class DeviceEngine:
             return
         graph = None
         if self.use_graph and self.profile_group is None:
-            try:
-                graph = self._graph_for(lr, sgd)
-            except Exception as exc:               # capture unsupported here: same kernels, launched eagerly
-                warnings.warn(f"lhvi: CUDA-graph capture failed ({exc}); launching eagerly")
-                self.use_graph = False
+            # a failed capture is an error, not a reason to fall back silently (use_graph = False
+            # asks for eager launches explicitly)
+            graph = self._graph_for(lr, sgd)
         if not self._grad_clean:
             self.grad[:self.n_param].zero_()
             self._grad_clean = True
@@ -593,9 +631,10 @@ class DeviceEngine:
         dim = self._dev(np.asarray(q_dim, dtype=np.int32))
         kind = self._dev(np.asarray(q_kind, dtype=np.uint8))
         xs = self._dev(np.asarray(x, dtype=np.float64), self.tdtype)
+        eta = self.plan.merge(self.eta)      # sharded records: a rank steps only the variables it owns
         _cabi.check(self.lib.lhvi_mixture_belief(
             self.dcode, self.K, n, off.data_ptr(), dim.data_ptr(), kind.data_ptr(), xs.data_ptr(),
-            self.eta.data_ptr(), self.w.data_ptr(), out.data_ptr(), self._stream()), self.lib)
+            eta.data_ptr(), self.w.data_ptr(), out.data_ptr(), self._stream()), self.lib)
         return out
 
     def mixture_map(self, q_off=None, q_dim=None, q_kind=None):

@@ -1039,6 +1039,9 @@ class C2FArrayVI:
                                          gaussian_obs=self.gaussian_obs, min_obs_var=self.min_obs_var,
                                          degrees=self.degrees, stats=self.stats)
             t = clock("lower", t)
+            old = getattr(self, "engine", None)
+            if old is not None and hasattr(old, "close"):
+                old.close()                      # graphs, peer buffers of the previous round's engine
             self.engine = self._make_engine(self.model)
             self._push(self.model, self.engine)
             t = clock("upload", t)

@@ -13,17 +13,12 @@ import specs
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-# Goldens that have not run on a B200 yet are pinned on the CPU side only (three oracles, host logic,
-# lifting) and held back from the ``-m gpu`` parametrisations: name them here.  (``edge_mix`` was
-# held back for part of round 1 and passed its 8 GPU cases on the first run: profiles/r1_gpu_tests_s4.txt.)
-GPU_PENDING = {"hmln_demo", "robot_demo"}        # added after the round-1 GPU budget was spent
-if "LHVI_GPU_PENDING" in os.environ:             # e.g. LHVI_GPU_PENDING= to run them on a GPU box
+# Goldens held back from the ``-m gpu`` parametrisations until they have run on a B200 once (pinned on
+# the CPU side meanwhile).  Empty: ``hmln_demo`` / ``robot_demo`` and the RGM / RKF demo twins passed
+# their first B200 run in round 2 (profiles/r2_gpu_tests_pending.txt).
+GPU_PENDING = set()
+if "LHVI_GPU_PENDING" in os.environ:             # e.g. LHVI_GPU_PENDING=name,name to hold some back
     GPU_PENDING = set(filter(None, os.environ["LHVI_GPU_PENDING"].split(",")))
-
-
-# GPU tests written without a B200 at hand: collected under ``-m gpu`` but skipped until
-# ``LHVI_GPU_PENDING=`` (empty) asks for everything that is pending
-RUN_PENDING_GPU = os.environ.get("LHVI_GPU_PENDING", None) == ""
 
 DEMO_SIZED = {"hmln_demo", "robot_demo"}      # the reference's demos at their own size (thousands of factors)
 

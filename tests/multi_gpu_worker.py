@@ -51,6 +51,16 @@ def main():
                 np.testing.assert_allclose(eng.last_free_energy(), fe_last, rtol=tol)
                 np.testing.assert_allclose(e1, ref.eta, rtol=tol * 10, atol=tol * 10)
                 np.testing.assert_allclose(wt1, ref.w_tau, rtol=tol * 10, atol=tol * 10)
+                # belief / MAP queries read the merged state (every rank answers for every variable)
+                m = model
+                cont = np.flatnonzero(m.var_kind == 0)[:64]
+                xq = ref.eta[m.var_off[cont]] + 0.3
+                got = eng.mixture_belief(m.var_off[cont], m.var_dim[cont], m.var_kind[cont], xq).double().cpu().numpy()
+                want = np.zeros(cont.size)
+                for k in range(m.K):
+                    mu, var = ref.eta[m.var_off[cont] + 2 * k], ref.eta[m.var_off[cont] + 2 * k + 1]
+                    want += ref.w[k] * np.exp(-(xq - mu) ** 2 / (2 * var)) / (2.506628274631 * var)
+                np.testing.assert_allclose(got, want, rtol=tol * 100, atol=tol * 100)
                 # replicas of the shared state agree bit for bit
                 wt = torch.as_tensor(wt1, device=f"cuda:{local}")
                 lo, hi = wt.clone(), wt.clone()

@@ -137,7 +137,6 @@ def test_c2f_follows_the_reference_round_by_round(tag, rns):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not helpers.RUN_PENDING_GPU, reason="written without a B200 at hand: run with LHVI_GPU_PENDING=")
 @pytest.mark.parametrize("tag", ["5", "20"])
 def test_gpu_lifted_and_c2f_runs_on_the_device(tag, rns):
     """The same demo on the CUDA path (fp64): the lifted run ends at the reference's free energy; the

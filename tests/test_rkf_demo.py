@@ -126,7 +126,6 @@ def test_tree_demo_grounding_and_lrkf_means(i):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not helpers.RUN_PENDING_GPU, reason="written without a B200 at hand: run with LHVI_GPU_PENDING=")
 @pytest.mark.parametrize("i", sorted(int(k) for k in FIX["lvi"]))
 def test_gpu_lifted_run_on_the_device(i):
     """The cycle demo on the CUDA path (fp64): reference free energy, classes and exact means."""
