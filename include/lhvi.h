@@ -38,6 +38,11 @@
  *                             these are still its `energy -= ...` / `g_w[k] -= ...` /
  *                             `g_mu -= ...` sums (VarInference.py:72,88,120-129), split by rank.
  *   lhvi_finish_step          lhvi_finish + lhvi_param_step fused into one launch.
+ *   lhvi_iterate              n whole iterations -- every group's factor pass, lhvi_finish and
+ *                             lhvi_param_step -- in ONE persistent cooperative launch: the loop
+ *                             `for itr in range(iteration)` of ADAM_update / GD_update
+ *                             (VarInference.py:249-331) with the grid barrier in the place of the
+ *                             launch boundaries.
  *   lhvi_peer_*               life cycle of the peer-visible exchange buffers (CUDA IPC).
  *   lhvi_state_pack/unpack    the compact per-variable parameter arrays of the reference
  *                             (eta[rv], VarInference.py:197-213) <-> the padded device slots.
@@ -55,7 +60,7 @@
 extern "C" {
 #endif
 
-#define LHVI_ABI_VERSION 3
+#define LHVI_ABI_VERSION 4
 
 /* element type of every `void*` buffer of reals */
 #define LHVI_F32 0
@@ -264,6 +269,47 @@ int lhvi_finish_step(const lhvi_model* m, int64_t rows, const lhvi_exchange* x, 
                      const int32_t* var_off, void* tau, void* mom1, void* mom2, void* wstate,
                      const double* step, double lr, double b1, double b2, double eps,
                      double var_threshold, int sgd, void* stream);
+
+/*
+ * Optimiser-side buffers of lhvi_iterate: what lhvi_finish_step takes as loose arguments.
+ */
+typedef struct lhvi_optim {
+    int64_t n_vars, n_owned;       /* variable table; entries n_owned .. n_vars-1 are the shared ones */
+    const uint8_t* var_kind;       /* [n_vars] 0 continuous / 1 discrete */
+    const int32_t* var_dim;        /* [n_vars] 2 / D */
+    const int32_t* var_off;        /* [n_vars] slot offsets */
+    void* tau;                     /* [n_param] logits of the discrete slots */
+    void* mom1;                    /* [n_param] Adam first moments */
+    void* mom2;                    /* [n_param] Adam second moments */
+    void* wstate;                  /* [5K] w_tau | w | mom1_w | mom2_w | scratch */
+    double* step;                  /* [4] t, 1-b1^t, 1-b2^t, unused (advanced once per iteration unless sgd) */
+    int32_t* sm_count;             /* [256] zero-initialised scratch counters owned by the caller (may be NULL) */
+    double lr, b1, b2, eps, var_threshold;
+    int32_t sgd;                   /* != 0: theta -= lr * g, moments and step counter untouched */
+    int32_t reserved;
+} lhvi_optim;
+
+/*
+ * n_iter Jacobi iterations in ONE cooperative launch of a persistent grid (2 blocks per SM): per
+ * iteration every block works through its slice of every record group (the same device code as
+ * lhvi_factor_expect_grad's kernels, region i of m->partials belonging to groups[i]), a grid
+ * barrier, then block 0 does lhvi_finish's work (x != NULL and x->world > 1: with the exchange,
+ * x->blocks must be 1; every rank must make the matching call with the same n_iter) and steps the
+ * mixture weights and the shared variables while the other blocks step the owned ones, and a
+ * second grid barrier.  grad must be clean (all parameter-gradient slots zero) on entry and is
+ * left clean; grad[n_param ..] holds G_w and the free energy of the LAST pass (at the parameters
+ * before its step).  Equivalent to n_iter times { lhvi_factor_expect_grad for every group;
+ * lhvi_step_tick; lhvi_finish_step }.
+ * Returns 0, a negative error code, or 1 when some group has no body in the iteration kernel
+ * (hidden discrete arguments, T != 3, K > 3, more than 12 groups, an exchange that needs more
+ * than one block): nothing was launched, use the per-group calls.
+ */
+int lhvi_iterate(const lhvi_model* m, const lhvi_group* groups, int32_t n_groups, const lhvi_exchange* x,
+                 const lhvi_optim* opt, int32_t n_iter, void* stream);
+
+/* 1 if lhvi_iterate would take this model (only the descriptors' shapes are looked at), else 0. */
+int lhvi_iterate_supported(const lhvi_model* m, const lhvi_group* groups, int32_t n_groups,
+                           const lhvi_exchange* x);
 
 /*
  * The state a reference caller holds between ADAM_update calls is eta[rv] as K x 2 / K x D arrays

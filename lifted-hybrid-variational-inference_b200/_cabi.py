@@ -17,14 +17,15 @@ LHVI_FOLD_TILE = 1024
 LHVI_MAX_PEERS = 16
 LHVI_RUN_MAX_HUBS = 16
 LHVI_IPC_HANDLE_BYTES = 64
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblhvi.so")
 
 SYMBOLS = ("lhvi_last_error", "lhvi_abi_version", "lhvi_has_specialisation",
            "lhvi_factor_expect_grad", "lhvi_elbo_reduce", "lhvi_step_tick",
            "lhvi_param_step", "lhvi_mixture_belief", "lhvi_mixture_map", "lhvi_finish", "lhvi_state_pack", "lhvi_state_unpack", "lhvi_finish_step",
-           "lhvi_peer_alloc", "lhvi_peer_open", "lhvi_peer_close", "lhvi_peer_free")
+           "lhvi_peer_alloc", "lhvi_peer_open", "lhvi_peer_close", "lhvi_peer_free",
+           "lhvi_iterate", "lhvi_iterate_supported")
 
 
 class LhviGroup(C.Structure):
@@ -59,6 +60,18 @@ class LhviExchange(C.Structure):
         ("recv", C.c_void_p * LHVI_MAX_PEERS),
         ("flags", C.c_void_p * LHVI_MAX_PEERS),
         ("seq", C.c_void_p), ("status", C.c_void_p),
+    ]
+
+
+class LhviOptim(C.Structure):
+    _fields_ = [
+        ("n_vars", C.c_int64), ("n_owned", C.c_int64),
+        ("var_kind", C.c_void_p), ("var_dim", C.c_void_p), ("var_off", C.c_void_p),
+        ("tau", C.c_void_p), ("mom1", C.c_void_p), ("mom2", C.c_void_p), ("wstate", C.c_void_p),
+        ("step", C.c_void_p), ("sm_count", C.c_void_p),
+        ("lr", C.c_double), ("b1", C.c_double), ("b2", C.c_double), ("eps", C.c_double),
+        ("var_threshold", C.c_double),
+        ("sgd", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -127,6 +140,12 @@ def load(build_if_missing: bool = False):
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
                                      C.c_double, C.c_int, C.c_void_p]
+    lib.lhvi_iterate.restype = C.c_int
+    lib.lhvi_iterate.argtypes = [C.POINTER(LhviModel), C.POINTER(LhviGroup), C.c_int32, C.POINTER(LhviExchange),
+                                 C.POINTER(LhviOptim), C.c_int32, C.c_void_p]
+    lib.lhvi_iterate_supported.restype = C.c_int
+    lib.lhvi_iterate_supported.argtypes = [C.POINTER(LhviModel), C.POINTER(LhviGroup), C.c_int32,
+                                           C.POINTER(LhviExchange)]
     for fn in (lib.lhvi_state_pack, lib.lhvi_state_unpack):
         fn.restype = C.c_int
         fn.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -88,6 +88,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 // launch's region and block 0 records how many rows are valid in the header row, so the
 // reduction needs no zero-filled buffer.
 __device__ __forceinline__ void publish_partials(const double* vals, int nvals, double* scratch, double* region);
+__device__ __forceinline__ void publish_partials(const double* vals, int nvals, double* scratch, double* region,
+                                                 int bid, int nblocks);
 
 __device__ __forceinline__ void block_sum_to(const double* vals, int nvals, double* scratch,
                                              double* out) {
@@ -105,10 +107,23 @@ __device__ __forceinline__ void block_sum_to(const double* vals, int nvals, doub
     __syncthreads();
 }
 
-__device__ __forceinline__ void publish_partials(const double* vals, int nvals, double* scratch, double* region) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) region[-nvals] = (double)gridDim.x;
-    block_sum_to(vals, nvals, scratch, region + (long long)blockIdx.x * nvals);
+// `bid` of `nblocks`: the block's index among the blocks working on this record group (the
+// launch's blockIdx / gridDim for a per-group kernel; a slice of the persistent grid inside the
+// iteration kernel)
+__device__ __forceinline__ void publish_partials(const double* vals, int nvals, double* scratch, double* region,
+                                                 int bid, int nblocks) {
+    if (bid == 0 && threadIdx.x == 0) region[-nvals] = (double)nblocks;
+    block_sum_to(vals, nvals, scratch, region + (long long)bid * nvals);
 }
+
+__device__ __forceinline__ void publish_partials(const double* vals, int nvals, double* scratch, double* region) {
+    publish_partials(vals, nvals, scratch, region, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Which slice of a record group a thread block works on, and the shared memory it may use.
+struct BlockSlice {
+    int bid, nblocks;
+};
 
 // ---- typed view of a record group ---------------------------------------------------------
 

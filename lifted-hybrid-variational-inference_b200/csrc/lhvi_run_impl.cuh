@@ -60,31 +60,41 @@ __device__ __forceinline__ double ld_stream(const double* p, unsigned long long 
     return v;
 }
 
+template <typename real, int K, int T>
+struct RunShared {
+    static constexpr int TP = (T + 3) / 4 * 4;
+    alignas(16) real hq[kRunMaxHubs][K][K][TP];    // q_{k2}(x_{k,t}) of every hub
+    alignas(16) real hnrm[kRunMaxHubs][4];         // 1 / (sqrt(2 pi) var_k2)
+    alignas(16) real hms[kRunMaxHubs][K][4];       // mu_k, sqrt(2 var_k), 2 var_k, 1 / var_k
+    double scratch[(kRunThreads / 32) * (K + 1)];
+    double gw[K][kRunThreads];
+    real w[K];
+    real quad[2 * T];                              // for the literal (checked) path only
+    int hkey[kRunMaxHubs];
+};
+
+// s_acc: [n_hubs][2K][kRunThreads] thread-private hub sums (dynamic shared memory)
 template <typename real, int K, int T, int NE, bool WEIGHTED, int HUBPOS>
-__global__ void __launch_bounds__(kRunThreads, kRunBlocks)
-factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
+__device__ __forceinline__ void
+factor_run_body(const GroupView<real>& g, const RunLaunch<real, T>& L, const int H, const BlockSlice bs,
+                RunShared<real, K, T>& sh, real* s_acc) {
     using F = Fast<real>;
     constexpr int NC = 2, NG = 0, NCT = 2 + NE, NV = 2 * K;
     using C = Ctx<real, K, T, NC, NG, NE>;
     constexpr int NQ = C::NQ;
-    constexpr int TP = (T + 3) / 4 * 4;
     constexpr int RA = 1 - HUBPOS;                  // canonical position of the run argument
     static_assert(K <= 4, "hub normalisers are stored four to a row");
 
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    real* s_acc = reinterpret_cast<real*>(s_dyn);   // [n_hubs][NV][kRunThreads] thread-private sums
-
-    __shared__ real s_w[K];
-    __shared__ real s_quad[2 * T];      // for the literal (checked) path only
-    __shared__ __align__(16) real s_hq[kRunMaxHubs][K][K][TP];   // q_{k2}(x_{k,t}) of every hub
-    __shared__ __align__(16) real s_hnrm[kRunMaxHubs][4];        // 1 / (sqrt(2 pi) var_k2)
-    __shared__ __align__(16) real s_hms[kRunMaxHubs][K][4];      // mu_k, sqrt(2 var_k), 2 var_k, 1 / var_k
-    __shared__ int s_hkey[kRunMaxHubs];
-    __shared__ double s_scratch[(kRunThreads / 32) * (K + 1)];
-    __shared__ double s_gw[K][kRunThreads];
+    auto& s_w = sh.w;
+    auto& s_quad = sh.quad;
+    auto& s_hq = sh.hq;
+    auto& s_hnrm = sh.hnrm;
+    auto& s_hms = sh.hms;
+    auto& s_hkey = sh.hkey;
+    auto& s_scratch = sh.scratch;
+    auto& s_gw = sh.gw;
 
     const int tid = threadIdx.x;
-    const int H = L.n_hubs;
     for (int i = tid; i < 2 * T; i += blockDim.x) s_quad[i] = g.quad[i];
     for (int i = tid; i < K; i += blockDim.x) s_w[i] = g.w[i];
     for (int k = 0; k < K; ++k) s_gw[k][tid] = 0.0;
@@ -123,8 +133,8 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
     auto own_floor = [](real own) { return own < F::kBFloor; };
 
     const unsigned long long pol = l2_evict_first_policy();
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long run = (long long)blockIdx.x * blockDim.x + tid; run < g.n_runs; run += stride) {
+    const long long stride = (long long)bs.nblocks * blockDim.x;
+    for (long long run = (long long)bs.bid * blockDim.x + tid; run < g.n_runs; run += stride) {
         const int keyE = __ldg(g.run_key + run);
         const int r0 = __ldg(g.run_start + run), r1 = __ldg(g.run_start + run + 1);
         // the next run's first record and slot are fetched now and used to warm L1 once this
@@ -367,7 +377,7 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
         acc[K] += (double)s_w[k] * acc[k];
     }
 
-    publish_partials(acc, K + 1, s_scratch, g.partials);      // ends with a barrier
+    publish_partials(acc, K + 1, s_scratch, g.partials, bs.bid, bs.nblocks);      // ends with a barrier
 
     // ---- hub gradients: sum the thread-private slots, one warp per hub at a time
     {
@@ -396,6 +406,15 @@ factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
             }
         }
     }
+}
+
+template <typename real, int K, int T, int NE, bool WEIGHTED, int HUBPOS>
+__global__ void __launch_bounds__(kRunThreads, kRunBlocks)
+factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    __shared__ RunShared<real, K, T> sh;
+    factor_run_body<real, K, T, NE, WEIGHTED, HUBPOS>(g, L, L.n_hubs, BlockSlice{(int)blockIdx.x, (int)gridDim.x}, sh,
+                                                      reinterpret_cast<real*>(s_dyn));
 }
 
 template <typename real, int K, int T, int NE>

@@ -84,15 +84,17 @@ template <> struct Fast<double> {
 
 // ---- vector helpers ------------------------------------------------------------------------
 
+// (plain loads, not ld.global.nc: these read parameter slots, which the persistent iteration kernel
+// rewrites between two passes of the same launch)
 template <int N>
-__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[N]) {
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[N]) {
     if constexpr (N == 2) {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        const float2 t = *reinterpret_cast<const float2*>(p);
         v[0] = t.x; v[1] = t.y;
     } else {
 #pragma unroll
         for (int c = 0; c < (N + 3) / 4; ++c) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p) + c);
+            const float4 t = *(reinterpret_cast<const float4*>(p) + c);
             if (4 * c + 0 < N) v[4 * c + 0] = t.x;
             if (4 * c + 1 < N) v[4 * c + 1] = t.y;
             if (4 * c + 2 < N) v[4 * c + 2] = t.z;
@@ -102,10 +104,10 @@ __device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)
 }
 
 template <int N>
-__device__ __forceinline__ void load_vec(const double* __restrict__ p, double (&v)[N]) {
+__device__ __forceinline__ void load_vec(const double* p, double (&v)[N]) {
 #pragma unroll
     for (int c = 0; c < N / 2; ++c) {
-        const double2 t = __ldg(reinterpret_cast<const double2*>(p) + c);
+        const double2 t = *(reinterpret_cast<const double2*>(p) + c);
         v[2 * c] = t.x; v[2 * c + 1] = t.y;
     }
 }
@@ -144,7 +146,7 @@ struct PointCtx {
 
 // log(b + 1e-100) (in the walk's units) with the belief recomputed in double from the parameters
 template <typename real, int K, int NC, int NG>
-__device__ __noinline__ real checked_log_belief(const real* __restrict__ eta, const real* s_w,
+__device__ __noinline__ real checked_log_belief(const real* eta, const real* s_w,
                                                  const PointCtx<real, NC, NG> c) {
     double b = 0.0;
     for (int k2 = 0; k2 < K; ++k2) {
@@ -275,28 +277,53 @@ struct SpecLaunch {
     long long chunk;      // records per block (multiple of the block size)
 };
 
+// Shared memory of one block of the record-major walk (a static allocation in the per-group kernel,
+// a view of the dynamic allocation inside the persistent iteration kernel).
+template <typename real, int K, int T, int NC, int FL, int HUB>
+struct SpecShared {
+    static constexpr int NV = 2 * K;
+    static constexpr bool kHubTab = FL == kFull && HUB >= 0;
+    static constexpr int TP = (T + 3) / 4 * 4;
+    static constexpr int kSlotElems = NV <= 2 ? 2 : ((NV + 3) / 4) * 4;
+    static constexpr int kStageArgs = FL == kFull ? NC - (HUB >= 0 ? 1 : 0) : 0;
+    static constexpr int kSlotBytes = kSlotElems * (int)sizeof(real);
+    static constexpr bool kStage = kStageArgs > 0 && 2 * kStageArgs * kSlotBytes * kSpecThreads <= 32768;
+    alignas(16) unsigned char stage[kStage ? 2 * kStageArgs * kSlotBytes * kSpecThreads : 16];
+    // axis table of the hub variable the block is working on (full records with a hub argument):
+    // cross densities q_{k2}(x_{k,t}) and the per-component scalars, built once per hub and block
+    alignas(16) real hq[kHubTab ? K : 1][kHubTab ? K : 1][TP];
+    double scratch[(kSpecThreads / 32) * (K + 1)];
+    real quad[2 * T];
+    real eq[T];
+    real w[K];
+    real val[kCacheSlots][NV];
+    real hpar[5][K];                   // mu, var, hvar, nrm, sdev
+    real mom[5];                       // cm0, cm2, cm4, cm22, max |xi| (computed once per block)
+    int tag[kCacheSlots];
+};
+
 // HUB: index of the hidden argument accumulated per thread across records (-1: none)
 template <typename real, int K, int T, int NC, int NG, int NE, int FL, bool WEIGHTED, int HUB>
-__global__ void __launch_bounds__(kSpecThreads, 2)
-factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
+__device__ __forceinline__ void
+factor_spec_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice bs,
+                 SpecShared<real, K, T, NC, FL, HUB>& sh) {
     using F = Fast<real>;
     using C = Ctx<real, K, T, NC, NG, NE>;
     constexpr int NA = C::NA, NCT = C::NCT, NQ = C::NQ, NV = 2 * K;
     constexpr int NCS = NC > 0 ? NC : 1;
     constexpr int kSlotElems = NV <= 2 ? 2 : ((NV + 3) / 4) * 4;
 
-    __shared__ real s_quad[2 * T];
-    __shared__ real s_eq[T];
-    __shared__ real s_w[K];
-    __shared__ int s_tag[kCacheSlots];
-    __shared__ real s_val[kCacheSlots][NV];
-    __shared__ double s_scratch[(kSpecThreads / 32) * (K + 1)];
-    // axis table of the hub variable the block is working on (full records with a hub argument):
-    // cross densities q_{k2}(x_{k,t}) and the per-component scalars, built once per hub and block
+    auto& s_quad = sh.quad;
+    auto& s_eq = sh.eq;
+    auto& s_w = sh.w;
+    auto& s_tag = sh.tag;
+    auto& s_val = sh.val;
+    auto& s_scratch = sh.scratch;
     constexpr bool kHubTab = FL == kFull && HUB >= 0;
-    constexpr int TP = (T + 3) / 4 * 4;
-    __shared__ __align__(16) real s_hq[kHubTab ? K : 1][kHubTab ? K : 1][TP];
-    __shared__ real s_hpar[5][K];          // mu, var, hvar, nrm, sdev
+    auto& s_hq = sh.hq;
+    auto& s_hpar = sh.hpar;
+    auto& s_mom = sh.mom;
+    auto& s_stage = sh.stage;
 
     for (int i = threadIdx.x; i < 2 * T; i += blockDim.x) s_quad[i] = g.quad[i];
     for (int i = threadIdx.x; i < T; i += blockDim.x) s_eq[i] = (real)::exp(-(double)g.quad[i] * (double)g.quad[i]);
@@ -326,7 +353,6 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
     // even moments (the rule is mirror-symmetric, odd moments vanish) -- only -log b is walked.
     //   sum W = M0^NA, sum W xi_a^2 = M0^(NA-1) M2, sum W xi_a^4 = M0^(NA-1) M4,
     //   sum W xi_a^2 xi_b^2 = M0^(NA-2) M2^2
-    __shared__ real s_mom[5];              // cm0, cm2, cm4, cm22, max |xi| (computed once per block)
     if constexpr (FL == kFull) {
         if (threadIdx.x == 0) {
             real M0 = real(0), M2 = real(0), M4 = real(0), xm = real(0);
@@ -380,7 +406,7 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
     real node_x[K][T], node_s[K], node_inv[K];
 
     const int lane = threadIdx.x & 31;
-    const long long lo = (long long)blockIdx.x * L.chunk;
+    const long long lo = (long long)bs.bid * L.chunk;
     const long long hi = lo + L.chunk < g.n ? lo + L.chunk : g.n;
 
     // software pipeline: record columns are fetched one tile ahead (plain register arrays --
@@ -415,7 +441,7 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
     constexpr int kChunkBytes = kSlotBytes < 16 ? kSlotBytes : 16;
     constexpr int kChunks = kSlotBytes / kChunkBytes;
     constexpr bool kStage = kStageArgs > 0 && 2 * kStageArgs * kSlotBytes * kSpecThreads <= 32768;
-    __shared__ __align__(16) unsigned char s_stage[kStage ? 2 * kStageArgs * kSlotBytes * kSpecThreads : 16];
+    static_assert(kStage == SpecShared<real, K, T, NC, FL, HUB>::kStage, "stage buffer size");
     auto stage_slots = [&](int buf, const int (&off)[NCS]) {
         if constexpr (kStage) {
             int sa = 0;
@@ -970,7 +996,7 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
         }
     }
 
-    publish_partials(acc, K + 1, s_scratch, g.partials);
+    publish_partials(acc, K + 1, s_scratch, g.partials, bs.bid, bs.nblocks);
 
     // flush the hub cache (block_sum_to ends with a barrier, so every shared atomic has landed)
     if constexpr (HUB >= 0) {
@@ -984,6 +1010,13 @@ factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
             }
         }
     }
+}
+
+template <typename real, int K, int T, int NC, int NG, int NE, int FL, bool WEIGHTED, int HUB>
+__global__ void __launch_bounds__(kSpecThreads, 2)
+factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
+    __shared__ SpecShared<real, K, T, NC, FL, HUB> sh;
+    factor_spec_body<real, K, T, NC, NG, NE, FL, WEIGHTED, HUB>(g, L, BlockSlice{(int)blockIdx.x, (int)gridDim.x}, sh);
 }
 
 template <typename KernelT>
@@ -1026,19 +1059,28 @@ __device__ __forceinline__ void load_quad(const T* __restrict__ p, T (&v)[kQuad]
     }
 }
 
+template <typename real, int K, int T>
+struct PureUnaryShared {
+    double scratch[(kSpecThreads / 32) * (K + 1)];
+    real quad[2 * T];
+    real w[K];
+    real val[kCacheSlots][2 * K];
+    int tag[kCacheSlots];
+};
+
 template <typename real, int K, int T, int NE, bool WEIGHTED, bool USE_CACHE>
-__global__ void __launch_bounds__(kSpecThreads, 2)
-pure_unary_kernel(const GroupView<real> g, const SpecLaunch L) {
+__device__ __forceinline__ void
+pure_unary_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice bs, PureUnaryShared<real, K, T>& sh) {
     using F = Fast<real>;
     constexpr int NV = 2 * K, NCT = 1 + NE, NCOEF = (NCT + 1) * (NCT + 2) / 2;
     constexpr int kSlotElems = NV <= 2 ? 2 : ((NV + 3) / 4) * 4;
     constexpr int NES = NE > 0 ? NE : 1;
 
-    __shared__ real s_quad[2 * T];
-    __shared__ real s_w[K];
-    __shared__ int s_tag[kCacheSlots];
-    __shared__ real s_val[kCacheSlots][NV];
-    __shared__ double s_scratch[(kSpecThreads / 32) * (K + 1)];
+    auto& s_quad = sh.quad;
+    auto& s_w = sh.w;
+    auto& s_tag = sh.tag;
+    auto& s_val = sh.val;
+    auto& s_scratch = sh.scratch;
     for (int i = threadIdx.x; i < 2 * T; i += blockDim.x) s_quad[i] = g.quad[i];
     for (int i = threadIdx.x; i < K; i += blockDim.x) s_w[i] = g.w[i];
     for (int i = threadIdx.x; i < kCacheSlots; i += blockDim.x) s_tag[i] = -1;
@@ -1079,7 +1121,7 @@ pure_unary_kernel(const GroupView<real> g, const SpecLaunch L) {
         red_vec<NV>(g.grad + key, v);
     };
 
-    const long long lo = (long long)blockIdx.x * L.chunk;
+    const long long lo = (long long)bs.bid * L.chunk;
     const long long hi = lo + L.chunk < g.n ? lo + L.chunk : g.n;
     const long long stride = (long long)blockDim.x * kQuad;
 
@@ -1221,7 +1263,7 @@ pure_unary_kernel(const GroupView<real> g, const SpecLaunch L) {
         }
     }
 
-    publish_partials(acc, K + 1, s_scratch, g.partials);
+    publish_partials(acc, K + 1, s_scratch, g.partials, bs.bid, bs.nblocks);
 
     if constexpr (USE_CACHE) {
         for (int slot = threadIdx.x; slot < kCacheSlots; slot += blockDim.x) {
@@ -1234,6 +1276,13 @@ pure_unary_kernel(const GroupView<real> g, const SpecLaunch L) {
             }
         }
     }
+}
+
+template <typename real, int K, int T, int NE, bool WEIGHTED, bool USE_CACHE>
+__global__ void __launch_bounds__(kSpecThreads, 2)
+pure_unary_kernel(const GroupView<real> g, const SpecLaunch L) {
+    __shared__ PureUnaryShared<real, K, T> sh;
+    pure_unary_body<real, K, T, NE, WEIGHTED, USE_CACHE>(g, L, BlockSlice{(int)blockIdx.x, (int)gridDim.x}, sh);
 }
 
 template <typename real, int K, int T, int NE>
@@ -1292,7 +1341,7 @@ static_assert(kFoldTile == 1024, "lhvi.h documents n_pad as a multiple of 1024")
 
 // literal evaluation of one record (floor possibly active); adds into acc / rg
 template <typename real, int K>
-__device__ __noinline__ void fold_slow_record(const real* __restrict__ slot, const real* s_quad, int T,
+__device__ __noinline__ void fold_slow_record(const real* slot, const real* s_quad, int T,
                                               const real* s_w, double c0, double l0, double a0,
                                               double wf, double gam, double* acc, double* rg) {
     double esum = 0.0;
@@ -1329,7 +1378,7 @@ template <typename real> struct RunStart { real xbar, R; };
 
 // expansion point (belief mean) and node radius of a variable's run
 template <typename real, int K>
-__device__ __noinline__ RunStart<real> fold_begin_run(const real* __restrict__ eta, int key,
+__device__ __noinline__ RunStart<real> fold_begin_run(const real* eta, int key,
                                                       const FoldShared<real, K>* sh) {
     constexpr int NV = 2 * K;
     real slot[NV];
@@ -1353,7 +1402,7 @@ __device__ __noinline__ RunStart<real> fold_begin_run(const real* __restrict__ e
 // close a run: per-component formulas on the accumulated sums (in double), gradient out through
 // the block's shared cache (hubs) or vector REDs
 template <typename real, int K, bool USE_CACHE>
-__device__ __forceinline__ void fold_close_run(const real* __restrict__ eta, real* grad, int key, real xbar,
+__device__ __forceinline__ void fold_close_run(const real* eta, real* grad, int key, real xbar,
                                             real sg0, real sg1, real sg2, real sw0, real sw1, real sw2,
                                             FoldShared<real, K>* sh, double* acc, double* rg) {
     constexpr int NV = 2 * K;
@@ -1482,7 +1531,7 @@ __device__ __noinline__ void fold_slow_tile(const FoldCols<real>* c, FoldState<r
 // and lets one lane apply them.  Out of line, state through memory: the streaming loop keeps its
 // registers.  G_w / energy go to sa->acc; the sums and sa->rg are cleared.
 template <typename real, int K, bool USE_CACHE>
-__device__ __noinline__ void fold_close_warp(const real* __restrict__ eta, real* grad, FoldState<real>* st,
+__device__ __noinline__ void fold_close_warp(const real* eta, real* grad, FoldState<real>* st,
                                              FoldShared<real, K>* sh, FoldSlowAcc<K>* sa, bool slow_used) {
     constexpr int NV = 2 * K;
     const int lane = threadIdx.x & 31;
@@ -1520,13 +1569,19 @@ __device__ __noinline__ void fold_close_warp(const real* __restrict__ eta, real*
     st->sg0 = st->sg1 = st->sg2 = st->sw0 = st->sw1 = st->sw2 = real(0);
 }
 
+template <typename real, int K>
+struct FoldBlockShared {
+    FoldShared<real, K> sh;
+    double scratch[(kFoldThreads / 32) * (K + 1)];
+};
+
 template <typename real, int K, bool WEIGHTED, bool USE_CACHE>
-__global__ void __launch_bounds__(kFoldThreads, LHVI_FOLD_BLOCKS)
-unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
+__device__ __forceinline__ void
+unary_fold_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice bs, FoldBlockShared<real, K>& shb) {
     constexpr int NV = 2 * K;
 
-    __shared__ FoldShared<real, K> sh;
-    __shared__ double s_scratch[(kFoldThreads / 32) * (K + 1)];
+    FoldShared<real, K>& sh = shb.sh;
+    auto& s_scratch = shb.scratch;
     const int T = g.T;
     for (int i = threadIdx.x; i < 2 * T; i += blockDim.x) sh.quad[i] = g.quad[i];
     for (int i = threadIdx.x; i < K; i += blockDim.x) sh.w[i] = g.w[i];
@@ -1546,8 +1601,8 @@ unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
     // 32-bit record indices (n_pad < 2^31 is checked at launch).  L.chunk holds the number of
     // tiles: block b takes tiles [tiles b / B, tiles (b + 1) / B), so that block sizes differ by
     // at most one tile and every SM (4 resident blocks) streams the same number of bytes.
-    const unsigned lo = (unsigned)(L.chunk * blockIdx.x / gridDim.x) * kFoldTile;
-    const unsigned hi = (unsigned)(L.chunk * (blockIdx.x + 1) / gridDim.x) * kFoldTile;
+    const unsigned lo = (unsigned)(L.chunk * bs.bid / bs.nblocks) * kFoldTile;
+    const unsigned hi = (unsigned)(L.chunk * (bs.bid + 1) / bs.nblocks) * kFoldTile;
     const real* __restrict__ col0 = g.fold;
     const real* __restrict__ col1 = g.fold + g.n_pad;
     const real* __restrict__ col2 = g.fold + 2 * g.n_pad;
@@ -1678,7 +1733,7 @@ unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
         }
     }
 
-    publish_partials(acc, K + 1, s_scratch, g.partials);
+    publish_partials(acc, K + 1, s_scratch, g.partials, bs.bid, bs.nblocks);
 
     if constexpr (USE_CACHE) {
         for (int slot = threadIdx.x; slot < kCacheSlots; slot += blockDim.x) {
@@ -1691,6 +1746,13 @@ unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
             }
         }
     }
+}
+
+template <typename real, int K, bool WEIGHTED, bool USE_CACHE>
+__global__ void __launch_bounds__(kFoldThreads, LHVI_FOLD_BLOCKS)
+unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
+    __shared__ FoldBlockShared<real, K> shb;
+    unary_fold_body<real, K, WEIGHTED, USE_CACHE>(g, L, BlockSlice{(int)blockIdx.x, (int)gridDim.x}, shb);
 }
 
 template <typename real, int K>

@@ -54,9 +54,10 @@ def hub_mask(g):
 
 FOLD_ALIGN_MIN_TILES = 4   # runs of a streamed group at least this long are padded to whole tiles
 FOLD_BLOCK_SLOTS = 148 * 4  # resident blocks of the streaming kernel on one B200 (a hint: launch_unary_fold)
+ITER_BLOCK_SLOTS = 148 * 2  # resident blocks of the persistent iteration kernel (lhvi_iterate)
 
 
-def align_runs(g, null_pot, tile):
+def align_runs(g, null_pot, tile, FOLD_BLOCK_SLOTS=FOLD_BLOCK_SLOTS):
     """Pad the long runs (records on one variable) of a streamed unary group to whole tiles with
     null records -- coefficient block ``null_pot`` (log psi = 0), zero weights, zero evidence, the
     run's own offset -- so that a hub boundary never falls inside a tile of the streaming kernel
@@ -154,6 +155,10 @@ class DeviceEngine:
         self.profile_group = None
         self.dom_events = []
         self.use_graph = True          # replay one captured iteration instead of ~8 launches
+        # lhvi_iterate: n iterations in one persistent cooperative launch whenever every record group
+        # has a body in that kernel (else the captured per-group launches); LHVI_PERSISTENT=0 turns it off
+        self.use_persistent = os.environ.get("LHVI_PERSISTENT", "1") != "0" and not self.force_generic
+        self.launch_count = 0          # kernels of liblhvi.so launched by iterate() so far
         self.parallel_groups = True    # independent group launches on parallel graph branches
         # lhvi_finish_step instead of lhvi_finish + lhvi_param_step: on for one GPU (measured 143.1 ->
         # 141.7 us per iteration), off for several unless LHVI_FUSED_STEP=1 (measured 89.5 -> 91.6 us
@@ -293,7 +298,7 @@ class DeviceEngine:
                 if nct not in null_pot:
                     null_pot[nct] = ptab_host.size
                     ptab_host = np.concatenate([ptab_host, np.zeros((nct + 1) * (nct + 2) // 2)])
-                g = align_runs(g, null_pot[nct], tile)
+                g = align_runs(g, null_pot[nct], tile, ITER_BLOCK_SLOTS if self.use_persistent else FOLD_BLOCK_SLOTS)
                 d.n = int(g.n)
             fold = fold_unary(g, ptab_host) if (self.symmetric_rule and g.n > 0) else None
             n_pad = (g.n + tile - 1) // tile * tile if fold is not None else g.n
@@ -343,6 +348,11 @@ class DeviceEngine:
         md.grad, md.partials = self.grad.data_ptr(), self.partials.data_ptr()
         self.desc = md
         self.launches_per_pass = 0
+        self.group_table = (_cabi.LhviGroup * max(1, len(self.groups)))()
+        for i, (d, _, _) in enumerate(self.groups):
+            C.memmove(C.byref(self.group_table, i * C.sizeof(_cabi.LhviGroup)), C.byref(d), C.sizeof(_cabi.LhviGroup))
+        self.sm_count = torch.zeros(256, dtype=torch.int32, device=self.device)
+        self._persistent = None        # lhvi_iterate_supported, asked once
 
     # ---- state exchange with the host -----------------------------------------------------
     @property
@@ -549,6 +559,34 @@ class DeviceEngine:
         self.param_step(lr, sgd=sgd, zero_grad=True)
         self.launches_per_pass = launches + 1
 
+    def persistent(self):
+        """True when ``iterate`` runs as one persistent launch (``lhvi_iterate``)."""
+        if not self.use_persistent:
+            return False
+        if self._persistent is None:
+            x = C.byref(self.peer.desc) if (self.plan.active and self.exchange == "p2p") else None
+            ok = (not self.plan.active) or self.exchange == "p2p"       # the collective exchange is a host-side call
+            self._persistent = bool(ok and self.lib.lhvi_iterate_supported(
+                C.byref(self.desc), self.group_table, len(self.groups), x))
+        return self._persistent
+
+    def _iterate_persistent(self, n, lr, sgd):
+        o = _cabi.LhviOptim()
+        o.n_vars, o.n_owned = self.n_vars, self.n_owned
+        o.var_kind, o.var_dim, o.var_off = self.var_kind.data_ptr(), self.var_dim.data_ptr(), self.var_off.data_ptr()
+        o.tau, o.mom1, o.mom2 = self.tau.data_ptr(), self.mom1.data_ptr(), self.mom2.data_ptr()
+        o.wstate, o.step, o.sm_count = self.wstate.data_ptr(), self.step.data_ptr(), self.sm_count.data_ptr()
+        o.lr, o.b1, o.b2, o.eps, o.var_threshold = float(lr), self.b1, self.b2, self.eps, self.var_threshold
+        o.sgd = int(bool(sgd))
+        x = C.byref(self.peer.desc) if self.plan.active else None
+        rc = self.lib.lhvi_iterate(C.byref(self.desc), self.group_table, len(self.groups), x, C.byref(o), int(n),
+                                   self._stream())
+        if rc == 1:
+            raise _cabi.LhviError("lhvi_iterate refused a model lhvi_iterate_supported accepted")
+        _cabi.check(rc, self.lib)
+        self.launch_count += 1
+        self.launches_per_pass = 0
+
     def _graph_for(self, lr, sgd):
         """CUDA graph of one iteration for these hyper-parameters (captured once).  The step
         counter and bias corrections live on the device, so the same graph serves every t."""
@@ -589,6 +627,12 @@ class DeviceEngine:
         n = int(n)
         if n <= 0:
             return
+        if self.profile_group is None and self.persistent():
+            if not self._grad_clean:
+                self.grad[:self.n_param].zero_()
+                self._grad_clean = True
+            self._iterate_persistent(n, lr, sgd)
+            return
         graph = None
         if self.use_graph and self.profile_group is None:
             # a failed capture is an error, not a reason to fall back silently (use_graph = False
@@ -602,10 +646,12 @@ class DeviceEngine:
                 graph.replay()
             else:
                 self._iteration(lr, sgd)
+        self.launch_count += n * self.launches_per_iteration
 
     @property
     def launches_per_iteration(self):
-        """Kernels of liblhvi.so per iteration: the group launches, lhvi_finish, lhvi_param_step."""
+        """Kernels of liblhvi.so per iteration on the per-group path: the group launches, lhvi_finish,
+        lhvi_param_step (the persistent path is one launch per ``iterate`` call: ``launch_count``)."""
         return self.launches_per_pass + 1
 
     def last_free_energy(self):
