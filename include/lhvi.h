@@ -132,6 +132,13 @@ typedef struct lhvi_group {
     int64_t n_runs;
     int32_t n_hubs;
     int32_t run_hub_arg;
+    /* lhvi_iterate only: how many blocks of the persistent grid work on this group.  0: every block
+       takes a slice of the group (the blocks walk the groups one after the other); > 0: the group
+       gets that many blocks of its own, disjoint from the other groups' (the groups then run side by
+       side, each block with one group's prologue and epilogue per iteration).  Either all groups
+       carry a count or none does.  A hint for the schedule: results do not depend on it. */
+    int32_t iter_blocks;
+    int32_t reserved;
 } lhvi_group;
 
 /* Model-wide device buffers shared by every group launch. */
@@ -287,6 +294,13 @@ typedef struct lhvi_optim {
     double lr, b1, b2, eps, var_threshold;
     int32_t sgd;                   /* != 0: theta -= lr * g, moments and step counter untouched */
     int32_t reserved;
+    double* accum;                 /* NULL, or [K + 1] zero-initialised doubles owned by the caller: the blocks add
+                                      their (G_w, energy) sums here with atomics and block 0 publishes and clears
+                                      them after the barrier (NULL: rows of m->partials, summed by block 0) */
+    uint64_t* trace;               /* NULL, or [n_iter][blocks][16] device words: %globaltimer (ns) of every block
+                                      at the start of an iteration (0), after group i of the table (1 + i, i < 11),
+                                      after the first grid barrier (12), after its share of the step (13) and
+                                      after the second barrier (14); 15 = the SM it runs on.  For tools/iter_trace.py. */
 } lhvi_optim;
 
 /*
@@ -310,6 +324,12 @@ int lhvi_iterate(const lhvi_model* m, const lhvi_group* groups, int32_t n_groups
 /* 1 if lhvi_iterate would take this model (only the descriptors' shapes are looked at), else 0. */
 int lhvi_iterate_supported(const lhvi_model* m, const lhvi_group* groups, int32_t n_groups,
                            const lhvi_exchange* x);
+
+/* Blocks of lhvi_iterate's persistent grid that are resident on the current device for this model
+ * (2 per SM unless a group's shared memory allows only 1): what lhvi_group::iter_blocks may add up
+ * to.  0: lhvi_iterate would not take the model; negative: error.  Queries the device, launches nothing. */
+int lhvi_iterate_blocks(const lhvi_model* m, const lhvi_group* groups, int32_t n_groups,
+                        const lhvi_exchange* x);
 
 /*
  * The state a reference caller holds between ADAM_update calls is eta[rv] as K x 2 / K x D arrays

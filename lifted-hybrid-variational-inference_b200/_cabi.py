@@ -25,7 +25,7 @@ SYMBOLS = ("lhvi_last_error", "lhvi_abi_version", "lhvi_has_specialisation",
            "lhvi_factor_expect_grad", "lhvi_elbo_reduce", "lhvi_step_tick",
            "lhvi_param_step", "lhvi_mixture_belief", "lhvi_mixture_map", "lhvi_finish", "lhvi_state_pack", "lhvi_state_unpack", "lhvi_finish_step",
            "lhvi_peer_alloc", "lhvi_peer_open", "lhvi_peer_close", "lhvi_peer_free",
-           "lhvi_iterate", "lhvi_iterate_supported")
+           "lhvi_iterate", "lhvi_iterate_supported", "lhvi_iterate_blocks")
 
 
 class LhviGroup(C.Structure):
@@ -40,6 +40,7 @@ class LhviGroup(C.Structure):
         ("fold", C.c_void_p), ("n_pad", C.c_int64),
         ("run_start", C.c_void_p), ("run_key", C.c_void_p), ("run_hid", C.c_void_p), ("hub_keys", C.c_void_p),
         ("n_runs", C.c_int64), ("n_hubs", C.c_int32), ("run_hub_arg", C.c_int32),
+        ("iter_blocks", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -72,6 +73,7 @@ class LhviOptim(C.Structure):
         ("lr", C.c_double), ("b1", C.c_double), ("b2", C.c_double), ("eps", C.c_double),
         ("var_threshold", C.c_double),
         ("sgd", C.c_int32), ("reserved", C.c_int32),
+        ("accum", C.c_void_p), ("trace", C.c_void_p),
     ]
 
 
@@ -143,9 +145,9 @@ def load(build_if_missing: bool = False):
     lib.lhvi_iterate.restype = C.c_int
     lib.lhvi_iterate.argtypes = [C.POINTER(LhviModel), C.POINTER(LhviGroup), C.c_int32, C.POINTER(LhviExchange),
                                  C.POINTER(LhviOptim), C.c_int32, C.c_void_p]
-    lib.lhvi_iterate_supported.restype = C.c_int
-    lib.lhvi_iterate_supported.argtypes = [C.POINTER(LhviModel), C.POINTER(LhviGroup), C.c_int32,
-                                           C.POINTER(LhviExchange)]
+    for fn in (lib.lhvi_iterate_supported, lib.lhvi_iterate_blocks):
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(LhviModel), C.POINTER(LhviGroup), C.c_int32, C.POINTER(LhviExchange)]
     for fn in (lib.lhvi_state_pack, lib.lhvi_state_unpack):
         fn.restype = C.c_int
         fn.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

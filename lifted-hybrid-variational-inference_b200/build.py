@@ -52,6 +52,32 @@ def headers():
         + [h for h in glob.glob(os.path.join(INCLUDE, "*.h")) if os.path.basename(h) != "lhvi_lift.h"]
 
 
+_INCLUDE_RE = None
+
+
+def includes_of(path, seen=None):
+    """Transitive closure of the quoted #include files of ``path`` (csrc/ and include/), so that a
+    translation unit is rebuilt only when a header it actually uses changed."""
+    import re
+    global _INCLUDE_RE
+    if _INCLUDE_RE is None:
+        _INCLUDE_RE = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+    seen = set() if seen is None else seen
+    try:
+        text = open(path).read()
+    except OSError:
+        return seen
+    for name in _INCLUDE_RE.findall(text):
+        for base in (os.path.dirname(path), CSRC, INCLUDE):
+            cand = os.path.normpath(os.path.join(base, name))
+            if os.path.exists(cand):
+                if cand not in seen:
+                    seen.add(cand)
+                    includes_of(cand, seen)
+                break
+    return seen
+
+
 def up_to_date() -> bool:
     if not os.path.exists(LIB_PATH):
         return False
@@ -62,7 +88,7 @@ def up_to_date() -> bool:
 def _compile(src: str, verbose: bool) -> str:
     obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
     if os.path.exists(obj):
-        newest = max(os.path.getmtime(p) for p in [src] + headers() + [os.path.abspath(__file__)])
+        newest = max(os.path.getmtime(p) for p in [src] + sorted(includes_of(src)) + [os.path.abspath(__file__)])
         if os.path.getmtime(obj) >= newest:
             return obj
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]

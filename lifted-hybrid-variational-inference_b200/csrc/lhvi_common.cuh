@@ -87,9 +87,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Every factor kernel ends with this: block b writes its partial sums to data row b of the
 // launch's region and block 0 records how many rows are valid in the header row, so the
 // reduction needs no zero-filled buffer.
-__device__ __forceinline__ void publish_partials(const double* vals, int nvals, double* scratch, double* region);
-__device__ __forceinline__ void publish_partials(const double* vals, int nvals, double* scratch, double* region,
-                                                 int bid, int nblocks);
 
 __device__ __forceinline__ void block_sum_to(const double* vals, int nvals, double* scratch,
                                              double* out) {
@@ -107,23 +104,40 @@ __device__ __forceinline__ void block_sum_to(const double* vals, int nvals, doub
     __syncthreads();
 }
 
-// `bid` of `nblocks`: the block's index among the blocks working on this record group (the
-// launch's blockIdx / gridDim for a per-group kernel; a slice of the persistent grid inside the
-// iteration kernel)
+// Which slice of a record group a thread block works on: block `bid` of the `nblocks` blocks working
+// on the group (the launch's blockIdx / gridDim for a per-group kernel; a share of the persistent
+// grid inside the iteration kernel).  accum != nullptr: the block adds its (G_w, energy) sums to
+// these K + 1 doubles with atomics instead of writing a row of `partials` (the iteration kernel:
+// nothing is left to reduce after the grid barrier).
+struct BlockSlice {
+    int bid, nblocks;
+    double* accum;
+};
+
 __device__ __forceinline__ void publish_partials(const double* vals, int nvals, double* scratch, double* region,
-                                                 int bid, int nblocks) {
-    if (bid == 0 && threadIdx.x == 0) region[-nvals] = (double)nblocks;
-    block_sum_to(vals, nvals, scratch, region + (long long)bid * nvals);
+                                                 const BlockSlice bs) {
+    if (bs.accum != nullptr) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int i = 0; i < nvals; ++i) {
+            double s = warp_sum(vals[i]);
+            if (lane == 0) scratch[warp * nvals + i] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < nvals) {
+            double s = 0.0;
+            for (int wp = 0; wp < nwarps; ++wp) s += scratch[wp * nvals + threadIdx.x];
+            atomicAdd(bs.accum + threadIdx.x, s);
+        }
+        __syncthreads();
+        return;
+    }
+    if (bs.bid == 0 && threadIdx.x == 0) region[-nvals] = (double)bs.nblocks;
+    block_sum_to(vals, nvals, scratch, region + (long long)bs.bid * nvals);
 }
 
 __device__ __forceinline__ void publish_partials(const double* vals, int nvals, double* scratch, double* region) {
-    publish_partials(vals, nvals, scratch, region, (int)blockIdx.x, (int)gridDim.x);
+    publish_partials(vals, nvals, scratch, region, BlockSlice{(int)blockIdx.x, (int)gridDim.x, nullptr});
 }
-
-// Which slice of a record group a thread block works on, and the shared memory it may use.
-struct BlockSlice {
-    int bid, nblocks;
-};
 
 // ---- typed view of a record group ---------------------------------------------------------
 

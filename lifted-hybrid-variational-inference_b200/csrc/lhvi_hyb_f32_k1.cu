@@ -1,0 +1,9 @@
+// Instantiation unit of the kernels for records with hidden discrete arguments / quadrature degree 10:
+// float, K=1 (see lhvi_hyb_impl.cuh).
+#include "lhvi_hyb_impl.cuh"
+
+namespace lhvi {
+int hyb_f32_k1(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStream_t s) {
+    return launch_hyb_k<float, 1>(m, g, row0, s);
+}
+}  // namespace lhvi

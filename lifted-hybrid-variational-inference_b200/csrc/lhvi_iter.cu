@@ -18,7 +18,7 @@ static int iterate_impl(const lhvi_model* m, const lhvi_group* groups, int32_t n
     if (m->dtype != LHVI_F32 && m->dtype != LHVI_F64) { set_error("dtype %d is neither LHVI_F32 nor LHVI_F64", m->dtype); return LHVI_EINVAL; }
     if (m->K < 1 || m->K > LHVI_MAX_K) { set_error("K=%d out of range 1..%d", m->K, LHVI_MAX_K); return LHVI_ELIMIT; }
     if (n_groups < 0 || n_iter < 0) { set_error("lhvi_iterate: negative group or iteration count"); return LHVI_EINVAL; }
-    if (!probe_only) {
+    if (probe_only == 0) {
         if (!m->quad || !m->eta || !m->w || !m->grad || !m->partials) { set_error("null model buffer (quad/eta/w/grad/partials)"); return LHVI_EINVAL; }
         if (!o->tau || !o->mom1 || !o->mom2 || !o->wstate || !o->step) { set_error("lhvi_iterate: null optimiser buffer"); return LHVI_EINVAL; }
         if (o->n_vars > 0 && (!o->var_kind || !o->var_dim || !o->var_off)) { set_error("lhvi_iterate: null variable table"); return LHVI_EINVAL; }
@@ -45,6 +45,13 @@ static int iterate_impl(const lhvi_model* m, const lhvi_group* groups, int32_t n
 extern "C" int lhvi_iterate(const lhvi_model* m, const lhvi_group* groups, int32_t n_groups, const lhvi_exchange* x,
                             const lhvi_optim* opt, int32_t n_iter, void* stream) {
     return iterate_impl(m, groups, n_groups, x, opt, n_iter, 0, stream);
+}
+
+extern "C" int lhvi_iterate_blocks(const lhvi_model* m, const lhvi_group* groups, int32_t n_groups,
+                                   const lhvi_exchange* x) {
+    lhvi_optim none = {};
+    const int rc = iterate_impl(m, groups, n_groups, x, &none, 1, 2, nullptr);
+    return rc == 1 ? 0 : rc;      // "unsupported" (1) would read as one block
 }
 
 extern "C" int lhvi_iterate_supported(const lhvi_model* m, const lhvi_group* groups, int32_t n_groups,

@@ -29,6 +29,8 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#include <cstring>
+
 #include "lhvi_opt_impl.cuh"
 #include "lhvi_spec_impl.cuh"
 
@@ -78,6 +80,7 @@ struct IterPhase {
     int rot;             // block `rot` is the group's block 0 (small groups start on different blocks)
     int n_hubs;          // run-major groups
     long long chunk;     // SpecLaunch::chunk for `nblocks` blocks
+    double* accum;       // IterArgs::accum (nullptr: rows of `partials`)
 };
 
 template <typename real>
@@ -89,7 +92,15 @@ struct IterArgs {
     StepArgs<real> step;
     double* step_rw;                     // the step counter (advanced here when `tick`)
     long long n_owned;
+    unsigned long long* trace;           // lhvi_optim::trace
+    double* accum;                       // lhvi_optim::accum: [K + 1] running (G_w, energy) sums of the pass
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // The quadrature rule of the run-major body travels in constant memory (see RunLaunch): a noinline
 // function cannot take it from the kernel's parameters as constant-bank operands.
@@ -98,8 +109,15 @@ template <typename real, int T> struct IterRule;
     static __constant__ RunLaunch<REAL, 3> NAME;                                     \
     template <> struct IterRule<REAL, 3> {                                      \
         static __device__ __forceinline__ const RunLaunch<REAL, 3>& get() { return NAME; } \
+        /* copied only when the values change (the rule is a property of the model, not of a call) */ \
         static cudaError_t set(const RunLaunch<REAL, 3>& v, cudaStream_t s) {   \
-            return cudaMemcpyToSymbolAsync(NAME, &v, sizeof(v), 0, cudaMemcpyHostToDevice, s); \
+            static RunLaunch<REAL, 3> last;                                     \
+            static bool have = false;                                           \
+            if (have && memcmp(&last, &v, sizeof(v)) == 0) return cudaSuccess;  \
+            cudaError_t e = cudaMemcpyToSymbolAsync(NAME, &v, sizeof(v), 0, cudaMemcpyHostToDevice, s); \
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);   /* `v` is a stack object */ \
+            if (e == cudaSuccess) { last = v; have = true; }                    \
+            return e;                                                           \
         }                                                                       \
     };
 LHVI_ITER_RULE(float, c_iter_rule_f32)
@@ -114,7 +132,7 @@ __device__ __noinline__ void phase_spec(const IterPhase<real>* ph, int vb, unsig
     SpecLaunch L;
     L.chunk = ph->chunk;
     factor_spec_body<real, K, T, NC, NG, NE, FL, W, HUB>(
-        g, L, BlockSlice{vb, ph->nblocks}, *reinterpret_cast<SpecShared<real, K, T, NC, FL, HUB>*>(smem));
+        g, L, BlockSlice{vb, ph->nblocks, ph->accum}, *reinterpret_cast<SpecShared<real, K, T, NC, FL, HUB>*>(smem));
 }
 
 template <typename real, int K, int T, int NE, bool W, bool CACHE>
@@ -122,7 +140,7 @@ __device__ __noinline__ void phase_pun(const IterPhase<real>* ph, int vb, unsign
     const GroupView<real> g = ph->view;
     SpecLaunch L;
     L.chunk = ph->chunk;
-    pure_unary_body<real, K, T, NE, W, CACHE>(g, L, BlockSlice{vb, ph->nblocks},
+    pure_unary_body<real, K, T, NE, W, CACHE>(g, L, BlockSlice{vb, ph->nblocks, ph->accum},
                                               *reinterpret_cast<PureUnaryShared<real, K, T>*>(smem));
 }
 
@@ -131,7 +149,7 @@ __device__ __noinline__ void phase_fold(const IterPhase<real>* ph, int vb, unsig
     const GroupView<real> g = ph->view;
     SpecLaunch L;
     L.chunk = ph->chunk;
-    unary_fold_body<real, K, W, CACHE>(g, L, BlockSlice{vb, ph->nblocks},
+    unary_fold_body<real, K, W, CACHE>(g, L, BlockSlice{vb, ph->nblocks, ph->accum},
                                        *reinterpret_cast<FoldBlockShared<real, K>*>(smem));
 }
 
@@ -141,7 +159,7 @@ __host__ __device__ constexpr size_t run_shared_bytes() { return (sizeof(RunShar
 template <typename real, int K, int T, int NE, bool W, int HUBPOS>
 __device__ __noinline__ void phase_run(const IterPhase<real>* ph, int vb, unsigned char* smem) {
     const GroupView<real> g = ph->view;
-    factor_run_body<real, K, T, NE, W, HUBPOS>(g, IterRule<real, T>::get(), ph->n_hubs, BlockSlice{vb, ph->nblocks},
+    factor_run_body<real, K, T, NE, W, HUBPOS>(g, IterRule<real, T>::get(), ph->n_hubs, BlockSlice{vb, ph->nblocks, ph->accum},
                                                *reinterpret_cast<RunShared<real, K, T>*>(smem),
                                                reinterpret_cast<real*>(smem + run_shared_bytes<real, K, T>()));
 }
@@ -213,6 +231,13 @@ iterate_kernel(const __grid_constant__ IterArgs<real> A) {
     const bool reversed = s_order != 0;
 
     for (int it = 0; it < A.n_iter; ++it) {
+        unsigned long long* tr = (A.trace != nullptr && threadIdx.x == 0) ? A.trace + ((size_t)it * nb + bid) * 16 : nullptr;
+        if (tr) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            tr[0] = global_timer_ns();
+            tr[15] = smid;
+        }
         if (A.tick && bid == 0 && threadIdx.x == 0) {
             // t, 1 - b1^t, 1 - b2^t (VarInference.py:253,272-273); read after the first grid barrier
             double* st = A.step_rw;
@@ -221,22 +246,34 @@ iterate_kernel(const __grid_constant__ IterArgs<real> A) {
             st[2] = 1.0 - (1.0 - st[2]) * A.fin.b2;
         }
         for (int j = 0; j < A.n_phases; ++j) {
-            const IterPhase<real>* ph = &A.phase[reversed ? A.n_phases - 1 - j : j];
+            const int p = reversed ? A.n_phases - 1 - j : j;
+            const IterPhase<real>* ph = &A.phase[p];
             int vb = bid - ph->rot;
             if (vb < 0) vb += nb;
             if (vb < ph->nblocks) {
                 run_phase<real, K, T>(ph, vb, s_dyn);
                 __syncthreads();           // the next phase re-uses the shared memory
+                if (tr && p < 11) tr[1 + p] = global_timer_ns();
             }
         }
         grid.sync();
+        if (tr) tr[12] = global_timer_ns();
 
         const real c1 = (real)A.step.step[1], c2 = (real)A.step.step[2];
         if (bid == 0) {
-            finish_reduce<real>(A.fin, s_red, s_res);
+            if (A.accum != nullptr) {
+                // every block has added its sums to `accum` before the barrier: publish and clear
+                if (threadIdx.x <= K) {
+                    A.fin.grad[A.fin.n_param + threadIdx.x] = (real)__ldcg(A.accum + threadIdx.x);
+                    A.accum[threadIdx.x] = 0.0;
+                }
+                __syncthreads();
+            } else {
+                finish_reduce<real>(A.fin, s_red, s_res);
+            }
             if (A.fin.world > 1) finish_exchange<real>(A.fin, 1);
             __syncthreads();
-            if (threadIdx.x == 0) step_mixture_weights<real>(A.step, c1, c2);
+            if (threadIdx.x < 32) step_mixture_weights_warp<real>(A.step, c1, c2);
             for (long long v = A.n_owned + threadIdx.x; v < A.step.n_vars; v += blockDim.x)
                 step_variable<real>(A.step, v, c1, c2);
             if (nb == 1)
@@ -246,7 +283,9 @@ iterate_kernel(const __grid_constant__ IterArgs<real> A) {
                  v += (long long)(nb - 1) * blockDim.x)
                 step_variable<real>(A.step, v, c1, c2);
         }
-        grid.sync();
+        if (tr) tr[13] = global_timer_ns();
+        if (it + 1 < A.n_iter) grid.sync();        // the end of the launch orders the last step
+        if (tr) tr[14] = global_timer_ns();
     }
 }
 
@@ -303,70 +342,102 @@ int launch_iterate_kt(const lhvi_model* m, const lhvi_group* groups, int n_group
         ph.view = make_view<real>(m, g, (int64_t)i * LHVI_PARTIAL_ROWS);
         ph.code = code;
         ph.n_hubs = g->n_hubs;
+        ph.accum = o->accum;
     }
     // (an empty group's region of `partials` must read "0 valid rows": the buffer starts zeroed,
     // lhvi_factor_expect_grad writes that header for an empty group, and nothing here touches it)
-    if (probe_only) return 0;
+    if (probe_only == 1) return 0;
 
     auto kernel = iterate_kernel<real, K, T>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    if (e != cudaSuccess) { set_error("iterate_kernel: cudaFuncSetAttribute(%zu bytes): %s", dyn, cudaGetErrorString(e)); cudaGetLastError(); return LHVI_ECUDA; }
-    int dev = 0, per_sm = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kIterThreads, dyn);
+    cudaError_t e = cudaSuccess;
+    static size_t set_dyn = 0, occ_dyn = (size_t)-1;       // per instantiation: attribute / occupancy asked once per size
+    static int occ_per_sm = 0, occ_sms = 0;
+    if (dyn > set_dyn) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) { set_error("iterate_kernel: cudaFuncSetAttribute(%zu bytes): %s", dyn, cudaGetErrorString(e)); cudaGetLastError(); return LHVI_ECUDA; }
+        set_dyn = dyn;
+    }
+    if (dyn != occ_dyn) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&occ_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_per_sm, kernel, kIterThreads, dyn);
+        occ_dyn = dyn;
+    }
+    int per_sm = occ_per_sm;
+    const int sms = occ_sms;
     if (per_sm < 1) { set_error("iterate_kernel: no resident block with %zu bytes of shared memory", dyn); return LHVI_ELIMIT; }
     if (per_sm > 2) per_sm = 2;
     const int resident = per_sm * (sms > 0 ? sms : 148);
+    if (probe_only == 2) return resident;
 
-    // slices: every group is cut into up to `resident` slices of whole tiles; the grid is as large
-    // as the largest group (and the optimiser step) can use
+    // Schedule.  Sliced (no group carries iter_blocks): every group is cut into up to `resident`
+    // slices of whole tiles and every block walks the groups one after the other; the grid is as
+    // large as the largest group (and the optimiser step) can use.  Partitioned (iter_blocks > 0
+    // everywhere): group p gets iter_blocks[p] blocks of its own, [rot, rot + nblocks), so that the
+    // groups run side by side as they do on parallel branches of a CUDA graph.
+    bool partitioned = A.n_phases > 0;
+    for (int i = 0; i < n_groups; ++i)
+        if (groups[i].n > 0 && groups[i].iter_blocks <= 0) partitioned = false;
     int grid = 2;
     int rot = 0;
-    for (int p = 0; p < A.n_phases; ++p) {
-        IterPhase<real>& ph = A.phase[p];
-        const long long n = ph.view.n;
-        const int fam = ph.code >> 24;
-        long long blocks, chunk;
-        if (fam == kFamFold) {
-            const long long tiles = ph.view.n_pad / kFoldTile;
-            const long long c = (tiles + resident - 1) / resident;
-            blocks = (tiles + c - 1) / c;
-            chunk = tiles;                              // the body splits `chunk` tiles over `nblocks` blocks
-        } else if (fam == kFamRun) {
-            blocks = (ph.view.n_runs + kRunThreads - 1) / kRunThreads;
-            if (blocks > resident) blocks = resident;
-            chunk = 0;
-        } else {
-            const long long tile = fam == kFamPun ? (long long)kSpecThreads * kQuad : (long long)kSpecThreads;
-            blocks = (n + tile - 1) / tile;
-            if (blocks > resident) blocks = resident;
-            chunk = ((n + blocks - 1) / blocks + tile - 1) / tile * tile;
-            blocks = (n + chunk - 1) / chunk;
-        }
-        if (blocks < 1) blocks = 1;
-        if (blocks > LHVI_PARTIAL_ROWS - 1) return 1;
-        ph.nblocks = (int)blocks;
-        ph.chunk = chunk;
-        if (ph.nblocks > grid) grid = ph.nblocks;
-    }
     {
+        int p = 0;
+        for (int i = 0; i < n_groups; ++i) {
+            if (groups[i].n == 0) continue;
+            IterPhase<real>& ph = A.phase[p++];
+            const long long n = ph.view.n;
+            const int fam = ph.code >> 24;
+            const long long cap = partitioned ? (groups[i].iter_blocks < resident ? groups[i].iter_blocks : resident) : resident;
+            long long blocks, chunk;
+            if (fam == kFamFold) {
+                const long long tiles = ph.view.n_pad / kFoldTile;
+                const long long c = (tiles + cap - 1) / cap;
+                blocks = (tiles + c - 1) / c;
+                chunk = tiles;                              // the body splits `chunk` tiles over `nblocks` blocks
+            } else if (fam == kFamRun) {
+                blocks = (ph.view.n_runs + kRunThreads - 1) / kRunThreads;
+                if (blocks > cap) blocks = cap;
+                chunk = 0;
+            } else {
+                const long long tile = fam == kFamPun ? (long long)kSpecThreads * kQuad : (long long)kSpecThreads;
+                blocks = (n + tile - 1) / tile;
+                if (blocks > cap) blocks = cap;
+                chunk = ((n + blocks - 1) / blocks + tile - 1) / tile * tile;
+                blocks = (n + chunk - 1) / chunk;
+            }
+            if (blocks < 1) blocks = 1;
+            if (blocks > LHVI_PARTIAL_ROWS - 1) return 1;
+            ph.nblocks = (int)blocks;
+            ph.chunk = chunk;
+            if (partitioned) {
+                ph.rot = rot;
+                rot += ph.nblocks;
+            } else if (ph.nblocks > grid) {
+                grid = ph.nblocks;
+            }
+        }
+    }
+    if (partitioned) {
+        if (rot > resident) { set_error("lhvi_iterate: iter_blocks add up to %d, only %d blocks are resident", rot, resident); return LHVI_EINVAL; }
+        grid = rot > 2 ? rot : 2;
+    } else {
         const long long vb = (o->n_owned + kIterThreads - 1) / kIterThreads + 1;
         if (vb > grid) grid = (int)(vb < resident ? vb : resident);
-    }
-    for (int p = 0; p < A.n_phases; ++p) {           // small groups start on different blocks
-        IterPhase<real>& ph = A.phase[p];
-        ph.rot = 0;
-        if (ph.nblocks < grid) {
-            ph.rot = rot % grid;
-            rot += ph.nblocks;
+        for (int p = 0; p < A.n_phases; ++p) {           // small groups start on different blocks
+            IterPhase<real>& ph = A.phase[p];
+            ph.rot = 0;
+            if (ph.nblocks < grid) {
+                ph.rot = rot % grid;
+                rot += ph.nblocks;
+            }
         }
     }
 
     // run-major rule constants
     {
         RunLaunch<real, T> L;
-        L.n_hubs = 0;
+        memset(&L, 0, sizeof(L));
         double M0 = 0.0, M2 = 0.0, M4 = 0.0, xm = 0.0, eqm = 1.0;
         for (int t = 0; t < T; ++t) {
             const double xq = m->quad_host[t], om = m->quad_host[T + t];
@@ -389,6 +460,8 @@ int launch_iterate_kt(const lhvi_model* m, const lhvi_group* groups, int n_group
     A.sm_count = o->sm_count;
     A.step_rw = o->step;
     A.n_owned = o->n_owned;
+    A.trace = (unsigned long long*)o->trace;
+    A.accum = o->accum;
     FinishArgs<real>& f = A.fin;
     f.partials = m->partials; f.regions = n_groups; f.K = m->K;
     f.grad = (real*)m->grad; f.n_param = m->n_param;

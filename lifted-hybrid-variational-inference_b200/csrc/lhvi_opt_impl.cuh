@@ -240,6 +240,37 @@ __device__ void step_mixture_weights(const StepArgs<real>& a, real c1, real c2) 
     for (int k = 0; k < K; ++k) w[k] = M::exp(w_tau[k] - mx) / z;
 }
 
+// the same with one lane per component (lanes 0..K-1 of ONE full warp; every load of a lane is
+// independent, so the whole step costs one round trip to memory instead of a chain of them)
+template <typename real>
+__device__ void step_mixture_weights_warp(const StepArgs<real>& a, real c1, real c2) {
+    using M = Math<real>;
+    const int K = a.K, k = threadIdx.x & 31;
+    const bool on = k < K;
+    real* ws = a.wstate;
+    const real G = on ? a.grad[a.n_param + k] : real(0);
+    const real w = on ? ws[K + k] : real(0);
+    real wt = on ? ws[k] : real(0);
+    real m1 = on ? ws[2 * K + k] : real(0), m2 = on ? ws[3 * K + k] : real(0);
+    real dot = G * w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const real gk = w * (G - dot);                                   // VarInference.py:90
+    if (on) wt = moved<real>(wt, gk, m1, m2, a, c1, c2);
+    real mx = on ? wt : real(-1e30);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const real v = __shfl_xor_sync(0xffffffffu, mx, o); mx = v > mx ? v : mx; }
+    const real e = on ? M::exp(wt - mx) : real(0);
+    real z = e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    if (on) {
+        ws[k] = wt;
+        ws[K + k] = e / z;
+        if (!a.sgd) { ws[2 * K + k] = m1; ws[3 * K + k] = m2; }
+    }
+}
+
 // one variable: softmax Jacobian (discrete), Adam / SGD, variance clip, re-normalisation, and the
 // reset of the gradient slots it consumed
 template <typename real>

@@ -377,7 +377,7 @@ factor_run_body(const GroupView<real>& g, const RunLaunch<real, T>& L, const int
         acc[K] += (double)s_w[k] * acc[k];
     }
 
-    publish_partials(acc, K + 1, s_scratch, g.partials, bs.bid, bs.nblocks);      // ends with a barrier
+    publish_partials(acc, K + 1, s_scratch, g.partials, bs);      // ends with a barrier
 
     // ---- hub gradients: sum the thread-private slots, one warp per hub at a time
     {
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kRunThreads, kRunBlocks)
 factor_run_kernel(const GroupView<real> g, const RunLaunch<real, T> L) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ RunShared<real, K, T> sh;
-    factor_run_body<real, K, T, NE, WEIGHTED, HUBPOS>(g, L, L.n_hubs, BlockSlice{(int)blockIdx.x, (int)gridDim.x}, sh,
+    factor_run_body<real, K, T, NE, WEIGHTED, HUBPOS>(g, L, L.n_hubs, BlockSlice{(int)blockIdx.x, (int)gridDim.x, nullptr}, sh,
                                                       reinterpret_cast<real*>(s_dyn));
 }
 

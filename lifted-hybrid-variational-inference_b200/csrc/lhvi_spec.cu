@@ -3,6 +3,7 @@
 // build parallelises.
 #include "lhvi_common.cuh"
 #include "lhvi_spec_sigs.h"
+#include "lhvi_hyb_sigs.h"
 
 namespace lhvi {
 
@@ -12,8 +13,21 @@ int spec_f32_k3(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
 int spec_f64_k1(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
 int spec_f64_k2(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
 int spec_f64_k3(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+// records with hidden discrete arguments, quadrature degree 10 (lhvi_hyb_impl.cuh)
+int hyb_f32_k1(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+int hyb_f32_k2(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+int hyb_f32_k3(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+int hyb_f64_k1(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+int hyb_f64_k2(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+int hyb_f64_k3(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
+
+static bool walk_available(const lhvi_model* m, const lhvi_group* g);
 
 bool spec_available(const lhvi_model* m, const lhvi_group* g) {
+    return walk_available(m, g) || hyb_available(m, g);
+}
+
+static bool walk_available(const lhvi_model* m, const lhvi_group* g) {
     if (g->nd != 0 || m->K < 1 || m->K > 3) return false;
     // the streaming unary kernel takes T at run time (it only needs the rule's even moments)
     if (g->fold && g->pure && !g->node && g->nc == 1 && g->ng == 0) return true;
@@ -39,6 +53,14 @@ bool spec_available(const lhvi_model* m, const lhvi_group* g) {
 int launch_spec(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStream_t s) {
     if (!spec_available(m, g)) return 1;
     const bool f64 = m->dtype == LHVI_F64;
+    if (!walk_available(m, g)) {
+        switch (m->K) {
+            case 1: return f64 ? hyb_f64_k1(m, g, row0, s) : hyb_f32_k1(m, g, row0, s);
+            case 2: return f64 ? hyb_f64_k2(m, g, row0, s) : hyb_f32_k2(m, g, row0, s);
+            case 3: return f64 ? hyb_f64_k3(m, g, row0, s) : hyb_f32_k3(m, g, row0, s);
+            default: return 1;
+        }
+    }
     switch (m->K) {
         case 1: return f64 ? spec_f64_k1(m, g, row0, s) : spec_f32_k1(m, g, row0, s);
         case 2: return f64 ? spec_f64_k2(m, g, row0, s) : spec_f32_k2(m, g, row0, s);

@@ -168,7 +168,10 @@ __device__ __noinline__ real checked_log_psi(real q) {
 
 // ---- compile-time grid walk ------------------------------------------------------------------
 
+#ifndef LHVI_FLAVOURS_DEFINED
+#define LHVI_FLAVOURS_DEFINED
 enum Flavour { kFull = 0, kPure = 1, kNode = 2 };
+#endif
 
 template <typename real, int K, int T, int NC, int NG, int NE>
 struct Ctx {
@@ -432,7 +435,7 @@ factor_spec_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice
     } while (0)
     // non-hub parameter slots are prefetched into L1 one tile ahead, which needs their offsets
     // two tiles ahead (f_poff)
-    constexpr bool kSlotPrefetch = FL == kFull;
+    constexpr bool kSlotPrefetch = FL == kFull || (FL == kNode && NC > 0);
     // ... and from there into shared memory with cp.async (one tile ahead, double-buffered, laid
     // out [buffer][argument][16-byte chunk][thread] so that the reads are conflict-free): the gather
     // latency of the non-hub slots is then off the record's critical path without costing registers
@@ -996,7 +999,7 @@ factor_spec_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice
         }
     }
 
-    publish_partials(acc, K + 1, s_scratch, g.partials, bs.bid, bs.nblocks);
+    publish_partials(acc, K + 1, s_scratch, g.partials, bs);
 
     // flush the hub cache (block_sum_to ends with a barrier, so every shared atomic has landed)
     if constexpr (HUB >= 0) {
@@ -1016,7 +1019,7 @@ template <typename real, int K, int T, int NC, int NG, int NE, int FL, bool WEIG
 __global__ void __launch_bounds__(kSpecThreads, 2)
 factor_spec_kernel(const GroupView<real> g, const SpecLaunch L) {
     __shared__ SpecShared<real, K, T, NC, FL, HUB> sh;
-    factor_spec_body<real, K, T, NC, NG, NE, FL, WEIGHTED, HUB>(g, L, BlockSlice{(int)blockIdx.x, (int)gridDim.x}, sh);
+    factor_spec_body<real, K, T, NC, NG, NE, FL, WEIGHTED, HUB>(g, L, BlockSlice{(int)blockIdx.x, (int)gridDim.x, nullptr}, sh);
 }
 
 template <typename KernelT>
@@ -1149,10 +1152,27 @@ pure_unary_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice 
 
     long long r = lo + (long long)threadIdx.x * kQuad;
     if (r < hi) LHVI_FETCH_QUAD(r, c_pot, c_off, c_ec, c_wf, c_gam);
+    // the parameter slots of the next tile are prefetched into L1 while this tile is worked on, which
+    // needs the offsets two tiles ahead (f_off): without it every record waits for its own gather
+    // (offset -> slot: two dependent round trips to memory per record, ~2 us, nothing to hide them
+    // behind at 8 warps per block)
+    int f_off[kQuad];
+#pragma unroll
+    for (int j = 0; j < kQuad; ++j) f_off[j] = -1;
+    if (r + stride + kQuad <= hi) load_quad<int>(g.poff + r + stride, f_off);
 
     for (; r < hi; r += stride) {
         const long long rn = r + stride;
+#pragma unroll
+        for (int j = 0; j < kQuad; ++j)
+            if (f_off[j] >= 0 && f_off[j] != run_key) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.eta + f_off[j]));
         if (rn < hi) LHVI_FETCH_QUAD(rn, n_pot, n_off, n_ec, n_wf, n_gam);
+        if (rn + stride + kQuad <= hi) {
+            load_quad<int>(g.poff + rn + stride, f_off);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kQuad; ++j) f_off[j] = -1;
+        }
 
 #pragma unroll
         for (int j = 0; j < kQuad; ++j) {
@@ -1263,7 +1283,7 @@ pure_unary_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice 
         }
     }
 
-    publish_partials(acc, K + 1, s_scratch, g.partials, bs.bid, bs.nblocks);
+    publish_partials(acc, K + 1, s_scratch, g.partials, bs);
 
     if constexpr (USE_CACHE) {
         for (int slot = threadIdx.x; slot < kCacheSlots; slot += blockDim.x) {
@@ -1282,7 +1302,7 @@ template <typename real, int K, int T, int NE, bool WEIGHTED, bool USE_CACHE>
 __global__ void __launch_bounds__(kSpecThreads, 2)
 pure_unary_kernel(const GroupView<real> g, const SpecLaunch L) {
     __shared__ PureUnaryShared<real, K, T> sh;
-    pure_unary_body<real, K, T, NE, WEIGHTED, USE_CACHE>(g, L, BlockSlice{(int)blockIdx.x, (int)gridDim.x}, sh);
+    pure_unary_body<real, K, T, NE, WEIGHTED, USE_CACHE>(g, L, BlockSlice{(int)blockIdx.x, (int)gridDim.x, nullptr}, sh);
 }
 
 template <typename real, int K, int T, int NE>
@@ -1733,7 +1753,7 @@ unary_fold_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice 
         }
     }
 
-    publish_partials(acc, K + 1, s_scratch, g.partials, bs.bid, bs.nblocks);
+    publish_partials(acc, K + 1, s_scratch, g.partials, bs);
 
     if constexpr (USE_CACHE) {
         for (int slot = threadIdx.x; slot < kCacheSlots; slot += blockDim.x) {
@@ -1752,7 +1772,7 @@ template <typename real, int K, bool WEIGHTED, bool USE_CACHE>
 __global__ void __launch_bounds__(kFoldThreads, LHVI_FOLD_BLOCKS)
 unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
     __shared__ FoldBlockShared<real, K> shb;
-    unary_fold_body<real, K, WEIGHTED, USE_CACHE>(g, L, BlockSlice{(int)blockIdx.x, (int)gridDim.x}, shb);
+    unary_fold_body<real, K, WEIGHTED, USE_CACHE>(g, L, BlockSlice{(int)blockIdx.x, (int)gridDim.x, nullptr}, shb);
 }
 
 template <typename real, int K>

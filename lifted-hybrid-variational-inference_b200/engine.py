@@ -55,6 +55,8 @@ def hub_mask(g):
 FOLD_ALIGN_MIN_TILES = 4   # runs of a streamed group at least this long are padded to whole tiles
 FOLD_BLOCK_SLOTS = 148 * 4  # resident blocks of the streaming kernel on one B200 (a hint: launch_unary_fold)
 ITER_BLOCK_SLOTS = 148 * 2  # resident blocks of the persistent iteration kernel (lhvi_iterate)
+ITER_TUNE_ROUNDS = 2
+PERSISTENT_MAX_RECORDS = 3_500_000   # LHVI_PERSISTENT=auto: larger rank-local models use the per-group launches
 
 
 def align_runs(g, null_pot, tile, FOLD_BLOCK_SLOTS=FOLD_BLOCK_SLOTS):
@@ -134,6 +136,71 @@ def run_layout(g, K, elem_bytes):
     return sg, starts.astype(np.int32), run_key.astype(np.int32), hid.astype(np.int32), hubs.astype(np.int32), hub_arg
 
 
+# ---- schedule of the persistent iteration kernel (lhvi_iterate) ---------------------------------
+# Per record group: nanoseconds per record for ONE block of 256 threads, and a fixed prologue +
+# epilogue latency per block and iteration in microseconds (hub tables, shared-memory set-up, block
+# reduction, flushes) -- rough figures from the per-group kernels timed alone on a B200 (fp32, K = 3;
+# profiles/r2_iter_plan.md).  Only the split of the grid depends on them, never a result.
+ITER_COST_NS = {"run": 6.5, "fold": 1.1, "node": 5.6, "pun": 8.8, "const": 3.0, "full": 10.0}
+ITER_FIXED_US = {"run": 3.5, "fold": 2.5, "node": 2.5, "pun": 2.5, "const": 2.5, "full": 2.5}
+
+
+def iteration_kind(g, runs, streamed):
+    if g.node:
+        return "node"
+    if runs is not None:
+        return "run"
+    if streamed:
+        return "fold"
+    if g.pure:
+        return "pun" if g.nc == 1 else "const"
+    return "full"
+
+
+def iteration_cost(kind, n, K, esize):
+    """Estimated block-microseconds of one pass over a group of ``n`` records (before any measurement)."""
+    c = ITER_COST_NS[kind]
+    if kind in ("run", "node", "full"):             # walks over K x K cross densities
+        c *= (K / 3.0) ** 2 * (2.5 if esize == 8 else 1.0)
+    else:                                            # streaming / closed forms: bytes and a few FMAs
+        c *= (K / 3.0) * (2.0 if esize == 8 else 1.0)
+    return c * 1e-3 * n
+
+
+def iteration_plan(work, fixed, blocks, pinned=None):
+    """Blocks of the persistent grid per record group so that the groups, running side by side, end
+    together: the smallest T with sum_p ceil(work_p / (T - fixed_p)) <= blocks (``work`` in
+    block-microseconds, ``fixed`` = per-block prologue + epilogue in microseconds).  ``pinned``
+    {index: blocks} keeps those groups' shares (a streamed group whose runs were padded to its
+    share of the grid)."""
+    pinned = pinned or {}
+    free = [i for i in range(len(work)) if i not in pinned]
+    budget = blocks - sum(pinned.values())
+    plan = [pinned.get(i, 1) for i in range(len(work))]
+    if not free:
+        return plan
+    budget = max(budget, len(free))
+
+    def need(T):
+        return [max(1, int(np.ceil(work[i] / (T - fixed[i])))) for i in free]
+    lo, hi = max(fixed[i] for i in free) + 1e-3, max(fixed[i] for i in free) + sum(work[i] for i in free) + 1.0
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if sum(need(mid)) <= budget:
+            hi = mid
+        else:
+            lo = mid
+    for i, b in zip(free, need(hi)):
+        plan[i] = b
+    # hand the blocks the ceilings left over to the groups with the most work per block
+    spare = budget - sum(plan[i] for i in free)
+    while spare > 0:
+        i = max(free, key=lambda j: work[j] / plan[j])
+        plan[i] += 1
+        spare -= 1
+    return plan
+
+
 class DeviceEngine:
     def __init__(self, model: LoweredModel, dtype="float64", device=None, var_threshold=0.1,
                  process_group=None, shard=True, force_generic=False, run_major=True):
@@ -157,7 +224,10 @@ class DeviceEngine:
         self.use_graph = True          # replay one captured iteration instead of ~8 launches
         # lhvi_iterate: n iterations in one persistent cooperative launch whenever every record group
         # has a body in that kernel (else the captured per-group launches); LHVI_PERSISTENT=0 turns it off
-        self.use_persistent = os.environ.get("LHVI_PERSISTENT", "1") != "0" and not self.force_generic
+        # ("auto", the default: for rank-local models up to PERSISTENT_MAX_RECORDS records -- above that
+        # the per-group kernels, which run at twice the occupancy, win: profiles/r2_iter_plan.md)
+        self.persistent_mode = os.environ.get("LHVI_PERSISTENT", "auto")
+        self.use_persistent = self.persistent_mode != "0" and not self.force_generic
         self.launch_count = 0          # kernels of liblhvi.so launched by iterate() so far
         self.parallel_groups = True    # independent group launches on parallel graph branches
         # lhvi_finish_step instead of lhvi_finish + lhvi_param_step: on for one GPU (measured 143.1 ->
@@ -171,6 +241,8 @@ class DeviceEngine:
         self.plan = ShardPlan(process_group, enabled=shard)
         self.world, self.rank = self.plan.world, self.plan.rank
         self.model = self.plan.shard(model)
+        if self.persistent_mode == "auto" and self.model.n_records > PERSISTENT_MAX_RECORDS:
+            self.use_persistent = False
         self.reduce_grads = self.plan.active
 
         self._upload()
@@ -276,11 +348,32 @@ class DeviceEngine:
         self.groups = []      # (descriptor struct, tensors kept alive, RecordGroup)
         esize = 8 if self.dtype_name == "float64" else 4
         null_pot = {}           # nct -> offset of an all-zero coefficient block appended to ptab
-        for g in self.model.groups:
+        tile = _cabi.LHVI_FOLD_TILE
+
+        def is_streamed(g):
+            return (self.symmetric_rule and g.n > 0 and not g.node and g.pure and g.nd == 0 and g.nc == 1
+                    and g.ng == 0 and K <= 3 and bool((hub_mask(g) >> g.nd) & 1))
+        layouts = [run_layout(g, K, esize) if (self.run_major and self.mirror_rule and self.T == 3 and K <= 3) else None
+                   for g in self.model.groups]
+        # schedule of the persistent kernel: "split" gives every group blocks of its own (the groups run
+        # side by side, as on the branches of the CUDA graph), "slice" lets every block walk all groups
+        self.iter_plan = None
+        mode = os.environ.get("LHVI_ITER_PLAN", "split")
+        live = [i for i, g in enumerate(self.model.groups) if g.n > 0]
+        if self.use_persistent and mode != "slice" and live and all(self.model.groups[i].nd == 0 for i in live):
+            kinds = [iteration_kind(self.model.groups[i], layouts[i], is_streamed(self.model.groups[i])) for i in live]
+            blocks = int(os.environ.get("LHVI_ITER_BLOCKS", ITER_BLOCK_SLOTS))
+            if len(live) <= blocks:
+                work = [iteration_cost(k, self.model.groups[i].n, K, esize) for k, i in zip(kinds, live)]
+                shares = iteration_plan(work, [ITER_FIXED_US[k] for k in kinds], blocks)
+                self.iter_plan = dict(zip(live, shares))
+                self.iter_kinds = dict(zip(live, kinds))
+                self.iter_work = dict(zip(live, work))
+        for gi, g in enumerate(self.model.groups):
             keep = {}
             g_report = g        # what bench.py and callers see: the group as lowered
             d = _cabi.LhviGroup()
-            runs = run_layout(g, K, esize) if (self.run_major and self.mirror_rule and self.T == 3 and K <= 3) else None
+            runs = layouts[gi]
             if runs is not None:
                 g = runs[0]
             d.nd, d.nc, d.ng, d.ne = g.nd, g.nc, g.ng, g.ne
@@ -290,15 +383,17 @@ class DeviceEngine:
             d.hub_mask = hub_mask(g)
             d.pure = int(g.pure)
 
-            tile = _cabi.LHVI_FOLD_TILE
-            streamed = (self.symmetric_rule and g.n > 0 and not g.node and g.pure and g.nd == 0 and g.nc == 1
-                        and g.ng == 0 and K <= 3 and bool((hub_mask(g) >> g.nd) & 1))
+            d.iter_blocks = int(self.iter_plan[gi]) if (self.iter_plan and gi in self.iter_plan) else 0
+            streamed = is_streamed(g)
             if streamed:
                 nct = g.nc + g.ne
                 if nct not in null_pot:
                     null_pot[nct] = ptab_host.size
                     ptab_host = np.concatenate([ptab_host, np.zeros((nct + 1) * (nct + 2) // 2)])
-                g = align_runs(g, null_pot[nct], tile, ITER_BLOCK_SLOTS if self.use_persistent else FOLD_BLOCK_SLOTS)
+                # the blocks that will stream this group: its share of the persistent grid, else the
+                # whole grid (sliced schedule) or the streaming kernel's own resident blocks
+                slots = d.iter_blocks or (ITER_BLOCK_SLOTS if self.use_persistent else FOLD_BLOCK_SLOTS)
+                g = align_runs(g, null_pot[nct], tile, slots)
                 d.n = int(g.n)
             fold = fold_unary(g, ptab_host) if (self.symmetric_rule and g.n > 0) else None
             n_pad = (g.n + tile - 1) // tile * tile if fold is not None else g.n
@@ -352,7 +447,9 @@ class DeviceEngine:
         for i, (d, _, _) in enumerate(self.groups):
             C.memmove(C.byref(self.group_table, i * C.sizeof(_cabi.LhviGroup)), C.byref(d), C.sizeof(_cabi.LhviGroup))
         self.sm_count = torch.zeros(256, dtype=torch.int32, device=self.device)
+        self.iter_accum = torch.zeros(K + 1, dtype=torch.float64, device=self.device)
         self._persistent = None        # lhvi_iterate_supported, asked once
+        self._iter_tuned = 0           # how often the grid split has been re-planned from a measured launch
 
     # ---- state exchange with the host -----------------------------------------------------
     @property
@@ -568,9 +665,64 @@ class DeviceEngine:
             ok = (not self.plan.active) or self.exchange == "p2p"       # the collective exchange is a host-side call
             self._persistent = bool(ok and self.lib.lhvi_iterate_supported(
                 C.byref(self.desc), self.group_table, len(self.groups), x))
+            if self._persistent and self.iter_plan:
+                # the split was planned for 2 blocks per SM; a group that needs more shared memory than
+                # that allows (fp64 run-major tables) halves the grid: plan again for what is resident
+                resident = int(self.lib.lhvi_iterate_blocks(C.byref(self.desc), self.group_table, len(self.groups), x))
+                if resident < 0:
+                    _cabi.check(resident, self.lib)
+                if 0 < resident < sum(self.iter_plan.values()):
+                    self._replan(max(resident, len(self.iter_plan)))
         return self._persistent
 
+    def _replan(self, blocks, pinned=None):
+        live = sorted(self.iter_plan)
+        pin = {live.index(i): b for i, b in (pinned or {}).items()}
+        shares = iteration_plan([self.iter_work[i] for i in live], [ITER_FIXED_US[self.iter_kinds[i]] for i in live],
+                                blocks, pin)
+        self.iter_plan = dict(zip(live, shares))
+        for i in live:
+            self.group_table[i].iter_blocks = int(self.iter_plan[i])
+
+    def _retune(self, trace, iters):
+        """Re-split the persistent grid from what the groups' blocks measured in the launch just done
+        (``lhvi_optim::trace``, last traced iteration): work_p = (mean time in the group - fixed) x its
+        blocks.  A streamed group keeps its share (its hub runs are padded to it)."""
+        blocks = sum(self.iter_plan.values())
+        grid = int(np.count_nonzero(trace.reshape(-1, 16)[:, 0])) // iters       # blocks actually launched
+        if grid < 1:
+            return
+        t = trace[:iters * grid * 16].reshape(iters, grid, 16)[-1]
+        live = sorted(self.iter_plan)
+        for p, i in enumerate(live):
+            if p >= 11:
+                continue
+            rows = t[t[:, 1 + p] > 0]                  # the blocks that worked on group p
+            if rows.shape[0] == 0:
+                continue
+            dur = float(np.mean(rows[:, 1 + p] - rows[:, 0])) * 1e-3          # microseconds
+            fixed = ITER_FIXED_US[self.iter_kinds[i]]
+            self.iter_work[i] = max(dur - fixed, 0.05 * dur, 0.05) * rows.shape[0]
+        pinned = {i: self.iter_plan[i] for i in live if self.iter_kinds[i] == "fold"}
+        self._replan(blocks, pinned)
+
     def _iterate_persistent(self, n, lr, sgd):
+        while (self.iter_plan and self._iter_tuned < ITER_TUNE_ROUNDS and len(self.iter_plan) > 1 and n > 0
+               and os.environ.get("LHVI_ITER_ADAPT", "1") != "0"):
+            # the first launches measure: two iterations with per-block timestamps, then the grid is
+            # re-split so that the groups end together (the iterations themselves are ordinary ones;
+            # twice, because a group's speed depends on what shares its SMs)
+            self._iter_tuned += 1
+            k = min(int(n), 2)
+            self._launch_persistent(k, lr, sgd, trace=True)
+            torch.cuda.synchronize(self.device)
+            self._retune(self.iter_trace.cpu().numpy(), k)
+            n -= k
+        if n <= 0:
+            return
+        self._launch_persistent(n, lr, sgd, trace=bool(os.environ.get("LHVI_ITER_TRACE")))
+
+    def _launch_persistent(self, n, lr, sgd, trace=False):
         o = _cabi.LhviOptim()
         o.n_vars, o.n_owned = self.n_vars, self.n_owned
         o.var_kind, o.var_dim, o.var_off = self.var_kind.data_ptr(), self.var_dim.data_ptr(), self.var_off.data_ptr()
@@ -578,6 +730,11 @@ class DeviceEngine:
         o.wstate, o.step, o.sm_count = self.wstate.data_ptr(), self.step.data_ptr(), self.sm_count.data_ptr()
         o.lr, o.b1, o.b2, o.eps, o.var_threshold = float(lr), self.b1, self.b2, self.eps, self.var_threshold
         o.sgd = int(bool(sgd))
+        o.accum = self.iter_accum.data_ptr()
+        self.iter_trace = None
+        if trace:                  # per-block timestamps of the launch (_retune, tools/iter_trace.py)
+            self.iter_trace = torch.zeros(int(n) * 2 * 160 * 16, dtype=torch.int64, device=self.device)
+            o.trace = self.iter_trace.data_ptr()
         x = C.byref(self.peer.desc) if self.plan.active else None
         rc = self.lib.lhvi_iterate(C.byref(self.desc), self.group_table, len(self.groups), x, C.byref(o), int(n),
                                    self._stream())

@@ -1,0 +1,111 @@
+"""Records with hidden discrete arguments and quadrature degree 10 on the template-specialised
+kernels (``csrc/lhvi_hyb_impl.cuh``; reference: ``gradient_category_tau``, ``VarInference.py:133-160``,
+and ``expectation`` over mixed discrete / continuous arguments, ``:40-55``).
+
+* every record group of the goldens with hidden booleans / three-state variables is served by a
+  specialised kernel (``lhvi_has_specialisation``), not by the generic fallback;
+* BASELINE config 1 at its own size and settings -- the paper-popularity hybrid MLN of
+  ``Demo/HMLN/DemoPaperPopularity.py`` (3 390 factors, 2 173 hidden booleans), K = 2, Gauss-Hermite
+  degree 10: free energy / G_w / gradients against the numpy oracle (fp64 1e-9, fp32), the fp64 engine on
+  the oracle's trajectory and the fp32 engine's final beliefs within 1e-4 after 1000 iterations
+  (north_star's criterion for this configuration)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers
+import lhvi_b200
+import specs
+from oracle.vi_numpy import NumpyVI, grad_pass, norm_pdf_ref
+
+pytestmark = pytest.mark.gpu
+
+DISCRETE_GOLDENS = ["smokers", "chain_table", "tri_table3", "hmln_hidden", "robot_like", "hmln_demo",
+                    "robot_demo", "edge_mix"]
+
+
+def _engine(model, dtype="float64", **kw):
+    from lhvi_b200.engine import DeviceEngine
+    return DeviceEngine(model, dtype=dtype, **kw)
+
+
+@pytest.mark.parametrize("name", DISCRETE_GOLDENS)
+@pytest.mark.parametrize("engine", ["ground", "lifted"])
+def test_discrete_signatures_take_the_specialised_kernels(name, engine, ns):
+    builder, K, T, _ = specs.CASES[name]
+    g, rvs = builder(ns)
+    handles, _, cg = helpers.setup_mode(g, engine)
+    model = helpers.lower_for(engine, g, cg, K, T)
+    assert any(gr.nd > 0 for gr in model.groups)
+    for dtype in ("float64", "float32"):
+        eng = _engine(model, dtype)
+        for d, _, gr in eng.groups:
+            assert eng.lib.lhvi_has_specialisation(C.byref(eng.desc), C.byref(d)) == 1, \
+                (name, engine, dtype, (gr.nd, gr.nc, gr.ng, gr.ne, gr.dims, gr.node, gr.pure))
+
+
+def _config1_model(ns, K=2, T=10):
+    builder, _, _, _ = specs.CASES["hmln_demo"]
+    g, rvs = builder(ns)
+    return lhvi_b200.lowering.lower_ground(g, K, T)
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-9), ("float32", 5e-5)])
+def test_config1_model_k2_t10_snapshot(dtype, tol, ns):
+    model = _config1_model(ns)
+    assert model.n_records >= 3390
+    eta, tau, w_tau = lhvi_b200.synthetic.random_state(model, 3)
+    e = np.e ** w_tau
+    w = e / e.sum()
+    og, ogw, oe = grad_pass(model, eta, w)
+    spec = _engine(model, dtype)
+    for d, _, gr in spec.groups:
+        assert spec.lib.lhvi_has_specialisation(C.byref(spec.desc), C.byref(d)) == 1, (gr.nd, gr.nc, gr.ne, gr.node, gr.pure)
+    for eng in (spec, _engine(model, dtype, force_generic=True)):
+        eng.set_state(eta, tau, w_tau)
+        grad, g_w, energy = eng.gradients()
+        np.testing.assert_allclose(energy, oe, rtol=tol)
+        np.testing.assert_allclose(g_w, ogw, rtol=tol, atol=tol * np.abs(ogw).max())
+        np.testing.assert_allclose(grad, og, rtol=tol, atol=tol * np.abs(og).max())
+
+
+def _beliefs(model, eta, w, xs):
+    """Mixture beliefs of every hidden variable: continuous ones at the probe points, discrete ones
+    over their states."""
+    K = model.K
+    cont, disc = [], []
+    for off, kind, dim in zip(model.var_off, model.var_kind, model.var_dim):
+        if kind == 0:
+            mu, var = eta[off:off + 2 * K:2], eta[off + 1:off + 2 * K:2]
+            cont.append([(w * norm_pdf_ref(x, mu, var)).sum() for x in xs])
+        else:
+            disc.append(w @ eta[off:off + K * dim].reshape(K, dim))
+    return np.array(cont), np.concatenate(disc)
+
+
+def test_config1_model_1000_iterations(ns):
+    """BASELINE config 1: 1000 Adam iterations at lr 0.2 (the demo's setting)."""
+    model = _config1_model(ns)
+    eta, tau, w_tau = lhvi_b200.synthetic.random_state(model, 3)
+    ref = NumpyVI(model)
+    ref.eta[:], ref.tau[:], ref.w_tau = eta, tau, w_tau
+    ref.refresh()
+    for _ in range(1000):
+        fe_ref = ref.adam_step(0.2)
+    xs = np.linspace(-2.0, 12.0, 8)
+    want_c, want_d = _beliefs(model, ref.eta, ref.w, xs)
+    out = {}
+    for dtype in ("float64", "float32"):
+        eng = _engine(model, dtype)
+        eng.set_state(eta, tau, w_tau)
+        eng.reset_moments()
+        eng.iterate(1000, 0.2)
+        e, _, wt, w = eng.get_state()
+        out[dtype] = (e, wt, eng.last_free_energy()) + _beliefs(model, e, w, xs)
+    # fp64: on the oracle's trajectory (north_star: 1e-6 relative)
+    np.testing.assert_allclose(out["float64"][2], fe_ref, rtol=1e-6)
+    np.testing.assert_allclose(out["float64"][0], ref.eta, rtol=1e-6, atol=1e-7)
+    # fp32: final beliefs within 1e-4
+    np.testing.assert_allclose(out["float32"][3], want_c, rtol=0, atol=1e-4)
+    np.testing.assert_allclose(out["float32"][4], want_d, rtol=0, atol=1e-4)

@@ -51,7 +51,7 @@ def test_persistent_matches_oracle_and_per_group_launches(name, dtype, tol):
         fe_last = ref.adam_step(0.1)
     eng, (e1, t1, wt1, w1, fe1, mom) = _run(model, dtype, True, steps)
     assert eng.persistent(), "the model must run in the persistent kernel (no silent fall-back)"
-    assert eng.launch_count == 1
+    assert eng.launch_count <= 3            # the first two launches measure (two iterations each) and re-split
     np.testing.assert_allclose(fe1, fe_last, rtol=tol)
     np.testing.assert_allclose(e1, ref.eta, rtol=tol * 10, atol=tol * 10)
     np.testing.assert_allclose(wt1, ref.w_tau, rtol=tol * 10, atol=tol * 10)
