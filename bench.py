@@ -55,6 +55,10 @@ def parse():
     ap.add_argument("--generic", action="store_true", help="force the generic kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c2f", action="store_true", help="skip the auxiliary coarse-to-fine figure")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the auxiliary figures of BASELINE configs 1-4, the fp64 line and the drop-in classes")
+    ap.add_argument("--config", default="all",
+                    help="which auxiliary configs to run beside the headline (config 5): all, or a list like 1,3")
     ap.add_argument("--cpu-sample-entities", type=int, default=200_000)
     return ap.parse_args()
 
@@ -69,7 +73,8 @@ def workload_config(a, n_records, parallelism=None):
         "record_order": f"generator: {a.order}-major; the engine re-sorts the two-hidden-argument group run-major "
                         "and pads hub runs of the streamed group to whole tiles (results are order-independent)",
         "l2_policy": "inputs larger than L2 (record table ~1 GB >> 126 MB), no explicit flush",
-        "parallelism": parallelism or f"{a.gpus} rank(s), owner-computes record partition",
+        # (the same text in both arms; what the partition came out as is reported beside `config`)
+        "parallelism": f"{a.gpus} rank(s), owner-computes record partition",
     }
 
 
@@ -237,11 +242,22 @@ def cpu_baseline(a, n_records_full, seconds=12.0):
         its += 1
     dt = (time.perf_counter() - t0) / its
     rec_per_s = model.n_records / dt
+    sample = (f"{its} iterations of the same generator at {sample_P} entities ({model.n_records} factor "
+              f"records, {dt * 1e3:.1f} ms/iteration, {runner.describe}); scaled linearly to "
+              f"{n_records_full} records")
+    # the unmodified Python reference cannot travel to the GPU box: its figure for this generator was
+    # measured once in the build container (tools/ref_time.py) and is quoted here for scale
+    ref_path = os.path.join(ROOT, "profiles", "r2_reference_python_timing.json")
+    if os.path.exists(ref_path):
+        ref = json.load(open(ref_path))
+        parts = [f"{k} {v['ground_factors_per_s']:.0f} ground factors/s ({v['s_per_iter']:.2f} s/iteration at "
+                 f"{v['ground_factors']} factors)" for k, v in ref.items() if isinstance(v, dict)]
+        hours = n_records_full / min(v["ground_factors_per_s"] for v in ref.values() if isinstance(v, dict)) / 3600
+        sample += ("; the unmodified Python reference on the object-graph twin of this generator, one core of the "
+                   "build container: " + ", ".join(parts) + f" -- about {hours:.1f} hours per iteration at this size")
     return {
         "value": rec_per_s / n_records_full, "unit": UNIT, "cores": runner.cores, "kind": "port",
-        "sample": f"{its} iterations of the same generator at {sample_P} entities ({model.n_records} factor "
-                  f"records, {dt * 1e3:.1f} ms/iteration, {runner.describe}); scaled linearly to "
-                  f"{n_records_full} records",
+        "sample": sample,
         "records_per_s": rec_per_s,
     }
 
@@ -250,6 +266,12 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # all host threads, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for N > 1, which
+    # made the reference arm 16x slower at N >= 2 than at N = 1 in round 1): must be set before the
+    # OpenMP runtime of the C port starts
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
     n_full = a.entities * a.groups + a.entities + a.groups * (a.groups - 1)
     t0 = time.perf_counter()
     base = cpu_baseline(a, n_full, seconds=max(5.0, 2.0 * (a.steps + a.warmup)))
@@ -469,8 +491,8 @@ def run_ours(a):
             "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if s == 4 else "f64", "data": "synthetic",
-            "config": workload_config(a, model.n_records, eng.plan.describe() + (
-                f"; exchange={eng.exchange}" if eng.exchange else "")),
+            "config": workload_config(a, model.n_records),
+            "partition": eng.plan.describe() + (f"; exchange={eng.exchange}" if eng.exchange else ""),
             "clocks": clocks.summary(),
             "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "per step: variational parameters (compact eta[rv] arrays) host->device from pinned "
@@ -493,6 +515,31 @@ def run_ours(a):
                 line["c2f"] = c2f_probe(a)
             except Exception as exc:            # an auxiliary figure must not cost the bench line
                 line["c2f"] = {"error": repr(exc)[:300]}
+        if world == 1 and not a.no_configs:
+            # free the headline engine's record table first (config 4 and the fp64 line need the room)
+            eng.close()
+            del eng
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs
+            wanted = list(bench_configs.ALL) if a.config == "all" else [c.strip() for c in a.config.split(",")]
+            line["configs"] = {}
+            for c in wanted:
+                if c not in bench_configs.ALL:
+                    continue
+                t0 = time.perf_counter()
+                try:
+                    line["configs"][f"config{c}"] = bench_configs.ALL[c]()
+                except Exception as exc:
+                    line["configs"][f"config{c}"] = {"error": repr(exc)[:300]}
+                line["configs"][f"config{c}"]["wall_s"] = round(time.perf_counter() - t0, 2)
+                torch.cuda.empty_cache()
+            for key, fn in (("fp64", lambda: bench_configs.fp64_headline(a)), ("dropin", bench_configs.dropin_rgm)):
+                try:
+                    line[key] = fn()
+                except Exception as exc:
+                    line[key] = {"error": repr(exc)[:300]}
+                torch.cuda.empty_cache()
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

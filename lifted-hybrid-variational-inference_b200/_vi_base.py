@@ -179,7 +179,7 @@ class VIBase:
         m, K = self._model, self.K
         for h, i in m.index.items():
             off, d = int(m.var_off[i]), int(m.var_dim[i])
-            block = flat[off:off + K * d].reshape(K, d).copy()
+            block = flat[off:off + K * d].reshape(K, d)        # a view of the pulled vector: no copy per variable
             if m.var_kind[i] == 0:
                 cont_dict[h] = block
             elif disc_dict is not None:
@@ -286,19 +286,37 @@ class VIBase:
             eng.iterate(iteration, lr, sgd=False)
             self._pull(moments=True)
             return
-        for _ in range(int(iteration)):
+        # Logging costs one scalar read per iteration.  The reference prints the objective AFTER each
+        # update (VarInference.py:290-300); the fused pass of an iteration evaluates the free energy
+        # at the parameters BEFORE its step, i.e. after the previous update -- so the entry of
+        # iteration i is completed by the pass of iteration i + 1 (printed one iteration late, same
+        # values and order), and only the last one needs a pass of its own.  The host copies of the
+        # parameters are refreshed once, at the end.
+        def emit(t, fe):
+            if sgd:
+                print(fe)
+            else:
+                print(fe, t)
+                self.time_log.append([t, fe])
+        by_pass = sgd or self.log_fe                     # the logged objective is the free energy
+        stamp = None
+        for i in range(int(iteration)):
             self._sync()
             start = time.perf_counter()
             eng.iterate(1, lr, sgd=sgd)
             self._sync()
             self.total_time += time.perf_counter() - start
-            self._pull(moments=not sgd)
-            if sgd:
-                print(self.free_energy())
-            elif self.is_log:
-                fe = self._objective_for_log()
-                print(fe, self.total_time)
-                self.time_log.append([self.total_time, fe])
+            self._grad_cache = None
+            self._map_cache = None
+            if by_pass:
+                if i > 0:
+                    emit(stamp, eng.last_free_energy())
+                stamp = self.total_time
+            else:
+                emit(self.total_time, self._objective_for_log())      # MAP assignment from the device state
+        if by_pass and int(iteration) > 0:
+            emit(stamp, eng.free_energy())
+        self._pull(moments=not sgd)
 
     def ADAM_update(self, iteration):
         """``iteration`` Jacobi Adam steps (VarInference.py:249-300); ``self.t`` persists."""

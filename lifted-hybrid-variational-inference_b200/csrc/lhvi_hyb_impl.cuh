@@ -99,7 +99,7 @@ factor_hyb_kernel(const GroupView<real> g) {
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < g.n;
          r += (long long)gridDim.x * blockDim.x) {
         const real wf = (weighted || FL == kNode) ? g.wf[r] : real(1);
-        int off[NH];
+        int off[NH > 0 ? NH : 1];
 #pragma unroll
         for (int a = 0; a < NH; ++a) off[a] = g.poff[a * g.n + r];
         real ev[NES];
@@ -371,6 +371,15 @@ int launch_hyb_k(const lhvi_model* m, const lhvi_group* g, int64_t row0, cudaStr
                 }                                                                                 \
                 return 1;
             LHVI_HYB_MIXED(X)
+#undef X
+            default: return 1;
+        }
+    }
+    if (g->nc == 0) {
+        switch (code) {
+#define X(ND_, NC_, NE_, FL_) \
+            case hyb_code(ND_, NC_, NE_, FL_): return launch_hyb_one<real, K, 1, 0, 2, NC_, NE_, FL_>(m, g, row0, s);
+            LHVI_HYB_CONST(X)
 #undef X
             default: return 1;
         }

@@ -25,6 +25,8 @@ enum Flavour { kFull = 0, kPure = 1, kNode = 2 };
 #define LHVI_HYB_CONT(X)                                                                      \
     X(0, 1, 0, kNode) X(0, 1, 0, kPure) X(0, 1, 1, kPure) X(0, 1, 2, kPure)                    \
     X(0, 2, 0, kFull) X(0, 2, 1, kFull)
+// records whose arguments are all observed (constants of the free energy): no rule involved, any T
+#define LHVI_HYB_CONST(X) X(0, 0, 1, kPure) X(0, 0, 2, kPure)
 
 constexpr int hyb_code(int nd, int nc, int ne, int fl) { return ((nd * 8 + nc) * 8 + ne) * 4 + fl; }
 
@@ -56,6 +58,14 @@ inline bool hyb_available(const lhvi_model* m, const lhvi_group* g) {
         switch (code) {
 #define X(ND_, NC_, NE_, FL_) case hyb_code(ND_, NC_, NE_, FL_): return true;
             LHVI_HYB_MIXED(X)
+#undef X
+            default: return false;
+        }
+    }
+    if (g->nc == 0) {
+        switch (code) {
+#define X(ND_, NC_, NE_, FL_) case hyb_code(ND_, NC_, NE_, FL_): return true;
+            LHVI_HYB_CONST(X)
 #undef X
             default: return false;
         }

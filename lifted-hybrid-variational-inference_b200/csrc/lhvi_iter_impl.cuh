@@ -81,6 +81,7 @@ struct IterPhase {
     int n_hubs;          // run-major groups
     long long chunk;     // SpecLaunch::chunk for `nblocks` blocks
     double* accum;       // IterArgs::accum (nullptr: rows of `partials`)
+    unsigned int* counter;   // run-major groups: the shared run counter of this group (or nullptr)
 };
 
 template <typename real>
@@ -104,6 +105,10 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 
 // The quadrature rule of the run-major body travels in constant memory (see RunLaunch): a noinline
 // function cannot take it from the kernel's parameters as constant-bank operands.
+// (anonymous namespace: the constant, the setter and the setter's cache are per translation unit --
+// with external linkage the linker would merge the setters of the K = 1, 2, 3 units into one that
+// fills only ITS unit's constant)
+namespace {
 template <typename real, int T> struct IterRule;
 #define LHVI_ITER_RULE(REAL, NAME)                                              \
     static __constant__ RunLaunch<REAL, 3> NAME;                                     \
@@ -123,6 +128,7 @@ template <typename real, int T> struct IterRule;
 LHVI_ITER_RULE(float, c_iter_rule_f32)
 LHVI_ITER_RULE(double, c_iter_rule_f64)
 #undef LHVI_ITER_RULE
+}  // namespace
 
 // ---- phases -------------------------------------------------------------------------------------------
 
@@ -132,7 +138,7 @@ __device__ __noinline__ void phase_spec(const IterPhase<real>* ph, int vb, unsig
     SpecLaunch L;
     L.chunk = ph->chunk;
     factor_spec_body<real, K, T, NC, NG, NE, FL, W, HUB>(
-        g, L, BlockSlice{vb, ph->nblocks, ph->accum}, *reinterpret_cast<SpecShared<real, K, T, NC, FL, HUB>*>(smem));
+        g, L, BlockSlice{vb, ph->nblocks, ph->accum, ph->counter}, *reinterpret_cast<SpecShared<real, K, T, NC, FL, HUB>*>(smem));
 }
 
 template <typename real, int K, int T, int NE, bool W, bool CACHE>
@@ -140,7 +146,7 @@ __device__ __noinline__ void phase_pun(const IterPhase<real>* ph, int vb, unsign
     const GroupView<real> g = ph->view;
     SpecLaunch L;
     L.chunk = ph->chunk;
-    pure_unary_body<real, K, T, NE, W, CACHE>(g, L, BlockSlice{vb, ph->nblocks, ph->accum},
+    pure_unary_body<real, K, T, NE, W, CACHE>(g, L, BlockSlice{vb, ph->nblocks, ph->accum, ph->counter},
                                               *reinterpret_cast<PureUnaryShared<real, K, T>*>(smem));
 }
 
@@ -149,7 +155,7 @@ __device__ __noinline__ void phase_fold(const IterPhase<real>* ph, int vb, unsig
     const GroupView<real> g = ph->view;
     SpecLaunch L;
     L.chunk = ph->chunk;
-    unary_fold_body<real, K, W, CACHE>(g, L, BlockSlice{vb, ph->nblocks, ph->accum},
+    unary_fold_body<real, K, W, CACHE>(g, L, BlockSlice{vb, ph->nblocks, ph->accum, ph->counter},
                                        *reinterpret_cast<FoldBlockShared<real, K>*>(smem));
 }
 
@@ -159,7 +165,7 @@ __host__ __device__ constexpr size_t run_shared_bytes() { return (sizeof(RunShar
 template <typename real, int K, int T, int NE, bool W, int HUBPOS>
 __device__ __noinline__ void phase_run(const IterPhase<real>* ph, int vb, unsigned char* smem) {
     const GroupView<real> g = ph->view;
-    factor_run_body<real, K, T, NE, W, HUBPOS>(g, IterRule<real, T>::get(), ph->n_hubs, BlockSlice{vb, ph->nblocks, ph->accum},
+    factor_run_body<real, K, T, NE, W, HUBPOS>(g, IterRule<real, T>::get(), ph->n_hubs, BlockSlice{vb, ph->nblocks, ph->accum, ph->counter},
                                                *reinterpret_cast<RunShared<real, K, T>*>(smem),
                                                reinterpret_cast<real*>(smem + run_shared_bytes<real, K, T>()));
 }
@@ -208,6 +214,41 @@ static size_t phase_shared_bytes(int code, int n_hubs) {
     }
 }
 
+// ---- grid barrier -------------------------------------------------------------------------------------
+// Arrivals are atomics on `count`, waiting blocks poll `gen` -- two different cache lines, so that the
+// last arrival does not queue behind 295 polling loads (cooperative_groups' grid.sync() polls the
+// word it adds to: 5.5 us measured for the barrier after the optimiser step, where every block but one
+// is already waiting; profiles/r2_iter_plan.md).  Self-resetting; the launch must be cooperative
+// (all blocks resident).  Memory ordering: release fence before arriving, acquire fence (which also
+// invalidates L1) after leaving -- parameters rewritten before the barrier are re-read after it.
+struct GridBarrier {
+    unsigned int count;
+    unsigned int pad0[31];
+    unsigned int gen;
+    unsigned int pad1[31];
+};
+
+__device__ __forceinline__ void grid_barrier(GridBarrier* bar, unsigned int nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int gen;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(&bar->gen) : "memory");
+        __threadfence();
+        if (atomicAdd(&bar->count, 1u) == nblocks - 1) {
+            bar->count = 0;
+            __threadfence();
+            atomicAdd(&bar->gen, 1u);
+        } else {
+            unsigned int now;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(&bar->gen) : "memory");
+            } while (now == gen);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------------
 
 template <typename real, int K, int T>
@@ -217,8 +258,8 @@ iterate_kernel(const __grid_constant__ IterArgs<real> A) {
     __shared__ double s_red[(kIterThreads / 32) * (LHVI_MAX_K + 1)];
     __shared__ double s_res[LHVI_MAX_K + 1];
     __shared__ int s_order;
-    cg::grid_group grid = cg::this_grid();
     const int nb = (int)gridDim.x, bid = (int)blockIdx.x;
+    GridBarrier* bar = reinterpret_cast<GridBarrier*>(A.sm_count + 256);
 
     // the two blocks of an SM walk the phases in opposite orders (arrival parity on the SM; a
     // hint: results do not depend on it)
@@ -256,11 +297,16 @@ iterate_kernel(const __grid_constant__ IterArgs<real> A) {
                 if (tr && p < 11) tr[1 + p] = global_timer_ns();
             }
         }
-        grid.sync();
+        grid_barrier(bar, (unsigned)nb);
         if (tr) tr[12] = global_timer_ns();
 
         const real c1 = (real)A.step.step[1], c2 = (real)A.step.step[2];
         if (bid == 0) {
+            if (threadIdx.x >= 32 && threadIdx.x < 32 + kIterMaxPhases) {
+                // the run counters of the run-major groups start the next pass at zero
+                const int p = threadIdx.x - 32;
+                if (p < A.n_phases && A.phase[p].counter != nullptr) *A.phase[p].counter = 0u;
+            }
             if (A.accum != nullptr) {
                 // every block has added its sums to `accum` before the barrier: publish and clear
                 if (threadIdx.x <= K) {
@@ -284,7 +330,7 @@ iterate_kernel(const __grid_constant__ IterArgs<real> A) {
                 step_variable<real>(A.step, v, c1, c2);
         }
         if (tr) tr[13] = global_timer_ns();
-        if (it + 1 < A.n_iter) grid.sync();        // the end of the launch orders the last step
+        if (it + 1 < A.n_iter) grid_barrier(bar, (unsigned)nb);        // the end of the launch orders the last step
         if (tr) tr[14] = global_timer_ns();
     }
 }
@@ -325,6 +371,7 @@ int launch_iterate_kt(const lhvi_model* m, const lhvi_group* groups, int n_group
                       const lhvi_optim* o, int n_iter, int probe_only, cudaStream_t s) {
     if (m->T != T || !m->rule_symmetric) return 1;
     if (x != nullptr && x->world > 1 && x->blocks != 1) return 1;
+    if (probe_only == 0 && o->sm_count == nullptr) { set_error("lhvi_iterate: lhvi_optim::sm_count (512 zero-initialised words of scratch) is required"); return LHVI_EINVAL; }
     IterArgs<real> A;
     A.n_phases = 0;
     size_t dyn = 0;
@@ -343,6 +390,9 @@ int launch_iterate_kt(const lhvi_model* m, const lhvi_group* groups, int n_group
         ph.code = code;
         ph.n_hubs = g->n_hubs;
         ph.accum = o->accum;
+        ph.counter = nullptr;
+        if ((code >> 24) == kFamRun && o->sm_count != nullptr)
+            ph.counter = reinterpret_cast<unsigned int*>(o->sm_count) + 384 + (A.n_phases - 1);
     }
     // (an empty group's region of `partials` must read "0 valid rows": the buffer starts zeroed,
     // lhvi_factor_expect_grad writes that header for an empty group, and nothing here touches it)

@@ -446,7 +446,7 @@ class DeviceEngine:
         self.group_table = (_cabi.LhviGroup * max(1, len(self.groups)))()
         for i, (d, _, _) in enumerate(self.groups):
             C.memmove(C.byref(self.group_table, i * C.sizeof(_cabi.LhviGroup)), C.byref(d), C.sizeof(_cabi.LhviGroup))
-        self.sm_count = torch.zeros(256, dtype=torch.int32, device=self.device)
+        self.sm_count = torch.zeros(512, dtype=torch.int32, device=self.device)
         self.iter_accum = torch.zeros(K + 1, dtype=torch.float64, device=self.device)
         self._persistent = None        # lhvi_iterate_supported, asked once
         self._iter_tuned = 0           # how often the grid split has been re-planned from a measured launch

@@ -52,9 +52,13 @@ class OracleEngine:
         self.vi.var_threshold = self.var_threshold
         for _ in range(int(n)):
             if sgd:
-                self.vi.sgd_step(lr)
+                self._last_fe = self.vi.sgd_step(lr)
             else:
-                self.vi.adam_step(lr, self.b1, self.b2, self.eps)
+                self._last_fe = self.vi.adam_step(lr, self.b1, self.b2, self.eps)
+
+    def last_free_energy(self):
+        """Free energy evaluated by the most recent pass (at the parameters before its step)."""
+        return float(self._last_fe)
 
     def gradients(self):
         from oracle.vi_numpy import grad_pass

@@ -113,3 +113,30 @@ def test_gd_update(ns):
     with contextlib.redirect_stdout(io.StringIO()):
         vi.GD_update(5, 0.01)
     assert vi.free_energy() < f0
+
+
+def test_logged_objective_is_the_free_energy_after_each_update(ns):
+    """``time_log[i]`` holds the free energy AFTER update i + 1, as the reference logs it
+    (``VarInference.py:290-300``) -- the drop-in takes it from the next iteration's fused pass."""
+    name, engine = "hmln_evidence", "ground"
+    gold = helpers.load_golden([p for p in helpers.golden_files() if helpers.golden_id(p) == "hmln_evidence__ground"][0])[2]
+    builder, K, T, _ = specs.CASES[name]
+
+    def fresh():
+        g, rvs = builder(ns)
+        vi = use_oracle_engine(ENGINE_CLASS[engine]()(g, K, T))
+        vi.init_param = make_injector(vi, rvs, engine, K, int(gold["seed"]))
+        return vi
+    logged = fresh()
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        logged.run(4, lr=0.1, is_log=True, log_fe=True)
+    assert len(logged.time_log) == 4
+    printed = [float(line.split()[0]) for line in out.getvalue().strip().splitlines()]
+    for n in range(1, 5):
+        vi = fresh()
+        with contextlib.redirect_stdout(io.StringIO()):
+            vi.run(n, lr=0.1, is_log=False)
+        np.testing.assert_allclose(logged.time_log[n - 1][1], vi.free_energy(), rtol=1e-12)
+        np.testing.assert_allclose(printed[n - 1], vi.free_energy(), rtol=1e-12)
+    # and the state the caller sees afterwards is the state after the last update
+    np.testing.assert_allclose(logged.free_energy(), logged.time_log[-1][1], rtol=1e-12)
