@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--config", default="all",
                     help="which auxiliary configs to run beside the headline (config 5): all, or a list like 1,3")
     ap.add_argument("--cpu-sample-entities", type=int, default=200_000)
+    ap.add_argument("--write-reference", action="store_true",
+                    help="N=1 only: store the free energy of the initial state for the checks of the N>1 runs")
     return ap.parse_args()
 
 
@@ -297,6 +299,10 @@ def c2f_probe(a, iterations=50):
     import lhvi_b200
     lifting, syn = lhvi_b200.lifting, lhvi_b200.synthetic
     entities = max(1000, min(100_000, a.entities // 10))
+    # warm-up on a small model: the first launch of a kernel pays its module load (the persistent
+    # iteration kernel is tens of megabytes of SASS), which is not part of a refinement round
+    warm = lifting.C2FArrayVI(syn.relational_hybrid_arrays(2000, a.groups, observed_frac=0.7, seed=1), a.K, a.T, dtype=a.dtype)
+    warm.run(20, 0.05)
     ga = syn.relational_hybrid_arrays(entities, a.groups, observed_frac=0.7, seed=0)
     vi = lifting.C2FArrayVI(ga, a.K, a.T, dtype=a.dtype)
     t0 = time.perf_counter()
@@ -307,6 +313,7 @@ def c2f_probe(a, iterations=50):
             "classes_per_round": [n for n, _ in vi.history], "records_last_round": vi.model.n_records,
             "run_s": round(total, 4), "host_passes_s": round(host, 4), "upload_s": round(vi.timing["upload"], 4),
             "device_iterations_s": round(vi.timing["iterate"], 4), "readback_s": round(vi.timing["pull"], 4),
+            "per_round_s": [{k: round(v, 4) for k, v in r.items()} for r in vi.timing_rounds],
             "free_energy_finite": bool(np.isfinite(vi.free_energy()))}
 
 
@@ -354,6 +361,21 @@ def run_ours(a):
         kind = "node" if g.node else ("pure" if g.pure else "full")
         stream = " streamed" if (d.fold and (d.hub_mask >> g.nd) & 1) else ""
         return f"{kind}{stream} nd={g.nd} nc={g.nc} ng={g.ng} ne={g.ne} n={g.n}" + (" [run-major]" if d.run_start else "")
+
+    # the free energy of the (deterministic) initial state must not depend on how the records are
+    # sharded: every run computes it once (dense sum over the ranks) and compares it with the value an
+    # N=1 run stored under profiles/ (fp32 sums of 11 M terms, double partial sums: 1e-5 relative)
+    fe0 = float(eng.free_energy())
+    ref_key = f"{a.entities}x{a.groups} K={a.K} T={a.T} {a.dtype} {a.order}"
+    ref_path = os.path.join(ROOT, "profiles", "r2_free_energy_initial.json")
+    ref_table = json.load(open(ref_path)) if os.path.exists(ref_path) else {}
+    if a.write_reference and world == 1:
+        ref_table[ref_key] = fe0
+        json.dump(ref_table, open(ref_path, "w"), indent=1, sort_keys=True)
+    fe0_ref = ref_table.get(ref_key)
+    if fe0_ref is not None and not abs(fe0 - fe0_ref) <= 1e-5 * abs(fe0_ref):
+        raise SystemExit(f"bench.py: free energy of the initial state {fe0!r} differs from the single-GPU value "
+                         f"{fe0_ref!r} ({world} ranks): the sharded pass does not compute the same sums")
 
     # a step = one Jacobi iteration; `iterate(n)` is the reference's `for itr in range(iteration)` of
     # ADAM_update (VarInference.py:249-300): on the persistent path the K timed steps are ONE
@@ -500,6 +522,8 @@ def run_ours(a):
                             "free energy device->host; record table resident; with N ranks every rank "
                             "moves the variables it owns plus the shared ones (bytes are summed over the ranks)",
                     "free_energy_last": fe_last},
+            "free_energy_initial": {"value": fe0, "single_gpu_reference": fe0_ref,
+                                    "checked": fe0_ref is not None, "rtol": 1e-5},
             "gpu_launches": launches,
             "launch_mode": ("persistent: the K timed steps are one cooperative launch of lhvi_iterate" if persistent
                             else "CUDA graph of per-group launches, replayed K times"),

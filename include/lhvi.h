@@ -292,7 +292,7 @@ typedef struct lhvi_optim {
     double* step;                  /* [4] t, 1-b1^t, 1-b2^t, unused (advanced once per iteration unless sgd) */
     int32_t* sm_count;             /* [512] zero-initialised scratch words owned by the caller and used by no other
                                       stream at the same time: per-SM arrival counters [0, 256), the grid barrier
-                                      [256, 384), the run counters of the run-major groups [384, 396) */
+                                      [256, 384), the rest reserved */
     double lr, b1, b2, eps, var_threshold;
     int32_t sgd;                   /* != 0: theta -= lr * g, moments and step counter untouched */
     int32_t reserved;

@@ -112,7 +112,6 @@ __device__ __forceinline__ void block_sum_to(const double* vals, int nvals, doub
 struct BlockSlice {
     int bid, nblocks;
     double* accum;
-    unsigned int* counter = nullptr;    // run-major groups: shared run counter (dynamic hand-out), or nullptr
 };
 
 __device__ __forceinline__ void publish_partials(const double* vals, int nvals, double* scratch, double* region,

@@ -63,6 +63,12 @@ __host__ __device__ constexpr int run_code(int ne, int w, int hubpos) { return (
     X(2, 0, 1, kFull, 0, -1) X(2, 0, 1, kFull, 1, -1) X(2, 0, 1, kFull, 0, 0) X(2, 0, 1, kFull, 1, 0) \
     X(2, 0, 1, kFull, 0, 1) X(2, 0, 1, kFull, 1, 1)                                                 \
     X(1, 1, 0, kFull, 0, -1) X(1, 1, 0, kFull, 1, -1) X(1, 1, 1, kFull, 0, -1) X(1, 1, 1, kFull, 1, -1)
+// a factor whose only integrated argument is a Gaussian-evidence class (C2F rounds).  Single precision
+// only: ptxas did not finish the double-precision K = 3 unit with these bodies in it within 16 minutes
+// (the same kernels compile in seconds as stand-alone launches), so double-precision C2F models run
+// as per-group launches
+#define LHVI_ITER_SPEC_F32(X)                                                                       \
+    X(0, 1, 0, kFull, 0, -1) X(0, 1, 0, kFull, 1, -1) X(0, 1, 1, kFull, 0, -1) X(0, 1, 1, kFull, 1, -1)
 // X(NE, W, CACHE): pure unary records, one variable per record or short runs
 #define LHVI_ITER_PUN(X)                                                                            \
     X(0, 0, 0) X(0, 0, 1) X(0, 1, 0) X(0, 1, 1) X(1, 0, 0) X(1, 0, 1) X(1, 1, 0) X(1, 1, 1)         \
@@ -81,7 +87,6 @@ struct IterPhase {
     int n_hubs;          // run-major groups
     long long chunk;     // SpecLaunch::chunk for `nblocks` blocks
     double* accum;       // IterArgs::accum (nullptr: rows of `partials`)
-    unsigned int* counter;   // run-major groups: the shared run counter of this group (or nullptr)
 };
 
 template <typename real>
@@ -138,7 +143,7 @@ __device__ __noinline__ void phase_spec(const IterPhase<real>* ph, int vb, unsig
     SpecLaunch L;
     L.chunk = ph->chunk;
     factor_spec_body<real, K, T, NC, NG, NE, FL, W, HUB>(
-        g, L, BlockSlice{vb, ph->nblocks, ph->accum, ph->counter}, *reinterpret_cast<SpecShared<real, K, T, NC, FL, HUB>*>(smem));
+        g, L, BlockSlice{vb, ph->nblocks, ph->accum}, *reinterpret_cast<SpecShared<real, K, T, NC, FL, HUB>*>(smem));
 }
 
 template <typename real, int K, int T, int NE, bool W, bool CACHE>
@@ -146,7 +151,7 @@ __device__ __noinline__ void phase_pun(const IterPhase<real>* ph, int vb, unsign
     const GroupView<real> g = ph->view;
     SpecLaunch L;
     L.chunk = ph->chunk;
-    pure_unary_body<real, K, T, NE, W, CACHE>(g, L, BlockSlice{vb, ph->nblocks, ph->accum, ph->counter},
+    pure_unary_body<real, K, T, NE, W, CACHE>(g, L, BlockSlice{vb, ph->nblocks, ph->accum},
                                               *reinterpret_cast<PureUnaryShared<real, K, T>*>(smem));
 }
 
@@ -155,8 +160,8 @@ __device__ __noinline__ void phase_fold(const IterPhase<real>* ph, int vb, unsig
     const GroupView<real> g = ph->view;
     SpecLaunch L;
     L.chunk = ph->chunk;
-    unary_fold_body<real, K, W, CACHE>(g, L, BlockSlice{vb, ph->nblocks, ph->accum, ph->counter},
-                                       *reinterpret_cast<FoldBlockShared<real, K>*>(smem));
+    unary_fold_body<real, K, W, CACHE, true>(g, L, BlockSlice{vb, ph->nblocks, ph->accum},
+                                             *reinterpret_cast<FoldBlockShared<real, K, true>*>(smem));
 }
 
 template <typename real, int K, int T>
@@ -165,7 +170,7 @@ __host__ __device__ constexpr size_t run_shared_bytes() { return (sizeof(RunShar
 template <typename real, int K, int T, int NE, bool W, int HUBPOS>
 __device__ __noinline__ void phase_run(const IterPhase<real>* ph, int vb, unsigned char* smem) {
     const GroupView<real> g = ph->view;
-    factor_run_body<real, K, T, NE, W, HUBPOS>(g, IterRule<real, T>::get(), ph->n_hubs, BlockSlice{vb, ph->nblocks, ph->accum, ph->counter},
+    factor_run_body<real, K, T, NE, W, HUBPOS>(g, IterRule<real, T>::get(), ph->n_hubs, BlockSlice{vb, ph->nblocks, ph->accum},
                                                *reinterpret_cast<RunShared<real, K, T>*>(smem),
                                                reinterpret_cast<real*>(smem + run_shared_bytes<real, K, T>()));
 }
@@ -176,6 +181,12 @@ __device__ __forceinline__ void run_phase(const IterPhase<real>* ph, int vb, uns
 #define X(NC, NG, NE, FL, W, HUB) \
         case spec_code(NC, NG, NE, FL, W, HUB): phase_spec<real, K, T, NC, NG, NE, FL, (W) != 0, HUB>(ph, vb, smem); break;
         LHVI_ITER_SPEC(X)
+#undef X
+#define X(NC, NG, NE, FL, W, HUB) \
+        case spec_code(NC, NG, NE, FL, W, HUB): \
+            if constexpr (sizeof(real) == 4) phase_spec<real, K, T, NC, NG, NE, FL, (W) != 0, HUB>(ph, vb, smem); \
+            break;
+        LHVI_ITER_SPEC_F32(X)
 #undef X
 #define X(NE, W, CACHE) \
         case pun_code(NE, W, CACHE): phase_pun<real, K, T, NE, (W) != 0, (CACHE) != 0>(ph, vb, smem); break;
@@ -200,10 +211,14 @@ static size_t phase_shared_bytes(int code, int n_hubs) {
 #define X(NC, NG, NE, FL, W, HUB) case spec_code(NC, NG, NE, FL, W, HUB): return sizeof(SpecShared<real, K, T, NC, FL, HUB>);
         LHVI_ITER_SPEC(X)
 #undef X
+#define X(NC, NG, NE, FL, W, HUB) case spec_code(NC, NG, NE, FL, W, HUB): \
+            return sizeof(real) == 4 ? sizeof(SpecShared<real, K, T, NC, FL, HUB>) : (size_t)-1;
+        LHVI_ITER_SPEC_F32(X)
+#undef X
 #define X(NE, W, CACHE) case pun_code(NE, W, CACHE): return sizeof(PureUnaryShared<real, K, T>);
         LHVI_ITER_PUN(X)
 #undef X
-#define X(W, CACHE) case fold_code(W, CACHE): return sizeof(FoldBlockShared<real, K>);
+#define X(W, CACHE) case fold_code(W, CACHE): return sizeof(FoldBlockShared<real, K, true>);
         LHVI_ITER_FOLD(X)
 #undef X
 #define X(NE, W, HUBPOS) case run_code(NE, W, HUBPOS): \
@@ -302,11 +317,6 @@ iterate_kernel(const __grid_constant__ IterArgs<real> A) {
 
         const real c1 = (real)A.step.step[1], c2 = (real)A.step.step[2];
         if (bid == 0) {
-            if (threadIdx.x >= 32 && threadIdx.x < 32 + kIterMaxPhases) {
-                // the run counters of the run-major groups start the next pass at zero
-                const int p = threadIdx.x - 32;
-                if (p < A.n_phases && A.phase[p].counter != nullptr) *A.phase[p].counter = 0u;
-            }
             if (A.accum != nullptr) {
                 // every block has added its sums to `accum` before the barrier: publish and clear
                 if (threadIdx.x <= K) {
@@ -358,8 +368,8 @@ static int iter_phase_code(const lhvi_model* m, const lhvi_group* g) {
         if (g->nc == 2 && g->ng == 0 && g->ne <= 1) {
             if (g->run_start != nullptr && g->n_hubs >= 1 && g->n_hubs <= kRunMaxHubs) code = run_code(g->ne, w, g->run_hub_arg);
             else code = spec_code(2, 0, g->ne, kFull, w, hub);
-        } else if (g->nc == 1 && g->ng == 1 && g->ne <= 1) {
-            code = spec_code(1, 1, g->ne, kFull, w, -1);
+        } else if (g->nc <= 1 && g->ng == 1 && g->ne <= 1) {
+            code = spec_code(g->nc, 1, g->ne, kFull, w, -1);
         }
     }
     (void)m;
@@ -390,9 +400,6 @@ int launch_iterate_kt(const lhvi_model* m, const lhvi_group* groups, int n_group
         ph.code = code;
         ph.n_hubs = g->n_hubs;
         ph.accum = o->accum;
-        ph.counter = nullptr;
-        if ((code >> 24) == kFamRun && o->sm_count != nullptr)
-            ph.counter = reinterpret_cast<unsigned int*>(o->sm_count) + 384 + (A.n_phases - 1);
     }
     // (an empty group's region of `partials` must read "0 valid rows": the buffer starts zeroed,
     // lhvi_factor_expect_grad writes that header for an empty group, and nothing here touches it)

@@ -133,31 +133,13 @@ factor_run_body(const GroupView<real>& g, const RunLaunch<real, T>& L, const int
     auto own_floor = [](real own) { return own < F::kBFloor; };
 
     const unsigned long long pol = l2_evict_first_policy();
-    // Runs are handed out a warp at a time (32 consecutive runs): statically, block after block in
-    // a grid-stride order, or -- bs.counter != nullptr, the persistent iteration kernel -- from a
-    // shared counter, so that the blocks of the group end together although their SMs run at
-    // different speeds (the neighbours of a block differ from SM to SM: without it the slowest
-    // block of the group ended 25 % after the average one).  The next batch is taken before the
-    // current one is worked on: the atomic's latency hides behind the records.
     const long long stride = (long long)bs.nblocks * blockDim.x;
-    const int lane_r = tid & 31;
-    const bool dynamic = bs.counter != nullptr;
-    auto grab = [&]() -> long long {
-        unsigned b = 0;
-        if (lane_r == 0) b = atomicAdd(bs.counter, 32u);
-        return (long long)__shfl_sync(0xffffffffu, b, 0);
-    };
-    long long wbase = dynamic ? grab() : (long long)bs.bid * blockDim.x + (tid - lane_r);
-    while (wbase < g.n_runs) {                      // warp-uniform
-        const long long nbase = dynamic ? grab() : wbase + stride;
-        const long long run = wbase + lane_r;
-        wbase = nbase;
-        if (run >= g.n_runs) continue;
+    for (long long run = (long long)bs.bid * blockDim.x + tid; run < g.n_runs; run += stride) {
         const int keyE = __ldg(g.run_key + run);
         const int r0 = __ldg(g.run_start + run), r1 = __ldg(g.run_start + run + 1);
         // the next run's first record and slot are fetched now and used to warm L1 once this
         // run's records are done (by then the two loads have long arrived)
-        const long long nxt = nbase + lane_r;
+        const long long nxt = run + stride;
         int rn = -1, keyn = 0;
         if (nxt < g.n_runs) {
             rn = __ldg(g.run_start + nxt);

@@ -26,6 +26,8 @@
 // arguments use a warp-level segmented reduction over runs of equal offsets followed by vector
 // REDs (REDG.E.ADD.F32x4) to global memory.
 #pragma once
+#include <type_traits>
+
 #include "lhvi_common.cuh"
 #include "lhvi_spec_sigs.h"
 
@@ -1589,15 +1591,68 @@ __device__ __noinline__ void fold_close_warp(const real* eta, real* grad, FoldSt
     st->sg0 = st->sg1 = st->sg2 = st->sw0 = st->sw1 = st->sw2 = real(0);
 }
 
-template <typename real, int K>
+// ---- TMA ring of the streaming kernel -----------------------------------------------------------------
+// The record columns of a tile (1024 records: slot offsets, c0, l0, a0 and -- lifted models -- W_f,
+// gamma) are brought into shared memory by the TMA unit (cp.async.bulk, one 4 KB / 8 KB copy per
+// column, issued by one thread, completion counted in bytes on an mbarrier) kFoldStages tiles ahead
+// of the arithmetic.  What keeps HBM busy is then the depth of the ring (2 x 24 KB per block in
+// flight or landed), not the number of resident warps: the LDG version kept 6 x 512 B per warp in
+// flight and needed 32 warps per SM for 3.8 TB/s, which the persistent iteration kernel (16 warps per
+// SM next to the 128-register run-major records) cannot give it.  Two stages, not more: with four
+// (96 KB per block, 192 KB per SM) the persistent kernel's other record groups lost the L1 cache
+// they gather through and ran 1.5x slower (profiles/r2_iter_plan.md).
+//
+// Used by the persistent iteration kernel only (TMA = true).  Alone on the GPU the streaming kernel is
+// NOT faster with it -- 44.1 us with four stages at 2 blocks per SM, 56.3 us with two stages at 4
+// blocks per SM, against 44.4 us for the LDG loop at 4 blocks per SM (7.0 M records, B200) -- because
+// bytes in flight are not what limits it there: the per-tile dependency chain is (IPC 0.8 per SM).
+// Inside the persistent kernel, at 16 warps per SM, the ring makes the streamed group 20 % faster
+// (97 -> 79 block-microseconds per block at 67 blocks).
+template <typename real> struct FoldRingShape {
+    static constexpr int kStages = 2;
+    static constexpr int kColBytes = kFoldTile * (int)sizeof(real);
+};
+
+template <typename real, int K, bool TMA = false>
 struct FoldBlockShared {
+    // [stage][column][bytes of one column tile]; columns: poff, c0, l0, a0, wf, gam
+    alignas(128) unsigned char ring[TMA ? FoldRingShape<real>::kStages : 1][TMA ? 6 : 1]
+                                   [TMA ? FoldRingShape<real>::kColBytes : 16];
+    alignas(8) unsigned long long full[FoldRingShape<real>::kStages];     // mbarriers: bytes of a stage have landed
     FoldShared<real, K> sh;
     double scratch[(kFoldThreads / 32) * (K + 1)];
 };
 
-template <typename real, int K, bool WEIGHTED, bool USE_CACHE>
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned long long* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LHVI_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LHVI_MBAR_DONE;\n"
+        "bra LHVI_MBAR_WAIT;\n"
+        "LHVI_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// one column tile, global -> shared, completion on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+template <typename real, int K, bool WEIGHTED, bool USE_CACHE, bool TMA>
 __device__ __forceinline__ void
-unary_fold_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice bs, FoldBlockShared<real, K>& shb) {
+unary_fold_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice bs, FoldBlockShared<real, K, TMA>& shb) {
     constexpr int NV = 2 * K;
 
     FoldShared<real, K>& sh = shb.sh;
@@ -1627,6 +1682,28 @@ unary_fold_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice 
     const real* __restrict__ col1 = g.fold + g.n_pad;
     const real* __restrict__ col2 = g.fold + 2 * g.n_pad;
 
+    if constexpr (TMA) {
+    // first tiles in flight before anything else happens in this block
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < FoldRingShape<real>::kStages; ++st) mbar_init(&shb.full[st], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int tiles0 = (int)((hi - lo) / kFoldTile);
+        constexpr unsigned cb = (unsigned)FoldRingShape<real>::kColBytes;
+        for (int t = 0; t < tiles0 && t < FoldRingShape<real>::kStages; ++t) {
+            const unsigned r0 = lo + (unsigned)t * kFoldTile;
+            mbar_expect_tx(&shb.full[t], kFoldTile * 4u + (WEIGHTED ? 5u : 3u) * cb);
+            tma_load_1d(shb.ring[t][0], g.poff + r0, kFoldTile * 4u, &shb.full[t]);
+            tma_load_1d(shb.ring[t][1], col0 + r0, cb, &shb.full[t]);
+            tma_load_1d(shb.ring[t][2], col1 + r0, cb, &shb.full[t]);
+            tma_load_1d(shb.ring[t][3], col2 + r0, cb, &shb.full[t]);
+            if constexpr (WEIGHTED) {
+                tma_load_1d(shb.ring[t][4], g.wf + r0, cb, &shb.full[t]);
+                tma_load_1d(shb.ring[t][5], g.gam + r0, cb, &shb.full[t]);
+            }
+        }
+    }
+    __syncthreads();                     // the barriers are initialised before anybody waits on them
+    }
     FoldSlowAcc<K> sa;                   // written by the uncommon paths only (local memory)
     for (int i = 0; i <= K; ++i) sa.acc[i] = 0.0;
     for (int i = 0; i < 2 * K; ++i) sa.rg[i] = 0.0;
@@ -1646,17 +1723,68 @@ unary_fold_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice 
     real sg0 = real(0), sg1 = real(0), sg2 = real(0);
     real sw0 = real(0), sw1 = real(0), sw2 = real(0);
 
-    // The loads are kept in flight by occupancy (4 blocks x 8 warps per SM, six 512-byte requests
-    // per warp and tile) rather than by a second set of column registers.
+    // producer side of the ring (TMA): one thread arms a stage's mbarrier with the bytes to expect and
+    // issues the column copies of one tile
+    constexpr int kStages = FoldRingShape<real>::kStages;
+    constexpr unsigned kColBytes = (unsigned)FoldRingShape<real>::kColBytes;
+    constexpr unsigned kOffBytes = kFoldTile * 4u;
+    constexpr unsigned kStageBytes = kOffBytes + (WEIGHTED ? 5u : 3u) * kColBytes;
+    const int n_tiles = (int)((hi - lo) / kFoldTile);
+    auto issue = [&](int tile) {
+        if constexpr (TMA) {
+            const int st = tile % kStages;
+            const unsigned r0 = lo + (unsigned)tile * kFoldTile;
+            mbar_expect_tx(&shb.full[st], kStageBytes);
+            tma_load_1d(shb.ring[st][0], g.poff + r0, kOffBytes, &shb.full[st]);
+            tma_load_1d(shb.ring[st][1], col0 + r0, kColBytes, &shb.full[st]);
+            tma_load_1d(shb.ring[st][2], col1 + r0, kColBytes, &shb.full[st]);
+            tma_load_1d(shb.ring[st][3], col2 + r0, kColBytes, &shb.full[st]);
+            if constexpr (WEIGHTED) {
+                tma_load_1d(shb.ring[st][4], g.wf + r0, kColBytes, &shb.full[st]);
+                tma_load_1d(shb.ring[st][5], g.gam + r0, kColBytes, &shb.full[st]);
+            }
+        }
+    };
+    // (TMA: the barriers were initialised and the first kStages tiles issued at the top of the kernel.
+    // LDG: the loads are kept in flight by occupancy -- 4 blocks x 8 warps per SM, six 512-byte requests
+    // per warp and tile -- rather than by a second set of column registers.)
+    int tile_i = 0;
 #pragma unroll 1
-    for (; r < hi; r += kFoldTile) {
+    for (; r < hi; r += kFoldTile, ++tile_i) {
         real q_c0[kQuad], q_l0[kQuad], q_a0[kQuad], q_wf[kQuad], q_gam[kQuad];
         int q_off[kQuad];
-        load_quad<int>(g.poff + r, q_off);
-        load_quad<real>(col0 + r, q_c0);
-        load_quad<real>(col1 + r, q_l0);
-        load_quad<real>(col2 + r, q_a0);
-        if constexpr (WEIGHTED) { load_quad<real>(g.wf + r, q_wf); load_quad<real>(g.gam + r, q_gam); }
+        if constexpr (TMA) {
+            const int st = tile_i % kStages;
+            mbar_wait(&shb.full[st], (unsigned)((tile_i / kStages) & 1));
+            const unsigned char* base = shb.ring[st][0];
+            auto quad_of = [&](int col, auto (&dst)[kQuad]) {
+                using E = typename std::remove_reference<decltype(dst[0])>::type;
+                const unsigned char* p = base + (size_t)col * kColBytes + (size_t)threadIdx.x * kQuad * sizeof(E);
+                if constexpr (sizeof(E) == 4) {
+                    const int4 t = *reinterpret_cast<const int4*>(p);
+                    dst[0] = *reinterpret_cast<const E*>(&t.x); dst[1] = *reinterpret_cast<const E*>(&t.y);
+                    dst[2] = *reinterpret_cast<const E*>(&t.z); dst[3] = *reinterpret_cast<const E*>(&t.w);
+                } else {
+                    const double2 a = *reinterpret_cast<const double2*>(p);
+                    const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+                    dst[0] = a.x; dst[1] = a.y; dst[2] = b.x; dst[3] = b.y;
+                }
+            };
+            quad_of(0, q_off);
+            quad_of(1, q_c0);
+            quad_of(2, q_l0);
+            quad_of(3, q_a0);
+            if constexpr (WEIGHTED) { quad_of(4, q_wf); quad_of(5, q_gam); }
+            // every thread has its quad in registers: the stage can take the tile kStages ahead
+            __syncthreads();
+            if (threadIdx.x == 0 && tile_i + kStages < n_tiles) issue(tile_i + kStages);
+        } else {
+            load_quad<int>(g.poff + r, q_off);
+            load_quad<real>(col0 + r, q_c0);
+            load_quad<real>(col1 + r, q_l0);
+            load_quad<real>(col2 + r, q_a0);
+            if constexpr (WEIGHTED) { load_quad<real>(g.wf + r, q_wf); load_quad<real>(g.gam + r, q_gam); }
+        }
 
         // a whole warp leaving its runs at this quad (the block's range crosses into the next hub's
         // records) closes them together: one close and one flush per warp instead of 32 closes and
@@ -1754,6 +1882,12 @@ unary_fold_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice 
     }
 
     publish_partials(acc, K + 1, s_scratch, g.partials, bs);
+    // (publish_partials ends with a barrier: nobody waits on the ring any more; the shared memory may
+    // be another record group's next)
+    if constexpr (TMA) {
+        if (threadIdx.x == 0)
+            for (int st = 0; st < FoldRingShape<real>::kStages; ++st) mbar_inval(&shb.full[st]);
+    }
 
     if constexpr (USE_CACHE) {
         for (int slot = threadIdx.x; slot < kCacheSlots; slot += blockDim.x) {
@@ -1771,8 +1905,8 @@ unary_fold_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice 
 template <typename real, int K, bool WEIGHTED, bool USE_CACHE>
 __global__ void __launch_bounds__(kFoldThreads, LHVI_FOLD_BLOCKS)
 unary_fold_kernel(const GroupView<real> g, const SpecLaunch L) {
-    __shared__ FoldBlockShared<real, K> shb;
-    unary_fold_body<real, K, WEIGHTED, USE_CACHE>(g, L, BlockSlice{(int)blockIdx.x, (int)gridDim.x, nullptr}, shb);
+    __shared__ FoldBlockShared<real, K, false> shb;
+    unary_fold_body<real, K, WEIGHTED, USE_CACHE, false>(g, L, BlockSlice{(int)blockIdx.x, (int)gridDim.x, nullptr}, shb);
 }
 
 template <typename real, int K>

@@ -96,17 +96,18 @@ def config1(cpu=True):
     return out
 
 
-def config2(dtype="float32", n=1000, t_steps=100):
+def config2(dtype="float32", n=1000, t_steps=100, period=10):
     import lhvi_b200
     lifting, syn = lhvi_b200.lifting, lhvi_b200.synthetic
     t0 = time.perf_counter()
-    ga, _ = syn.kalman_arrays(n, t_steps, levels=2, seed=0)
+    ga, _ = syn.kalman_arrays(n, t_steps, levels=2, seed=0, period=period)
     t_build = time.perf_counter() - t0
     t0 = time.perf_counter()
     vi = lifting.ArrayVI(ga, 1, 3, lifted=True, dtype=dtype)
     t_lift = time.perf_counter() - t0
     ms = _timed_iterations(vi.engine, 200, 0.1)
-    out = {"workload": f"relational Kalman filter, {n} state dimensions x {t_steps} steps (synthetic.kalman_arrays), "
+    out = {"workload": f"relational Kalman filter, {n} state dimensions x {t_steps} steps, sparse transition, observations "
+                       f"quantised to 2 levels and repeating every {period} state dimensions (synthetic.kalman_arrays), "
                        "LiftedVarInference over the colour-passing partition (lifting.ArrayVI)",
            "ground_variables": int(ga.n_vars), "ground_factors": int(ga.n_factors),
            "variable_classes": int(vi.quotient.n_var_classes), "compressed_records": int(vi.model.n_records),
@@ -184,7 +185,7 @@ def grid_with_observations(n, K, T, *, obs_var=0.5, seed=0):
     return model, J, y / obs_var
 
 
-def config4(dtype="float32", n=1000, iterations=1500, lr=0.05):
+def config4(dtype="float32", n=1000, iterations=3000, lr=0.05):
     import scipy.sparse.linalg as spla
 
     import lhvi_b200
