@@ -228,6 +228,10 @@ class DeviceEngine:
         # the per-group kernels, which run at twice the occupancy, win: profiles/r2_iter_plan.md)
         self.persistent_mode = os.environ.get("LHVI_PERSISTENT", "auto")
         self.use_persistent = self.persistent_mode != "0" and not self.force_generic
+        self.persistent_min_iters = int(os.environ.get("LHVI_PERSISTENT_MIN_ITERS", "2"))
+        self._iter_adapt = os.environ.get("LHVI_ITER_ADAPT", "1") != "0"
+        self._iter_trace_env = bool(os.environ.get("LHVI_ITER_TRACE"))
+        self._optim_cache = {}
         self.launch_count = 0          # kernels of liblhvi.so launched by iterate() so far
         self.parallel_groups = True    # independent group launches on parallel graph branches
         # lhvi_finish_step instead of lhvi_finish + lhvi_param_step: on for one GPU (measured 143.1 ->
@@ -708,7 +712,7 @@ class DeviceEngine:
 
     def _iterate_persistent(self, n, lr, sgd):
         while (self.iter_plan and self._iter_tuned < ITER_TUNE_ROUNDS and len(self.iter_plan) > 1 and n > 0
-               and os.environ.get("LHVI_ITER_ADAPT", "1") != "0"):
+               and self._iter_adapt):
             # the first launches measure: two iterations with per-block timestamps, then the grid is
             # re-split so that the groups end together (the iterations themselves are ordinary ones;
             # twice, because a group's speed depends on what shares its SMs)
@@ -720,17 +724,22 @@ class DeviceEngine:
             n -= k
         if n <= 0:
             return
-        self._launch_persistent(n, lr, sgd, trace=bool(os.environ.get("LHVI_ITER_TRACE")))
+        self._launch_persistent(n, lr, sgd, trace=self._iter_trace_env)
 
     def _launch_persistent(self, n, lr, sgd, trace=False):
-        o = _cabi.LhviOptim()
-        o.n_vars, o.n_owned = self.n_vars, self.n_owned
-        o.var_kind, o.var_dim, o.var_off = self.var_kind.data_ptr(), self.var_dim.data_ptr(), self.var_off.data_ptr()
-        o.tau, o.mom1, o.mom2 = self.tau.data_ptr(), self.mom1.data_ptr(), self.mom2.data_ptr()
-        o.wstate, o.step, o.sm_count = self.wstate.data_ptr(), self.step.data_ptr(), self.sm_count.data_ptr()
-        o.lr, o.b1, o.b2, o.eps, o.var_threshold = float(lr), self.b1, self.b2, self.eps, self.var_threshold
-        o.sgd = int(bool(sgd))
-        o.accum = self.iter_accum.data_ptr()
+        key = (float(lr), bool(sgd), self.b1, self.b2, self.eps, self.var_threshold)
+        o = self._optim_cache.get(key)
+        if o is None:
+            o = _cabi.LhviOptim()
+            o.n_vars, o.n_owned = self.n_vars, self.n_owned
+            o.var_kind, o.var_dim, o.var_off = self.var_kind.data_ptr(), self.var_dim.data_ptr(), self.var_off.data_ptr()
+            o.tau, o.mom1, o.mom2 = self.tau.data_ptr(), self.mom1.data_ptr(), self.mom2.data_ptr()
+            o.wstate, o.step, o.sm_count = self.wstate.data_ptr(), self.step.data_ptr(), self.sm_count.data_ptr()
+            o.lr, o.b1, o.b2, o.eps, o.var_threshold = float(lr), self.b1, self.b2, self.eps, self.var_threshold
+            o.sgd = int(bool(sgd))
+            o.accum = self.iter_accum.data_ptr()
+            self._optim_cache[key] = o
+        o.trace = None
         self.iter_trace = None
         if trace:                  # per-block timestamps of the launch (_retune, tools/iter_trace.py)
             self.iter_trace = torch.zeros(int(n) * 2 * 160 * 16, dtype=torch.int64, device=self.device)
@@ -784,7 +793,11 @@ class DeviceEngine:
         n = int(n)
         if n <= 0:
             return
-        if self.profile_group is None and self.persistent():
+        # One launch per call only pays off when the call holds several iterations: a cooperative launch
+        # costs tens of microseconds more on the host than replaying a captured graph, which a caller who
+        # synchronises after every single iteration (bench.py's e2e loop, is_log=True) would pay each time
+        # (measured at 1.4 M records: 210 us per synchronised step against 133 us)
+        if self.profile_group is None and n >= self.persistent_min_iters and self.persistent():
             if not self._grad_clean:
                 self.grad[:self.n_param].zero_()
                 self._grad_clean = True

@@ -69,7 +69,7 @@ def test_one_launch_of_n_equals_n_launches_of_one():
     one launch (parameters, moments, step counter, clean gradient slots) is the state between launches."""
     model = _models()["relational_weighted"]
     _, a = _run(model, "float64", True, 6)
-    _, b = _run(model, "float64", True, 6, chunks=(1,) * 6)
+    _, b = _run(model, "float64", True, 6, chunks=(1,) * 6)       # single iterations: the captured per-group launches
     _, c = _run(model, "float64", True, 6, chunks=(2, 4))
     for x in (b, c):
         np.testing.assert_allclose(x[0], a[0], rtol=1e-11, atol=1e-13)
