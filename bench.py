@@ -400,7 +400,9 @@ def run_ours(a):
             barrier()
             repeats.append(ev0.elapsed_time(ev1))
             launches = eng.launch_count - l0
-        # one launch per step (what a caller who reads the state after every ADAM_update(1) gets)
+        # one call per step (what a caller who reads the state after every ADAM_update(1) gets: calls of a
+        # single iteration replay the captured per-group launches)
+        eng.iterate(1, lr)                      # (the graph is captured at its first use)
         barrier()
         ev0.record()
         for _ in range(a.steps):

@@ -60,7 +60,7 @@
 extern "C" {
 #endif
 
-#define LHVI_ABI_VERSION 4
+#define LHVI_ABI_VERSION 5
 
 /* element type of every `void*` buffer of reals */
 #define LHVI_F32 0
@@ -138,7 +138,10 @@ typedef struct lhvi_group {
        side, each block with one group's prologue and epilogue per iteration).  Either all groups
        carry a count or none does.  A hint for the schedule: results do not depend on it. */
     int32_t iter_blocks;
-    int32_t reserved;
+    /* != 0: lhvi_factor_expect_grad leaves the categorical gradients G_c of this group's hidden discrete
+       arguments out (energy, G_w and the (mu, var) gradients are computed as always): they come from
+       lhvi_category_grad_reference instead (the unmodified reference's behaviour, see there) */
+    int32_t no_category_grad;
 } lhvi_group;
 
 /* Model-wide device buffers shared by every group launch. */
@@ -276,6 +279,29 @@ int lhvi_finish_step(const lhvi_model* m, int64_t rows, const lhvi_exchange* x, 
                      const int32_t* var_off, void* tau, void* mom1, void* mom2, void* wstate,
                      const double* step, double lr, double b1, double b2, double eps,
                      double var_threshold, int sgd, void* stream);
+
+/*
+ * compat="reference": the categorical gradients as the UNMODIFIED reference computes them.
+ * gradient_category_tau (VarInference.py:133-160; LiftedVarInference.py:136-164) builds the quadrature
+ * axes of the OTHER hidden arguments of a factor from the domain of the discrete variable being
+ * differentiated (`rv.domain`, :147-150) instead of their own: another hidden argument b is
+ * "enumerated" over the values of argument a's domain, with row k of b's parameter table as weights
+ * (a categorical row, or (mu, var) for a continuous b).  Everything else of the reference is unaffected,
+ * so a caller who wants its numbers bit for bit sets lhvi_group::no_category_grad on the full groups
+ * with a hidden discrete argument and adds this call per such group.  Supported when every other hidden
+ * argument's table row is as long as a's domain (booleans next to reals, equal-cardinality discrete
+ * arguments): with unequal lengths the reference's zip(product, product) pairs values and weights in
+ * an order that depends on the factor's argument order, which the record groups do not keep.
+ *   dvals[a][j]   value j of hidden discrete argument a's domain
+ *   xmap[a][b][j] state index of hidden discrete argument b whose value equals dvals[a][j]
+ * Adds  -gamma * sum_grid prod(weights) * (log(psi + 1e-100) - log(b + 1e-100))  into grad.
+ */
+typedef struct lhvi_h2 {
+    double dvals[LHVI_MAX_AXES][LHVI_MAX_DSTATES];
+    int32_t xmap[LHVI_MAX_AXES][LHVI_MAX_AXES][LHVI_MAX_DSTATES];
+} lhvi_h2;
+
+int lhvi_category_grad_reference(const lhvi_model* m, const lhvi_group* g, const lhvi_h2* h, void* stream);
 
 /*
  * Optimiser-side buffers of lhvi_iterate: what lhvi_finish_step takes as loose arguments.

@@ -13,10 +13,10 @@ from .CompressedGraphWithObs import CompressedGraph
 
 
 class VarInference(VIBase):
-    def __init__(self, g, num_mixtures=5, num_quadrature_points=3, *, dtype="float64", device=None):
+    def __init__(self, g, num_mixtures=5, num_quadrature_points=3, *, dtype="float64", device=None, compat=None):
         self.g = CompressedGraph(g)
         self.g.run()
-        self._init_common(num_mixtures, num_quadrature_points, dtype, device)
+        self._init_common(num_mixtures, num_quadrature_points, dtype, device, compat)
 
     def _handles(self):
         return sorted(self.g.rvs)

@@ -17,7 +17,7 @@ LHVI_FOLD_TILE = 1024
 LHVI_MAX_PEERS = 16
 LHVI_RUN_MAX_HUBS = 16
 LHVI_IPC_HANDLE_BYTES = 64
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblhvi.so")
 
@@ -25,7 +25,7 @@ SYMBOLS = ("lhvi_last_error", "lhvi_abi_version", "lhvi_has_specialisation",
            "lhvi_factor_expect_grad", "lhvi_elbo_reduce", "lhvi_step_tick",
            "lhvi_param_step", "lhvi_mixture_belief", "lhvi_mixture_map", "lhvi_finish", "lhvi_state_pack", "lhvi_state_unpack", "lhvi_finish_step",
            "lhvi_peer_alloc", "lhvi_peer_open", "lhvi_peer_close", "lhvi_peer_free",
-           "lhvi_iterate", "lhvi_iterate_supported", "lhvi_iterate_blocks")
+           "lhvi_iterate", "lhvi_iterate_supported", "lhvi_iterate_blocks", "lhvi_category_grad_reference")
 
 
 class LhviGroup(C.Structure):
@@ -40,7 +40,7 @@ class LhviGroup(C.Structure):
         ("fold", C.c_void_p), ("n_pad", C.c_int64),
         ("run_start", C.c_void_p), ("run_key", C.c_void_p), ("run_hid", C.c_void_p), ("hub_keys", C.c_void_p),
         ("n_runs", C.c_int64), ("n_hubs", C.c_int32), ("run_hub_arg", C.c_int32),
-        ("iter_blocks", C.c_int32), ("reserved", C.c_int32),
+        ("iter_blocks", C.c_int32), ("no_category_grad", C.c_int32),
     ]
 
 
@@ -61,6 +61,16 @@ class LhviExchange(C.Structure):
         ("recv", C.c_void_p * LHVI_MAX_PEERS),
         ("flags", C.c_void_p * LHVI_MAX_PEERS),
         ("seq", C.c_void_p), ("status", C.c_void_p),
+    ]
+
+
+LHVI_MAX_DSTATES = 16
+
+
+class LhviH2(C.Structure):
+    _fields_ = [
+        ("dvals", (C.c_double * LHVI_MAX_DSTATES) * LHVI_MAX_AXES),
+        ("xmap", ((C.c_int32 * LHVI_MAX_DSTATES) * LHVI_MAX_AXES) * LHVI_MAX_AXES),
     ]
 
 
@@ -145,6 +155,8 @@ def load(build_if_missing: bool = False):
     lib.lhvi_iterate.restype = C.c_int
     lib.lhvi_iterate.argtypes = [C.POINTER(LhviModel), C.POINTER(LhviGroup), C.c_int32, C.POINTER(LhviExchange),
                                  C.POINTER(LhviOptim), C.c_int32, C.c_void_p]
+    lib.lhvi_category_grad_reference.restype = C.c_int
+    lib.lhvi_category_grad_reference.argtypes = [C.POINTER(LhviModel), C.POINTER(LhviGroup), C.POINTER(LhviH2), C.c_void_p]
     for fn in (lib.lhvi_iterate_supported, lib.lhvi_iterate_blocks):
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(LhviModel), C.POINTER(LhviGroup), C.c_int32, C.POINTER(LhviExchange)]

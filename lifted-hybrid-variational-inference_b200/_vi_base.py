@@ -71,7 +71,7 @@ class VIBase:
     var_threshold = 0.1
 
     # ---- construction ---------------------------------------------------------------------
-    def _init_common(self, num_mixtures, num_quadrature_points, dtype, device):
+    def _init_common(self, num_mixtures, num_quadrature_points, dtype, device, compat=None):
         self.K = int(num_mixtures)
         self.T = int(num_quadrature_points)
         self.quad_x, self.quad_w = np.polynomial.hermite.hermgauss(self.T)
@@ -82,6 +82,12 @@ class VIBase:
         self.eta = dict()
         self.dtype = dtype
         self.device = device
+        # compat="reference": gradient_category_tau as the unmodified reference computes it (its axes of
+        # the other arguments come from the wrong domain, VarInference.py:147-150; SURVEY hazard H2);
+        # None: the intended mathematics
+        if compat not in (None, "reference"):
+            raise ValueError(f"compat must be None or 'reference', got {compat!r}")
+        self.compat = compat
         self.t = 0
         self.alpha = 0.1
         self.b1, self.b2, self.eps = 0.9, 0.999, 1e-8
@@ -113,7 +119,7 @@ class VIBase:
     def _make_engine(self, model):
         from .engine import DeviceEngine
         return DeviceEngine(model, dtype=self.dtype, device=self.device,
-                            var_threshold=self.var_threshold)
+                            var_threshold=self.var_threshold, compat=self.compat)
 
     # ---- parameters -----------------------------------------------------------------------
     def init_param(self):

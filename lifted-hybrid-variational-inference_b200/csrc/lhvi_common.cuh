@@ -144,6 +144,7 @@ __device__ __forceinline__ void publish_partials(const double* vals, int nvals, 
 template <typename real>
 struct GroupView {
     int nd, nc, ng, ne, node, weighted, pure;
+    int no_cat;           // lhvi_group::no_category_grad
     int dims[LHVI_MAX_AXES];
     long long n;
     const int* pot;
@@ -176,6 +177,7 @@ inline GroupView<real> make_view(const lhvi_model* m, const lhvi_group* g, int64
     GroupView<real> v;
     v.nd = g->nd; v.nc = g->nc; v.ng = g->ng; v.ne = g->ne;
     v.node = g->node; v.weighted = g->weighted; v.pure = g->pure;
+    v.no_cat = g->no_category_grad;
     for (int i = 0; i < LHVI_MAX_AXES; ++i) v.dims[i] = g->dims[i];
     v.n = g->n;
     v.pot = g->pot; v.poff = g->poff;

@@ -199,6 +199,7 @@ factor_generic_kernel(const GroupView<real> g) {
 
         // ---- scatter the parameter gradients
         for (int a = 0; a < nh; ++a) {
+            if (a < g.nd && g.no_cat) continue;          // compat="reference": lhvi_category_grad_reference
             const real gam = (g.weighted && !g.node ? g.gam[a * g.n + r] : real(1)) * nscale;
             if (gam == real(0)) continue;
             real* dst = g.grad + g.poff[a * g.n + r];

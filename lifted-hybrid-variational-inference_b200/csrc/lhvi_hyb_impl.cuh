@@ -305,6 +305,7 @@ factor_hyb_kernel(const GroupView<real> g) {
         const real nscale = FL == kNode ? g.nscale[r] : real(1);
 #pragma unroll
         for (int a = 0; a < ND; ++a) {
+            if (g.no_cat) continue;                      // compat="reference": lhvi_category_grad_reference
             const real gam = ((weighted && FL != kNode) ? g.gam[a * g.n + r] : real(1)) * nscale;
             if (gam == real(0)) continue;
             real v[K * D];

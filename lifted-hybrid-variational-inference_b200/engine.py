@@ -201,9 +201,43 @@ def iteration_plan(work, fixed, blocks, pinned=None):
     return plan
 
 
+def h2_tables(g):
+    """``lhvi_h2`` of a full group with hidden discrete arguments (compat="reference"): the domain
+    values of every such argument and, per pair (a, b), the state of b whose value is a's j-th value.
+    Raises where the unmodified reference's result is not reproduced (include/lhvi.h)."""
+    if g.ng != 0:
+        raise NotImplementedError("compat='reference': factors with Gaussian evidence next to a hidden discrete argument")
+    if len(g.dvals) != g.nd or any(len(v) != D for v, D in zip(g.dvals, g.dims)):
+        raise NotImplementedError("compat='reference' needs the domain values of the hidden discrete arguments "
+                                  "(models lowered from object graphs carry them)")
+    h = _cabi.LhviH2()
+    for a in range(g.nd):
+        if any(np.isnan(v) for v in g.dvals[a]):
+            raise NotImplementedError("compat='reference': non-numeric domain values")
+        if g.nc > 0 and g.dims[a] != 2:
+            raise NotImplementedError(
+                "compat='reference': a hidden discrete argument with more than two states next to a hidden "
+                "continuous one (the reference pairs the domain values with (mu, var) by position)")
+        for j, v in enumerate(g.dvals[a]):
+            h.dvals[a][j] = float(v)
+        for b in range(g.nd):
+            if b == a:
+                continue
+            if g.dims[b] != g.dims[a]:
+                raise NotImplementedError("compat='reference': discrete arguments of different cardinality in one "
+                                          "factor (the reference's pairing depends on the argument order)")
+            for j, v in enumerate(g.dvals[a]):
+                if v not in g.dvals[b]:
+                    raise ValueError("compat='reference': a value of one discrete argument is not in the domain of "
+                                     "another argument of the same factor (the unmodified reference raises here)")
+                h.xmap[a][b][j] = g.dvals[b].index(v)
+    return h
+
+
+
 class DeviceEngine:
     def __init__(self, model: LoweredModel, dtype="float64", device=None, var_threshold=0.1,
-                 process_group=None, shard=True, force_generic=False, run_major=True):
+                 process_group=None, shard=True, force_generic=False, run_major=True, compat=None):
         if not torch.cuda.is_available():
             raise RuntimeError(
                 "lhvi: no CUDA device visible. The variational-inference update loop runs only "
@@ -218,6 +252,12 @@ class DeviceEngine:
         self.var_threshold = float(var_threshold)
         self.force_generic = bool(force_generic)
         self.run_major = bool(run_major)     # False: keep every group record-major (tests)
+        # compat="reference": the categorical gradients as the UNMODIFIED reference computes them (its
+        # gradient_category_tau builds the other arguments' axes from the wrong domain, VarInference.py:147-150;
+        # SURVEY hazard H2) instead of the intended mathematics -- lhvi_category_grad_reference
+        if compat not in (None, "reference"):
+            raise ValueError(f"compat must be None or 'reference', got {compat!r}")
+        self.compat = compat
         self.b1, self.b2, self.eps = 0.9, 0.999, 1e-8      # VarInference.py:223-225
         self.profile_group = None
         self.dom_events = []
@@ -227,7 +267,7 @@ class DeviceEngine:
         # ("auto", the default: for rank-local models up to PERSISTENT_MAX_RECORDS records -- above that
         # the per-group kernels, which run at twice the occupancy, win: profiles/r2_iter_plan.md)
         self.persistent_mode = os.environ.get("LHVI_PERSISTENT", "auto")
-        self.use_persistent = self.persistent_mode != "0" and not self.force_generic
+        self.use_persistent = self.persistent_mode != "0" and not self.force_generic and self.compat is None
         self.persistent_min_iters = int(os.environ.get("LHVI_PERSISTENT_MIN_ITERS", "2"))
         self._iter_adapt = os.environ.get("LHVI_ITER_ADAPT", "1") != "0"
         self._iter_trace_env = bool(os.environ.get("LHVI_ITER_TRACE"))
@@ -386,6 +426,10 @@ class DeviceEngine:
             d.node, d.weighted, d.n = int(g.node), int(g.weighted), int(g.n)
             d.hub_mask = hub_mask(g)
             d.pure = int(g.pure)
+            h2 = None
+            if self.compat == "reference" and g.nd > 0 and not g.node and not g.pure and g.n > 0:
+                h2 = h2_tables(g)
+                d.no_category_grad = 1
 
             d.iter_blocks = int(self.iter_plan[gi]) if (self.iter_plan and gi in self.iter_plan) else 0
             streamed = is_streamed(g)
@@ -430,6 +474,8 @@ class DeviceEngine:
                     keep[name] = self._dev(arr, torch.int32)
                     setattr(d, name, keep[name].data_ptr())
                 d.n_runs, d.n_hubs, d.run_hub_arg = int(run_key.size), int(hubs.size), int(hub_arg)
+            if h2 is not None:
+                keep["h2"] = h2
             self.groups.append((d, keep, g_report))
 
         self.ptab = self._dev(ptab_host, self.tdtype)
@@ -552,10 +598,13 @@ class DeviceEngine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _launch_group(self, i, stream):
-        d = self.groups[i][0]
+        d, keep, _ = self.groups[i]
         _cabi.check(self.lib.lhvi_factor_expect_grad(
             C.byref(self.desc), C.byref(d), i * _cabi.LHVI_PARTIAL_ROWS, int(self.force_generic),
             C.c_void_p(stream.cuda_stream)), self.lib)
+        if "h2" in keep:
+            _cabi.check(self.lib.lhvi_category_grad_reference(
+                C.byref(self.desc), C.byref(d), C.byref(keep["h2"]), C.c_void_p(stream.cuda_stream)), self.lib)
 
     def _tick(self, stream):
         _cabi.check(self.lib.lhvi_step_tick(self.step.data_ptr(), self.b1, self.b2,
@@ -669,13 +718,17 @@ class DeviceEngine:
             ok = (not self.plan.active) or self.exchange == "p2p"       # the collective exchange is a host-side call
             self._persistent = bool(ok and self.lib.lhvi_iterate_supported(
                 C.byref(self.desc), self.group_table, len(self.groups), x))
-            if self._persistent and self.iter_plan:
-                # the split was planned for 2 blocks per SM; a group that needs more shared memory than
-                # that allows (fp64 run-major tables) halves the grid: plan again for what is resident
+            if self._persistent:
                 resident = int(self.lib.lhvi_iterate_blocks(C.byref(self.desc), self.group_table, len(self.groups), x))
                 if resident < 0:
                     _cabi.check(resident, self.lib)
-                if 0 < resident < sum(self.iter_plan.values()):
+                if self.persistent_mode == "auto" and 0 < resident < ITER_BLOCK_SLOTS:
+                    # a group whose shared memory leaves one block per SM (the fp64 run-major tables: 122 KB)
+                    # halves the persistent grid: the per-group launches are faster then (1.4 M records,
+                    # fp64: 167 us against 119 us)
+                    self._persistent = False
+                elif self.iter_plan and 0 < resident < sum(self.iter_plan.values()):
+                    # the split was planned for 2 blocks per SM: plan again for what is resident
                     self._replan(max(resident, len(self.iter_plan)))
         return self._persistent
 

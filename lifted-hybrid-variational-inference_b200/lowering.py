@@ -76,6 +76,8 @@ class RecordGroup:
     nscale: np.ndarray     # f64   [n]            node groups: parameter-gradient scale
     weighted: bool         # False -> wf == gam == 1 everywhere (columns not shipped)
     pure: bool = False     # True -> F = log psi only (the -log b part lives in the node records)
+    dvals: tuple = ()      # domain values of each hidden discrete argument (tuple of tuples of float; NaN for a
+                           # non-numeric value): the nodes the reference's H2 path puts on the OTHER arguments
 
     @property
     def n(self) -> int:
@@ -102,7 +104,7 @@ class RecordGroup:
         return RecordGroup(self.nd, self.nc, self.ng, self.ne, self.dims, self.node,
                            self.pot[sel], self.poff[:, sel], self.egval[:, sel],
                            self.egvar[:, sel], self.ecval[:, sel], self.wf[sel],
-                           self.gam[:, sel], self.nscale[sel], self.weighted, self.pure)
+                           self.gam[:, sel], self.nscale[sel], self.weighted, self.pure, self.dvals)
 
 
 @dataclass
@@ -343,9 +345,10 @@ def fold_unary(g: RecordGroup, ptab: np.ndarray):
 # ----------------------------------------------------------------------------------------
 
 class _GroupBuilder:
-    def __init__(self, nd, nc, ng, ne, dims, node, pure=False):
+    def __init__(self, nd, nc, ng, ne, dims, node, pure=False, dvals=()):
         self.sig = (nd, nc, ng, ne, tuple(dims), node)
         self.pure = pure
+        self.dvals = tuple(dvals)
         self.pot, self.poff, self.egval, self.egvar, self.ecval = [], [], [], [], []
         self.wf, self.gam, self.nscale = [], [], []
 
@@ -374,7 +377,7 @@ class _GroupBuilder:
                            np.asarray(self.pot, dtype=np.int32), cols(self.poff, nd + nc, np.int32),
                            cols(self.egval, ng, float), cols(self.egvar, ng, float),
                            cols(self.ecval, ne, float), wf, gam,
-                           np.asarray(self.nscale, dtype=float), weighted, self.pure)
+                           np.asarray(self.nscale, dtype=float), weighted, self.pure, self.dvals)
 
 
 def lower_graph(rvs, factors, K, T, *, factor_weight=None, arg_weight=None, var_weight=None,
@@ -426,11 +429,21 @@ def lower_graph(rvs, factors, K, T, *, factor_weight=None, arg_weight=None, var_
     table = PotentialTable()
     builders = {}
 
-    def builder(nd, nc, ng, ne, dims, node, pure=False):
-        key = (nd, nc, ng, ne, tuple(dims), node, pure)
+    def builder(nd, nc, ng, ne, dims, node, pure=False, dvals=()):
+        # (the domain values are part of the key: a group's hidden discrete arguments share them)
+        key = (nd, nc, ng, ne, tuple(dims), node, pure, tuple(dvals))
         if key not in builders:
-            builders[key] = _GroupBuilder(nd, nc, ng, ne, dims, node, pure)
+            builders[key] = _GroupBuilder(nd, nc, ng, ne, dims, node, pure, dvals)
         return builders[key]
+
+    def numeric(values):
+        out = []
+        for v in values:
+            try:
+                out.append(float(v))
+            except (TypeError, ValueError):
+                out.append(float("nan"))
+        return tuple(out)
 
     # ---- factor records
     unary_w = {}     # hidden variable -> sum of W_f over its unary (single integrated arg) factors
@@ -471,7 +484,8 @@ def lower_graph(rvs, factors, K, T, *, factor_weight=None, arg_weight=None, var_
             v = nb[hidden[0]]
             unary_w[v] = unary_w.get(v, 0.0) + w_f
             unary_g[v] = unary_g.get(v, 0.0) + gam[0]
-        builder(nd, nc, ng, ne, dims, False, pure).add(
+        dvals = tuple(numeric(args[i]) for i in pos[HD])
+        builder(nd, nc, ng, ne, dims, False, pure, dvals).add(
             table.block(f.potential, roles, args),
             [off[index[nb[i]]] for i in hidden],
             [args[i] for i in pos[EG]],
@@ -489,7 +503,7 @@ def lower_graph(rvs, factors, K, T, *, factor_weight=None, arg_weight=None, var_
             if kind[h] == 0:
                 b = builder(0, 1, 0, 0, (), True)
             else:
-                b = builder(1, 0, 0, 0, (dim[h],), True)
+                b = builder(1, 0, 0, 0, (dim[h],), True, False, (numeric(rv.domain.values),))
             b.add(0, [off[h]], [], [], s_e, [1.0], s_g)
         else:
             ge = gaussian_evidence(rv)

@@ -111,3 +111,33 @@ def test_align_runs_pads_long_runs_to_whole_tiles(P, G):
     b = grad_pass(dataclasses.replace(unweighted, groups=groups, ptab=ptab), eta, w)
     np.testing.assert_allclose(b[0], a[0], rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(b[2], a[2], rtol=1e-12)
+
+
+def test_compat_reference_tables(ns):
+    """compat="reference" (SURVEY hazard H2): the lowering carries the domain values of the hidden discrete
+    arguments, `engine.h2_tables` turns them into the value -> state maps of `lhvi_h2`, and refuses the
+    shapes in which the unmodified reference's pairing depends on the argument order."""
+    import specs
+    from lhvi_b200.engine import h2_tables
+    g, _ = specs.hmln_hidden(ns)
+    model = lhvi_b200.lowering.lower_ground(g, 2, 3)
+    full = [gr for gr in model.groups if gr.nd > 0 and not gr.node and not gr.pure]
+    assert full
+    for gr in full:
+        assert len(gr.dvals) == gr.nd and all(tuple(v) == (0.0, 1.0) for v in gr.dvals)
+        h = h2_tables(gr)
+        for a in range(gr.nd):
+            assert [h.dvals[a][j] for j in range(2)] == [0.0, 1.0]
+            for b in range(gr.nd):
+                if b != a:
+                    assert [h.xmap[a][b][j] for j in range(2)] == [0, 1]
+        assert gr.take(np.arange(gr.n)[::-1]).dvals == gr.dvals
+    d3 = ns.Domain((0, 1, 2))
+    dc = ns.Domain((-5, 5), continuous=True)
+    a, x = ns.RV(d3), ns.RV(dc)
+    g2 = ns.Graph()
+    g2.rvs, g2.factors = {a, x}, {ns.F(ns.MLNPotential(lambda v: -(v[0] - v[1]) ** 2, 1.0), [a, x])}
+    g2.init_nb()
+    gr = [q for q in lhvi_b200.lowering.lower_ground(g2, 2, 3).groups if q.nd and not q.node][0]
+    with pytest.raises(NotImplementedError):
+        h2_tables(gr)
