@@ -332,6 +332,44 @@ class VIBase:
         """Plain gradient descent (VarInference.py:302-331); prints the free energy each step."""
         self._update_loop(iteration, lr, sgd=True)
 
+    # ---- checkpoint / resume (not in the reference, whose run() re-randomises every call) ----
+    def state_dict(self):
+        """Everything an interrupted optimisation needs to go on: mixture logits, per-variable
+        parameters (continuous: (mu, var); discrete: logits) and the Adam moments and step counter,
+        keyed by the position of the variable in this engine's sorted handle list (ground: ``rv.id``
+        order; lifted: class order), as plain numpy arrays."""
+        order = {h: i for i, h in enumerate(self._handles())}
+
+        def by_index(d):
+            return {order[h]: np.array(v, dtype=float, copy=True) for h, v in d.items() if h in order}
+        cont = {h: v for h, v in self.eta.items() if h.domain.continuous}
+        return {"K": self.K, "T": self.T, "t": int(self.t), "w_tau": np.array(self.w_tau, dtype=float),
+                "eta": by_index(cont), "eta_tau": by_index(self.eta_tau),
+                "w_tau_g": [np.array(v, dtype=float) for v in self.w_tau_g],
+                "eta_g": [by_index(d) for d in self.eta_g], "eta_tau_g": [by_index(d) for d in self.eta_tau_g]}
+
+    def load_state_dict(self, state):
+        """Inverse of ``state_dict`` on an engine over the same graph; continue with ``ADAM_update``."""
+        if int(state["K"]) != self.K or int(state["T"]) != self.T:
+            raise ValueError("state_dict belongs to an engine with other K / T")
+        handles = self._handles()
+
+        def by_handle(d):
+            return {handles[int(i)]: np.array(v, dtype=float, copy=True) for i, v in d.items()}
+        self.w_tau = np.array(state["w_tau"], dtype=float)
+        self.w = softmax(self.w_tau)
+        self.eta = by_handle(state["eta"])
+        self.eta_tau = by_handle(state["eta_tau"])
+        for h, table in self.eta_tau.items():
+            self.eta[h] = softmax(table, 1)
+        self.w_tau_g = [np.array(v, dtype=float) for v in state["w_tau_g"]]
+        self.eta_g = [by_handle(d) for d in state["eta_g"]]
+        self.eta_tau_g = [by_handle(d) for d in state["eta_tau_g"]]
+        self.t = int(state["t"])
+        self._pushed = None
+        self._grad_cache = None
+        self._map_cache = None
+
     # ---- queries --------------------------------------------------------------------------
     def _gauss_evidence(self, h):
         return None

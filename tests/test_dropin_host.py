@@ -140,3 +140,24 @@ def test_logged_objective_is_the_free_energy_after_each_update(ns):
         np.testing.assert_allclose(printed[n - 1], vi.free_energy(), rtol=1e-12)
     # and the state the caller sees afterwards is the state after the last update
     np.testing.assert_allclose(logged.free_energy(), logged.time_log[-1][1], rtol=1e-12)
+
+
+def test_state_dict_resumes_an_interrupted_run(ns):
+    """5 iterations = 2 iterations, ``state_dict`` into a fresh engine over the same graph, 3 more."""
+    g, rvs = specs.hmln_evidence(ns)
+    np.random.seed(3)
+    whole = use_oracle_engine(lhvi_b200.VarInference.VarInference(g, 2, 3))
+    with contextlib.redirect_stdout(io.StringIO()):
+        whole.run(2, lr=0.1, is_log=False)
+    state = whole.state_dict()
+    whole.ADAM_update(3)
+    resumed = use_oracle_engine(lhvi_b200.VarInference.VarInference(g, 2, 3))
+    resumed.alpha = 0.1
+    resumed.load_state_dict(state)
+    resumed.ADAM_update(3)
+    assert resumed.t == whole.t == 5
+    np.testing.assert_allclose(resumed.w_tau, whole.w_tau, rtol=1e-12)
+    for rv in rvs:
+        if rv.value is None:
+            np.testing.assert_allclose(resumed.eta[rv], whole.eta[rv], rtol=1e-12)
+    np.testing.assert_allclose(resumed.free_energy(), whole.free_energy(), rtol=1e-12)
