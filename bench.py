@@ -134,11 +134,11 @@ def traffic_from_profile(persistent, group_name, a, world):
     if persistent:          # captured per launch of `steps_per_launch` iterations
         return entry["dram_bytes"] / entry["steps_per_launch"] * a.steps
     return entry["dram_bytes"]
-NOTE = ("the full (two hidden arguments) group runs in the run-major kernel: 530 instructions per record, issue "
-        "slots 69% busy, FMA pipe 49%, XU 31%, 15 of 16 resident warps per SM (128 registers), DRAM at 15% -- its "
+NOTE = ("the full (two hidden arguments) group runs in the run-major kernel: 523 instructions per record, issue "
+        "slots 67% busy, FMA pipe 46%, XU 31%, 16 resident warps per SM (128 registers), DRAM at 15% -- its "
         "limiter is instruction issue / latency at that occupancy, not HBM: the entity slots are hit ten times each "
-        "and stay in L1/L2, so physical traffic (89 MB) is a quarter of the algorithmic bytes SURVEY 8d counts "
-        "(361 MB) and the fraction of the HBM roofline is reported as asked (profiles/r1_ncu_summary.md)")
+        "and stay in L1/L2, so physical traffic (86 MB) is a quarter of the algorithmic bytes SURVEY 8d counts "
+        "(361 MB) and the fraction of the HBM roofline is reported as asked (profiles/r2_ncu_summary.md)")
 
 
 # ---- clocks ------------------------------------------------------------------------------------

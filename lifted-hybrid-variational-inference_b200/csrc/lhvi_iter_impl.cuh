@@ -3,10 +3,12 @@
 // Reference: the body of ADAM_update / GD_update (VarInference.py:249-331) -- all gradients at the
 // old parameters, then the step -- repeated `iteration` times by run() (:215-247).
 //
-// One grid of resident blocks (2 per SM x 148 SMs) loops over the iterations.  Inside an iteration
-// every block works through the model's record groups ("phases"): each phase is the body of the
-// per-group kernel (lhvi_spec_impl.cuh / lhvi_run_impl.cuh) applied to this block's slice of the
-// group, so the arithmetic -- and the results -- are those of the per-group launches.  Then
+// One grid of resident blocks (2 per SM x 148 SMs, launched cooperatively so that they ARE resident)
+// loops over the iterations.  Inside an iteration every block works through the record groups
+// ("phases") it is assigned to -- all of them, a slice of each, or (lhvi_group::iter_blocks) the one
+// group it belongs to: each phase is the body of the per-group kernel (lhvi_spec_impl.cuh /
+// lhvi_run_impl.cuh) applied to this block's slice of the group, so the arithmetic -- and the
+// results -- are those of the per-group launches.  Then
 //
 //     grid barrier
 //     block 0:  partial rows -> G_w, free energy; (several GPUs) exchange of [G_w | energy | shared
@@ -16,10 +18,9 @@
 //     grid barrier
 //
 // What this buys over the CUDA graph of per-group launches: no launch levels (a launch costs 3-10 us
-// of fixed latency, which is all an iteration has left on an eighth of the model), small groups are
-// a slice of work instead of a launch, and the two blocks of an SM walk the phases in opposite
-// orders, so that the issue-bound run-major records of one overlap the DRAM-bound streamed records
-// of the other.
+// of fixed latency, which is all an iteration has left on an eighth of the model) and small groups
+// that are a share of the grid instead of a launch.  Measured schedules: DESIGN.md section 3,
+// profiles/r2_iter_plan.md.
 //
 // The phases are noinline functions (one per instantiated body): the kernel's register count is
 // their maximum and ptxas compiles them one by one.  Shared memory is one dynamic allocation viewed
@@ -27,16 +28,12 @@
 // so nothing here may read them with ld.global.nc (the bodies use plain loads; the grid barrier's
 // acquire fence invalidates L1).
 #pragma once
-#include <cooperative_groups.h>
-
 #include <cstring>
 
 #include "lhvi_opt_impl.cuh"
 #include "lhvi_spec_impl.cuh"
 
 namespace lhvi {
-
-namespace cg = cooperative_groups;
 
 constexpr int kIterThreads = 256;
 constexpr int kIterMaxPhases = 12;
