@@ -60,7 +60,7 @@
 extern "C" {
 #endif
 
-#define LHVI_ABI_VERSION 5
+#define LHVI_ABI_VERSION 6
 
 /* element type of every `void*` buffer of reals */
 #define LHVI_F32 0
@@ -83,6 +83,14 @@ extern "C" {
 #define LHVI_RUN_MAX_HUBS 16 /* distinct hub variables of a run-major group (lhvi_group::run_*) */
 #define LHVI_MAX_PEERS 16    /* GPUs of one NVLink domain taking part in lhvi_finish's exchange */
 #define LHVI_IPC_HANDLE_BYTES 64
+
+/* lhvi_group::pot_kind: how a coefficient block of ptab turns into log psi at a grid point */
+#define LHVI_POT_QUADRATIC 0   /* log psi = the block's quadratic (every exp-quadratic / table potential) */
+#define LHVI_POT_HARD 1        /* psi = 1 where the block's quadratic is > 0, else 0
+                                  (MLNHardPotential over continuous arguments, MLNPotential.py:43-49) */
+#define LHVI_POT_IMAGE_EDGE 2  /* block = [distant_cof, scaling_cof, max_threshold, exp(-thr / scaling), 0, 0];
+                                  d = |x0 - x1|, psi = d distant_cof + (d > thr ? block[3] : exp(-d / scaling_cof))
+                                  (ImageEdgePotential, Potential.py:411-424); two continuous arguments */
 
 /*
  * One record group: `n` factor records sharing a canonical signature.  Arguments are
@@ -142,6 +150,10 @@ typedef struct lhvi_group {
        arguments out (energy, G_w and the (mu, var) gradients are computed as always): they come from
        lhvi_category_grad_reference instead (the unmodified reference's behaviour, see there) */
     int32_t no_category_grad;
+    /* LHVI_POT_*: != LHVI_POT_QUADRATIC groups are evaluated point by point in the generic kernel (no
+       specialised kernel, no fold / run-major columns, not part of lhvi_iterate) */
+    int32_t pot_kind;
+    int32_t reserved0;
 } lhvi_group;
 
 /* Model-wide device buffers shared by every group launch. */
@@ -369,6 +381,44 @@ int lhvi_iterate_blocks(const lhvi_model* m, const lhvi_group* groups, int32_t n
  */
 int lhvi_state_pack(int dtype, int64_t n, const int32_t* map, const void* state, void* packed, void* stream);
 int lhvi_state_unpack(int dtype, int64_t n, const int32_t* map, const void* packed, void* state, void* stream);
+
+/*
+ * Gaussian belief propagation in information form: the device replacement of the reference's GaBP
+ * (GaBP.py:7-216; run :139-165, message_rv_to_f :19-35, message_f_to_rv :37-136, get_belief_params
+ * :183-195), SURVEY section 8 f-4 (the config-4 cross-check at full size).
+ *
+ * n_vars hidden variables; every pairwise factor f over hidden variables (i, j) with
+ * log psi_f = -1/2 x' Jf x + hf' x contributes two directed message slots e = (f: i -> j) and
+ * rev[e] = (f: j -> i) with coef = [Jf_ss | Jf_dd | Jf_sd | hf_s | hf_d] (s = src[e], d = dst[e]),
+ * column-major [5][n_edges].  jd / hd [n_vars] are the constant messages of the unary and
+ * evidence-reduced factors.  P, H [2][n_edges] (message precision, potential) and SP, SH [2][n_vars]
+ * (per-variable totals of the incoming messages) are double-buffered; `parity` says which half is
+ * current.  One sweep is the reference's pair of loops (all variable -> factor messages, then all
+ * factor -> variable messages, both from the previous sweep's values):
+ *     a = SP[s] - P[rev], b = SH[s] - H[rev];  P' = J_dd - J_sd^2 / (J_ss + a);  H' = h_d - J_sd (h_s + b) / (J_ss + a)
+ * The reference starts every message at (mu, sig) = (0, 1): P = 1, H = 0, SP = number of factors on
+ * the variable, SH = 0 (set by the caller).  After n sweeps the current half is (parity + n) & 1.
+ */
+typedef struct lhvi_gabp {
+    int32_t dtype;                 /* LHVI_F32 | LHVI_F64 */
+    int32_t parity;                /* 0 | 1: the half of P / H / SP / SH that holds the current state */
+    int64_t n_vars, n_edges;
+    const int32_t* src;            /* [n_edges] */
+    const int32_t* dst;            /* [n_edges] */
+    const int32_t* rev;            /* [n_edges] */
+    const void* coef;              /* [5][n_edges] */
+    const void* jd;                /* [n_vars] */
+    const void* hd;                /* [n_vars] */
+    void* P;                       /* [2][n_edges] */
+    void* H;                       /* [2][n_edges] */
+    void* SP;                      /* [2][n_vars] */
+    void* SH;                      /* [2][n_vars] */
+} lhvi_gabp;
+
+/* n_sweeps synchronous sweeps (2 launches each: seed the new totals with jd / hd, update every edge). */
+int lhvi_gabp_sweeps(const lhvi_gabp* g, int32_t n_sweeps, void* stream);
+/* mean[i] = SH[i] / SP[i], var[i] = 1 / SP[i] from the current half (GaBP.py:183-195). */
+int lhvi_gabp_marginals(const lhvi_gabp* g, void* mean, void* var, void* stream);
 
 #ifdef __cplusplus
 }

@@ -78,8 +78,10 @@ class MLNPotential(_FormulaPotential):
 
 
 class MLNHardPotential(_FormulaPotential):
-    """Indicator of ``formula(x) > 0`` (reference ``MLNPotential.py:43-49``); only lowerable when
-    every argument is discrete."""
+    """Indicator of ``formula(x) > 0`` (reference ``MLNPotential.py:43-49``).  Over discrete arguments
+    it is tabulated; with continuous arguments the formula (at most quadratic in them, like every
+    formula of the reference) is lowered to its coefficient block and the device tests its sign at
+    every grid point (``LHVI_POT_HARD``, generic kernel)."""
 
     def get(self, parameters):
         return 1 if self.formula(parameters) > 0 else 0

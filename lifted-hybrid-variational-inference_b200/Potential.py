@@ -159,7 +159,8 @@ class HybridQuadraticPotential(Potential):
 
 
 class ImageNodePotential(Potential):
-    """Gaussian pdf of (x0 - x1 - mu); only meaningful to the BP baselines."""
+    """Gaussian pdf of (x0 - x1 - mu) (reference ``Potential.py:400-408``): exp-quadratic, lowered like
+    any other potential."""
 
     def __init__(self, mu, sig):
         super().__init__(symmetric=True)
@@ -172,8 +173,9 @@ class ImageNodePotential(Potential):
 
 
 class ImageEdgePotential(Potential):
-    """Truncated-Laplacian smoothness prior; not exp-quadratic, so it cannot be lowered
-    to the kernels' table form (SURVEY section 8 a-P) and the engines reject it."""
+    """Truncated-Laplacian smoothness prior of the denoising demo (reference ``Potential.py:411-424``).
+    Not exp-quadratic: its three coefficients travel in the coefficient block and the device evaluates
+    ``log(psi + 1e-100)`` at every grid point (``LHVI_POT_IMAGE_EDGE``, generic kernel)."""
 
     def __init__(self, distant_cof, scaling_cof, max_threshold):
         super().__init__(symmetric=True)

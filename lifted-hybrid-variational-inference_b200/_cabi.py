@@ -17,7 +17,7 @@ LHVI_FOLD_TILE = 1024
 LHVI_MAX_PEERS = 16
 LHVI_RUN_MAX_HUBS = 16
 LHVI_IPC_HANDLE_BYTES = 64
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblhvi.so")
 
@@ -25,7 +25,8 @@ SYMBOLS = ("lhvi_last_error", "lhvi_abi_version", "lhvi_has_specialisation",
            "lhvi_factor_expect_grad", "lhvi_elbo_reduce", "lhvi_step_tick",
            "lhvi_param_step", "lhvi_mixture_belief", "lhvi_mixture_map", "lhvi_finish", "lhvi_state_pack", "lhvi_state_unpack", "lhvi_finish_step",
            "lhvi_peer_alloc", "lhvi_peer_open", "lhvi_peer_close", "lhvi_peer_free",
-           "lhvi_iterate", "lhvi_iterate_supported", "lhvi_iterate_blocks", "lhvi_category_grad_reference")
+           "lhvi_iterate", "lhvi_iterate_supported", "lhvi_iterate_blocks", "lhvi_category_grad_reference",
+           "lhvi_gabp_sweeps", "lhvi_gabp_marginals")
 
 
 class LhviGroup(C.Structure):
@@ -41,6 +42,16 @@ class LhviGroup(C.Structure):
         ("run_start", C.c_void_p), ("run_key", C.c_void_p), ("run_hid", C.c_void_p), ("hub_keys", C.c_void_p),
         ("n_runs", C.c_int64), ("n_hubs", C.c_int32), ("run_hub_arg", C.c_int32),
         ("iter_blocks", C.c_int32), ("no_category_grad", C.c_int32),
+        ("pot_kind", C.c_int32), ("reserved0", C.c_int32),
+    ]
+
+
+class LhviGabp(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("parity", C.c_int32), ("n_vars", C.c_int64), ("n_edges", C.c_int64),
+        ("src", C.c_void_p), ("dst", C.c_void_p), ("rev", C.c_void_p), ("coef", C.c_void_p),
+        ("jd", C.c_void_p), ("hd", C.c_void_p),
+        ("P", C.c_void_p), ("H", C.c_void_p), ("SP", C.c_void_p), ("SH", C.c_void_p),
     ]
 
 
@@ -157,6 +168,10 @@ def load(build_if_missing: bool = False):
                                  C.POINTER(LhviOptim), C.c_int32, C.c_void_p]
     lib.lhvi_category_grad_reference.restype = C.c_int
     lib.lhvi_category_grad_reference.argtypes = [C.POINTER(LhviModel), C.POINTER(LhviGroup), C.POINTER(LhviH2), C.c_void_p]
+    lib.lhvi_gabp_sweeps.restype = C.c_int
+    lib.lhvi_gabp_sweeps.argtypes = [C.POINTER(LhviGabp), C.c_int32, C.c_void_p]
+    lib.lhvi_gabp_marginals.restype = C.c_int
+    lib.lhvi_gabp_marginals.argtypes = [C.POINTER(LhviGabp), C.c_void_p, C.c_void_p, C.c_void_p]
     for fn in (lib.lhvi_iterate_supported, lib.lhvi_iterate_blocks):
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(LhviModel), C.POINTER(LhviGroup), C.c_int32, C.POINTER(LhviExchange)]

@@ -45,6 +45,12 @@ static int validate(const lhvi_model* m, const lhvi_group* g, int64_t row0) {
         set_error("factor group without pot/ptab");
         return LHVI_EINVAL;
     }
+    if (g->pot_kind != LHVI_POT_QUADRATIC) {
+        if (g->pot_kind != LHVI_POT_HARD && g->pot_kind != LHVI_POT_IMAGE_EDGE) { set_error("pot_kind=%d is not a LHVI_POT_* code", g->pot_kind); return LHVI_EINVAL; }
+        if (g->node || g->fold || g->run_start) { set_error("pot_kind=%d: node groups, fold and run-major columns are defined for quadratic log-potentials only", g->pot_kind); return LHVI_EINVAL; }
+        if (g->pot_kind == LHVI_POT_IMAGE_EDGE && (g->nd != 0 || g->nc + g->ng + g->ne != 2)) { set_error("LHVI_POT_IMAGE_EDGE takes exactly two continuous arguments"); return LHVI_EINVAL; }
+        if (g->pot_kind == LHVI_POT_HARD && g->nc + g->ng + g->ne == 0) { set_error("LHVI_POT_HARD without a continuous argument: tabulate the potential instead"); return LHVI_EINVAL; }
+    }
     if (g->fold) {
         if (g->node || !g->pure || g->nd != 0 || g->nc != 1 || g->ng != 0) { set_error("fold columns are only defined for pure groups with one hidden continuous argument"); return LHVI_EINVAL; }
         if (g->n_pad < g->n || g->n_pad % 1024 != 0) { set_error("fold columns: n_pad=%lld must be a multiple of 1024 and >= n=%lld", (long long)g->n_pad, (long long)g->n); return LHVI_EINVAL; }

@@ -145,6 +145,7 @@ template <typename real>
 struct GroupView {
     int nd, nc, ng, ne, node, weighted, pure;
     int no_cat;           // lhvi_group::no_category_grad
+    int pot_kind;         // LHVI_POT_*
     int dims[LHVI_MAX_AXES];
     long long n;
     const int* pot;
@@ -178,6 +179,7 @@ inline GroupView<real> make_view(const lhvi_model* m, const lhvi_group* g, int64
     v.nd = g->nd; v.nc = g->nc; v.ng = g->ng; v.ne = g->ne;
     v.node = g->node; v.weighted = g->weighted; v.pure = g->pure;
     v.no_cat = g->no_category_grad;
+    v.pot_kind = g->pot_kind;
     for (int i = 0; i < LHVI_MAX_AXES; ++i) v.dims[i] = g->dims[i];
     v.n = g->n;
     v.pot = g->pot; v.poff = g->poff;

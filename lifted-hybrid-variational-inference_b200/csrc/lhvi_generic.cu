@@ -156,12 +156,22 @@ factor_generic_kernel(const GroupView<real> g) {
                         real xv[LHVI_MAX_AXES + 4];
                         for (int i = 0; i < g.nc + g.ng; ++i) xv[i] = xs[noff[g.nd + i] + idx[g.nd + i]];
                         for (int j = 0; j < g.ne; ++j) xv[g.nc + g.ng + j] = g.ecval[j * g.n + r];
-                        real q = cf[0];
-                        for (int i = 0; i < nct; ++i) q += cf[1 + i] * xv[i];
-                        int p = 1 + nct;
-                        for (int i = 0; i < nct; ++i)
-                            for (int j = i; j < nct; ++j) q += cf[p++] * xv[i] * xv[j];
-                        lpsi = M::log_psi(q);
+                        if (g.pot_kind == LHVI_POT_IMAGE_EDGE) {
+                            // psi = d distant_cof + (d > max_threshold ? v : exp(-d / scaling_cof)), d = |x0 - x1|
+                            // (Potential.py:419-424); evaluated in double: psi is not an exponential, so the
+                            // float shortcut of log_psi does not apply
+                            const double d = fabs((double)xv[0] - (double)xv[1]);
+                            const double psi = d * (double)cf[0] + (d > (double)cf[2] ? (double)cf[3] : ::exp(-d / (double)cf[1]));
+                            lpsi = (real)::log(psi + kEps);
+                        } else {
+                            real q = cf[0];
+                            for (int i = 0; i < nct; ++i) q += cf[1 + i] * xv[i];
+                            int p = 1 + nct;
+                            for (int i = 0; i < nct; ++i)
+                                for (int j = i; j < nct; ++j) q += cf[p++] * xv[i] * xv[j];
+                            // hard formula: psi = 1 if formula(x) > 0 else 0 (MLNPotential.py:48-49)
+                            lpsi = g.pot_kind == LHVI_POT_HARD ? (q > real(0) ? real(0) : (real)kLogEps) : M::log_psi(q);
+                        }
                     }
                     F = lpsi - lb;
                 }

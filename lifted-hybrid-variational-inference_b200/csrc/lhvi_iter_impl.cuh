@@ -387,6 +387,7 @@ int launch_iterate_kt(const lhvi_model* m, const lhvi_group* groups, int n_group
         if (g->n == 0) continue;
         if (A.n_phases >= kIterMaxPhases) return 1;
         if (g->n >= (1ll << 31) || g->n_pad >= (1ll << 31)) return 1;
+        if (g->pot_kind != LHVI_POT_QUADRATIC) return 1;          // point-by-point potentials: generic kernel only
         const int code = iter_phase_code(m, g);
         if (code < 0) return 1;
         const size_t need = phase_shared_bytes<real, K, T>(code, g->n_hubs);

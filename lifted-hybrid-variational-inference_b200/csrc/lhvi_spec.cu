@@ -24,6 +24,7 @@ int hyb_f64_k3(const lhvi_model*, const lhvi_group*, int64_t, cudaStream_t);
 static bool walk_available(const lhvi_model* m, const lhvi_group* g);
 
 bool spec_available(const lhvi_model* m, const lhvi_group* g) {
+    if (g->pot_kind != LHVI_POT_QUADRATIC) return false;     // evaluated point by point: generic kernel
     return walk_available(m, g) || hyb_available(m, g);
 }
 

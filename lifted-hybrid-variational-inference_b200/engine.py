@@ -97,7 +97,7 @@ def align_runs(g, null_pot, tile, FOLD_BLOCK_SLOTS=FOLD_BLOCK_SLOTS):
     poff = np.repeat(key[starts[:-1]], plen)[None, :].astype(g.poff.dtype)
     return RecordGroup(g.nd, g.nc, g.ng, g.ne, g.dims, g.node, spread(g.pot, null_pot), poff,
                        spread(g.egval, 0.0), spread(g.egvar, 1.0), spread(g.ecval, 0.0),
-                       spread(g.wf, 0.0), spread(g.gam, 0.0), spread(g.nscale, 0.0), g.weighted, g.pure)
+                       spread(g.wf, 0.0), spread(g.gam, 0.0), spread(g.nscale, 0.0), g.weighted, g.pure, g.dvals, g.kind)
 
 
 RUN_SPLIT = 64          # a longer run is split (one thread walks a run)
@@ -111,7 +111,7 @@ def run_layout(g, K, elem_bytes):
     """Run-major form of a full group with two hidden continuous arguments, one of which takes
     few distinct values (lhvi.h, lhvi_group::run_*): returns (sorted group, run_start, run_key,
     run_hid, hub_keys, hub_arg) or None when the group does not qualify."""
-    if g.node or g.pure or g.nd != 0 or g.nc != 2 or g.ng != 0 or g.ne > 1 or g.n < 2:
+    if g.node or g.pure or g.nd != 0 or g.nc != 2 or g.ng != 0 or g.ne > 1 or g.n < 2 or g.kind != 0:
         return None
     uniq = [np.unique(g.poff[a]) for a in (0, 1)]
     hub_arg = 0 if uniq[0].size < uniq[1].size else 1
@@ -396,7 +396,7 @@ class DeviceEngine:
 
         def is_streamed(g):
             return (self.symmetric_rule and g.n > 0 and not g.node and g.pure and g.nd == 0 and g.nc == 1
-                    and g.ng == 0 and K <= 3 and bool((hub_mask(g) >> g.nd) & 1))
+                    and g.ng == 0 and g.kind == 0 and K <= 3 and bool((hub_mask(g) >> g.nd) & 1))
         layouts = [run_layout(g, K, esize) if (self.run_major and self.mirror_rule and self.T == 3 and K <= 3) else None
                    for g in self.model.groups]
         # schedule of the persistent kernel: "split" gives every group blocks of its own (the groups run
@@ -426,6 +426,7 @@ class DeviceEngine:
             d.node, d.weighted, d.n = int(g.node), int(g.weighted), int(g.n)
             d.hub_mask = hub_mask(g)
             d.pure = int(g.pure)
+            d.pot_kind = int(g.kind)
             h2 = None
             if self.compat == "reference" and g.nd > 0 and not g.node and not g.pure and g.n > 0:
                 h2 = h2_tables(g)

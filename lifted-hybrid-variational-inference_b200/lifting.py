@@ -548,7 +548,8 @@ def lower_partition(ga: GroundArrays, var_colour, factor_colours, K, T, *, ev_va
                 np.add.at(unary_w, nb[:, hid[0]], w_f)
                 np.add.at(unary_g, nb[:, hid[0]], gam[0])
             pot = table.block(b.potential, r, args)
-            chunks.setdefault((nd, nc, ng, ne, dims, False, pure), []).append(dict(
+            pkind = lowering.potential_kind(b.potential, nc + ng + ne)
+            chunks.setdefault((nd, nc, ng, ne, dims, False, pure, pkind), []).append(dict(
                 uid=uid[sel], pot=np.full(sel.size, pot, dtype=np.int32),
                 poff=class_off[nb[:, hid]].T.reshape(len(hid), sel.size),
                 egval=mean[nb[:, pos[EG]]].T.reshape(ng, sel.size),
@@ -561,7 +562,7 @@ def lower_partition(ga: GroundArrays, var_colour, factor_colours, K, T, *, ev_va
     c_v = st["size"].astype(float)
     for is_disc, d in sorted({(int(k_), int(d_)) for k_, d_ in zip(kind, dim)}):
         pick = slot_class[(kind == is_disc) & (dim == d)]
-        key = (1, 0, 0, 0, (d,), True, False) if is_disc else (0, 1, 0, 0, (), True, False)
+        key = (1, 0, 0, 0, (d,), True, False, 0) if is_disc else (0, 1, 0, 0, (), True, False, 0)
         chunks.setdefault(key, []).append(dict(
             uid=pick, pot=np.zeros(pick.size, dtype=np.int32), poff=class_off[pick][None, :],
             egval=np.zeros((0, pick.size)), egvar=np.zeros((0, pick.size)), ecval=np.zeros((0, pick.size)),
@@ -569,13 +570,13 @@ def lower_partition(ga: GroundArrays, var_colour, factor_colours, K, T, *, ev_va
             nscale=scale[pick] - unary_g[pick]))
     pick = np.flatnonzero(cls_gauss)
     if pick.size:
-        chunks.setdefault((0, 0, 1, 0, (), True, False), []).append(dict(
+        chunks.setdefault((0, 0, 1, 0, (), True, False, 0), []).append(dict(
             uid=pick, pot=np.zeros(pick.size, dtype=np.int32), poff=np.zeros((0, pick.size), dtype=np.int64),
             egval=mean[pick][None, :], egvar=variance[pick][None, :], ecval=np.zeros((0, pick.size)),
             wf=c_v[pick] * scale[pick], gam=np.zeros((0, pick.size)), nscale=scale[pick]))
 
     groups = []
-    for (nd, nc, ng, ne, dims, node, pure), parts in chunks.items():
+    for (nd, nc, ng, ne, dims, node, pure, pkind), parts in chunks.items():
         cat = {k: np.concatenate([p[k] for p in parts], axis=-1) for k in parts[0]}
         order = np.argsort(cat["uid"], kind="stable")
         wf, gam = cat["wf"][order], cat["gam"][:, order]
@@ -585,8 +586,8 @@ def lower_partition(ga: GroundArrays, var_colour, factor_colours, K, T, *, ev_va
             np.ascontiguousarray(cat["poff"][:, order].astype(np.int32)),
             np.ascontiguousarray(cat["egval"][:, order]), np.ascontiguousarray(cat["egvar"][:, order]),
             np.ascontiguousarray(cat["ecval"][:, order]), wf, np.ascontiguousarray(gam),
-            cat["nscale"][order], weighted, pure))
-    groups.sort(key=lambda g: (not g.node, not g.pure, g.nd + g.nc + g.ng, g.nd, g.nc, g.ng, g.ne, g.dims))
+            cat["nscale"][order], weighted, pure, (), pkind))
+    groups.sort(key=lambda g: (not g.node, not g.pure, g.nd + g.nc + g.ng, g.nd, g.nc, g.ng, g.ne, g.dims, g.kind))
     return lowering.LoweredModel(K, T, max(n_param, 2), kind, dim, off, table.array(), groups, [], {},
                                  slot_class.astype(np.int64))
 

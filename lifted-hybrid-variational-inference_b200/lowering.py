@@ -78,6 +78,7 @@ class RecordGroup:
     pure: bool = False     # True -> F = log psi only (the -log b part lives in the node records)
     dvals: tuple = ()      # domain values of each hidden discrete argument (tuple of tuples of float; NaN for a
                            # non-numeric value): the nodes the reference's H2 path puts on the OTHER arguments
+    kind: int = 0          # POT_QUADRATIC | POT_HARD | POT_IMAGE_EDGE: how a coefficient block becomes log psi
 
     @property
     def n(self) -> int:
@@ -104,7 +105,7 @@ class RecordGroup:
         return RecordGroup(self.nd, self.nc, self.ng, self.ne, self.dims, self.node,
                            self.pot[sel], self.poff[:, sel], self.egval[:, sel],
                            self.egvar[:, sel], self.ecval[:, sel], self.wf[sel],
-                           self.gam[:, sel], self.nscale[sel], self.weighted, self.pure, self.dvals)
+                           self.gam[:, sel], self.nscale[sel], self.weighted, self.pure, self.dvals, self.kind)
 
 
 @dataclass
@@ -152,12 +153,37 @@ class LoweredModel:
 # potentials -> coefficient blocks
 # ----------------------------------------------------------------------------------------
 
+# How a coefficient block of ``ptab`` becomes log psi at a grid point (include/lhvi.h, LHVI_POT_*).
+POT_QUADRATIC, POT_HARD, POT_IMAGE_EDGE = 0, 1, 2
+
+
+def potential_kind(potential, n_continuous):
+    """``POT_*`` of a potential whose factor has ``n_continuous`` continuous arguments (hidden or
+    observed).  Everything exp-quadratic -- and every potential over discrete arguments only, which
+    is tabulated through ``get`` -- is ``POT_QUADRATIC``.  Two potentials of the reference are not
+    log-quadratic in their continuous arguments and are evaluated point by point on the device:
+
+    * ``MLNHardPotential`` (``MLNPotential.py:43-49``: 1 where ``formula(x) > 0``, else 0) -- recognised
+      by a ``formula`` without a weight ``w``; the formula itself must be (at most) quadratic in the
+      continuous arguments, as every formula of the reference is (SURVEY section 8, a-P);
+    * ``ImageEdgePotential`` (``Potential.py:411-424``) -- recognised by its three coefficients."""
+    if n_continuous == 0:
+        return POT_QUADRATIC
+    if getattr(potential, "formula", None) is not None and not hasattr(potential, "w"):
+        return POT_HARD
+    if all(hasattr(potential, a) for a in ("distant_cof", "scaling_cof", "max_threshold")):
+        return POT_IMAGE_EDGE
+    return POT_QUADRATIC
+
+
 def _log_psi_fn(potential):
     """Callable x -> log psi(x) for exp-type potentials (exact for MLN formulas)."""
     formula = getattr(potential, "formula", None)
     if formula is not None and hasattr(potential, "w"):
         w = potential.w
         return lambda x: float(formula(x) * w)
+    if formula is not None:               # POT_HARD: the block holds the formula, the kernels test its sign
+        return lambda x: float(formula(x))
 
     def via_get(x):
         v = float(np.asarray(potential.get(x)).reshape(-1)[0])
@@ -279,6 +305,12 @@ class PotentialTable:
                 template[i] = args[i]
         out = []
         quad = None
+        if potential_kind(potential, nct) == POT_IMAGE_EDGE:
+            if nct != 2 or n != 2:
+                raise NotImplementedError("ImageEdgePotential takes two continuous arguments")
+            v = float(getattr(potential, "v", math.exp(-potential.max_threshold / potential.scaling_cof)))
+            return np.array([float(potential.distant_cof), float(potential.scaling_cof),
+                             float(potential.max_threshold), v, 0.0, 0.0])
         if nct and not hd_pos and all(r != ED for r in roles) and hasattr(potential, "get_quadratic_params"):
             A, b, c = potential.get_quadratic_params()
             A = np.asarray(A, dtype=float)
@@ -315,7 +347,7 @@ def fold_unary(g: RecordGroup, ptab: np.ndarray):
     substituted (coefficient layout of ``ptab``: c, b[nct], upper-triangular A row-major;
     canonical argument order [hidden | evidence...]).  Returns ``[3, n]`` float64 or ``None``
     when the group has another shape."""
-    if g.node or not g.pure or g.nd != 0 or g.nc != 1 or g.ng != 0:
+    if g.node or not g.pure or g.nd != 0 or g.nc != 1 or g.ng != 0 or g.kind != POT_QUADRATIC:
         return None
     nct = 1 + g.ne
     ncoef = ncoef_for(nct)
@@ -345,10 +377,11 @@ def fold_unary(g: RecordGroup, ptab: np.ndarray):
 # ----------------------------------------------------------------------------------------
 
 class _GroupBuilder:
-    def __init__(self, nd, nc, ng, ne, dims, node, pure=False, dvals=()):
+    def __init__(self, nd, nc, ng, ne, dims, node, pure=False, dvals=(), kind=POT_QUADRATIC):
         self.sig = (nd, nc, ng, ne, tuple(dims), node)
         self.pure = pure
         self.dvals = tuple(dvals)
+        self.kind = kind
         self.pot, self.poff, self.egval, self.egvar, self.ecval = [], [], [], [], []
         self.wf, self.gam, self.nscale = [], [], []
 
@@ -377,7 +410,7 @@ class _GroupBuilder:
                            np.asarray(self.pot, dtype=np.int32), cols(self.poff, nd + nc, np.int32),
                            cols(self.egval, ng, float), cols(self.egvar, ng, float),
                            cols(self.ecval, ne, float), wf, gam,
-                           np.asarray(self.nscale, dtype=float), weighted, self.pure, self.dvals)
+                           np.asarray(self.nscale, dtype=float), weighted, self.pure, self.dvals, self.kind)
 
 
 def lower_graph(rvs, factors, K, T, *, factor_weight=None, arg_weight=None, var_weight=None,
@@ -429,11 +462,11 @@ def lower_graph(rvs, factors, K, T, *, factor_weight=None, arg_weight=None, var_
     table = PotentialTable()
     builders = {}
 
-    def builder(nd, nc, ng, ne, dims, node, pure=False, dvals=()):
+    def builder(nd, nc, ng, ne, dims, node, pure=False, dvals=(), kind=POT_QUADRATIC):
         # (the domain values are part of the key: a group's hidden discrete arguments share them)
-        key = (nd, nc, ng, ne, tuple(dims), node, pure, tuple(dvals))
+        key = (nd, nc, ng, ne, tuple(dims), node, pure, tuple(dvals), kind)
         if key not in builders:
-            builders[key] = _GroupBuilder(nd, nc, ng, ne, dims, node, pure, dvals)
+            builders[key] = _GroupBuilder(nd, nc, ng, ne, dims, node, pure, dvals, kind)
         return builders[key]
 
     def numeric(values):
@@ -485,7 +518,7 @@ def lower_graph(rvs, factors, K, T, *, factor_weight=None, arg_weight=None, var_
             unary_w[v] = unary_w.get(v, 0.0) + w_f
             unary_g[v] = unary_g.get(v, 0.0) + gam[0]
         dvals = tuple(numeric(args[i]) for i in pos[HD])
-        builder(nd, nc, ng, ne, dims, False, pure, dvals).add(
+        builder(nd, nc, ng, ne, dims, False, pure, dvals, potential_kind(f.potential, nc + ng + ne)).add(
             table.block(f.potential, roles, args),
             [off[index[nb[i]]] for i in hidden],
             [args[i] for i in pos[EG]],
@@ -512,7 +545,7 @@ def lower_graph(rvs, factors, K, T, *, factor_weight=None, arg_weight=None, var_
             # point evidence: b = sum_k w_k = 1, log term vanishes (VarInference.py:65-66)
 
     groups = [b.finish() for b in builders.values()]
-    groups.sort(key=lambda g: (not g.node, not g.pure, g.nd + g.nc + g.ng, g.nd, g.nc, g.ng, g.ne, g.dims))
+    groups.sort(key=lambda g: (not g.node, not g.pure, g.nd + g.nc + g.ng, g.nd, g.nc, g.ng, g.ne, g.dims, g.kind))
     return LoweredModel(K, T, max(cursor, 2), np.asarray(kind, dtype=np.uint8),
                         np.asarray(dim, dtype=np.int32), np.asarray(off, dtype=np.int32),
                         table.array(), groups, handles, index)

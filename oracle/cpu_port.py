@@ -28,7 +28,8 @@ class NumpyRunner:
 def make_runner(model, eta, tau, w_tau):
     try:
         from oracle import c_port
-        if c_port.available():
+        # (the C port evaluates quadratic log-potentials only; hard / image-edge groups go to numpy)
+        if c_port.available() and all(getattr(g, "kind", 0) == 0 for g in model.groups):
             return c_port.CRunner(model, eta, tau, w_tau)
     except ImportError:
         pass

@@ -116,16 +116,27 @@ def grad_pass(model, eta, w, chunk_elems=1 << 24):
                 else:
                     xs = [_on_axis(X[g.nd + c], 2, g.nd + c, n_ax) for c in range(g.nc + g.ng)]
                     xs += [g.ecval[j, sl].reshape([m, 1] + [1] * n_ax) for j in range(g.ne)]
-                    q = model.ptab[base]
-                    for i in range(g.nct):
-                        q = q + model.ptab[base + 1 + i] * xs[i]
-                    p = 1 + g.nct
-                    for i in range(g.nct):
-                        for j in range(i, g.nct):
-                            q = q + model.ptab[base + p] * xs[i] * xs[j]
-                            p += 1
-                    with np.errstate(over="ignore"):
-                        lpsi = np.log(np.exp(q) + EPS)
+                    kind = getattr(g, "kind", 0)
+                    if kind == 2:
+                        # ImageEdgePotential (Potential.py:419-424): block = [distant, scaling, threshold, v]
+                        d = np.abs(xs[0] - xs[1])
+                        tail = np.where(d > model.ptab[base + 2], model.ptab[base + 3], np.exp(-d / model.ptab[base + 1]))
+                        lpsi = np.log(d * model.ptab[base] + tail + EPS)
+                    else:
+                        q = model.ptab[base]
+                        for i in range(g.nct):
+                            q = q + model.ptab[base + 1 + i] * xs[i]
+                        p = 1 + g.nct
+                        for i in range(g.nct):
+                            for j in range(i, g.nct):
+                                q = q + model.ptab[base + p] * xs[i] * xs[j]
+                                p += 1
+                        if kind == 1:
+                            # MLNHardPotential (MLNPotential.py:48-49): psi = 1 where the formula is > 0, else 0
+                            lpsi = np.log(np.where(q > 0, 1.0, 0.0) + EPS)
+                        else:
+                            with np.errstate(over="ignore"):
+                                lpsi = np.log(np.exp(q) + EPS)
                 F = lpsi - lb
 
             Wgrid = np.ones([m, K] + [1] * n_ax)

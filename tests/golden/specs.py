@@ -295,6 +295,64 @@ def edge_mix(ns):
     return _graph(ns, [lonely_c, lonely_b, single, twice, other, seen_a, seen_b, flag], fs)
 
 
+def denoise(ns):
+    """3 x 3 crop of the reference's image-denoising model (Demo/old/DenoisingDemo.py:35-70): a hidden
+    pixel per observed one, ``ImageNodePotential`` between the two, ``ImageEdgePotential`` on the grid
+    edges -- the demo's (0, 3.5, 25) on the horizontal ones and, so that the distance term and the
+    truncation are exercised at these magnitudes, (0.05, 1.2, 1.0) on the vertical ones."""
+    rng = np.random.default_rng(11)
+    dom = ns.Domain((0, 255), continuous=True)
+    row = col = 3
+    obs = rng.uniform(-3.0, 6.0, size=(row, col))
+    x = [ns.RV(dom) for _ in range(row * col)]
+    y = [ns.RV(dom, float(obs[i, j])) for i in range(row) for j in range(col)]
+    pxo = ns.ImageNodePotential(0, 5)
+    ph = ns.ImageEdgePotential(0, 3.5, 25)
+    pv = ns.ImageEdgePotential(0.05, 1.2, 1.0)
+    fs = [ns.F(pxo, [x[i], y[i]]) for i in range(row * col)]
+    fs += [ns.F(ph, [x[i * col + j], x[i * col + j + 1]]) for i in range(row) for j in range(col - 1)]
+    fs += [ns.F(pv, [x[i * col + j], x[(i + 1) * col + j]]) for i in range(row - 1) for j in range(col)]
+    return _graph(ns, x + y, fs)
+
+
+def hard_mln(ns):
+    """``MLNHardPotential`` over continuous arguments (MLNPotential.py:43-49) next to soft factors: a
+    half-plane constraint between two hidden reals, a band constraint switched by a hidden boolean
+    against an observed real, and one against a discrete observation."""
+    dc = ns.Domain((-10, 10), continuous=True)
+    db = ns.Domain((0, 1))
+    a, b, c = ns.RV(dc), ns.RV(dc), ns.RV(dc)
+    seen = ns.RV(dc, 0.4)
+    flag, on = ns.RV(db), ns.RV(db, 1)
+    half = ns.MLNHardPotential(lambda x: x[0] - x[1] + 0.3)
+    band = ns.MLNHardPotential(lambda x: x[0] * (4.0 + ns.eq_op(x[1], x[2])) + (1 - x[0]) * 0.5)
+    gate = ns.MLNHardPotential(lambda x: x[0] * (2.0 - x[1] * x[1]) + 0.1)
+    soft = ns.MLNPotential(lambda x: x[0] * ns.eq_op(x[1], x[2]), w=0.6)
+    pg = ns.GaussianPotential([0.2, -0.1], [[1.5, 0.4], [0.4, 1.2]])
+    x2 = ns.X2Potential(1.0, 2.0)
+    fs = [ns.F(half, [a, b]), ns.F(band, [flag, c, seen]), ns.F(gate, [on, b]), ns.F(soft, [flag, a, c]),
+          ns.F(pg, [b, c]), ns.F(x2, [a]), ns.F(x2, [c])]
+    return _graph(ns, [a, b, c, seen, flag, on], fs)
+
+
+def gabp_grid(ns, row=4, col=4):
+    """Loopy grid for Gaussian belief propagation (reference GaBP.py): hidden x[i][j] with an observed
+    y[i][j]; ``LinearGaussianPotential`` between the two, an ``X2Potential`` prior on every x,
+    zero-mean ``GaussianPotential`` on the horizontal edges and ``XYPotential`` on the vertical ones."""
+    rng = np.random.default_rng(3)
+    dom = ns.Domain((-10, 10), continuous=True)
+    x = [ns.RV(dom) for _ in range(row * col)]
+    y = [ns.RV(dom, float(v)) for v in rng.uniform(-2.0, 2.0, size=row * col)]
+    obs = ns.LinearGaussianPotential(0.9, 0.6)
+    prior = ns.X2Potential(1.0, 2.5)
+    edge = ns.GaussianPotential([0.0, 0.0], [[2.0, 0.9], [0.9, 1.5]])
+    xy = ns.XYPotential(-0.5, 2.0)
+    fs = [ns.F(obs, [x[i], y[i]]) for i in range(row * col)] + [ns.F(prior, [x[i]]) for i in range(row * col)]
+    fs += [ns.F(edge, [x[i * col + j], x[i * col + j + 1]]) for i in range(row) for j in range(col - 1)]
+    fs += [ns.F(xy, [x[i * col + j], x[(i + 1) * col + j]]) for i in range(row - 1) for j in range(col)]
+    return _graph(ns, x + y, fs)
+
+
 CASES = {
     # name: (builder, K, T, engines)
     "chain_table": (chain_table, 3, 3, ("ground", "lifted", "c2f")),
@@ -311,6 +369,8 @@ CASES = {
     "edge_mix": (edge_mix, 2, 3, ("ground", "lifted")),
     "hmln_demo": (hmln_demo, 2, 3, ("ground", "lifted")),
     "robot_demo": (robot_demo, 2, 3, ("ground",)),
+    "denoise": (denoise, 2, 3, ("ground", "lifted")),
+    "hard_mln": (hard_mln, 2, 3, ("ground",)),
 }
 
 

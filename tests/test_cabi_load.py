@@ -50,18 +50,19 @@ def test_struct_layout_matches_header():
     import subprocess
     import tempfile
     from lhvi_b200 import _cabi
-    src = '#include <stdio.h>\n#include "lhvi.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(lhvi_group), sizeof(lhvi_model), sizeof(lhvi_exchange), sizeof(lhvi_optim), sizeof(lhvi_h2));return 0;}\n'
+    src = '#include <stdio.h>\n#include "lhvi.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(lhvi_group), sizeof(lhvi_model), sizeof(lhvi_exchange), sizeof(lhvi_optim), sizeof(lhvi_h2), sizeof(lhvi_gabp));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
-        sg, sm, sx, so, sh = map(int, subprocess.check_output([exe]).split())
+        sg, sm, sx, so, sh, sb = map(int, subprocess.check_output([exe]).split())
     assert sg == ctypes.sizeof(_cabi.LhviGroup)
     assert sm == ctypes.sizeof(_cabi.LhviModel)
     assert sx == ctypes.sizeof(_cabi.LhviExchange)
     assert so == ctypes.sizeof(_cabi.LhviOptim)
     assert sh == ctypes.sizeof(_cabi.LhviH2)
+    assert sb == ctypes.sizeof(_cabi.LhviGabp)
 
 
 def test_engine_refuses_to_run_without_gpu():

@@ -215,6 +215,30 @@ def config4(dtype="float32", n=1000, iterations=3000, lr=0.05):
            "cg_info": int(info), "cg_seconds": t_cg,
            "launch_mode": "persistent" if eng.persistent() else "CUDA graph of per-group launches"}
     eng.close()
+    # the cross-check BASELINE names: Gaussian belief propagation on the device at full size (GaBP.py,
+    # csrc/lhvi_gabp.cu), timed with CUDA events; bytes per sweep: per directed edge 3 indices + 5
+    # coefficients + 2 messages read, 2 written, 2 gathered totals, 2 REDs; per variable 2 read, 2 written
+    import torch
+    from lhvi_b200 import GaBP as gabp
+    arrays = gabp.gabp_from_model(model)
+    bp = gabp.DeviceGaBP(arrays, dtype)
+    sweeps = 200
+    bp.sweeps(5)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    bp.sweeps(sweeps)
+    ev1.record()
+    torch.cuda.synchronize()
+    gms = ev0.elapsed_time(ev1) / sweeps
+    gmean, gvar = bp.marginals()
+    gerr = np.abs(gmean.double().cpu().numpy() - exact)
+    esz = 4 if dtype == "float32" else 8
+    gbytes = int(arrays.src.size) * (3 * 4 + 13 * esz) + int(arrays.n_vars) * 4 * esz
+    out["gabp"] = {"engine": "DeviceGaBP (lhvi_gabp_sweeps)", "directed_edges": int(arrays.src.size), "sweeps": sweeps + 5,
+                   "ms_per_sweep": gms, "algorithmic_gbs": gbytes / (gms * 1e-3) / 1e9,
+                   "max_abs_mean_error_vs_exact": float(gerr.max()),
+                   "max_abs_vi_minus_gabp_mean": float(np.abs(mu - gmean.double().cpu().numpy()).max())}
     return out
 
 
