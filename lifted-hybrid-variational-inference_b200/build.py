@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-I", INCLUDE,
-]
+] + os.environ.get("LHVI_NVCC_EXTRA", "").split()      # e.g. -DLHVI_RUN_BLOCKS=3 for a tuning experiment (then --force)
 
 
 def nvcc_path() -> str:
