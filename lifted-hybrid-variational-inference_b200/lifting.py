@@ -794,8 +794,13 @@ class C2FArrayVI:
     var_threshold = 0.1
 
     def __init__(self, ga: GroundArrays, K, T, *, dtype="float64", device=None, engine_factory=None,
-                 init_fn=None, use_native=None):
+                 init_fn=None, use_native=None, device_passes=None):
         self.ga, self.K, self.T = ga, int(K), int(T)
+        # where the lifting passes of a round run (evidence split, colour passing, class statistics,
+        # inheritance, lowering): None -> on the GPU next to the kernels when there is one and the engine is
+        # the real one (``lifting_torch``: the ground graph is uploaded once and stays resident), else in the
+        # host library; False -> host; a torch device (e.g. "cpu" in the tests) -> there
+        self.device_passes = device_passes
         self.dtype, self.device = dtype, device
         self.engine_factory = engine_factory
         self.init_fn = init_fn            # (representative ground index, is_continuous, dim) -> [K, dim] or None
@@ -953,8 +958,11 @@ class C2FArrayVI:
         """One table per initial hidden class (one class per domain), ``VarInference.py:197-208``:
         ``P`` holds (mu, var) pairs of continuous classes and the logits of discrete ones, in the
         slot layout of the current partition; ``m1`` / ``m2`` are the Adam moments beside it."""
+        self._init_params_from(self._layout(self.vcol))
+
+    def _init_params_from(self, lay):
         K = self.K
-        lay = self.layout = self._layout(self.vcol)
+        self.layout = lay
         self.P = np.zeros(lay["n_param"])
         for r, kind, dim, off in zip(lay["rep"], lay["kind"], lay["dim"], lay["off"]):
             r, dim, cont = int(r), int(dim), kind == 0
@@ -998,10 +1006,27 @@ class C2FArrayVI:
         self.m_w, self.u_w, self.t = m_w, u_w, t
 
     # ---- the run ---------------------------------------------------------------------------
+    def _passes_device(self):
+        if self.device_passes is False:
+            return None
+        if self.device_passes is None:
+            import torch
+            if self.engine_factory is not None or not torch.cuda.is_available() or self.k_mean_k != 2:
+                return None
+            return torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device_passes is True:
+            import torch
+            return torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+        import torch
+        return torch.device(self.device_passes)
+
     def run(self, iteration=100, lr=0.1, log_fe=False):
         """``log_fe=True`` evaluates the free energy at the end of every refinement round (one more
         pass over the records) into ``history`` -- the reference logs it after every iteration
         (``C2FVarInference.py:354-377``)."""
+        dev = self._passes_device()
+        if dev is not None:
+            return self._run_resident(dev, iteration, lr, log_fe)
         ga = self.ga
         self.degrees = ga.degrees()
         # initial classes, parameters per initial class (one hidden class per domain), then the
@@ -1053,6 +1078,98 @@ class C2FArrayVI:
             self._pull(self.model, self.engine)
             clock("pull", t)
             self.history.append((self.quotient.n_var_classes, float(self.engine.free_energy()) if log_fe else None))
+        return self
+
+    def _run_resident(self, dev, iteration, lr, log_fe):
+        """``run`` with the lifting passes on ``dev`` (``lifting_torch``): the ground graph, the colourings
+        and the evidence book-keeping stay there between the rounds; the parameters and Adam moments
+        (one slot per hidden class) travel through the host as before.  Same partitions, class ids and
+        record columns as the host route (``tests/test_lifting_torch.py``)."""
+        import torch
+        from . import lifting_torch as lt
+        ga, K = self.ga, self.K
+        tg = getattr(ga, "_torch_graph", None)
+        if tg is None or tg.device != dev:
+            tg = ga._torch_graph = lt.TorchGraph(ga, dev)
+        cont, ddim = lt.domain_tables(ga.domains, dev)
+        self.degrees = None
+        to_host = lambda lay: {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in lay.items()}
+
+        def refine(vcol, may, has, val, lay_t):
+            new, fcols, _ = lt.colour_passing(tg, vcol)
+            may, has, val = lt.refine_bookkeeping(vcol, new, may, has, val)
+            new_lay_t, stats = lt.layout(tg, new, K, cont, ddim)
+            if lay_t is not None:
+                arrs = lt.inherit(lay_t, new_lay_t, vcol, K, [torch.as_tensor(a).to(dev) for a in (self.P, self.m1, self.m2)])
+                self.P, self.m1, self.m2 = (a.cpu().numpy() for a in arrs)
+            return new, fcols, may, has, val, new_lay_t, stats
+
+        vcol = torch.as_tensor(initial_colouring(ga, split_cont_evidence=False)).to(dev)
+        n0 = int(vcol.max()) + 1
+        may = torch.zeros(n0, dtype=torch.bool, device=dev)
+        may[vcol[~tg.hidden & cont[tg.var_dom]]] = True
+        has, val = torch.zeros(n0, dtype=torch.bool, device=dev), torch.zeros(n0, dtype=torch.float64, device=dev)
+        # parameters per initial hidden class (C2FVarInference.py:306-311), then the first colour passing
+        lay_t, _ = lt.layout(tg, vcol, K, cont, ddim)
+        self.vcol = vcol.cpu().numpy()
+        self.stats = None
+        self._init_params_from(to_host(lay_t))
+        vcol, fcols, may, has, val, lay_t, stats = refine(vcol, may, has, val, lay_t)
+        self.layout = to_host(lay_t)
+        ev = ~tg.hidden
+        if bool(ev.any()):
+            ecol = vcol[ev]
+            ids, inv, cnt = torch.unique(ecol, return_inverse=True, return_counts=True)
+            evar = lt._segment_var(tg.var_value[ev], inv, ids.numel(), cnt)
+            epsilon = float(torch.sqrt(evar.max()))
+        else:
+            epsilon = 0.0
+        d = epsilon * self.update_obs_its / (iteration - self.output_its)
+        epsilon -= d
+        self.history = []
+        self.timing = {"split": 0.0, "refine": 0.0, "lower": 0.0, "upload": 0.0, "iterate": 0.0, "pull": 0.0}
+        self.timing_rounds = []
+        sync = (lambda: torch.cuda.synchronize(dev)) if dev.type == "cuda" else (lambda: None)
+
+        def clock(phase, t0):
+            sync()
+            now = time.perf_counter()
+            self.timing[phase] += now - t0
+            self.timing_rounds[-1][phase] = now - t0
+            return now
+        for _ in range(int(iteration / self.update_obs_its)):          # remainder dropped (H10)
+            self.timing_rounds.append({})
+            sync()
+            t = time.perf_counter()
+            vcol, may, has, val = lt.split_evidence(tg, vcol, may, has, val, epsilon, self.k_mean_k, self.k_mean_its)
+            t = clock("split", t)
+            vcol, fcols, may, has, val, lay_t, stats = refine(vcol, may, has, val, lay_t)
+            self.layout = to_host(lay_t)
+            t = clock("refine", t)
+            epsilon = max(epsilon - d, self.min_obs_var)
+            self.model = lt.lower_partition(tg, ga, vcol, fcols, K, self.T, ev_value=(has, val),
+                                            gaussian_obs=self.gaussian_obs, min_obs_var=self.min_obs_var, stats=stats)
+            t = clock("lower", t)
+            old = getattr(self, "engine", None)
+            if old is not None and hasattr(old, "close"):
+                old.close()
+            self.engine = self._make_engine(self.model)
+            self._push(self.model, self.engine)
+            t = clock("upload", t)
+            self.engine.iterate(self.update_obs_its, lr)
+            if hasattr(self.engine, "synchronize"):
+                self.engine.synchronize()
+            t = clock("iterate", t)
+            self._pull(self.model, self.engine)
+            clock("pull", t)
+            n_classes = int(stats["n"])
+            self.history.append((n_classes, float(self.engine.free_energy()) if log_fe else None))
+        # the public attributes of a finished run, as the host route leaves them
+        self.vcol = vcol.cpu().numpy()
+        self.fcols = [f.cpu().numpy() for f in fcols]
+        self.may_split, self.ev_has, self.ev_val = may.cpu().numpy(), has.cpu().numpy(), val.cpu().numpy()
+        self.stats = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in stats.items()}
+        self.quotient = PartitionInfo(self.vcol, self.fcols)
         return self
 
     def free_energy(self):
