@@ -10,7 +10,7 @@ __all__ = ["Graph", "Potential", "MLNPotential", "CompressedGraphWithObs", "Rela
            "lowering", "lifting", "install_flat_aliases"]
 
 _FLAT = ("Graph", "Potential", "MLNPotential", "CompressedGraphWithObs", "RelationalGraph", "KalmanFilter", "utils",
-         "VarInference", "LiftedVarInference", "C2FVarInference")
+         "VarInference", "LiftedVarInference", "C2FVarInference", "GaBP")
 
 
 def __getattr__(name):

@@ -1088,6 +1088,8 @@ class C2FArrayVI:
         import torch
         from . import lifting_torch as lt
         ga, K = self.ga, self.K
+        sync = (lambda: torch.cuda.synchronize(dev)) if dev.type == "cuda" else (lambda: None)
+        t_setup = time.perf_counter()
         tg = getattr(ga, "_torch_graph", None)
         if tg is None or tg.device != dev:
             tg = ga._torch_graph = lt.TorchGraph(ga, dev)
@@ -1104,7 +1106,7 @@ class C2FArrayVI:
                 self.P, self.m1, self.m2 = (a.cpu().numpy() for a in arrs)
             return new, fcols, may, has, val, new_lay_t, stats
 
-        vcol = torch.as_tensor(initial_colouring(ga, split_cont_evidence=False)).to(dev)
+        vcol = lt.initial_colouring(tg, cont, split_cont_evidence=False)
         n0 = int(vcol.max()) + 1
         may = torch.zeros(n0, dtype=torch.bool, device=dev)
         may[vcol[~tg.hidden & cont[tg.var_dom]]] = True
@@ -1129,7 +1131,8 @@ class C2FArrayVI:
         self.history = []
         self.timing = {"split": 0.0, "refine": 0.0, "lower": 0.0, "upload": 0.0, "iterate": 0.0, "pull": 0.0}
         self.timing_rounds = []
-        sync = (lambda: torch.cuda.synchronize(dev)) if dev.type == "cuda" else (lambda: None)
+        sync()
+        self.timing["setup"] = time.perf_counter() - t_setup     # graph upload, initial classes, first colour passing
 
         def clock(phase, t0):
             sync()

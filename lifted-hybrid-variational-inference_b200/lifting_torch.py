@@ -167,6 +167,18 @@ def colour_passing(tg: TorchGraph, start, max_sweeps=1000):
     return vcol, fcol, sweeps
 
 
+def initial_colouring(tg: TorchGraph, cont, split_cont_evidence=True):
+    """``lifting.initial_colouring`` (``init_cluster``, ``CompressedGraphWithObs.py:187-234``): one class per
+    (domain, hidden | evidence value), ids in lexicographic order of that triple as the host pass numbers
+    them; ``split_cont_evidence=False`` puts all continuous observations of a domain in one class."""
+    val = torch.where(tg.hidden, torch.zeros_like(tg.var_value), tg.var_value)
+    if not split_cont_evidence:
+        val = torch.where(cont[tg.var_dom], torch.zeros_like(val), val)
+    uniq, val_id = torch.unique(val, return_inverse=True)
+    key = (tg.var_dom * 2 + tg.hidden.to(torch.int64)) * max(int(uniq.numel()), 1) + val_id
+    return torch.unique(key, return_inverse=True)[1]
+
+
 # ---- class statistics, parameter slots, inheritance -----------------------------------------------------
 
 def class_stats(tg: TorchGraph, vcol, ev_value=None, base=None):

@@ -60,5 +60,6 @@ def test_c2f_figure_of_the_bench_line(monkeypatch):
     assert out["rounds"] == 2 and out["iterations"] == 20 and out["free_energy_finite"]
     assert out["ground_factors"] == 1000 * 3 + 1000 + 3 * 2 or out["ground_factors"] > 3000
     assert out["classes_per_round"] == sorted(out["classes_per_round"])
-    parts = out["host_passes_s"] + out["upload_s"] + out["device_iterations_s"] + out["readback_s"]
+    parts = out["lifting_passes_s"] + out["upload_s"] + out["device_iterations_s"] + out["readback_s"] + out["setup_s"]
     assert 0 < parts <= out["run_s"] * 1.001
+    assert out["lifting_passes"].startswith("host")          # no GPU here: the passes run in the host library

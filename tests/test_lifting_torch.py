@@ -37,6 +37,15 @@ def test_colour_passing_gives_the_host_library_s_class_ids(ns, split):
         assert all(np.array_equal(a, b.numpy()) for a, b in zip(f0, f1)), name
 
 
+@pytest.mark.parametrize("split", [True, False])
+def test_initial_colouring_matches_the_host_pass(ns, split):
+    for name, ga in _models(ns):
+        tg = lt.TorchGraph(ga, "cpu")
+        cont, _ = lt.domain_tables(ga.domains, "cpu")
+        want = lifting.initial_colouring(ga, split_cont_evidence=split)
+        assert np.array_equal(lt.initial_colouring(tg, cont, split).numpy(), want), name
+
+
 def test_rank_first_survives_a_hash_collision():
     cols = [torch.tensor([5, 7, 5, 9, 7, 5]), torch.tensor([1, 1, 2, 1, 1, 1])]
     ids, n, first = lt.rank_first(torch.zeros(6, dtype=torch.int64), cols)          # every row "collides"
