@@ -19,7 +19,7 @@ MAX_AXES = 6
 class VoGroup(C.Structure):
     _fields_ = [("nd", C.c_int), ("nc", C.c_int), ("ng", C.c_int), ("ne", C.c_int),
                 ("dims", C.c_int * MAX_AXES), ("node", C.c_int), ("weighted", C.c_int), ("pure", C.c_int),
-                ("n", C.c_longlong), ("pot", C.c_void_p), ("poff", C.c_void_p),
+                ("kind", C.c_int), ("n", C.c_longlong), ("pot", C.c_void_p), ("poff", C.c_void_p),
                 ("egval", C.c_void_p), ("egvar", C.c_void_p), ("ecval", C.c_void_p),
                 ("wf", C.c_void_p), ("gam", C.c_void_p), ("nscale", C.c_void_p)]
 
@@ -59,6 +59,7 @@ class CModel:
             for i in range(MAX_AXES):
                 d.dims[i] = int(g.dims[i]) if i < len(g.dims) else 0
             d.node, d.weighted, d.pure, d.n = int(g.node), int(g.weighted), int(g.pure), int(g.n)
+            d.kind = int(getattr(g, "kind", 0))
             for name, arr, dt in (("pot", g.pot, np.int32), ("poff", g.poff, np.int32),
                                   ("egval", g.egval, np.float64), ("egvar", g.egvar, np.float64),
                                   ("ecval", g.ecval, np.float64), ("wf", g.wf, np.float64),

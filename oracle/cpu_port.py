@@ -28,8 +28,7 @@ class NumpyRunner:
 def make_runner(model, eta, tau, w_tau):
     try:
         from oracle import c_port
-        # (the C port evaluates quadratic log-potentials only; hard / image-edge groups go to numpy)
-        if c_port.available() and all(getattr(g, "kind", 0) == 0 for g in model.groups):
+        if c_port.available():
             return c_port.CRunner(model, eta, tau, w_tau)
     except ImportError:
         pass

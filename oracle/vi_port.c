@@ -36,6 +36,8 @@ typedef struct vo_group {
     int nd, nc, ng, ne;
     int dims[VO_MAX_AXES];
     int node, weighted, pure;
+    int kind;              /* 0: quadratic log-potential; 1: MLNHardPotential (MLNPotential.py:48-49);
+                              2: ImageEdgePotential (Potential.py:419-424), block = [distant, scaling, threshold, v] */
     long long n;
     const int* pot;        /* [n] */
     const int* poff;       /* [(nd+nc)*n] */
@@ -136,12 +138,17 @@ static void vo_record(const vo_group* g, long long r, int K, int T, const double
                     double xv[VO_MAX_AXES + 8];
                     for (int i = 0; i < g->nc + g->ng; ++i) xv[i] = xs[noff[g->nd + i] + idx[g->nd + i]];
                     for (int j = 0; j < g->ne; ++j) xv[g->nc + g->ng + j] = g->ecval[j * g->n + r];
-                    double q = cf[0];
-                    for (int i = 0; i < nct; ++i) q += cf[1 + i] * xv[i];
-                    int p = 1 + nct;
-                    for (int i = 0; i < nct; ++i)
-                        for (int j = i; j < nct; ++j) q += cf[p++] * xv[i] * xv[j];
-                    lpsi = log(exp(q) + VO_EPS);
+                    if (g->kind == 2) {
+                        const double d = fabs(xv[0] - xv[1]);
+                        lpsi = log(d * cf[0] + (d > cf[2] ? cf[3] : exp(-d / cf[1])) + VO_EPS);
+                    } else {
+                        double q = cf[0];
+                        for (int i = 0; i < nct; ++i) q += cf[1 + i] * xv[i];
+                        int p = 1 + nct;
+                        for (int i = 0; i < nct; ++i)
+                            for (int j = i; j < nct; ++j) q += cf[p++] * xv[i] * xv[j];
+                        lpsi = g->kind == 1 ? log((q > 0 ? 1.0 : 0.0) + VO_EPS) : log(exp(q) + VO_EPS);
+                    }
                 }
                 F = lpsi - lb;
             }
