@@ -683,17 +683,34 @@ class ArrayVI:
     the device engine (``LiftedVarInference.py:14-26`` + ``VarInference.run`` ``:215-247``).
     Per-variable results are expanded from the classes back to the ground variables."""
 
-    def __init__(self, ga: GroundArrays, K, T, *, lifted=True, dtype="float64", device=None, engine_factory=None):
+    def __init__(self, ga: GroundArrays, K, T, *, lifted=True, dtype="float64", device=None, engine_factory=None,
+                 device_passes=None):
         self.ga, self.K, self.T = ga, K, T
-        if lifted:
-            vcol, fcols, _ = colour_passing(ga)
-        else:                                   # every variable and factor its own class
-            vcol = np.arange(ga.n_vars, dtype=np.int64)
-            sizes = np.cumsum([0] + [b.n for b in ga.blocks])
-            fcols = [np.arange(b.n, dtype=np.int64) + o for b, o in zip(ga.blocks, sizes)]
+        dev = _passes_device(device_passes, device, engine_factory) if lifted else None
+        if dev is not None:
+            # colour passing, class statistics and lowering on the resident ground graph (lifting_torch):
+            # the host library's class ids and record columns
+            import torch
+            from . import lifting_torch as lt
+            tg = getattr(ga, "_torch_graph", None)
+            if tg is None or tg.device != dev:
+                tg = ga._torch_graph = lt.TorchGraph(ga, dev)
+            cont, _ = lt.domain_tables(ga.domains, dev)
+            vt, ft, _ = lt.colour_passing(tg, lt.initial_colouring(tg, cont, True))
+            stats = lt.class_stats(tg, vt)
+            self.model = lt.lower_partition(tg, ga, vt, ft, K, T, stats=stats)
+            vcol, fcols = vt.cpu().numpy(), [f.cpu().numpy() for f in ft]
+            self.class_rep = stats["rep"].cpu().numpy()
+        else:
+            if lifted:
+                vcol, fcols, _ = colour_passing(ga)
+            else:                                   # every variable and factor its own class
+                vcol = np.arange(ga.n_vars, dtype=np.int64)
+                sizes = np.cumsum([0] + [b.n for b in ga.blocks])
+                fcols = [np.arange(b.n, dtype=np.int64) + o for b, o in zip(ga.blocks, sizes)]
+            self.class_rep = class_stats(ga, vcol)["rep"]
+            self.model = lower_partition(ga, vcol, fcols, K, T)
         self.quotient = PartitionInfo(vcol, fcols)
-        self.class_rep = class_stats(ga, vcol)["rep"]
-        self.model = lower_partition(ga, vcol, fcols, K, T)
         if engine_factory is not None:
             self.engine = engine_factory(self.model)
         else:
@@ -751,6 +768,22 @@ class ArrayVI:
         col = self.quotient.var_colour
         hidden = np.flatnonzero(np.isnan(self.ga.var_value))
         return {int(v): tables[slot_of[col[v]]] for v in hidden}, w
+
+
+def _passes_device(device_passes, device, engine_factory, k_mean_k=2):
+    """Where the lifting passes run: ``None`` -> on the GPU next to the kernels when there is one and the
+    engine is the real one (``lifting_torch``), else in the host library; ``False`` -> host; ``True`` -> the
+    engine's GPU; anything else -> that torch device (``"cpu"`` in the tests)."""
+    if device_passes is False:
+        return None
+    import torch
+    if device_passes is None:
+        if engine_factory is not None or not torch.cuda.is_available() or k_mean_k != 2:
+            return None
+        device_passes = True
+    if device_passes is True:
+        return torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device_passes)
 
 
 def _kmeans_1d(values, k, iteration):
@@ -1007,18 +1040,7 @@ class C2FArrayVI:
 
     # ---- the run ---------------------------------------------------------------------------
     def _passes_device(self):
-        if self.device_passes is False:
-            return None
-        if self.device_passes is None:
-            import torch
-            if self.engine_factory is not None or not torch.cuda.is_available() or self.k_mean_k != 2:
-                return None
-            return torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
-        if self.device_passes is True:
-            import torch
-            return torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
-        import torch
-        return torch.device(self.device_passes)
+        return _passes_device(self.device_passes, self.device, self.engine_factory, self.k_mean_k)
 
     def run(self, iteration=100, lr=0.1, log_fe=False):
         """``log_fe=True`` evaluates the free energy at the end of every refinement round (one more

@@ -124,6 +124,18 @@ def test_resident_passes_on_a_hybrid_object_graph(ns):
     _same_run(*runs)
 
 
+def test_lifted_engine_with_resident_passes_equals_the_host_route():
+    ga = syn.kalman_arrays(30, 10, levels=3, seed=2)[0]
+    a, b = [lifting.ArrayVI(ga, 2, 3, engine_factory=lambda m: OracleEngine(m, var_threshold=0.1), device_passes=dp)
+            for dp in (False, "cpu")]
+    assert np.array_equal(a.quotient.var_colour, b.quotient.var_colour) and np.array_equal(a.class_rep, b.class_rep)
+    for ga_, gb_ in zip(a.model.groups, b.model.groups):
+        assert ga_.signature == gb_.signature and np.array_equal(ga_.poff, gb_.poff) and np.array_equal(ga_.wf, gb_.wf)
+    a.run(5, 0.1)
+    b.run(5, 0.1)
+    np.testing.assert_allclose(a.free_energy(), b.free_energy(), rtol=1e-12)
+
+
 @pytest.mark.gpu
 def test_coarse_to_fine_on_the_gpu_with_resident_passes_equals_the_host_route():
     ga = syn.relational_hybrid_arrays(20000, 6, seed=3)
