@@ -44,8 +44,10 @@ def _pass(model, state, dtype="float32", **kw):
 
 def _close(a, b, rel, hub_rel=None, model=None):
     """``rel`` of the largest entry for gradients, G_w and energy.  ``hub_rel``: the ten group-level variables
-    collect ~10^6 records each and their sums cancel to ~1e-3 of the summed magnitudes, so the float paths --
-    every term good to ~1e-6 of ITS size -- are only compared to ``hub_rel`` of the value there."""
+    collect ~10^6 records each (gradients of 5e5 .. 5e6 next to 36 for the largest other entry), so they are
+    compared on their own scale: the specialised float kernels (per-thread and per-block partial sums) reach
+    2e-6 of the value there, the generic float kernel -- one scalar atomicAdd per record into the same
+    address -- 4e-3 (``tools/fp32_hub_probe.py``)."""
     ga, gb = np.array(a[0]), np.array(b[0])
     if hub_rel is not None:
         hubs = _hub_elements(model)
@@ -75,7 +77,7 @@ def test_specialised_kernels_equal_the_generic_kernel_on_all_records(full):
     exact = _pass(model, state, "float64")
     _close(exact, _pass(model, state, "float64", force_generic=True), 1e-9)
     # in single precision both are compared with the double result
-    _close(_pass(model, state), exact, 3e-5, hub_rel=1e-2, model=model)
+    _close(_pass(model, state), exact, 3e-5, hub_rel=2e-5, model=model)
     _close(_pass(model, state, force_generic=True), exact, 3e-5, hub_rel=1e-2, model=model)
 
 
@@ -100,7 +102,7 @@ def test_the_sums_are_additive_over_the_records_and_independent_of_their_order(f
     rng = np.random.default_rng(2)
     shuffled = dataclasses.replace(model, groups=[g.take(rng.permutation(g.n)) for g in model.groups])
     _close(_pass(shuffled, state, "float64"), whole, 1e-9)
-    _close(_pass(shuffled, state, "float32"), whole, 3e-5, hub_rel=1e-2, model=model)
+    _close(_pass(shuffled, state, "float32"), whole, 3e-5, hub_rel=2e-5, model=model)
 
 
 def test_everything_is_linear_in_the_lifted_weights(full):
