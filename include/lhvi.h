@@ -285,6 +285,11 @@ int lhvi_mixture_map(int dtype, int K, int64_t n, const int32_t* q_off, const in
  * With one GPU n_owned = n_vars.  The step counter is NOT advanced here: call lhvi_step_tick
  * earlier in the iteration (it can run beside the factor kernels).  eta and grad are taken from
  * the model; gradient slots are always reset (zero_grad = 1).
+ *
+ * Uniform continuous slots: with var_kind = var_dim = var_off = NULL (one GPU, n_owned = n_vars) every one of
+ * the n_vars variables is continuous and variable v sits at element v * slot, slot = 2 for K = 1, else 2K
+ * rounded up to a multiple of 4 (float: K >= 2).  The launch then steps one 16-byte vector per thread,
+ * fully coalesced, without the variable table.
  */
 int lhvi_finish_step(const lhvi_model* m, int64_t rows, const lhvi_exchange* x, int64_t n_vars,
                      int64_t n_owned, const uint8_t* var_kind, const int32_t* var_dim,

@@ -172,6 +172,15 @@ static int finish_step_t(const lhvi_model* m, long long regions, const lhvi_exch
     a.m1 = (real*)m1; a.m2 = (real*)m2; a.wstate = (real*)wstate; a.step = step;
     a.lr = (real)lr; a.b1 = (real)b1; a.b2 = (real)b2; a.eps = (real)eps; a.var_floor = (real)var_floor;
     a.sgd = sgd; a.zero_grad = 1;
+    if (kind == nullptr) {
+        // uniform continuous slots (validated by the caller): one thread per 16-byte vector
+        constexpr int per = PairVec<real>::pairs;
+        const int slot = 2 * K <= 2 ? 2 : (2 * K + 3) / 4 * 4;
+        const int slot_vecs = slot / (2 * per);
+        const long long n_vec = (long long)n_vars * slot_vecs;
+        finish_step_flat_kernel<real><<<1 + grid_for(n_vec > 0 ? n_vec : 1, 256), 256, 0, s>>>(f, a, n_vec, slot_vecs);
+        return check_launch("finish_step_flat_kernel");
+    }
     finish_step_kernel<real><<<1 + grid_for(n_owned > 0 ? n_owned : 1, 256), 256, 0, s>>>(f, a, (long long)n_owned);
     return check_launch("finish_step_kernel");
 }
@@ -183,8 +192,15 @@ extern "C" int lhvi_finish_step(const lhvi_model* m, int64_t rows, const lhvi_ex
                                 double var_threshold, int sgd, void* stream) {
     if (!m || !m->partials || !m->grad || !m->eta || rows < 0) { set_error("lhvi_finish_step: null buffer or negative rows"); return LHVI_EINVAL; }
     if (!tau || !mom1 || !mom2 || !wstate || !step) { set_error("lhvi_finish_step: null buffer"); return LHVI_EINVAL; }
-    if (n_vars > 0 && (!var_kind || !var_dim || !var_off)) { set_error("lhvi_finish_step: null variable table"); return LHVI_EINVAL; }
+    const bool uniform = n_vars > 0 && !var_kind && !var_dim && !var_off;      // see lhvi.h: uniform continuous slots
+    if (n_vars > 0 && !uniform && (!var_kind || !var_dim || !var_off)) { set_error("lhvi_finish_step: null variable table"); return LHVI_EINVAL; }
     if (n_owned < 0 || n_owned > n_vars) { set_error("lhvi_finish_step: n_owned=%lld outside 0..n_vars=%lld", (long long)n_owned, (long long)n_vars); return LHVI_EINVAL; }
+    if (uniform) {
+        const int slot = 2 * m->K <= 2 ? 2 : (2 * m->K + 3) / 4 * 4;
+        if ((x != nullptr && x->world > 1) || n_owned != n_vars) { set_error("lhvi_finish_step: uniform slots are stepped on one GPU only (pass the variable table)"); return LHVI_EINVAL; }
+        if (m->dtype == LHVI_F32 && m->K < 2) { set_error("lhvi_finish_step: uniform float slots need K >= 2 (16-byte vectors)"); return LHVI_EINVAL; }
+        if (n_vars * (int64_t)slot > m->n_param) { set_error("lhvi_finish_step: %lld uniform slots of %d elements exceed n_param=%lld", (long long)n_vars, slot, (long long)m->n_param); return LHVI_EINVAL; }
+    }
     if (m->K < 1 || m->K > LHVI_MAX_K) { set_error("K=%d out of range 1..%d", m->K, LHVI_MAX_K); return LHVI_ELIMIT; }
     if (rows % LHVI_PARTIAL_ROWS != 0) { set_error("lhvi_finish_step: rows must be a multiple of LHVI_PARTIAL_ROWS"); return LHVI_EINVAL; }
     if (x != nullptr && x->world > 1) {

@@ -367,6 +367,14 @@ class DeviceEngine:
             is_shared = np.isin(m.var_off, shared_off)
             order = np.concatenate([np.flatnonzero(~is_shared), np.flatnonzero(is_shared)])
             self.n_owned = int((~is_shared).sum())
+        # every variable continuous, slots contiguous in variable order, one GPU: lhvi_finish_step steps one
+        # 16-byte vector per thread without the variable table (include/lhvi.h, "uniform continuous slots")
+        slot = 2 if 2 * K <= 2 else (2 * K + 3) // 4 * 4
+        self.uniform_slots = bool(
+            not self.plan.active and int(m.n_vars) > 0 and not np.any(m.var_kind != 0)
+            and (K >= 2 or self.dtype_name == "float64")
+            and np.array_equal(m.var_off.astype(np.int64), np.arange(int(m.n_vars), dtype=np.int64) * slot)
+            and int(m.n_vars) * slot <= n_param and os.environ.get("LHVI_UNIFORM_STEP", "1") != "0")
         self.var_kind = self._dev(m.var_kind[order].astype(np.uint8))
         self.var_dim = self._dev(m.var_dim[order].astype(np.int32))
         self.var_off = self._dev(m.var_off[order].astype(np.int32))
@@ -697,9 +705,10 @@ class DeviceEngine:
             # the step counter is advanced beside the factor kernels; finish + step are one launch
             launches = self._launch_groups(tick=not sgd)
             x = C.byref(self.peer.desc) if self.plan.active else None
+            tables = ((None, None, None) if self.uniform_slots else
+                      (self.var_kind.data_ptr(), self.var_dim.data_ptr(), self.var_off.data_ptr()))
             _cabi.check(self.lib.lhvi_finish_step(
-                C.byref(self.desc), self.partial_rows, x, self.n_vars, self.n_owned,
-                self.var_kind.data_ptr(), self.var_dim.data_ptr(), self.var_off.data_ptr(),
+                C.byref(self.desc), self.partial_rows, x, self.n_vars, self.n_owned, *tables,
                 self.tau.data_ptr(), self.mom1.data_ptr(), self.mom2.data_ptr(), self.wstate.data_ptr(),
                 self.step.data_ptr(), float(lr), self.b1, self.b2, self.eps, self.var_threshold,
                 int(bool(sgd)), self._stream()), self.lib)
