@@ -686,7 +686,10 @@ class ArrayVI:
     def __init__(self, ga: GroundArrays, K, T, *, lifted=True, dtype="float64", device=None, engine_factory=None,
                  device_passes=None):
         self.ga, self.K, self.T = ga, K, T
-        dev = _passes_device(device_passes, device, engine_factory) if lifted else None
+        # (a single colour passing: the host library is as fast as the device passes' first-use costs below
+        # ~10^6 factors, so the resident passes are opt-in here; C2FArrayVI, which refines every ten
+        # iterations, uses them by default)
+        dev = _passes_device(False if device_passes is None else device_passes, device, engine_factory) if lifted else None
         if dev is not None:
             # colour passing, class statistics and lowering on the resident ground graph (lifting_torch):
             # the host library's class ids and record columns
