@@ -145,3 +145,22 @@ def test_coarse_to_fine_on_the_gpu_with_resident_passes_equals_the_host_route():
     np.testing.assert_allclose([f for _, f in a.history], [f for _, f in b.history], rtol=1e-9)
     assert np.array_equal(a.vcol, b.vcol) and all(np.array_equal(x, y) for x, y in zip(a.fcols, b.fcols))
     np.testing.assert_allclose(a.P, b.P, rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_resident_passes_on_the_gpu_with_discrete_evidence_and_hidden_discrete_variables(ns):
+    """Object graphs with observed and hidden discrete variables (table / MLN potentials) through the array
+    engines: the resident passes on the GPU give the host route's partition, records and run."""
+    for name, its in (("hmln_evidence", 30), ("chain_table", 20), ("rgm_split", 30)):
+        g, _ = specs.CASES[name][0](ns)
+        ga = lifting.arrays_from_graph(g)[0]
+        a, b = [lifting.C2FArrayVI(ga, 2, 3, dtype="float64", device_passes=dp).run(its, 0.1, log_fe=True) for dp in (False, True)]
+        assert [n for n, _ in a.history] == [n for n, _ in b.history], name
+        np.testing.assert_allclose([f for _, f in a.history], [f for _, f in b.history], rtol=1e-9, err_msg=name)
+        assert np.array_equal(a.vcol, b.vcol), name
+        np.testing.assert_allclose(a.P, b.P, rtol=1e-8, atol=1e-10, err_msg=name)
+        la, lb = [lifting.ArrayVI(ga, 2, 3, dtype="float64", device_passes=dp) for dp in (False, True)]
+        assert np.array_equal(la.quotient.var_colour, lb.quotient.var_colour), name
+        la.run(5, 0.1)
+        lb.run(5, 0.1)
+        np.testing.assert_allclose(la.free_energy(), lb.free_energy(), rtol=1e-10, err_msg=name)
