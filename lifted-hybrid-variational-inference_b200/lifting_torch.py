@@ -61,20 +61,26 @@ def relabel_first(inv, n_uniq):
     return rank[inv], first[order]
 
 
-def rank_first(h, cols):
-    """Dense first-appearance ids of the rows ``cols`` (list of int64 tensors) through their 64-bit hash
-    ``h``; returns ``(ids, n_classes, first)`` with ``first[c]`` the first row of class c."""
+def rank_first(h, cols, h2=None):
+    """Dense first-appearance ids of the rows ``cols`` (int64 tensors, or a callable returning them) through
+    their 64-bit hash ``h``; returns ``(ids, n_classes, first)`` with ``first[c]`` the first row of class c.
+    The classes of ``h`` are verified -- every row must agree with its class's first row in an independent
+    second hash ``h2`` (a false merge then needs a 128-bit collision), or, without ``h2``, in every column --
+    and ranked exactly, column by column, if they do not."""
     n = h.numel()
     if n == 0:
         return h.clone(), 0, h.clone()
     uniq, inv = torch.unique(h, return_inverse=True)
     ids, first = relabel_first(inv, uniq.numel())
-    ok = True
-    for c in cols:                                  # exact check: every row equals its class's first row
-        ok = ok and bool((c[first][ids] == c).all())
-    if not ok:                                      # a 64-bit collision: rank the rows exactly, column by column
+    if h2 is not None:
+        ok = bool((h2[first][ids] == h2).all())
+    else:
+        ok = True
+        for c in (cols() if callable(cols) else cols):
+            ok = ok and bool((c[first][ids] == c).all())
+    if not ok:                                      # a hash collision: rank the rows exactly, column by column
         ids = torch.zeros(n, dtype=torch.int64, device=h.device)
-        for c in cols:
+        for c in (cols() if callable(cols) else cols):
             _, ci = torch.unique(c, return_inverse=True)
             _, ids = torch.unique(ids * (int(ci.max()) + 1) + ci, return_inverse=True)
         ids, first = relabel_first(ids, int(ids.max()) + 1)
@@ -138,23 +144,33 @@ def colour_passing(tg: TorchGraph, start, max_sweeps=1000):
         before = n_classes
         sweeps += 1
         # ---- factors: (header, own class, classes of the arguments; sorted for a symmetric potential)
-        hs, width = [], max([2 + a for a in tg.arity], default=2)
-        rows = []
+        hs, hs2, keys = [], [], []
+        width = max([2 + a for a in tg.arity], default=2)
         for args, own, hdr, sym in zip(tg.args, fcol, tg.header, tg.symmetric):
             k = vcol[args]
             if sym and k.shape[1] > 1:
                 k = torch.sort(k, dim=1).values
             h = mix(own, 0x452821E638D01377 + hdr)
+            g2 = mix(own, 0xC0AC29B7C97C50DD + hdr)                 # independent second hash (verification)
             for j in range(k.shape[1]):
                 h = mix(h ^ k[:, j], 0xBE5466CF34E90C6C)
+                g2 = mix(g2 ^ k[:, j], 0x3F84D5B5B5470917)
             hs.append(h)
-            pad = torch.zeros((k.shape[0], width - 2 - k.shape[1]), dtype=torch.int64, device=tg.device)
-            rows.append(torch.cat([torch.full((k.shape[0], 1), hdr, dtype=torch.int64, device=tg.device),
-                                   own[:, None], k, pad], dim=1))
-        if tg.n_fac:
+            hs2.append(g2)
+            keys.append((k, own, hdr))
+
+        def exact_rows():                                            # only built if the hashes disagree
+            rows = []
+            for k, own, hdr in keys:
+                pad = torch.zeros((k.shape[0], width - 2 - k.shape[1]), dtype=torch.int64, device=tg.device)
+                rows.append(torch.cat([torch.full((k.shape[0], 1), hdr, dtype=torch.int64, device=tg.device),
+                                       own[:, None], k, pad], dim=1))
             key = torch.cat(rows)
-            fid, _, _ = rank_first(torch.cat(hs), [key[:, j] for j in range(width)])
+            return [key[:, j] for j in range(width)]
+        if tg.n_fac:
+            fid, _, _ = rank_first(torch.cat(hs), exact_rows, torch.cat(hs2))
             fcol = [fid[int(a):int(b)] for a, b in zip(tg.foff[:-1], tg.foff[1:])]
+        del keys
         # ---- variables: (own class, multiset of incident factor classes) through two 64-bit sums
         if tg.n_fac:
             c = fid[tg.inc_fac]
@@ -163,7 +179,8 @@ def colour_passing(tg: TorchGraph, start, max_sweeps=1000):
         else:
             H1 = H2 = torch.zeros(tg.n_vars, dtype=torch.int64, device=tg.device)
         vh = mix(vcol, 0xA4093822299F31D0) + H1 + mix(H2, 0x082EFA98EC4E6C89)
-        vcol, n_classes, _ = rank_first(vh, [vcol, H1, H2])
+        vh2 = mix(mix(vcol, 0x9216D5D98979FB1B) ^ H2, 0xD1310BA698DFB5AC) + mix(H1, 0x2FFD72DBD01ADFB7)
+        vcol, n_classes, _ = rank_first(vh, [vcol, H1, H2], vh2)
     return vcol, fcol, sweeps
 
 

@@ -50,6 +50,12 @@ def test_rank_first_survives_a_hash_collision():
     cols = [torch.tensor([5, 7, 5, 9, 7, 5]), torch.tensor([1, 1, 2, 1, 1, 1])]
     ids, n, first = lt.rank_first(torch.zeros(6, dtype=torch.int64), cols)          # every row "collides"
     assert ids.tolist() == [0, 1, 2, 3, 1, 0] and n == 4 and first.tolist() == [0, 1, 2, 3]
+    # with a second hash as the verifier: a disagreement sends the rows to the exact ranking as well
+    h2 = lt.mix(cols[0], 11) ^ lt.mix(cols[1], 13)
+    ids, n, first = lt.rank_first(torch.zeros(6, dtype=torch.int64), lambda: cols, h2)
+    assert ids.tolist() == [0, 1, 2, 3, 1, 0] and n == 4
+    ids, n, _ = lt.rank_first(lt.mix(cols[0], 5) + cols[1], cols, h2)                    # no collision: fast path
+    assert ids.tolist() == [0, 1, 2, 3, 1, 0] and n == 4
 
 
 def test_statistics_layout_and_lowering_match_the_host_passes(ns):
