@@ -46,6 +46,40 @@ def test_initial_colouring_matches_the_host_pass(ns, split):
         assert np.array_equal(lt.initial_colouring(tg, cont, split).numpy(), want), name
 
 
+def test_colour_passing_on_random_graphs_gives_the_host_library_s_ids():
+    """Random small factor graphs: several blocks of arity 1-4, symmetric and ordered potentials, repeated
+    rows, blocks sharing a potential object, mixed evidence (``tests/test_lifting.py`` runs the same graphs
+    through the two host implementations)."""
+    class Stub:
+        def __init__(self, symmetric):
+            self.symmetric = symmetric
+    doms = [lhvi_b200.Graph.Domain((-5, 5), continuous=True), lhvi_b200.Graph.Domain((0, 1))]
+    for seed in range(60):
+        rng = np.random.default_rng(seed)
+        nv = int(rng.integers(3, 60))
+        var_dom = rng.integers(0, 2, nv).astype(np.int32)
+        val = np.full(nv, np.nan)
+        ev = rng.random(nv) < 0.4
+        val[ev] = np.where(var_dom[ev] == 0, rng.integers(0, 3, ev.sum()) * 0.5, rng.integers(0, 2, ev.sum()))
+        blocks = []
+        for _ in range(int(rng.integers(1, 5))):
+            arity, n = int(rng.integers(1, 5)), int(rng.integers(1, 40))
+            base = rng.integers(0, nv, (max(1, n // 3), arity))
+            blocks.append(lifting.FactorBlock(Stub(bool(rng.integers(0, 2))), base[rng.integers(0, base.shape[0], n)].astype(np.int64)))
+        if rng.random() < 0.3 and len(blocks) > 1:
+            blocks[1] = lifting.FactorBlock(blocks[0].potential, rng.integers(0, nv, (5, blocks[0].arity)).astype(np.int64))
+        ga = lifting.GroundArrays(doms, var_dom, val, blocks)
+        tg = lt.TorchGraph(ga, "cpu")
+        cont, _ = lt.domain_tables(doms, "cpu")
+        for split in (True, False):
+            v0, f0, s0 = lifting.colour_passing(ga, split_cont_evidence=split, use_native=True)
+            v1, f1, s1 = lt.colour_passing(tg, lt.initial_colouring(tg, cont, split))
+            assert s0 == s1 and np.array_equal(v0, v1.numpy()), (seed, split)
+            assert all(np.array_equal(a, b.numpy()) for a, b in zip(f0, f1)), (seed, split)
+            st0, st1 = lifting.class_stats(ga, v0), lt.class_stats(tg, v1)
+            assert np.array_equal(st0["rep"], st1["rep"].numpy()) and np.array_equal(st0["degree"], st1["degree"].numpy())
+
+
 def test_rank_first_survives_a_hash_collision():
     cols = [torch.tensor([5, 7, 5, 9, 7, 5]), torch.tensor([1, 1, 2, 1, 1, 1])]
     ids, n, first = lt.rank_first(torch.zeros(6, dtype=torch.int64), cols)          # every row "collides"
