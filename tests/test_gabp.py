@@ -69,6 +69,60 @@ def test_information_form_from_the_array_generators():
     np.testing.assert_allclose(mean, np.linalg.solve(Jd, hd), rtol=1e-8, atol=1e-10)
 
 
+def _random_tree(ns, n, seed):
+    """Random tree of hidden reals with LinearGaussian / Gaussian / XY edges, an X2 prior on every node and
+    a few observed leaves: Gaussian belief propagation is exact on it (means and variances)."""
+    rng = np.random.default_rng(seed)
+    dom = ns.Domain((-10, 10), continuous=True)
+    x = [ns.RV(dom) for _ in range(n)]
+    fs = [ns.F(ns.X2Potential(1.0, float(rng.uniform(1.0, 3.0))), [v]) for v in x]
+    for i in range(1, n):
+        j = int(rng.integers(0, i))
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            pot = ns.LinearGaussianPotential(float(rng.uniform(0.3, 1.2)), float(rng.uniform(0.5, 2.0)))
+        elif kind == 1:
+            c = float(rng.uniform(-0.6, 0.6))
+            pot = ns.GaussianPotential([0.0, 0.0], [[1.5, c], [c, 1.2]])
+        else:
+            pot = ns.XYPotential(float(rng.uniform(-0.4, 0.4)), 2.0)
+        fs.append(ns.F(pot, [x[j], x[i]]))
+    obs = []
+    for i in rng.choice(n, size=max(1, n // 4), replace=False):
+        y = ns.RV(dom, float(rng.uniform(-2, 2)))
+        obs.append(y)
+        fs.append(ns.F(ns.LinearGaussianPotential(0.9, 0.7), [x[int(i)], y]))
+    g = ns.Graph()
+    g.rvs, g.factors = set(x + obs), set(fs)
+    g.init_nb()
+    return g, x
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_exact_marginals_on_trees(ns, seed):
+    g, x = _random_tree(ns, 25, seed)
+    model = lhvi_b200.lowering.lower_ground(g, 1, 3)
+    a = gabp.gabp_from_model(model)
+    J, h = _dense(a)
+    cov = np.linalg.inv(J)
+    mean, var = gabp_numpy.run(a, 60)
+    np.testing.assert_allclose(mean, cov @ h, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(var, np.diag(cov), rtol=1e-9)
+
+
+@pytest.mark.gpu
+def test_device_gabp_is_exact_on_trees(ns):
+    for seed in range(3):
+        g, x = _random_tree(ns, 40, seed)
+        bp = gabp.GaBP(g).run(80)
+        J, h = _dense(bp.arrays)
+        cov = np.linalg.inv(J)
+        got = np.array([bp.get_belief_params(rv) for rv in x])
+        order = [bp.model.index[rv] for rv in x]
+        np.testing.assert_allclose(got[:, 0], (cov @ h)[order], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(got[:, 1], np.diag(cov)[order], rtol=1e-9)
+
+
 def test_unsupported_models_are_refused(ns):
     g, _ = specs.chain_table(ns)
     with pytest.raises(NotImplementedError):
