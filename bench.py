@@ -366,7 +366,11 @@ def run_ours(a):
         d, _, g = eng.groups[i]
         kind = "node" if g.node else ("pure" if g.pure else "full")
         stream = " streamed" if (d.fold and (d.hub_mask >> g.nd) & 1) else ""
-        return f"{kind}{stream} nd={g.nd} nc={g.nc} ng={g.ng} ne={g.ne} n={g.n}" + (" [run-major]" if d.run_start else "")
+        fused = eng.groups[i][1].get("fused")
+        tail = " [run-major]" if d.run_start else ""
+        if fused:
+            tail = f" [run-major, with {fused[0]} node-entropy and {fused[1]} unary records of its run variables]"
+        return f"{kind}{stream} nd={g.nd} nc={g.nc} ng={g.ng} ne={g.ne} n={g.n}" + tail
 
     # the free energy of the (deterministic) initial state must not depend on how the records are
     # sharded: every run computes it once (dense sum over the ranks) and compares it with the value an

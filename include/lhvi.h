@@ -60,7 +60,7 @@
 extern "C" {
 #endif
 
-#define LHVI_ABI_VERSION 6
+#define LHVI_ABI_VERSION 7
 
 /* element type of every `void*` buffer of reals */
 #define LHVI_F32 0
@@ -154,6 +154,19 @@ typedef struct lhvi_group {
        specialised kernel, no fold / run-major columns, not part of lhvi_iterate) */
     int32_t pot_kind;
     int32_t reserved0;
+    /* Optional, run-major groups only: records of the run variable itself, evaluated once per run inside
+       the run-major kernel, where the variable's parameters and axis tables are in registers anyway
+       (they would otherwise be separate record groups and launches).  A run that was cut into several
+       runs with the same key carries them on ONE of its pieces (zeros / -1 on the others).
+         run_node    [2][n_runs] reals: W (energy / G_w scale) and the parameter-gradient scale of the
+                     variable's node-entropy record (F = log b on its own quadrature nodes); 0, 0: none
+         run_una_pot [n_runs] offset in ptab of the coefficient block (c, l, a) of ONE pure unary record
+                     (nd=0, nc=1, ng=0, ne=0, LHVI_POT_QUADRATIC: F = log psi only) on the variable; -1: none
+         run_una_w   [2][n_runs] reals: W_f and gamma of that record
+       NULL: not provided.  Results equal those of the separate records. */
+    const void* run_node;
+    const int32_t* run_una_pot;
+    const void* run_una_w;
 } lhvi_group;
 
 /* Model-wide device buffers shared by every group launch. */

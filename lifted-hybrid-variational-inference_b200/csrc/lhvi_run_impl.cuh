@@ -183,6 +183,77 @@ factor_run_body(const GroupView<real>& g, const RunLaunch<real, T>& L, const int
         for (int i = 0; i < K; ++i) af[i] = real(0);
         c.pt.poff[0] = keyE;
 
+        // ---- the run variable's own records, fused (lhvi_group::run_node / run_una_*): its node-entropy
+        // record -- F = log b on the variable's own nodes, b from the cross densities that are in
+        // registers already -- and one pure unary quadratic factor (F = log psi, evaluated at the nodes
+        // like pure_unary_body does).  Same accumulators as the records below; F enters with the sign of
+        // `lpsi - lb`, so the node term is a record with lpsi = 0 and the belief term negated.
+        if (g.run_node != nullptr) {
+            const real wfN = g.run_node[run], nsN = g.run_node[g.n_runs + run];
+            if (wfN != real(0) || nsN != real(0)) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    real Lg[T];
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        real b = wnE[0] * qE[k][0][t];
+#pragma unroll
+                        for (int k2 = 1; k2 < K; ++k2) b += wnE[k2] * qE[k][k2][t];
+                        Lg[t] = F::log_belief(b);
+                    }
+                    if (own_floor(wnE[k] * L.eq_min)) {          // float only: the belief may have underflowed
+#pragma unroll
+                        for (int t = 0; t < T; ++t) {
+                            PointCtx<real, 1, 0> pc;
+                            pc.poff[0] = keyE;
+                            pc.x[0] = sdE[k] * L.xi[t] + muE[k];
+                            Lg[t] = checked_log_belief<real, K, 1, 0>(g.eta, s_w, pc);
+                        }
+                    }
+                    real e0 = real(0), e1 = real(0), e2 = real(0);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) { e0 += L.w0[t] * Lg[t]; e1 += L.w1[t] * Lg[t]; e2 += L.w2[t] * Lg[t]; }
+                    const real Ek = e0 * F::kUnit;
+                    G1[k] += nsN * e1;
+                    G2[k] += nsN * (e2 * F::kUnit - real(0.5) * Ek);
+                    af[k] += wfN * Ek;
+                }
+            }
+        }
+        if (g.run_una_pot != nullptr) {
+            const int up = g.run_una_pot[run];
+            if (up >= 0) {
+                const real wfU = g.run_una_w[run], gmU = g.run_una_w[g.n_runs + run];
+                constexpr real to_unit = real(1) / F::kUnit;
+                const real* cf = g.ptab + up;
+                const real c0 = __ldg(cf) * to_unit, l0 = __ldg(cf + 1) * to_unit, a0 = __ldg(cf + 2) * to_unit;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    real e0 = real(0), e1 = real(0), e2 = real(0), qmin = real(0);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        const real x = sdE[k] * L.xi[t] + muE[k];
+                        const real q = c0 + x * (l0 + a0 * x);
+                        qmin = F::min(qmin, q);
+                        e0 += L.w0[t] * q; e1 += L.w1[t] * q; e2 += L.w2[t] * q;
+                    }
+                    if (qmin < F::kQFloor) {                     // the 1e-100 floor is active: literal formula
+                        e0 = e1 = e2 = real(0);
+#pragma unroll
+                        for (int t = 0; t < T; ++t) {
+                            const real x = sdE[k] * L.xi[t] + muE[k];
+                            const real q = checked_log_psi<real>(c0 + x * (l0 + a0 * x));
+                            e0 += L.w0[t] * q; e1 += L.w1[t] * q; e2 += L.w2[t] * q;
+                        }
+                    }
+                    const real Ek = e0 * F::kUnit;
+                    G1[k] += gmU * e1;
+                    G2[k] += gmU * (e2 * F::kUnit - real(0.5) * Ek);
+                    af[k] += wfU * Ek;
+                }
+            }
+        }
+
         // ---- its records (columns fetched one record ahead)
         int n_pot = 0, n_h = 0;
         real n_wf = real(1), n_gE = real(1), n_gH = real(1);

@@ -136,6 +136,63 @@ def run_layout(g, K, elem_bytes):
     return sg, starts.astype(np.int32), run_key.astype(np.int32), hid.astype(np.int32), hubs.astype(np.int32), hub_arg
 
 
+def fuse_run_extras(groups, layouts):
+    """Move the records of a run-major group's run variables that the run-major kernel can evaluate once per
+    run -- the variable's node-entropy record and one pure unary quadratic factor (nd=0, nc=1, ng=0, ne=0) --
+    out of their own groups and into per-run columns of the run-major group (``lhvi_group::run_node /
+    run_una_pot / run_una_w``): the kernel has the variable's parameters and axis tables in registers at that
+    point, while as separate groups they are two more launches that the register-bound big kernels do not
+    overlap with (7 + 10 us of a 137 us iteration on the bench model, ``tools/small_group_probe.py``).
+    Returns ``(groups, extras)``: the reduced group list (same length and order) and ``{group index:
+    (run_node [2, n_runs] | None, run_una_pot [n_runs] | None, run_una_w [2, n_runs] | None, counts)}``.
+    Sums are unchanged: every record is still evaluated once per iteration."""
+    groups = list(groups)
+    extras = {}
+    for gi, lay in enumerate(layouts):
+        if lay is None:
+            continue
+        _, _, run_key, _, _, _ = lay
+        n_runs = int(run_key.size)
+        first = np.ones(n_runs, dtype=bool)
+        first[1:] = run_key[1:] != run_key[:-1]            # a run cut into pieces: the first piece carries the extras
+        pos_first = np.flatnonzero(first)
+        keys = run_key[pos_first].astype(np.int64)         # ascending (the group is sorted by this argument)
+        node = np.zeros((2, n_runs))
+        una_pot = np.full(n_runs, -1, dtype=np.int32)
+        una_w = np.zeros((2, n_runs))
+        n_node = n_una = 0
+        for gj, h in enumerate(groups):
+            if gj == gi or h.n == 0 or h.nd != 0 or h.ng != 0 or h.nc != 1 or h.ne != 0 or h.kind != 0:
+                continue
+            if not (h.node or h.pure):
+                continue
+            off = h.poff[0].astype(np.int64)
+            at = np.minimum(np.searchsorted(keys, off), keys.size - 1)
+            hit = keys[at] == off
+            # one record per variable goes along; further records on the same variable stay where they are
+            uniq_first = np.zeros(h.n, dtype=bool)
+            uniq_first[np.unique(off, return_index=True)[1]] = True
+            run = pos_first[at]
+            free = (node[0, run] == 0) & (node[1, run] == 0) if h.node else (una_pot[run] < 0)
+            take = hit & uniq_first & free
+            if h.node:
+                take &= (h.wf != 0) | (h.nscale != 0)       # (an all-zero node record contributes nothing either way)
+            if not take.any():
+                continue
+            r = run[take]
+            if h.node:
+                node[0, r], node[1, r] = h.wf[take], h.nscale[take]
+                n_node += int(take.sum())
+            else:
+                una_pot[r] = h.pot[take]
+                una_w[0, r], una_w[1, r] = h.wf[take], h.gam[0][take]
+                n_una += int(take.sum())
+            groups[gj] = h.take(np.flatnonzero(~take))
+        if n_node or n_una:
+            extras[gi] = (node if n_node else None, una_pot if n_una else None, una_w if n_una else None, (n_node, n_una))
+    return groups, extras
+
+
 # ---- schedule of the persistent iteration kernel (lhvi_iterate) ---------------------------------
 # Per record group: nanoseconds per record for ONE block of 256 threads, and a fixed prologue +
 # epilogue latency per block and iteration in microseconds (hub tables, shared-memory set-up, block
@@ -407,21 +464,25 @@ class DeviceEngine:
                     and g.ng == 0 and g.kind == 0 and K <= 3 and bool((hub_mask(g) >> g.nd) & 1))
         layouts = [run_layout(g, K, esize) if (self.run_major and self.mirror_rule and self.T == 3 and K <= 3) else None
                    for g in self.model.groups]
+        # records of the run variables themselves go into the run-major kernel (fuse_run_extras)
+        model_groups, self.fused_extras = list(self.model.groups), {}
+        if os.environ.get("LHVI_FUSE_RUN_EXTRAS", "1") != "0" and not self.force_generic and self.compat is None:
+            model_groups, self.fused_extras = fuse_run_extras(model_groups, layouts)
         # schedule of the persistent kernel: "split" gives every group blocks of its own (the groups run
         # side by side, as on the branches of the CUDA graph), "slice" lets every block walk all groups
         self.iter_plan = None
         mode = os.environ.get("LHVI_ITER_PLAN", "split")
-        live = [i for i, g in enumerate(self.model.groups) if g.n > 0]
-        if self.use_persistent and mode != "slice" and live and all(self.model.groups[i].nd == 0 for i in live):
-            kinds = [iteration_kind(self.model.groups[i], layouts[i], is_streamed(self.model.groups[i])) for i in live]
+        live = [i for i, g in enumerate(model_groups) if g.n > 0]
+        if self.use_persistent and mode != "slice" and live and all(model_groups[i].nd == 0 for i in live):
+            kinds = [iteration_kind(model_groups[i], layouts[i], is_streamed(model_groups[i])) for i in live]
             blocks = int(os.environ.get("LHVI_ITER_BLOCKS", ITER_BLOCK_SLOTS))
             if len(live) <= blocks:
-                work = [iteration_cost(k, self.model.groups[i].n, K, esize) for k, i in zip(kinds, live)]
+                work = [iteration_cost(k, model_groups[i].n, K, esize) for k, i in zip(kinds, live)]
                 shares = iteration_plan(work, [ITER_FIXED_US[k] for k in kinds], blocks)
                 self.iter_plan = dict(zip(live, shares))
                 self.iter_kinds = dict(zip(live, kinds))
                 self.iter_work = dict(zip(live, work))
-        for gi, g in enumerate(self.model.groups):
+        for gi, g in enumerate(model_groups):
             keep = {}
             g_report = g        # what bench.py and callers see: the group as lowered
             d = _cabi.LhviGroup()
@@ -483,6 +544,16 @@ class DeviceEngine:
                     keep[name] = self._dev(arr, torch.int32)
                     setattr(d, name, keep[name].data_ptr())
                 d.n_runs, d.n_hubs, d.run_hub_arg = int(run_key.size), int(hubs.size), int(hub_arg)
+                if gi in self.fused_extras:
+                    node, una_pot, una_w, counts = self.fused_extras[gi]
+                    if node is not None:
+                        keep["run_node"] = self._dev(node, self.tdtype)
+                        d.run_node = keep["run_node"].data_ptr()
+                    if una_pot is not None:
+                        keep["run_una_pot"] = self._dev(una_pot, torch.int32)
+                        keep["run_una_w"] = self._dev(una_w, self.tdtype)
+                        d.run_una_pot, d.run_una_w = keep["run_una_pot"].data_ptr(), keep["run_una_w"].data_ptr()
+                    keep["fused"] = counts
             if h2 is not None:
                 keep["h2"] = h2
             self.groups.append((d, keep, g_report))
