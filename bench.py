@@ -370,6 +370,8 @@ def run_ours(a):
         tail = " [run-major]" if d.run_start else ""
         if fused:
             tail = f" [run-major, with {fused[0]} node-entropy and {fused[1]} unary records of its run variables]"
+        if eng.groups[i][1].get("fused_constants"):
+            tail += f" [with {eng.groups[i][1]['fused_constants']} constant records]"
         return f"{kind}{stream} nd={g.nd} nc={g.nc} ng={g.ng} ne={g.ne} n={g.n}" + tail
 
     # the free energy of the (deterministic) initial state must not depend on how the records are

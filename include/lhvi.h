@@ -60,7 +60,7 @@
 extern "C" {
 #endif
 
-#define LHVI_ABI_VERSION 7
+#define LHVI_ABI_VERSION 8
 
 /* element type of every `void*` buffer of reals */
 #define LHVI_F32 0
@@ -167,6 +167,15 @@ typedef struct lhvi_group {
     const void* run_node;
     const int32_t* run_una_pot;
     const void* run_una_w;
+    /* Optional, streamed groups only (fold != NULL): cst_n records without any integrated argument (nd=nc=ng=0,
+       LHVI_POT_QUADRATIC: every argument observed) -- constants of the free energy and of G_w -- that the
+       streaming kernel evaluates beside its own records (one per thread and tile, so their loads hide behind
+       the tile's) instead of a launch of their own.  cst_q [cst_n]: the record's quadratic with its point
+       evidence substituted, as `fold` does for the streamed records (the kernel still applies
+       log(exp(q) + 1e-100) and the weight to every record in every pass); cst_wf [cst_n]: W_f (NULL: all 1). */
+    const void* cst_q;
+    const void* cst_wf;
+    int64_t cst_n;
 } lhvi_group;
 
 /* Model-wide device buffers shared by every group launch. */

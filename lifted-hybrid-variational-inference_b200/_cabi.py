@@ -17,7 +17,7 @@ LHVI_FOLD_TILE = 1024
 LHVI_MAX_PEERS = 16
 LHVI_RUN_MAX_HUBS = 16
 LHVI_IPC_HANDLE_BYTES = 64
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblhvi.so")
 
@@ -44,6 +44,7 @@ class LhviGroup(C.Structure):
         ("iter_blocks", C.c_int32), ("no_category_grad", C.c_int32),
         ("pot_kind", C.c_int32), ("reserved0", C.c_int32),
         ("run_node", C.c_void_p), ("run_una_pot", C.c_void_p), ("run_una_w", C.c_void_p),
+        ("cst_q", C.c_void_p), ("cst_wf", C.c_void_p), ("cst_n", C.c_int64),
     ]
 
 

@@ -57,6 +57,8 @@ static int validate(const lhvi_model* m, const lhvi_group* g, int64_t row0) {
     }
     if ((g->run_node || g->run_una_pot || g->run_una_w) && !g->run_start) { set_error("run_node / run_una_* are columns of a run-major group (run_start is null)"); return LHVI_EINVAL; }
     if ((g->run_una_pot != nullptr) != (g->run_una_w != nullptr)) { set_error("run_una_pot and run_una_w come together"); return LHVI_EINVAL; }
+    if (g->cst_n >= (1ll << 31)) { set_error("cst_n=%lld: at most 2^31 - 1 constant records per group", (long long)g->cst_n); return LHVI_ELIMIT; }
+    if (g->cst_n < 0 || (g->cst_n > 0 && (!g->fold || !g->cst_q))) { set_error("cst_* columns belong to a streamed group (fold columns) and need cst_q"); return LHVI_EINVAL; }
     if (g->run_start) {
         if (g->node || g->pure || g->nd != 0 || g->nc != 2 || g->ng != 0) { set_error("run-major columns are only defined for full groups with two hidden continuous arguments"); return LHVI_EINVAL; }
         if (!g->run_key || !g->run_hid || !g->hub_keys) { set_error("run-major group without run_key/run_hid/hub_keys"); return LHVI_EINVAL; }

@@ -166,6 +166,9 @@ struct GroupView {
     const real* run_node;       // lhvi_group::run_node / run_una_pot / run_una_w (fused records of the run variable)
     const int* run_una_pot;
     const real* run_una_w;
+    const real* cst_q;          // lhvi_group::cst_* (constant records evaluated by the streaming kernel)
+    const real* cst_wf;
+    long long cst_n;
     // model
     int K, T;
     const real* quad;
@@ -193,6 +196,7 @@ inline GroupView<real> make_view(const lhvi_model* m, const lhvi_group* g, int64
     v.run_start = g->run_start; v.run_key = g->run_key; v.run_hid = g->run_hid;
     v.hub_keys = g->hub_keys; v.n_runs = g->n_runs;
     v.run_node = (const real*)g->run_node; v.run_una_pot = g->run_una_pot; v.run_una_w = (const real*)g->run_una_w;
+    v.cst_q = (const real*)g->cst_q; v.cst_wf = (const real*)g->cst_wf; v.cst_n = g->cst_n;
     v.K = m->K; v.T = m->T;
     v.quad = (const real*)m->quad; v.ptab = (const real*)m->ptab;
     v.eta = (const real*)m->eta; v.w = (const real*)m->w;

@@ -1748,11 +1748,28 @@ unary_fold_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice 
     // (TMA: the barriers were initialised and the first kStages tiles issued at the top of the kernel.
     // LDG: the loads are kept in flight by occupancy -- 4 blocks x 8 warps per SM, six 512-byte requests
     // per warp and tile -- rather than by a second set of column registers.)
+    // constant records riding with this group (lhvi_group::cst_*): this block's slice, one record per thread
+    // and tile (the loads are independent of everything else and hide behind the tile's)
+    // (32-bit indices and a float partial sum -- a handful of records per thread -- keep the streaming loop
+    // within its 64 registers; cst_n < 2^31 is checked at launch)
+    unsigned cst_i = 0, cst_hi = 0;
+    real cst_sum = real(0);
+    if (g.cst_n > 0) {
+        const long long per = (g.cst_n + bs.nblocks - 1) / bs.nblocks;
+        const long long c_hi = per * (bs.bid + 1) < g.cst_n ? per * (bs.bid + 1) : g.cst_n;
+        cst_i = (unsigned)(per * bs.bid + threadIdx.x);
+        cst_hi = (unsigned)(c_hi > 0 ? c_hi : 0);
+    }
     int tile_i = 0;
 #pragma unroll 1
     for (; r < hi; r += kFoldTile, ++tile_i) {
         real q_c0[kQuad], q_l0[kQuad], q_a0[kQuad], q_wf[kQuad], q_gam[kQuad];
         int q_off[kQuad];
+        if (cst_i < cst_hi) {
+            const real wf = g.cst_wf != nullptr ? __ldg(g.cst_wf + cst_i) : real(1);
+            cst_sum += wf * Math<real>::log_psi(__ldg(g.cst_q + cst_i));
+            cst_i += blockDim.x;
+        }
         if constexpr (TMA) {
             const int st = tile_i % kStages;
             mbar_wait(&shb.full[st], (unsigned)((tile_i / kStages) & 1));
@@ -1879,6 +1896,19 @@ unary_fold_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice 
 #pragma unroll
             for (int i = 0; i <= K; ++i) acc[i] += sa.acc[i];
         }
+    }
+
+    // ---- constant records fused into this group (lhvi_group::cst_*): what is left of this block's slice
+    // after the tiles (a block with few tiles), then the sums: E_k[F] = log(psi + 1e-100) for every k
+    if (g.cst_n > 0) {
+        for (; cst_i < cst_hi; cst_i += blockDim.x) {
+            const real wf = g.cst_wf != nullptr ? __ldg(g.cst_wf + cst_i) : real(1);
+            cst_sum += wf * Math<real>::log_psi(__ldg(g.cst_q + cst_i));
+        }
+        double wsum = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { acc[k] -= (double)cst_sum; wsum += (double)sh.w[k]; }
+        acc[K] -= (double)cst_sum * wsum;
     }
 
     publish_partials(acc, K + 1, s_scratch, g.partials, bs);

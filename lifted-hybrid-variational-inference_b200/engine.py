@@ -193,6 +193,42 @@ def fuse_run_extras(groups, layouts):
     return groups, extras
 
 
+def fuse_constants(groups, streamed, ptab):
+    """Records without any integrated argument (every argument observed: constants of the free energy and of
+    G_w) leave their group and travel as extra columns of the largest streamed group (``lhvi_group::cst_*``):
+    the streaming kernel evaluates one of them per thread and tile beside its own records, instead of one more
+    launch behind the register-bound kernels (8.6 us of the bench iteration, ``tools/small_group_probe.py``).
+    Like ``fold_unary`` for the streamed records, the point evidence is substituted into the record's quadratic
+    here (``cst_q``); the floor and the weight are applied to every record in every pass on the device.
+    Returns ``(groups, {streamed group index: (q, wf | None)})``."""
+    groups = list(groups)
+    target = max((i for i in range(len(groups)) if streamed[i]), key=lambda i: groups[i].n, default=None)
+    if target is None:
+        return groups, {}
+    qs, wfs, weighted = [], [], False
+    for gj, h in enumerate(groups):
+        if gj == target or h.n == 0 or h.node or not h.pure or h.nd or h.nc or h.ng or h.kind != 0 or h.ne < 1:
+            continue
+        nct = h.ne
+        ncoef = (nct + 1) * (nct + 2) // 2
+        coef = ptab[h.pot.astype(np.int64)[:, None] + np.arange(ncoef)[None, :]]
+        q = coef[:, 0].copy()
+        for i in range(nct):
+            q += coef[:, 1 + i] * h.ecval[i]
+        p = 1 + nct
+        for i in range(nct):
+            for j in range(i, nct):
+                q += coef[:, p] * h.ecval[i] * h.ecval[j]
+                p += 1
+        qs.append(q)
+        wfs.append(h.wf)
+        weighted = weighted or bool(h.weighted)
+        groups[gj] = h.take(np.zeros(0, dtype=np.int64))
+    if not qs:
+        return groups, {}
+    return groups, {target: (np.concatenate(qs), np.concatenate(wfs) if weighted else None)}
+
+
 # ---- schedule of the persistent iteration kernel (lhvi_iterate) ---------------------------------
 # Per record group: nanoseconds per record for ONE block of 256 threads, and a fixed prologue +
 # epilogue latency per block and iteration in microseconds (hub tables, shared-memory set-up, block
@@ -468,6 +504,10 @@ class DeviceEngine:
         model_groups, self.fused_extras = list(self.model.groups), {}
         if os.environ.get("LHVI_FUSE_RUN_EXTRAS", "1") != "0" and not self.force_generic and self.compat is None:
             model_groups, self.fused_extras = fuse_run_extras(model_groups, layouts)
+        self.fused_constants = {}
+        if os.environ.get("LHVI_FUSE_CONSTANTS", "1") != "0" and not self.force_generic and self.compat is None:
+            model_groups, self.fused_constants = fuse_constants(model_groups, [is_streamed(g) for g in model_groups],
+                                                                np.asarray(m.ptab, dtype=np.float64))
         # schedule of the persistent kernel: "split" gives every group blocks of its own (the groups run
         # side by side, as on the branches of the CUDA graph), "slice" lets every block walk all groups
         self.iter_plan = None
@@ -537,6 +577,14 @@ class DeviceEngine:
                 cols = np.zeros((3, n_pad))
                 cols[:, :g.n] = fold
                 d.fold, d.n_pad = put("fold", cols, self.tdtype), n_pad
+            if gi in self.fused_constants and padded:
+                cq, cwf = self.fused_constants[gi]
+                keep["cst_q"] = self._dev(cq, self.tdtype)
+                d.cst_q, d.cst_n = keep["cst_q"].data_ptr(), int(cq.size)
+                if cwf is not None:
+                    keep["cst_wf"] = self._dev(cwf, self.tdtype)
+                    d.cst_wf = keep["cst_wf"].data_ptr()
+                keep["fused_constants"] = int(cq.size)
             d.run_start, d.n_runs, d.n_hubs, d.run_hub_arg = None, 0, 0, 0
             if runs is not None:
                 _, starts, run_key, hid, hubs, hub_arg = runs

@@ -1,6 +1,7 @@
 """Records of a run-major group's run variables evaluated inside the run-major kernel (``engine.fuse_run_extras``,
 ``lhvi_group::run_node / run_una_pot / run_una_w``): the node-entropy record and one pure unary factor per
-variable leave their own groups; every sum must stay what it was."""
+variable leave their own groups; constant records (no integrated argument) ride with the streamed group
+(``engine.fuse_constants``, ``lhvi_group::cst_*``).  Every sum must stay what it was."""
 import numpy as np
 import pytest
 
@@ -14,10 +15,12 @@ pytestmark = pytest.mark.gpu
 def _pass(model, state, dtype, monkeypatch, fuse, **kw):
     from lhvi_b200.engine import DeviceEngine
     monkeypatch.setenv("LHVI_FUSE_RUN_EXTRAS", "1" if fuse else "0")
+    monkeypatch.setenv("LHVI_FUSE_CONSTANTS", "1" if fuse else "0")
     eng = DeviceEngine(model, dtype=dtype, **kw)
     eng.set_state(*state)
     grad, g_w, energy = eng.gradients()
-    fused = {i: k.get("fused") for i, (d, k, g) in enumerate(eng.groups) if k.get("fused")}
+    fused = {i: (k.get("fused"), k.get("fused_constants")) for i, (d, k, g) in enumerate(eng.groups)
+             if k.get("fused") or k.get("fused_constants")}
     sizes = [g.n for _, _, g in eng.groups]
     out = np.array(grad, dtype=np.float64), np.array(g_w, dtype=np.float64), float(energy)
     eng.close()
@@ -36,6 +39,7 @@ def test_fused_and_separate_records_give_the_same_sums(monkeypatch, weighted, K)
         a, fa, na = _pass(model, state, dtype, monkeypatch, True)
         b, fb, nb = _pass(model, state, dtype, monkeypatch, False)
         assert fa and not fb and sum(na) < sum(nb)             # the fusion happened: records left their groups
+        assert any(c for _, c in fa.values())                  # ... the constant records among them
         scale = max(1.0, np.abs(want[0]).max())
         for got in (a, b):
             np.testing.assert_allclose(got[0], want[0], rtol=tol, atol=tol * scale)
@@ -75,6 +79,7 @@ def test_fused_records_through_iterations_on_both_paths(monkeypatch):
     for fuse in ("1", "0"):
         for persistent in ("1", "0"):
             monkeypatch.setenv("LHVI_FUSE_RUN_EXTRAS", fuse)
+            monkeypatch.setenv("LHVI_FUSE_CONSTANTS", fuse)
             monkeypatch.setenv("LHVI_PERSISTENT", persistent)
             eng = DeviceEngine(model, dtype="float64")
             eng.set_state(eta, tau, w_tau)
