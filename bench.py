@@ -134,11 +134,13 @@ def traffic_from_profile(persistent, group_name, a, world):
     if persistent:          # captured per launch of `steps_per_launch` iterations
         return entry["dram_bytes"] / entry["steps_per_launch"] * a.steps
     return entry["dram_bytes"]
-NOTE = ("the full (two hidden arguments) group runs in the run-major kernel: 523 instructions per record, issue "
-        "slots 67% busy, FMA pipe 46%, XU 31%, 16 resident warps per SM (128 registers), DRAM at 15% -- its "
+NOTE = ("the full (two hidden arguments) group runs in the run-major kernel, which also evaluates the node-entropy and "
+        "unary records of its run variables (one launch instead of three): 571 instructions per link record, issue "
+        "slots 66% busy, FMA pipe 43%, XU 29%, 16 resident warps per SM (128 registers), DRAM at 15% -- its "
         "limiter is instruction issue / latency at that occupancy, not HBM: the entity slots are hit ten times each "
-        "and stay in L1/L2, so physical traffic (86 MB) is a quarter of the algorithmic bytes SURVEY 8d counts "
-        "(361 MB) and the fraction of the HBM roofline is reported as asked (profiles/r2_ncu_summary.md)")
+        "and stay in L1/L2, so physical traffic (92 MB) is a quarter of the algorithmic bytes SURVEY 8d counts "
+        "(398 MB with the fused records) and the fraction of the HBM roofline is reported as asked "
+        "(profiles/r2_ncu_summary.md)")
 
 
 # ---- clocks ------------------------------------------------------------------------------------
@@ -358,9 +360,23 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def per_record(pred):
+        """Algorithmic bytes per record of the (unfused) groups of the model that match ``pred``."""
+        gs = [g for g in eng.full_model.groups if g.n > 0 and pred(g)]
+        return group_bytes(gs[0], a.K, s) / gs[0].n if gs else 0.0
+
     def gbytes(i):
-        d, _, g = eng.groups[i]
-        return group_bytes(g, a.K, s, hub=bool(d.fold) and bool((d.hub_mask >> g.nd) & 1))
+        # records that the engine moved into another group's kernel (fuse_run_extras / fuse_constants) are
+        # counted where they are evaluated, with the bytes SURVEY 8d gives them (the accounting does not
+        # depend on the layout)
+        d, keep, g = eng.groups[i]
+        total = group_bytes(g, a.K, s, hub=bool(d.fold) and bool((d.hub_mask >> g.nd) & 1))
+        if keep.get("fused"):
+            total += keep["fused"][0] * per_record(lambda h: h.node and h.nc == 1 and h.nd == 0)
+            total += keep["fused"][1] * per_record(lambda h: h.pure and not h.node and h.nc == 1 and h.ne == 0 and h.nd == 0)
+        if keep.get("fused_constants"):
+            total += keep["fused_constants"] * per_record(lambda h: h.pure and not h.node and h.nc == 0 and h.nd == 0 and h.ng == 0)
+        return int(total)
 
     def gname(i):
         d, _, g = eng.groups[i]

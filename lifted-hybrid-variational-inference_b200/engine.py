@@ -727,6 +727,10 @@ class DeviceEngine:
 
     def _launch_group(self, i, stream):
         d, keep, _ = self.groups[i]
+        if int(d.n) == 0:
+            # a group whose records all went into another group's kernel (fuse_run_extras / fuse_constants): its
+            # region of `partials` keeps the zero header it was allocated with -- no valid rows, nothing to launch
+            return
         _cabi.check(self.lib.lhvi_factor_expect_grad(
             C.byref(self.desc), C.byref(d), i * _cabi.LHVI_PARTIAL_ROWS, int(self.force_generic),
             C.c_void_p(stream.cuda_stream)), self.lib)
@@ -745,6 +749,7 @@ class DeviceEngine:
         stream with CUDA events around that group's launch (bench.py roofline)."""
         main = torch.cuda.current_stream(self.device)
         n = len(self.groups)
+        n_launched = sum(1 for d, _, _ in self.groups if int(d.n) > 0)      # (empty groups are not launched)
         if self.profile_group is not None or not self.parallel_groups or n < 2:
             if tick:
                 self._tick(main)
@@ -756,8 +761,9 @@ class DeviceEngine:
                 self._launch_group(i, main)
                 if timed:
                     ev[1].record(main)
-                    self.dom_events.append((i, ev[0], ev[1]))
-            return n
+                    if int(self.groups[i][0].n) > 0:
+                        self.dom_events.append((i, ev[0], ev[1]))
+            return n_launched
         while len(self._side_streams) < n:
             self._side_streams.append(torch.cuda.Stream(device=self.device))
         order = sorted(range(n), key=lambda i: -self.groups[i][2].n)
@@ -778,7 +784,7 @@ class DeviceEngine:
             join = torch.cuda.Event()
             join.record(side)
             main.wait_event(join)
-        return n
+        return n_launched
 
     def _finish(self, tick, exchange):
         lib, st = self.lib, self._stream()
