@@ -141,3 +141,51 @@ def test_compat_reference_tables(ns):
     gr = [q for q in lhvi_b200.lowering.lower_ground(g2, 2, 3).groups if q.nd and not q.node][0]
     with pytest.raises(NotImplementedError):
         h2_tables(gr)
+
+
+@pytest.mark.parametrize("weighted", [True, False])
+def test_fused_records_are_the_records_that_left_their_groups(weighted):
+    """``engine.fuse_run_extras`` / ``engine.fuse_constants`` (host logic; the kernels are checked under -m gpu):
+    every record that leaves a group reappears exactly once as a per-run column of the run-major group (on the
+    first piece of its variable's run) or as a folded constant of the streamed group, and nothing else moves."""
+    syn = lhvi_b200.synthetic
+    model = syn.relational_hybrid(3000, 6, 3, 3, seed=5, weighted=weighted)
+    layouts = [eng_mod.run_layout(g, 3, 4) for g in model.groups]
+    gi = next(i for i, l in enumerate(layouts) if l is not None)
+    groups, extras = eng_mod.fuse_run_extras(model.groups, layouts)
+    node, una_pot, una_w, counts = extras[gi]
+    run_key = layouts[gi][2]
+    assert len(groups) == len(model.groups)
+    # node records: (slot offset, W, gradient scale) of what left = of what arrived
+    for orig, left in zip(model.groups, groups):
+        if orig.node and orig.nc == 1:
+            carried = np.flatnonzero((node[0] != 0) | (node[1] != 0))
+            assert counts[0] == carried.size == orig.n - left.n
+            assert np.unique(run_key[carried]).size == carried.size            # once per variable
+            gone = ~np.isin(orig.poff[0], left.poff[0])
+            a = sorted(zip(orig.poff[0][gone], orig.wf[gone], orig.nscale[gone]))
+            b = sorted(zip(run_key[carried], node[0][carried], node[1][carried]))
+            assert a == b
+        elif orig.pure and not orig.node and orig.nc == 1 and orig.ne == 0:
+            carried = np.flatnonzero(una_pot >= 0)
+            assert counts[1] == carried.size == orig.n - left.n
+            gone = ~np.isin(orig.poff[0], left.poff[0])
+            a = sorted(zip(orig.poff[0][gone], orig.pot[gone], orig.wf[gone], orig.gam[0][gone]))
+            b = sorted(zip(run_key[carried], una_pot[carried], una_w[0][carried], una_w[1][carried]))
+            assert a == b
+        elif not (orig.node or orig.pure):
+            assert left is orig or left.n == orig.n
+    # pieces of a run that was cut carry nothing beyond the first one
+    later = np.r_[False, run_key[1:] == run_key[:-1]]
+    assert not np.any((node[0][later] != 0) | (node[1][later] != 0)) and np.all(una_pot[later] < 0)
+
+    streamed = [bool(g.pure and not g.node and g.nc == 1 and g.ne == 1 and g.n > 1000) for g in groups]
+    groups2, consts = eng_mod.fuse_constants(groups, streamed, np.asarray(model.ptab, dtype=float))
+    (target, (q, wf)), = consts.items()
+    assert streamed[target]
+    orig = next(g for g in groups if g.pure and not g.node and g.nc == 0 and g.ne == 1 and g.n)
+    assert q.size == orig.n and all(g.n == 0 for g in groups2 if g.pure and not g.node and g.nc == 0)
+    coef = np.asarray(model.ptab)[orig.pot.astype(np.int64)[:, None] + np.arange(3)[None, :]]
+    x = orig.ecval[0]
+    np.testing.assert_allclose(q, coef[:, 0] + x * (coef[:, 1] + coef[:, 2] * x), rtol=1e-12, atol=1e-13)
+    assert (wf is None) == (not weighted) and (wf is None or np.array_equal(wf, orig.wf))
