@@ -305,7 +305,9 @@ def c2f_probe(a, iterations=100):
     entities = max(1000, a.entities)
     # warm-up on a small model: the first launch of a kernel pays its module load (the persistent
     # iteration kernel is tens of megabytes of SASS), which is not part of a refinement round
-    warm = lifting.C2FArrayVI(syn.relational_hybrid_arrays(2000, a.groups, observed_frac=0.7, seed=1), a.K, a.T, dtype=a.dtype)
+    # (large enough that the sort / unique / scan kernels the lifting passes use at full size are loaded too)
+    warm_entities = 50_000 if entities >= 500_000 else 2000
+    warm = lifting.C2FArrayVI(syn.relational_hybrid_arrays(warm_entities, a.groups, observed_frac=0.7, seed=1), a.K, a.T, dtype=a.dtype)
     warm.run(20, 0.05)
     ga = syn.relational_hybrid_arrays(entities, a.groups, observed_frac=0.7, seed=0)
     vi = lifting.C2FArrayVI(ga, a.K, a.T, dtype=a.dtype)
