@@ -1,6 +1,10 @@
-import os, sys, dataclasses
-sys.path.insert(0, "/root/repo")
-import numpy as np, torch
+"""What each small record group of the bench model costs the iteration: the replayed iteration with all groups,
+and with the node-entropy / unary-prior / constant groups taken out of the model one at a time (results are then
+wrong; only the time matters).  With the engine's fusions on (default) those groups are empty and the numbers
+coincide; LHVI_FUSE_RUN_EXTRAS=0 LHVI_FUSE_CONSTANTS=0 shows what they cost as launches of their own."""
+import dataclasses, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
 import lhvi_b200
 from lhvi_b200.engine import DeviceEngine
 syn = lhvi_b200.synthetic
