@@ -1351,8 +1351,12 @@ static int launch_pure_unary(const lhvi_model* m, const lhvi_group* g, int64_t r
 // The quadrature rule enters through its even moments M0, M2, M4 (the rule is symmetric, the host
 // checks it), so T is a run-time value here.
 
+// Resident blocks per SM of the streaming kernel.  Two (16 warps, up to 128 registers: no spills, the compiler
+// keeps a tile's six 16-byte loads per thread in flight) measured better than three and four on a B200 --
+// 42.4 / 47.2 / 47.5 us launched alone at 7.0 M records, 121.3 / 123.3 / 125.7 us per iteration -- in line with
+// the six-column read micro-benchmark (profiles/r2_stream6_microbench.txt: 8 blocks per SM 42 us, 4 blocks 35 us).
 #ifndef LHVI_FOLD_BLOCKS
-#define LHVI_FOLD_BLOCKS 4
+#define LHVI_FOLD_BLOCKS 2
 #endif
 #ifndef LHVI_FOLD_WAVES
 #define LHVI_FOLD_WAVES 1
@@ -1675,7 +1679,7 @@ unary_fold_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice 
 
     // 32-bit record indices (n_pad < 2^31 is checked at launch).  L.chunk holds the number of
     // tiles: block b takes tiles [tiles b / B, tiles (b + 1) / B), so that block sizes differ by
-    // at most one tile and every SM (4 resident blocks) streams the same number of bytes.
+    // at most one tile and every SM (LHVI_FOLD_BLOCKS resident blocks) streams the same number of bytes.
     const unsigned lo = (unsigned)(L.chunk * bs.bid / bs.nblocks) * kFoldTile;
     const unsigned hi = (unsigned)(L.chunk * (bs.bid + 1) / bs.nblocks) * kFoldTile;
     const real* __restrict__ col0 = g.fold;
@@ -1746,7 +1750,7 @@ unary_fold_body(const GroupView<real>& g, const SpecLaunch& L, const BlockSlice 
         }
     };
     // (TMA: the barriers were initialised and the first kStages tiles issued at the top of the kernel.
-    // LDG: the loads are kept in flight by occupancy -- 4 blocks x 8 warps per SM, six 512-byte requests
+    // LDG: the loads are kept in flight by occupancy -- LHVI_FOLD_BLOCKS blocks x 8 warps per SM, six 512-byte requests
     // per warp and tile -- rather than by a second set of column registers.)
     // constant records riding with this group (lhvi_group::cst_*): this block's slice, one record per thread
     // and tile (the loads are independent of everything else and hide behind the tile's)

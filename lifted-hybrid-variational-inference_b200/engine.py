@@ -53,7 +53,7 @@ def hub_mask(g):
 
 
 FOLD_ALIGN_MIN_TILES = 4   # runs of a streamed group at least this long are padded to whole tiles
-FOLD_BLOCK_SLOTS = 148 * 4  # resident blocks of the streaming kernel on one B200 (a hint: launch_unary_fold)
+FOLD_BLOCK_SLOTS = 148 * 2  # resident blocks of the streaming kernel on one B200 (a hint: launch_unary_fold, LHVI_FOLD_BLOCKS)
 ITER_BLOCK_SLOTS = 148 * 2  # resident blocks of the persistent iteration kernel (lhvi_iterate)
 ITER_TUNE_ROUNDS = 2
 PERSISTENT_MAX_RECORDS = 3_500_000   # LHVI_PERSISTENT=auto: larger rank-local models use the per-group launches
