@@ -66,12 +66,10 @@ def gabp_from_model(model: lowering.LoweredModel) -> GabpArrays:
     if np.any(model.var_kind != 0):
         raise NotImplementedError("GaBP: discrete hidden variables (the reference's GaBP is Gaussian only)")
     V = model.n_vars
-    var_of = {int(o): i for i, o in enumerate(model.var_off)}
-    lookup = np.full(int(model.var_off.max()) + 1 if V else 1, -1, dtype=np.int64)
-    for o, i in var_of.items():
-        lookup[o] = i
+    lookup = np.full(int(model.var_off.max()) + 1 if V else 1, -1, dtype=np.int64)      # slot offset -> variable
+    lookup[model.var_off.astype(np.int64)] = np.arange(V)
     jd, hd, nfac = np.zeros(V), np.zeros(V), np.zeros(V, dtype=np.int64)
-    src, dst, cols = [], [], []
+    blocks = []                           # per pairwise group: (v0, v1, [J00, J11, J01, h0, h1])
     ptab = np.asarray(model.ptab, dtype=np.float64)
     for g in model.groups:
         if g.node or g.n == 0:
@@ -86,32 +84,28 @@ def gabp_from_model(model: lowering.LoweredModel) -> GabpArrays:
         coef = ptab[g.pot.astype(np.int64)[:, None] + np.arange(ncoef)[None, :]]
         lin, quad = reduce_quadratic(coef, g.nc, g.ecval)
         v0 = lookup[g.poff[0]]
-        if g.nc == 1:
+        np.add.at(nfac, v0, 1)
+        if g.nc == 1:                      # unary or evidence-reduced factor: a constant message of its variable
             np.add.at(jd, v0, -2.0 * quad[(0, 0)])
             np.add.at(hd, v0, lin[0])
-            np.add.at(nfac, v0, 1)
             continue
         v1 = lookup[g.poff[1]]
         if np.any(v0 == v1):
             raise NotImplementedError("GaBP: a factor that takes the same variable twice")
-        np.add.at(nfac, v0, 1)
         np.add.at(nfac, v1, 1)
-        j00, j11, j01 = -2.0 * quad[(0, 0)], -2.0 * quad[(1, 1)], -quad[(0, 1)]
-        src += [v0, v1]                     # slots 2r (0 -> 1) and 2r + 1 (1 -> 0) of record r, interleaved below
+        blocks.append((v0, v1, np.stack([-2.0 * quad[(0, 0)], -2.0 * quad[(1, 1)], -quad[(0, 1)], lin[0], lin[1]])))
+    # directed slots: per group the messages 0 -> 1 of all its factors, then the messages 1 -> 0; rev pairs them
+    src, dst, rev, cols, at = [], [], [], [], 0
+    for v0, v1, c in blocks:
+        n = v0.size
+        src += [v0, v1]
         dst += [v1, v0]
-        cols += [np.stack([j00, j11, j01, lin[0], lin[1]]), np.stack([j11, j00, j01, lin[1], lin[0]])]
-    if src:
-        # per group: forward block then backward block; rev pairs them
-        s = np.concatenate(src).astype(np.int32)
-        d = np.concatenate(dst).astype(np.int32)
+        cols += [c, c[[1, 0, 2, 4, 3]]]
+        rev += [np.arange(at + n, at + 2 * n), np.arange(at, at + n)]
+        at += 2 * n
+    if blocks:
+        s, d, rev = (np.concatenate(x).astype(np.int32) for x in (src, dst, rev))
         c = np.concatenate(cols, axis=1)
-        rev = np.empty(s.size, dtype=np.int32)
-        at = 0
-        for blk in src[::2]:
-            n = blk.size
-            rev[at:at + n] = np.arange(at + n, at + 2 * n)
-            rev[at + n:at + 2 * n] = np.arange(at, at + n)
-            at += 2 * n
     else:
         s = d = rev = np.zeros(0, dtype=np.int32)
         c = np.zeros((5, 0))
