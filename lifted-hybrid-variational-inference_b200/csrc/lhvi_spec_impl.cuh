@@ -1353,7 +1353,8 @@ static int launch_pure_unary(const lhvi_model* m, const lhvi_group* g, int64_t r
 
 // Resident blocks per SM of the streaming kernel.  Two (16 warps, up to 128 registers: no spills, the compiler
 // keeps a tile's six 16-byte loads per thread in flight) measured better than three and four on a B200 --
-// 42.4 / 47.2 / 47.5 us launched alone at 7.0 M records, 121.3 / 123.3 / 125.7 us per iteration -- in line with
+// 42.4 / 47.2 / 47.5 us launched alone at 7.0 M records, 121.3 / 123.3 / 125.7 us per iteration (one block: 56.2 /
+// 134.6) -- in line with
 // the six-column read micro-benchmark (profiles/r2_stream6_microbench.txt: 8 blocks per SM 42 us, 4 blocks 35 us).
 #ifndef LHVI_FOLD_BLOCKS
 #define LHVI_FOLD_BLOCKS 2
